@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- MFCC/log-mel front-end throughput (BASELINE.json configs[1]) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the front-end over one batch of 65 536 synthetic 1 s / 16 kHz clips per GPU
+(clips shard by clip: no data-path collective, weak scaling).  One JSON line is printed by rank 0:
+
+  value      clips/s, whole job, inputs already resident in HBM, CUDA events on the launching stream
+  e2e        the same metric through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside)
+  roofline   HBM: 71 840 algorithmic bytes/clip (16 000*4 read + 49*40*4 written) / kernel time,
+             against MEASURED_PEAKS.json hbm_gbs (else the 6 650 GB/s fallback)
+  cpu_baseline  the plain-C/OpenMP oracle port on this host's cores, bounded sample (N=1 only)
+
+--impl reference times the CPU path alone (the reference has no feature code, so this is the oracle
+port of the declared spec) on a bounded sample per step, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_SAMPLES = 16000
+N_FRAMES = 49
+N_OUT = 40
+BYTES_PER_CLIP = N_SAMPLES * 4 + N_FRAMES * N_OUT * 4      # 71 840
+METRIC = "mfcc_clips_per_sec"
+UNIT = "clips/s"
+
+
+def workload_config(clips: int, n_gpus: int) -> dict:
+    return {
+        "workload": "BASELINE configs[1]: MFCC front-end, 40 mel x 49 frames (+DCT-II), "
+                    f"{clips} synthetic 1 s 16 kHz fp32 clips per GPU",
+        "clips_per_gpu": clips, "n_samples": N_SAMPLES, "frames": N_FRAMES, "features": N_OUT,
+        "sharding": f"clips partitioned across {n_gpus} GPU(s), no collective",
+        "cache": f"inputs ({clips * N_SAMPLES * 4 / 1e9:.2f} GB/GPU) larger than L2 (126 MB); no flush needed",
+    }
+
+
+def measured_peak() -> tuple[float, str]:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic(clips: int):
+    """dram bytes per launch from the committed ncu --set full capture (profiles/roofline.json), scaled
+    linearly in clips; None when no capture has been recorded."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline.json")) as fh:
+            rec = json.load(fh)["mfcc_kernel"]
+        return rec["dram_bytes_per_clip"] * clips
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed regions run."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.ok:
+            self._stop.clear()
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread:
+            self._stop.set()
+            self._thread.join()
+            self._thread = None
+
+    def summary(self) -> dict:
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def time_cpu_port(target_seconds: float, threads_note: bool = True) -> dict:
+    """Time the C/OpenMP oracle port on a bounded sample of the same workload."""
+    import numpy as np
+    from oracle import build_c
+    from cmoop_audio_processing_b200 import synth
+
+    lib = build_c.load()
+    cores = int(lib.cmoop_oracle_num_threads())
+    probe = synth.uniform_clips(max(64, 8 * cores), seed=2)
+    build_c.mfcc(probe[:cores])                                   # warm up threads
+    t0 = time.perf_counter()
+    build_c.mfcc(probe)
+    rate = len(probe) / (time.perf_counter() - t0)
+    n = int(min(65536, max(len(probe), rate * target_seconds)))
+    sample = synth.uniform_clips(n, seed=2)
+    t0 = time.perf_counter()
+    build_c.mfcc(sample)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} clips of the same U(-1,1) 16 000-sample workload, {dt:.1f} s, C/OpenMP fp64 oracle "
+                      "(oracle/c/mfcc_oracle.c; the reference has no feature-extraction code to time)"}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import build_c
+    from cmoop_audio_processing_b200 import synth
+
+    lib = build_c.load()
+    cores = int(lib.cmoop_oracle_num_threads())
+    probe = synth.uniform_clips(max(64, 8 * cores), seed=2)
+    build_c.mfcc(probe[:cores])
+    t0 = time.perf_counter()
+    build_c.mfcc(probe)
+    rate = len(probe) / (time.perf_counter() - t0)
+    budget = 150.0 / max(1, args.steps + args.warmup)              # whole run within a few minutes
+    n = int(min(65536, max(len(probe), rate * min(budget, 4.0))))
+    sample = synth.uniform_clips(n, seed=2)
+    for _ in range(args.warmup):
+        build_c.mfcc(sample)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        build_c.mfcc(sample)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.clips, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"each step = {n} clips of the workload (bounded sample), C/OpenMP fp64 oracle "
+                                   "port of the declared front-end spec; the reference repo has no feature code and "
+                                   "its librosa dependency is not installed"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from cmoop_audio_processing_b200 import _lib
+    from cmoop_audio_processing_b200.features import MfccFrontEnd
+
+    lib = _lib.load()
+    _lib.check(lib.cmoop_set_device(local_rank), "cmoop_set_device")
+    clips = args.clips
+    dev = torch.device("cuda", local_rank)
+    gen = torch.Generator(device=dev).manual_seed(2 + rank)
+    wave = torch.rand((clips, N_SAMPLES), generator=gen, device=dev, dtype=torch.float32).mul_(2).sub_(1)
+    out = torch.empty((clips, N_FRAMES, N_OUT), device=dev, dtype=torch.float32)
+    fe = MfccFrontEnd()
+    assert fe.n_frames(N_SAMPLES) == N_FRAMES and fe.n_out == N_OUT
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    for _ in range(args.warmup):
+        fe(wave, out=out)
+    barrier()
+
+    # ---- device-resident timing (value + roofline): one kernel launch per step
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = lib.cmoop_launch_count()
+    sampler.start()
+    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_all0.record()
+    for s, e in ev:
+        s.record()
+        fe(wave, out=out)
+        e.record()
+    t_all1.record()
+    barrier()
+    launches = int(lib.cmoop_launch_count() - launches0)
+    total_ms = t_all0.elapsed_time(t_all1)
+    kernel_ms = [s.elapsed_time(e) for s, e in ev]
+
+    # ---- end-to-end through the host-buffer C-ABI call (pinned host memory; H2D + D2H inside)
+    e2e_steps = max(1, min(args.steps, 8))
+    h_wave = torch.empty((clips, N_SAMPLES), dtype=torch.float32, pin_memory=True)
+    h_out = torch.empty((clips, N_FRAMES, N_OUT), dtype=torch.float32, pin_memory=True)
+    h_wave.copy_(wave)
+    torch.cuda.synchronize()
+    np_wave, np_out = h_wave.numpy(), h_out.numpy()
+    fe(np_wave, out=np_out)                                       # warm-up (allocates library scratch)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        fe(np_wave, out=np_out)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop()
+    checksum = float(np_out[:: max(1, clips // 64)].sum())        # the host really has the result
+
+    stats = torch.tensor([total_ms, e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = float(stats[0]), float(stats[1])
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        kernel_avg_ms = sum(kernel_ms) / len(kernel_ms)
+        achieved = BYTES_PER_CLIP * clips / (kernel_avg_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * clips * args.steps / (total_ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(clips, world),
+            "e2e": {"value": world * clips * e2e_steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": clips * N_SAMPLES * 4, "d2h_bytes_per_step": clips * N_FRAMES * N_OUT * 4,
+                    "steps": e2e_steps, "api": "cmoop_mfcc_fwd_host via MfccFrontEnd(host array), pinned host buffers",
+                    "checksum": checksum},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "mfcc_kernel<10>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": recorded_traffic(clips),
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_CLIP * clips,
+                         "kernel_ms_avg": kernel_avg_ms, "kernel_ms_min": min(kernel_ms)},
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = time_cpu_port(args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--clips", type=int, default=65536, help="clips per GPU (BASELINE configs[1]: 65 536)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size in seconds of work")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3                                            # timing rule: W >= 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,41 @@
+// Shared host-side plumbing for libcmoop_b200: error reporting, launch counter,
+// library-owned device scratch for the *_host entry points.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cmoop_b200.h"
+
+namespace cmoop {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+// Grow-only device/pinned scratch owned by the library (one per slot).
+void* device_scratch(int slot, size_t bytes);
+void* pinned_scratch(int slot, size_t bytes);
+cudaStream_t internal_stream();
+bool ensure_device();   // false (and error set) when no CUDA device is usable
+
+#define CMOOP_CUDA_OK(expr)                                                                 \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            cmoop::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return CMOOP_ERR_CUDA;                                                          \
+        }                                                                                   \
+    } while (0)
+
+#define CMOOP_REQUIRE(cond, ...)                \
+    do {                                        \
+        if (!(cond)) {                          \
+            cmoop::set_error(__VA_ARGS__);      \
+            return CMOOP_ERR_INVALID;           \
+        }                                       \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace cmoop

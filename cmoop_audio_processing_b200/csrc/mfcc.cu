@@ -1,0 +1,573 @@
+// Log-mel / MFCC front-end: one warp per frame, whole pipeline fused in one kernel.
+//
+// The reference has no feature-extraction code (features are loaded pre-computed,
+// nsga_penalty.py:64-71, sa_nsga_penalty.py:42-63); the spec is oracle/mfcc_ref.py:
+//   frame (no padding) -> periodic Hann -> |rfft(.,1024)|^2 -> 40 Slaney mel bands
+//   -> 10*log10(max(.,1e-10)) -> [orthonormal DCT-II] -> [per-feature standardise]
+// Output layout (clip, frame, feature) is what prepare_dataset expects
+// (nsga_penalty.py:104-114).
+//
+// Kernel design (tools/fft_lane_model.py is the NumPy model of the data movement):
+//   * a warp owns a frame; lane l loads float2 samples z[32a+l] = x[2n] + i x[2n+1]
+//     straight from global memory (256 B per warp-load, fully coalesced; each sample
+//     is touched by two frames and the second touch is an L1/L2 hit, so HBM sees the
+//     waveform once) and multiplies by the window from shared memory
+//   * 1024-point real FFT = 512-point complex FFT (16 x 32 Cooley-Tukey):
+//       radix-16 in registers over a (inputs a >= frame_length/64 are structural zeros
+//       and pruned at compile time) -> W512 twiddle -> transpose through a padded,
+//       conflict-free shared-memory tile -> radix-16 over even/odd halves -> W32
+//       combine with the neighbour lane via one shuffle per value
+//   * real-FFT unpack: Z[k], Z[512-k] pairs from a padded natural-order tile give
+//     |X[k]|^2 and |X[512-k]|^2 together
+//   * mel: lane b owns bands b and b+32, sparse triangular weights (only the non-zero
+//     taps are stored); log10; DCT from a shared-memory table, lane c owns coefficient
+//     c and c+32; optional (x-mean)*inv_scale; 160-B coalesced stores per frame
+//   * persistent grid (multiple of the SM count), all tables staged once per CTA
+// Bound: HBM by contract (71 840 B/clip) but ~1.6 MFLOP/clip of fp32 butterflies puts
+// it between the HBM and the fp32-pipe roofs; bench.py reports the HBM fraction.
+#include <math.h>
+
+#include <type_traits>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;            // warps (frames in flight) per CTA
+constexpr int kNfft = 1024;
+constexpr int kHalf = kNfft / 2;     // complex FFT length
+constexpr int kBins = kHalf + 1;
+constexpr int kMaxMel = 64;
+constexpr int kMaxOut = 64;
+constexpr int kTileStride = 34;      // 16 x 34 floats per plane: conflict-free transpose
+constexpr int kZPlane = 544;         // natural-order plane with 16 floats of padding at k>=256
+
+__host__ __device__ constexpr float cos32(int j) {
+    constexpr float t[16] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                             0.70710678118654757f, 0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f,
+                             0.f, -0.19509032201612819f, -0.38268343236508973f, -0.55557023301960196f,
+                             -0.70710678118654746f, -0.83146961230254535f, -0.92387953251128674f,
+                             -0.98078528040323043f};
+    return t[j];
+}
+__host__ __device__ constexpr float sin32(int j) {
+    constexpr float t[16] = {0.f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
+                             0.70710678118654746f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f,
+                             1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254546f,
+                             0.70710678118654757f, 0.55557023301960218f, 0.38268343236508989f, 0.19509032201612861f};
+    return t[j];
+}
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+    return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+}
+
+// a * exp(-2*pi*i*J/32), J a compile-time constant in [0,16)
+template <int J>
+__device__ __forceinline__ float2 mul_w32(float2 a) {
+    if constexpr (J == 0) {
+        return a;
+    } else if constexpr (J == 8) {
+        return make_float2(a.y, -a.x);
+    } else if constexpr (J == 4) {
+        constexpr float s = 0.70710678118654757f;
+        return make_float2((a.x + a.y) * s, (a.y - a.x) * s);
+    } else if constexpr (J == 12) {
+        constexpr float s = 0.70710678118654757f;
+        return make_float2((a.y - a.x) * s, -(a.x + a.y) * s);
+    } else {
+        constexpr float c = cos32(J), s = sin32(J);      // w = c - i s
+        return make_float2(fmaf(a.y, s, a.x * c), fmaf(-a.x, s, a.y * c));
+    }
+}
+
+__host__ __device__ constexpr int brev4(int i) {
+    return ((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3);
+}
+
+// In-place 16-point DIF FFT; result X[brev4(i)] = v[i].  Inputs v[NZ..15] are known zeros.
+template <int NZ>
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+    static_for<0, 8>([&](auto jc) {
+        constexpr int J = decltype(jc)::value;
+        if constexpr (J + 8 < NZ) {
+            const float2 u = v[J], t = v[J + 8];
+            v[J] = cadd(u, t);
+            v[J + 8] = mul_w32<2 * J>(csub(u, t));
+        } else {
+            v[J + 8] = mul_w32<2 * J>(v[J]);
+        }
+    });
+    static_for<0, 2>([&](auto bc) {
+        constexpr int B = decltype(bc)::value * 8;
+        static_for<0, 4>([&](auto jc) {
+            constexpr int J = decltype(jc)::value;
+            const float2 u = v[B + J], t = v[B + J + 4];
+            v[B + J] = cadd(u, t);
+            v[B + J + 4] = mul_w32<4 * J>(csub(u, t));
+        });
+    });
+    static_for<0, 4>([&](auto bc) {
+        constexpr int B = decltype(bc)::value * 4;
+        static_for<0, 2>([&](auto jc) {
+            constexpr int J = decltype(jc)::value;
+            const float2 u = v[B + J], t = v[B + J + 2];
+            v[B + J] = cadd(u, t);
+            v[B + J + 2] = mul_w32<8 * J>(csub(u, t));
+        });
+    });
+    static_for<0, 8>([&](auto bc) {
+        constexpr int B = decltype(bc)::value * 2;
+        const float2 u = v[B], t = v[B + 1];
+        v[B] = cadd(u, t);
+        v[B + 1] = csub(u, t);
+    });
+}
+
+// Device-resident tables, one contiguous float buffer (offsets in floats).
+struct Tables {
+    int window2;   // float2 [half_len]           (w[2n], w[2n+1])
+    int tw512;     // float2 [16][32]             exp(-2 pi i l k1 / 512)
+    int tw1024;    // float2 [256]                exp(-2 pi i k / 1024)
+    int mel_w;     // float  [mel_taps]
+    int mel_meta;  // int2   [n_mels]             (first bin, tap offset) ; count in mel_cnt
+    int mel_cnt;   // int    [n_mels]
+    int dct;       // float  [n_mels][n_out]      (b-major)
+    int mean;      // float  [n_out]
+    int inv_scale; // float  [n_out]
+    int total;
+};
+
+struct Params {
+    const float* wave;
+    float* out;
+    const float* tables;
+    Tables t;
+    long long n_frames_total;
+    int n_samples, frames_per_clip, frame_length, hop, half_len;
+    int n_mels, n_out, use_dct, vec2;
+    float log_floor;
+};
+
+constexpr int kWarpFloats = 2 * 16 * kTileStride + kBins + 7 + kMaxMel;   // tile planes | power | logmel
+static_assert(2 * 16 * kTileStride >= 2 * kZPlane, "natural-order planes must fit in the transpose tile");
+
+template <int NZ>
+__global__ void __launch_bounds__(kWarps * 32, 3) mfcc_kernel(Params p) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // ---- stage tables once per CTA
+    for (int i = threadIdx.x; i < p.t.total; i += blockDim.x) smem[i] = p.tables[i];
+    __syncthreads();
+    const float2* s_win = reinterpret_cast<const float2*>(smem + p.t.window2);
+    const float2* s_tw512 = reinterpret_cast<const float2*>(smem + p.t.tw512);
+    const float2* s_tw1024 = reinterpret_cast<const float2*>(smem + p.t.tw1024);
+    const float* s_melw = smem + p.t.mel_w;
+    const int2* s_meta = reinterpret_cast<const int2*>(smem + p.t.mel_meta);
+    const int* s_cnt = reinterpret_cast<const int*>(smem + p.t.mel_cnt);
+    const float* s_dct = smem + p.t.dct;
+    const float* s_mean = smem + p.t.mean;
+    const float* s_inv = smem + p.t.inv_scale;
+    float* w_base = smem + ((p.t.total + 3) & ~3) + warp * kWarpFloats;
+    float* t_re = w_base;                       // transpose tile, later natural-order planes
+    float* t_im = w_base + 16 * kTileStride;
+    float* z_re = w_base;
+    float* z_im = w_base + kZPlane;
+    float* s_pow = w_base + 2 * 16 * kTileStride;
+    float* s_lm = s_pow + kBins + 7;
+
+    const int h = lane & 1, k1o = lane >> 1;
+    const long long stride = (long long)gridDim.x * kWarps;
+    for (long long f = (long long)blockIdx.x * kWarps + warp; f < p.n_frames_total; f += stride) {
+        const long long clip = f / p.frames_per_clip;
+        const int t = (int)(f - clip * p.frames_per_clip);
+        const float* src = p.wave + (size_t)clip * p.n_samples + (size_t)t * p.hop;
+
+        // ---- load + window: lane holds z[32a + lane]
+        float2 v[16];
+#pragma unroll
+        for (int a = 0; a < 16; ++a) {
+            if (a < NZ) {
+                const int n = 32 * a + lane;
+                float2 x = make_float2(0.f, 0.f);
+                if (n < p.half_len) {
+                    if (p.vec2) {
+                        x = __ldg(reinterpret_cast<const float2*>(src) + n);
+                    } else {
+                        x.x = __ldg(src + 2 * n);
+                        x.y = __ldg(src + 2 * n + 1);
+                    }
+                    const float2 w = s_win[n];
+                    x.x *= w.x;
+                    x.y *= w.y;
+                }
+                v[a] = x;
+            } else {
+                v[a] = make_float2(0.f, 0.f);
+            }
+        }
+        // ---- radix-16 over a, W512 twiddle, transpose
+        dft16<NZ>(v);
+        static_for<0, 16>([&](auto ic) {
+            constexpr int I = decltype(ic)::value;
+            constexpr int K1 = brev4(I);
+            float2 y = v[I];
+            if constexpr (K1 != 0) y = cmul(y, s_tw512[K1 * 32 + lane]);
+            t_re[K1 * kTileStride + lane] = y.x;
+            t_im[K1 * kTileStride + lane] = y.y;
+        });
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            v[m].x = t_re[k1o * kTileStride + h + 2 * m];
+            v[m].y = t_im[k1o * kTileStride + h + 2 * m];
+        }
+        __syncwarp();
+        // ---- radix-16 over m, W32 combine with the neighbour lane
+        dft16<16>(v);
+        static_for<0, 16>([&](auto ic) {
+            constexpr int I = decltype(ic)::value;
+            constexpr int Q = brev4(I);
+            float2 s = v[I];
+            if (h) s = mul_w32<Q>(s);
+            float2 r;
+            r.x = __shfl_xor_sync(0xffffffffu, s.x, 1);
+            r.y = __shfl_xor_sync(0xffffffffu, s.y, 1);
+            const float sg = h ? -1.f : 1.f;
+            const float2 zk = make_float2(fmaf(sg, s.x, r.x), fmaf(sg, s.y, r.y));
+            const int k = k1o + 16 * Q + 256 * h;        // natural-order bin of the 512-pt FFT
+            z_re[k + 16 * h] = zk.x;
+            z_im[k + 16 * h] = zk.y;
+        });
+        __syncwarp();
+        // ---- real-FFT unpack -> power spectrum
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = lane + 32 * j;
+            const int kb = (kHalf - k) & (kHalf - 1);
+            const int pb = kb + ((kb >> 8) << 4);
+            const float ar = z_re[k], ai = z_im[k];
+            const float br = z_re[pb], bi = -z_im[pb];
+            const float er = 0.5f * (ar + br), ei = 0.5f * (ai + bi);
+            const float orr = 0.5f * (ai - bi), oi = -0.5f * (ar - br);     // -i/2 * (A - B)
+            const float2 w = s_tw1024[k];
+            const float pr = fmaf(orr, w.x, -oi * w.y), pi = fmaf(orr, w.y, oi * w.x);
+            const float xr = er + pr, xi = ei + pi, yr = er - pr, yi = ei - pi;
+            s_pow[k] = fmaf(xr, xr, xi * xi);
+            s_pow[kHalf - k] = fmaf(yr, yr, yi * yi);
+        }
+        if (lane == 0) {
+            const float r = z_re[256 + 16], i = z_im[256 + 16];
+            s_pow[256] = fmaf(r, r, i * i);
+        }
+        __syncwarp();
+        // ---- mel + log
+        for (int b = lane; b < p.n_mels; b += 32) {
+            const int2 meta = s_meta[b];
+            const int cnt = s_cnt[b];
+            float acc = 0.f;
+            for (int i = 0; i < cnt; ++i) acc = fmaf(s_melw[meta.y + i], s_pow[meta.x + i], acc);
+            s_lm[b] = 10.f * log10f(fmaxf(acc, p.log_floor));
+        }
+        __syncwarp();
+        // ---- DCT / standardise / store
+        float* dst = p.out + (size_t)f * p.n_out;
+        for (int c = lane; c < p.n_out; c += 32) {
+            float acc;
+            if (p.use_dct) {
+                acc = 0.f;
+                for (int b = 0; b < p.n_mels; ++b) acc = fmaf(s_dct[b * p.n_out + c], s_lm[b], acc);
+            } else {
+                acc = s_lm[c];
+            }
+            dst[c] = (acc - s_mean[c]) * s_inv[c];
+        }
+        __syncwarp();
+    }
+}
+
+// ---- host-side table construction (fp64, mirrors oracle/mfcc_ref.py)
+double hz_to_mel(double f) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + log(f / min_log_hz) / logstep : f / f_sp;
+}
+double mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+}  // namespace
+
+struct cmoop_mfcc {
+    cmoop_mfcc_config cfg;
+    int n_out = 0, half_len = 0, nz = 0;
+    Tables t{};
+    std::vector<float> host_tables;
+    float* d_tables = nullptr;
+    size_t smem_bytes = 0;
+    int sm_count = 0;
+};
+
+namespace {
+
+int upload_tables(cmoop_mfcc* h) {
+    CMOOP_CUDA_OK(cudaMemcpy(h->d_tables, h->host_tables.data(), h->host_tables.size() * sizeof(float),
+                             cudaMemcpyHostToDevice));
+    return CMOOP_OK;
+}
+
+template <int NZ>
+int launch_nz(const Params& p, int grid, size_t smem, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        CMOOP_CUDA_OK(cudaFuncSetAttribute(mfcc_kernel<NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    mfcc_kernel<NZ><<<grid, kWarps * 32, smem, st>>>(p);
+    cmoop::count_launch();
+    CMOOP_CUDA_OK(cudaGetLastError());
+    return CMOOP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cmoop_mfcc_destroy(cmoop_mfcc_handle h) {
+    if (!h) return CMOOP_OK;
+    if (h->d_tables) cudaFree(h->d_tables);
+    delete h;
+    return CMOOP_OK;
+}
+
+int cmoop_mfcc_create(const cmoop_mfcc_config* cfg, cmoop_mfcc_handle* out) {
+    CMOOP_REQUIRE(cfg && out, "mfcc_create: null pointer");
+    *out = nullptr;
+    if (cfg->n_fft != kNfft) {
+        cmoop::set_error("mfcc_create: n_fft=%d not implemented (only 1024)", cfg->n_fft);
+        return CMOOP_ERR_UNSUPPORTED;
+    }
+    CMOOP_REQUIRE(cfg->frame_length > 0 && cfg->frame_length <= kNfft && cfg->frame_length % 2 == 0,
+                  "mfcc_create: frame_length=%d must be even and in (0,%d]", cfg->frame_length, kNfft);
+    CMOOP_REQUIRE(cfg->hop > 0, "mfcc_create: hop must be positive");
+    CMOOP_REQUIRE(cfg->n_mels > 0 && cfg->n_mels <= kMaxMel, "mfcc_create: n_mels=%d outside [1,%d]", cfg->n_mels,
+                  kMaxMel);
+    CMOOP_REQUIRE(cfg->n_mfcc >= 0 && cfg->n_mfcc <= cfg->n_mels, "mfcc_create: n_mfcc=%d outside [0,n_mels]",
+                  cfg->n_mfcc);
+    CMOOP_REQUIRE(cfg->sample_rate > 0 && cfg->f_min >= 0.f && cfg->f_max > cfg->f_min &&
+                      cfg->f_max <= 0.5f * cfg->sample_rate,
+                  "mfcc_create: need 0 <= f_min < f_max <= sample_rate/2");
+    if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
+
+    cmoop_mfcc* h = new cmoop_mfcc();
+    h->cfg = *cfg;
+    h->n_out = cfg->n_mfcc > 0 ? cfg->n_mfcc : cfg->n_mels;
+    h->half_len = cfg->frame_length / 2;
+    h->nz = (h->half_len + 31) / 32;
+    const int n_mels = cfg->n_mels, n_out = h->n_out;
+    const double pi = 3.14159265358979323846;
+
+    // mel filterbank (Slaney scale + area normalisation), sparse taps
+    std::vector<double> hz(n_mels + 2);
+    {
+        const double m_lo = hz_to_mel(cfg->f_min), m_hi = hz_to_mel(cfg->f_max);
+        for (int i = 0; i < n_mels + 2; ++i) hz[i] = mel_to_hz(m_lo + (m_hi - m_lo) * i / (n_mels + 1));
+    }
+    std::vector<float> taps;
+    std::vector<int> first(n_mels), offset(n_mels), count(n_mels);
+    for (int b = 0; b < n_mels; ++b) {
+        const double norm = 2.0 / (hz[b + 2] - hz[b]);
+        int lo = -1, hi = -1;
+        std::vector<double> w(kBins);
+        for (int k = 0; k < kBins; ++k) {
+            const double fk = 0.5 * cfg->sample_rate * k / (kBins - 1);
+            const double rising = (fk - hz[b]) / (hz[b + 1] - hz[b]);
+            const double falling = (hz[b + 2] - fk) / (hz[b + 2] - hz[b + 1]);
+            double v = rising < falling ? rising : falling;
+            v = v > 0.0 ? v : 0.0;
+            w[k] = v * norm;
+            if (v > 0.0) {
+                if (lo < 0) lo = k;
+                hi = k;
+            }
+        }
+        first[b] = lo < 0 ? 0 : lo;
+        count[b] = lo < 0 ? 0 : hi - lo + 1;
+        offset[b] = (int)taps.size();
+        for (int k = 0; k < count[b]; ++k) taps.push_back((float)w[first[b] + k]);
+    }
+
+    Tables& t = h->t;
+    int off = 0;
+    auto take = [&](int floats) {
+        const int at = off;
+        off += (floats + 3) & ~3;
+        return at;
+    };
+    t.window2 = take(2 * h->half_len);
+    t.tw512 = take(2 * 16 * 32);
+    t.tw1024 = take(2 * 256);
+    t.mel_w = take((int)taps.size());
+    t.mel_meta = take(2 * n_mels);
+    t.mel_cnt = take(n_mels);
+    t.dct = take(n_mels * n_out);
+    t.mean = take(n_out);
+    t.inv_scale = take(n_out);
+    t.total = off;
+    h->host_tables.assign(off, 0.f);
+    float* T = h->host_tables.data();
+    for (int n = 0; n < cfg->frame_length; ++n)
+        T[t.window2 + n] = (float)(0.5 - 0.5 * cos(2.0 * pi * n / cfg->frame_length));
+    for (int k1 = 0; k1 < 16; ++k1)
+        for (int l = 0; l < 32; ++l) {
+            const double ang = -2.0 * pi * (double)(l * k1) / 512.0;
+            T[t.tw512 + 2 * (k1 * 32 + l)] = (float)cos(ang);
+            T[t.tw512 + 2 * (k1 * 32 + l) + 1] = (float)sin(ang);
+        }
+    for (int k = 0; k < 256; ++k) {
+        const double ang = -2.0 * pi * k / 1024.0;
+        T[t.tw1024 + 2 * k] = (float)cos(ang);
+        T[t.tw1024 + 2 * k + 1] = (float)sin(ang);
+    }
+    for (size_t i = 0; i < taps.size(); ++i) T[t.mel_w + i] = taps[i];
+    int* meta = reinterpret_cast<int*>(T + t.mel_meta);
+    int* cnt = reinterpret_cast<int*>(T + t.mel_cnt);
+    for (int b = 0; b < n_mels; ++b) {
+        meta[2 * b] = first[b];
+        meta[2 * b + 1] = t.mel_w + offset[b] - t.mel_w;   // tap offset relative to mel_w
+        cnt[b] = count[b];
+    }
+    for (int b = 0; b < n_mels; ++b)
+        for (int c = 0; c < n_out; ++c) {
+            double v = cos(pi * c * (2 * b + 1) / (2.0 * n_mels)) * sqrt(2.0 / n_mels);
+            if (c == 0) v *= sqrt(0.5);
+            T[t.dct + b * n_out + c] = (float)v;
+        }
+    for (int c = 0; c < n_out; ++c) {
+        T[t.mean + c] = 0.f;
+        T[t.inv_scale + c] = 1.f;
+    }
+    if (cudaMalloc((void**)&h->d_tables, (size_t)off * sizeof(float)) != cudaSuccess) {
+        cmoop::set_error("mfcc_create: cudaMalloc failed");
+        delete h;
+        return CMOOP_ERR_CUDA;
+    }
+    int rc = upload_tables(h);
+    if (rc != CMOOP_OK) {
+        cmoop_mfcc_destroy(h);
+        return rc;
+    }
+    h->smem_bytes = ((size_t)((off + 3) & ~3) + (size_t)kWarps * kWarpFloats) * sizeof(float);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    *out = h;
+    return CMOOP_OK;
+}
+
+int cmoop_mfcc_n_frames(cmoop_mfcc_handle h, int n_samples) {
+    if (!h || n_samples < h->cfg.frame_length) return 0;
+    return 1 + (n_samples - h->cfg.frame_length) / h->cfg.hop;
+}
+
+int cmoop_mfcc_n_out(cmoop_mfcc_handle h) { return h ? h->n_out : 0; }
+
+int cmoop_mfcc_set_standardise(cmoop_mfcc_handle h, const float* mean, const float* scale) {
+    CMOOP_REQUIRE(h != nullptr, "mfcc_set_standardise: null handle");
+    CMOOP_REQUIRE((mean == nullptr) == (scale == nullptr), "mfcc_set_standardise: pass both or neither");
+    float* T = h->host_tables.data();
+    for (int c = 0; c < h->n_out; ++c) {
+        T[h->t.mean + c] = mean ? mean[c] : 0.f;
+        T[h->t.inv_scale + c] = scale ? 1.f / scale[c] : 1.f;
+    }
+    CMOOP_CUDA_OK(cudaDeviceSynchronize());
+    return upload_tables(h);
+}
+
+int cmoop_mfcc_fwd_dev(cmoop_mfcc_handle h, const float* wave, int64_t n_clips, int n_samples, float* out,
+                       void* stream) {
+    CMOOP_REQUIRE(h != nullptr, "mfcc_fwd: null handle");
+    CMOOP_REQUIRE(n_clips >= 0 && n_samples >= 0, "mfcc_fwd: negative size");
+    const int frames = cmoop_mfcc_n_frames(h, n_samples);
+    if (n_clips == 0 || frames == 0) return CMOOP_OK;
+    CMOOP_REQUIRE(wave && out, "mfcc_fwd: null pointer");
+    Params p{};
+    p.wave = wave;
+    p.out = out;
+    p.tables = h->d_tables;
+    p.t = h->t;
+    p.n_frames_total = (long long)n_clips * frames;
+    p.n_samples = n_samples;
+    p.frames_per_clip = frames;
+    p.frame_length = h->cfg.frame_length;
+    p.hop = h->cfg.hop;
+    p.half_len = h->half_len;
+    p.n_mels = h->cfg.n_mels;
+    p.n_out = h->n_out;
+    p.use_dct = h->cfg.n_mfcc > 0;
+    p.vec2 = (n_samples % 2 == 0) && (h->cfg.hop % 2 == 0) && (((uintptr_t)wave & 7u) == 0);
+    p.log_floor = h->cfg.log_floor;
+    const long long blocks_needed = (p.n_frames_total + kWarps - 1) / kWarps;
+    const long long persistent = (long long)h->sm_count * 3;
+    const int grid = (int)(blocks_needed < persistent ? blocks_needed : persistent);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (h->nz) {
+        case 1: case 2: case 3: case 4: case 5: case 6: case 7: case 8:
+            return launch_nz<8>(p, grid, h->smem_bytes, st);
+        case 9: case 10:
+            return launch_nz<10>(p, grid, h->smem_bytes, st);
+        case 11: case 12: case 13:
+            return launch_nz<13>(p, grid, h->smem_bytes, st);
+        default:
+            return launch_nz<16>(p, grid, h->smem_bytes, st);
+    }
+}
+
+int cmoop_mfcc_fwd_host(cmoop_mfcc_handle h, const float* wave, int64_t n_clips, int n_samples, float* out) {
+    CMOOP_REQUIRE(h != nullptr, "mfcc_fwd: null handle");
+    CMOOP_REQUIRE(n_clips >= 0 && n_samples >= 0, "mfcc_fwd: negative size");
+    const int frames = cmoop_mfcc_n_frames(h, n_samples);
+    if (n_clips == 0 || frames == 0) return CMOOP_OK;
+    CMOOP_REQUIRE(wave && out, "mfcc_fwd: null pointer");
+    // Chunked double-buffered pipeline: H2D(i+1) overlaps kernel(i) overlaps D2H(i-1).
+    const int64_t chunk = 2048;
+    const size_t in_bytes = (size_t)chunk * n_samples * sizeof(float);
+    const size_t out_bytes = (size_t)chunk * frames * h->n_out * sizeof(float);
+    char* d = (char*)cmoop::device_scratch(4, 2 * (cmoop::align_up(in_bytes, 256) + cmoop::align_up(out_bytes, 256)));
+    if (!d) return CMOOP_ERR_CUDA;
+    static cudaStream_t streams[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; ++i)
+        if (!streams[i]) CMOOP_CUDA_OK(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
+    float* d_in[2] = {(float*)d, (float*)(d + cmoop::align_up(in_bytes, 256))};
+    float* d_out[2] = {(float*)(d + 2 * cmoop::align_up(in_bytes, 256)),
+                       (float*)(d + 2 * cmoop::align_up(in_bytes, 256) + cmoop::align_up(out_bytes, 256))};
+    int slot = 0;
+    for (int64_t c0 = 0; c0 < n_clips; c0 += chunk, slot ^= 1) {
+        const int64_t nc = (n_clips - c0) < chunk ? (n_clips - c0) : chunk;
+        cudaStream_t st = streams[slot];
+        CMOOP_CUDA_OK(cudaMemcpyAsync(d_in[slot], wave + (size_t)c0 * n_samples, (size_t)nc * n_samples * sizeof(float),
+                                      cudaMemcpyHostToDevice, st));
+        int rc = cmoop_mfcc_fwd_dev(h, d_in[slot], nc, n_samples, d_out[slot], st);
+        if (rc != CMOOP_OK) return rc;
+        CMOOP_CUDA_OK(cudaMemcpyAsync(out + (size_t)c0 * frames * h->n_out, d_out[slot],
+                                      (size_t)nc * frames * h->n_out * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    CMOOP_CUDA_OK(cudaStreamSynchronize(streams[0]));
+    CMOOP_CUDA_OK(cudaStreamSynchronize(streams[1]));
+    return CMOOP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+"""Log-mel / MFCC front-end (host mirror of cmoop_mfcc_*).
+
+The reference loads pre-computed features shaped (N, T, F) and standardises them per
+feature (prepare_dataset, nsga_penalty.py:85-155); this module produces that tensor on
+the GPU from raw waveforms.  Spec = oracle/mfcc_ref.py (frames of 640 @ hop 320, no
+padding, periodic Hann, 1024-point power spectrum, 40 Slaney mel bands, 10*log10,
+orthonormal DCT-II).  Torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+
+@dataclass(frozen=True)
+class MfccConfig:
+    sample_rate: int = 16000
+    frame_length: int = 640
+    hop: int = 320
+    n_fft: int = 1024
+    n_mels: int = 40
+    n_mfcc: int = 40          # 0 -> log-mel output
+    f_min: float = 0.0
+    f_max: float = 8000.0
+    log_floor: float = 1e-10
+
+
+class MfccFrontEnd:
+    def __init__(self, config: MfccConfig = MfccConfig()):
+        self._lib = _lib.load()
+        self.config = config
+        c = _lib.MfccConfig(config.sample_rate, config.frame_length, config.hop, config.n_fft, config.n_mels,
+                            config.n_mfcc, config.f_min, config.f_max, config.log_floor)
+        handle = C.c_void_p()
+        _lib.check(self._lib.cmoop_mfcc_create(C.byref(c), C.byref(handle)), "cmoop_mfcc_create")
+        self._handle = handle
+        self.n_out = int(self._lib.cmoop_mfcc_n_out(handle))
+
+    def n_frames(self, n_samples: int) -> int:
+        return int(self._lib.cmoop_mfcc_n_frames(self._handle, int(n_samples)))
+
+    def set_standardise(self, mean=None, scale=None):
+        """Fuse (x - mean[f]) / scale[f] into the kernel epilogue (StandardScaler statistics)."""
+        if mean is None:
+            _lib.check(self._lib.cmoop_mfcc_set_standardise(self._handle, None, None), "cmoop_mfcc_set_standardise")
+            return
+        m = np.ascontiguousarray(mean, np.float32)
+        s = np.ascontiguousarray(scale, np.float32)
+        if m.shape != (self.n_out,) or s.shape != (self.n_out,):
+            raise ValueError(f"mean/scale must have shape ({self.n_out},)")
+        _lib.check(self._lib.cmoop_mfcc_set_standardise(self._handle, _lib.ptr(m), _lib.ptr(s)),
+                   "cmoop_mfcc_set_standardise")
+
+    def __call__(self, wave, out=None):
+        """wave: (n_clips, n_samples) float32 -- a CUDA torch tensor (stream-ordered, no sync,
+        returns a CUDA tensor) or a host numpy array / CPU tensor (chunked overlapped copies,
+        returns numpy)."""
+        try:
+            import torch
+        except ImportError:  # pragma: no cover
+            torch = None
+        if torch is not None and isinstance(wave, torch.Tensor) and wave.is_cuda:
+            if wave.dtype != torch.float32 or wave.dim() != 2:
+                raise ValueError("wave must be a 2-D float32 tensor")
+            wave = wave.contiguous()
+            n_clips, n_samples = wave.shape
+            frames = self.n_frames(n_samples)
+            if out is None:
+                out = torch.empty((n_clips, frames, self.n_out), dtype=torch.float32, device=wave.device)
+            stream = torch.cuda.current_stream(wave.device).cuda_stream
+            with torch.cuda.device(wave.device):
+                _lib.check(self._lib.cmoop_mfcc_fwd_dev(self._handle, C.c_void_p(wave.data_ptr()), n_clips, n_samples,
+                                                        C.c_void_p(out.data_ptr()), C.c_void_p(stream)),
+                           "cmoop_mfcc_fwd_dev")
+            return out
+        if torch is not None and isinstance(wave, torch.Tensor):
+            wave = wave.numpy()
+        wave = np.ascontiguousarray(wave, np.float32)
+        if wave.ndim != 2:
+            raise ValueError("wave must be 2-D (n_clips, n_samples)")
+        n_clips, n_samples = wave.shape
+        frames = self.n_frames(n_samples)
+        if out is None:
+            out = np.empty((n_clips, frames, self.n_out), np.float32)
+        _lib.check(self._lib.cmoop_mfcc_fwd_host(self._handle, _lib.ptr(wave), n_clips, n_samples, _lib.ptr(out)),
+                   "cmoop_mfcc_fwd_host")
+        return out
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self._lib.cmoop_mfcc_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def mfcc(wave, config: MfccConfig = MfccConfig()):
+    """One-shot convenience wrapper."""
+    fe = MfccFrontEnd(config)
+    try:
+        return fe(wave)
+    finally:
+        fe.close()

@@ -1,0 +1,165 @@
+/* cmoop_b200.h -- C ABI of the B200-native population-fitness hot path.
+ *
+ * Drop-in boundary for sumansamui/CMOOP_Audio_Processing.  The reference has no
+ * FFI of its own: its seam is a set of Python functions called by the unmodified
+ * drivers nsga2() / run_mobo().  Each entry point below names the reference
+ * function(s) it replaces (file:line relative to the reference root); the Python
+ * shims in cmoop_audio_processing_b200/ bind them with ctypes under the
+ * reference's own names (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary
+ *   - *_dev entry points take DEVICE pointers and a cudaStream_t (as void*), are
+ *     stream-ordered and never synchronise; *_host entry points take HOST
+ *     pointers, stage through library-owned device scratch and return after the
+ *     result is in host memory
+ *   - every function returns 0 on success or a negative cmoop_status; the
+ *     message is available from cmoop_last_error().  There is no CPU fallback:
+ *     without a usable sm_100 device every compute call returns CMOOP_ERR_CUDA.
+ *   - one host thread per process drives the library (the reference is
+ *     single-threaded); handles are not thread-safe.
+ */
+#ifndef CMOOP_B200_H
+#define CMOOP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    CMOOP_OK = 0,
+    CMOOP_ERR_INVALID = -1,      /* bad argument (shape, null pointer, unsupported size) */
+    CMOOP_ERR_CUDA = -2,         /* CUDA runtime error or no device */
+    CMOOP_ERR_UNSUPPORTED = -3,  /* configuration outside what the kernels implement */
+    CMOOP_ERR_NOT_FITTED = -4
+} cmoop_status;
+
+int cmoop_abi_version(void);
+const char* cmoop_last_error(void);
+/* number of CUDA devices visible; 0 (not an error) on a CPU-only host */
+int cmoop_device_count(void);
+/* bind the calling thread (and the library's scratch/streams) to a device; one process per GPU */
+int cmoop_set_device(int device);
+/* kernel launches issued by this library since load (bench.py "gpu_launches") */
+uint64_t cmoop_launch_count(void);
+
+/* ------------------------------------------------------------------ (4) NDS + crowding
+ * Replaces dominates / fast_non_dominated_sort / crowding_distance
+ *   nsga_penalty.py:448-524, sa_nsga_penalty.py:382-442, ablation_study/sa_nsga_local.py:240-277.
+ * objs [batch][n][m] row-major fp64 RAW objectives, cv [batch][n] constraint violation.
+ * Penalised objectives P = f + lam*CV are formed with a separate multiply and add
+ * (no FMA) so ranks are bit-identical to CPython.
+ * Outputs per problem:
+ *   rank[n]           front index of every individual
+ *   order[n]          individuals listed front by front in the REFERENCE'S order
+ *                     (front 0 ascending; later fronts in discovery order)
+ *   front_offsets[n+1] start of each front inside order[]; entries >= n_fronts hold n
+ *   n_fronts[1]
+ *   crowd[n]          crowding distance of every individual inside its own front
+ *                     (raw objectives, stable sort, +inf at the ends)
+ * crowd_mode 0: objective skipped unless (max-min) >  eps   (sa_nsga_penalty.py:437)
+ * crowd_mode 1: objective skipped when   (max-min) <  eps   (nsga_penalty.py:518)
+ * n <= CMOOP_NDS_MAX_N, 1 <= m <= CMOOP_NDS_MAX_M.  Any output pointer may be NULL.
+ */
+#define CMOOP_NDS_MAX_N 8192
+#define CMOOP_NDS_MAX_M 8
+size_t cmoop_nds_workspace_bytes(int n, int m, int batch);
+int cmoop_nds_crowding_dev(const double* objs, const double* cv, int n, int m, int batch, double lam,
+                           double eps, int crowd_mode, int* rank, int* order, int* front_offsets,
+                           int* n_fronts, double* crowd, void* workspace, size_t workspace_bytes,
+                           void* stream);
+int cmoop_nds_crowding_host(const double* objs, const double* cv, int n, int m, int batch, double lam,
+                            double eps, int crowd_mode, int* rank, int* order, int* front_offsets,
+                            int* n_fronts, double* crowd);
+/* crowding_distance(front, results) for an arbitrary list of distinct indices:
+ * out[i] is the distance of front[i]. */
+int cmoop_crowding_distance_host(const double* objs, int n, int m, const int* front, int front_len,
+                                 double eps, int crowd_mode, double* out);
+
+/* ------------------------------------------------------------------ (3) GP posterior
+ * Replaces GaussianProcessRegressor.predict(X, return_std) as called from
+ *   SurrogateManager.predict  ablation_study/sa_nsga_local.py:212-223, sa_nsga_penalty.py:342-363
+ *   predict_gps               mobo_penalty.py:265-273
+ * (sklearn/gaussian_process/_gpr.py:446-499, kernels.py Matern).  Kernel is
+ * amplitude * Matern(length_scale, nu in {0.5,1.5,2.5}) [+ WhiteKernel(noise)].
+ * mean_out = (K* alpha) * y_scale + y_shift ; std_out = sqrt(max(0, amp+noise - |L^-1 K*^T|^2)) * y_scale.
+ */
+typedef struct {
+    int n_train;
+    int dim;
+    double amplitude;
+    double length_scale;
+    double nu;
+    double noise;
+    double y_scale;
+    double y_shift;
+    const double* x_train;    /* [n_train][dim] row-major, host */
+    const double* alpha;      /* [n_train], host */
+    const double* chol_lower; /* [n_train][n_train] row-major lower Cholesky factor, host (may be NULL: mean only) */
+} cmoop_gp_model;
+
+typedef struct cmoop_gp* cmoop_gp_handle;
+/* uploads n_models models (all with the same dim); the handle owns the device copies */
+int cmoop_gp_create(const cmoop_gp_model* models, int n_models, cmoop_gp_handle* out);
+int cmoop_gp_destroy(cmoop_gp_handle h);
+/* xq [q][dim] ; mean/std [n_models][q] ; std may be NULL */
+int cmoop_gp_predict_host(cmoop_gp_handle h, const double* xq, int q, double* mean, double* std);
+int cmoop_gp_predict_dev(cmoop_gp_handle h, const double* xq, int q, double* mean, double* std, void* stream);
+
+/* ------------------------------------------------------------------ (4) front quality
+ * Exact hypervolume for minimisation, m in {2,3}; replaces pg.hypervolume(points).compute(ref)
+ * (compare.ipynb cell 0, section 5).  Points not strictly better than ref in every
+ * objective contribute nothing.
+ */
+int cmoop_hypervolume_host(const double* points, int n, int m, const double* ref, double* out);
+int cmoop_hypervolume_dev(const double* points, int n, int m, const double* ref, double* out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+size_t cmoop_hypervolume_workspace_bytes(int n);
+/* generational_distance / inverted_gd / spread_metric of compare.ipynb sections 7-8.
+ * front [nf][m], true_front [nt][m]; out[0]=GD out[1]=IGD out[2]=Spread (NaN if nf<2). */
+int cmoop_front_metrics_host(const double* front, int nf, const double* true_front, int nt, int m,
+                             double* out3);
+/* non-dominated filter (compare.ipynb section 6 / mobo_penalty.py:478-485): mask[i]=1 if
+ * no other point dominates i; also coverage C(A,B) via cmoop_coverage_host. */
+int cmoop_nondominated_mask_host(const double* points, int n, int m, uint8_t* mask);
+int cmoop_coverage_host(const double* a, int na, const double* b, int nb, int m, double* out);
+
+/* ------------------------------------------------------------------ (1) log-mel / MFCC front-end
+ * No reference code exists for this stage (features are loaded pre-computed:
+ * nsga_penalty.py:64-71, sa_nsga_penalty.py:42-63); the spec is oracle/mfcc_ref.py.
+ * wave [n_clips][n_samples] fp32 ; out [n_clips][n_frames][n_out] fp32 with
+ * n_out = n_mfcc if n_mfcc > 0 else n_mels  -- the (N, T, F) layout prepare_dataset
+ * expects (nsga_penalty.py:104-114).
+ */
+typedef struct {
+    int sample_rate;   /* 16000 */
+    int frame_length;  /* 640  */
+    int hop;           /* 320  */
+    int n_fft;         /* 1024 */
+    int n_mels;        /* 40   */
+    int n_mfcc;        /* 40 ; 0 = log-mel output */
+    float f_min;       /* 0    */
+    float f_max;       /* 8000 */
+    float log_floor;   /* 1e-10 */
+} cmoop_mfcc_config;
+
+typedef struct cmoop_mfcc* cmoop_mfcc_handle;
+int cmoop_mfcc_create(const cmoop_mfcc_config* cfg, cmoop_mfcc_handle* out);
+int cmoop_mfcc_destroy(cmoop_mfcc_handle h);
+int cmoop_mfcc_n_frames(cmoop_mfcc_handle h, int n_samples);
+int cmoop_mfcc_n_out(cmoop_mfcc_handle h);
+int cmoop_mfcc_fwd_dev(cmoop_mfcc_handle h, const float* wave, int64_t n_clips, int n_samples, float* out,
+                       void* stream);
+/* host buffers (pinned or pageable); copies are chunked and overlapped with compute */
+int cmoop_mfcc_fwd_host(cmoop_mfcc_handle h, const float* wave, int64_t n_clips, int n_samples, float* out);
+/* optional fused per-feature standardisation (prepare_dataset, nsga_penalty.py:102-114):
+ * out = (out - mean[f]) / scale[f]; pass NULL/NULL to disable. mean/scale are host fp32 [n_out]. */
+int cmoop_mfcc_set_standardise(cmoop_mfcc_handle h, const float* mean, const float* scale);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMOOP_B200_H */
