@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) nds_crowding_kernel(Params p) {
     if (p.n_fronts && tid == 0) p.n_fronts[blockIdx.x] = nf;
 }
 
-const size_t kSmemLimit = 227 * 1024;
+const size_t kSmemLimit = 226 * 1024;   // 227 KiB per-CTA limit minus the kernel's static shared memory
 
 int launch(Params p, int batch, cudaStream_t stream) {
     const Arena A = make_arena(p.n, p.m);
