@@ -19,9 +19,12 @@
 //       combine with the neighbour lane via one shuffle per value
 //   * real-FFT unpack: Z[k], Z[512-k] pairs from a padded natural-order tile give
 //     |X[k]|^2 and |X[512-k]|^2 together
-//   * mel: lane b owns bands b and b+32, sparse triangular weights (only the non-zero
-//     taps are stored); log10; DCT from a shared-memory table, lane c owns coefficient
-//     c and c+32; optional (x-mean)*inv_scale; 160-B coalesced stores per frame
+//   * mel: lane l owns bins [17l, 17l+17) (odd stride: conflict-free); each bin feeds the rising
+//     edge of band s and the falling edge of band s-1 with per-bin weights; partial sums are
+//     flushed at mel-segment ends and combined per band (12 adds); log10
+//   * DCT-II folded by its even/odd symmetry (half the multiply-adds), lane c owns
+//     coefficient c, the last 8 coefficients use 4 lanes each; optional (x-mean)*inv_scale;
+//     160-B coalesced stores per frame
 //   * persistent grid (multiple of the SM count), all tables staged once per CTA
 // Bound: HBM by contract (71 840 B/clip) but ~1.6 MFLOP/clip of fp32 butterflies puts
 // it between the HBM and the fp32-pipe roofs; bench.py reports the HBM fraction.
@@ -42,6 +45,9 @@ constexpr int kMaxMel = 64;
 constexpr int kMaxOut = 64;
 constexpr int kTileStride = 34;      // 16 x 34 floats per plane: conflict-free transpose
 constexpr int kZPlane = 544;         // natural-order plane with 16 floats of padding at k>=256
+constexpr int kChunk = 17;           // mel: bins per lane (odd -> conflict-free strided reads), 31 lanes cover 513 bins
+constexpr int kPowFloats = 32 * kChunk;   // power spectrum padded so every lane can read a full chunk
+constexpr int kMaxFlush = 6;         // mel: segment partials per lane
 
 __host__ __device__ constexpr float cos32(int j) {
     constexpr float t[16] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
@@ -140,10 +146,14 @@ struct Tables {
     int window2;   // float2 [half_len]           (w[2n], w[2n+1])
     int tw512;     // float2 [16][32]             exp(-2 pi i l k1 / 512)
     int tw1024;    // float2 [256]                exp(-2 pi i k / 1024)
-    int mel_w;     // float  [mel_taps]
+    int mel_w;     // float  [mel_taps]           (mel_mode 0: per-band sparse taps)
     int mel_meta;  // int2   [n_mels]             (first bin, tap offset) ; count in mel_cnt
     int mel_cnt;   // int    [n_mels]
-    int dct;       // float  [n_mels][n_out]      (b-major)
+    int mel_wt;    // float2 [32*kChunk]          (mel_mode 1: per-bin rising / falling weight)
+    int mel_flush; // int    [32]                 per-lane flush mask
+    int mel_comb;  // int2   [n_mels]             packed (lane | k<<8 | n<<16) for the R and F partial runs
+    int dct;       // float  [n_mels][n_out]      (b-major; dct_mode 0)
+    int dcth;      // float  [n_mels/2][n_out]    (b-major; dct_mode 1: even/odd folded)
     int mean;      // float  [n_out]
     int inv_scale; // float  [n_out]
     int total;
@@ -156,12 +166,14 @@ struct Params {
     Tables t;
     long long n_frames_total;
     int n_samples, frames_per_clip, frame_length, hop, half_len;
-    int n_mels, n_out, use_dct, vec2;
+    int n_mels, n_out, use_dct, vec2, mel_mode, dct_mode;
     float log_floor;
 };
 
-constexpr int kWarpFloats = 2 * 16 * kTileStride + kBins + 7 + kMaxMel;   // tile planes | power | logmel
+constexpr int kWarpFloats = 2 * 16 * kTileStride + kPowFloats;   // tile planes (re-used for mel partials, logmel, folded DCT input) | power
 static_assert(2 * 16 * kTileStride >= 2 * kZPlane, "natural-order planes must fit in the transpose tile");
+static_assert(2 * 16 * kTileStride >= 2 * kMaxFlush * 32 + 2 * kMaxMel, "mel partials + logmel + folded input must fit in the tile");
+static_assert(kPowFloats >= kBins, "power buffer too small");
 
 template <int NZ>
 __global__ void __launch_bounds__(kWarps * 32, 3) mfcc_kernel(Params p) {
@@ -176,7 +188,11 @@ __global__ void __launch_bounds__(kWarps * 32, 3) mfcc_kernel(Params p) {
     const float* s_melw = smem + p.t.mel_w;
     const int2* s_meta = reinterpret_cast<const int2*>(smem + p.t.mel_meta);
     const int* s_cnt = reinterpret_cast<const int*>(smem + p.t.mel_cnt);
+    const float2* s_melwt = reinterpret_cast<const float2*>(smem + p.t.mel_wt);
+    const int2* s_comb = reinterpret_cast<const int2*>(smem + p.t.mel_comb);
     const float* s_dct = smem + p.t.dct;
+    const float* s_dcth = smem + p.t.dcth;
+    const unsigned flush_mask = p.mel_mode ? reinterpret_cast<const unsigned*>(smem + p.t.mel_flush)[lane] : 0u;
     const float* s_mean = smem + p.t.mean;
     const float* s_inv = smem + p.t.inv_scale;
     float* w_base = smem + ((p.t.total + 3) & ~3) + warp * kWarpFloats;
@@ -185,7 +201,11 @@ __global__ void __launch_bounds__(kWarps * 32, 3) mfcc_kernel(Params p) {
     float* z_re = w_base;
     float* z_im = w_base + kZPlane;
     float* s_pow = w_base + 2 * 16 * kTileStride;
-    float* s_lm = s_pow + kBins + 7;
+    float* part_r = w_base;                                  // [kMaxFlush][32]   (tile is dead once the power spectrum exists)
+    float* part_f = w_base + kMaxFlush * 32;
+    float* s_lm = w_base + 2 * kMaxFlush * 32;               // [kMaxMel]
+    float* s_sd = s_lm + kMaxMel;                            // [kMaxMel] folded DCT input
+    for (int i = kBins + lane; i < kPowFloats; i += 32) s_pow[i] = 0.f;   // padding read with zero weights
 
     const int h = lane & 1, k1o = lane >> 1;
     const long long stride = (long long)gridDim.x * kWarps;
@@ -273,25 +293,114 @@ __global__ void __launch_bounds__(kWarps * 32, 3) mfcc_kernel(Params p) {
         }
         __syncwarp();
         // ---- mel + log
-        for (int b = lane; b < p.n_mels; b += 32) {
-            const int2 meta = s_meta[b];
-            const int cnt = s_cnt[b];
-            float acc = 0.f;
-            for (int i = 0; i < cnt; ++i) acc = fmaf(s_melw[meta.y + i], s_pow[meta.x + i], acc);
-            s_lm[b] = 10.f * log10f(fmaxf(acc, p.log_floor));
+        if (p.mel_mode) {
+            // lane owns bins [17*lane, 17*lane+17): conflict-free; every bin feeds the rising edge of band s and
+            // the falling edge of band s-1 (s = its mel segment); partial sums are flushed at segment ends
+            float accr = 0.f, accf = 0.f;
+            int nfl = 0;
+            const int k0 = kChunk * lane;
+#pragma unroll
+            for (int i = 0; i < kChunk; ++i) {
+                const float pw = s_pow[k0 + i];
+                const float2 w = s_melwt[k0 + i];
+                accr = fmaf(w.x, pw, accr);
+                accf = fmaf(w.y, pw, accf);
+                if (flush_mask & (1u << i)) {
+                    part_r[nfl * 32 + lane] = accr;
+                    part_f[nfl * 32 + lane] = accf;
+                    accr = 0.f;
+                    accf = 0.f;
+                    ++nfl;
+                }
+            }
+            __syncwarp();
+            float mel[2];
+#pragma unroll
+            for (int rnd = 0; rnd < 2; ++rnd) {
+                const int b = lane + 32 * rnd;
+                float acc = 0.f;
+                if (b < p.n_mels) {
+                    const int2 cb = s_comb[b];
+                    int n = cb.x >> 16;
+                    if (n) {
+                        const int la = cb.x & 0xff;
+                        acc = part_r[((cb.x >> 8) & 0xff) * 32 + la];
+                        for (int j = 1; j < n; ++j) acc += part_r[la + j];
+                    }
+                    n = cb.y >> 16;
+                    if (n) {
+                        const int la = cb.y & 0xff;
+                        acc += part_f[((cb.y >> 8) & 0xff) * 32 + la];
+                        for (int j = 1; j < n; ++j) acc += part_f[la + j];
+                    }
+                }
+                mel[rnd] = acc;
+            }
+            __syncwarp();                                     // partials are read; logmel aliases nothing they use
+#pragma unroll
+            for (int rnd = 0; rnd < 2; ++rnd) {
+                const int b = lane + 32 * rnd;
+                if (b < p.n_mels) s_lm[b] = 10.f * log10f(fmaxf(mel[rnd], p.log_floor));
+            }
+        } else {
+            for (int b = lane; b < p.n_mels; b += 32) {
+                const int2 meta = s_meta[b];
+                const int cnt = s_cnt[b];
+                float acc = 0.f;
+                for (int i = 0; i < cnt; ++i) acc = fmaf(s_melw[meta.y + i], s_pow[meta.x + i], acc);
+                s_lm[b] = 10.f * log10f(fmaxf(acc, p.log_floor));
+            }
         }
         __syncwarp();
         // ---- DCT / standardise / store
         float* dst = p.out + (size_t)f * p.n_out;
-        for (int c = lane; c < p.n_out; c += 32) {
-            float acc;
-            if (p.use_dct) {
-                acc = 0.f;
-                for (int b = 0; b < p.n_mels; ++b) acc = fmaf(s_dct[b * p.n_out + c], s_lm[b], acc);
-            } else {
-                acc = s_lm[c];
+        if (p.use_dct && p.dct_mode) {
+            // D[c][n-1-b] = (-1)^c D[c][b]: fold the input once, halve the multiply-adds
+            const int half = p.n_mels >> 1;
+            for (int b = lane; b < half; b += 32) {
+                const float a = s_lm[b], z = s_lm[p.n_mels - 1 - b];
+                s_sd[b] = a + z;
+                s_sd[half + b] = a - z;
             }
-            dst[c] = (acc - s_mean[c]) * s_inv[c];
+            __syncwarp();
+            if (lane < p.n_out) {
+                const float* sd = s_sd + (lane & 1) * half;
+                float acc = 0.f;
+                for (int b = 0; b < half; ++b) acc = fmaf(s_dcth[b * p.n_out + lane], sd[b], acc);
+                dst[lane] = (acc - s_mean[lane]) * s_inv[lane];
+            }
+            const int rem = p.n_out - 32;
+            if (rem > 0 && rem <= 8) {
+                // the last <= 8 coefficients: 4 lanes per coefficient, strided terms, two shuffles
+                const int c = 32 + (lane >> 2), part = lane & 3;
+                float acc = 0.f;
+                if (c < p.n_out) {
+                    const float* sd = s_sd + (c & 1) * half;
+                    for (int b = part; b < half; b += 4) acc = fmaf(s_dcth[b * p.n_out + c], sd[b], acc);
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                if (part == 0 && c < p.n_out) dst[c] = (acc - s_mean[c]) * s_inv[c];
+            } else if (rem > 0) {
+                const int c = 32 + lane;
+                if (c < p.n_out) {
+                    const float* sd = s_sd + (c & 1) * half;
+                    float acc = 0.f;
+                    for (int b = 0; b < half; ++b) acc = fmaf(s_dcth[b * p.n_out + c], sd[b], acc);
+                    dst[c] = (acc - s_mean[c]) * s_inv[c];
+                }
+            }
+        } else {
+            for (int c = lane; c < p.n_out; c += 32) {
+                float acc;
+                if (p.use_dct) {
+                    acc = 0.f;
+                    for (int b = 0; b < p.n_mels; ++b) acc = fmaf(s_dct[b * p.n_out + c], s_lm[b], acc);
+                } else {
+                    acc = s_lm[c];
+                }
+                dst[c] = (acc - s_mean[c]) * s_inv[c];
+            }
         }
         __syncwarp();
     }
@@ -313,7 +422,7 @@ double mel_to_hz(double m) {
 
 struct cmoop_mfcc {
     cmoop_mfcc_config cfg;
-    int n_out = 0, half_len = 0, nz = 0;
+    int n_out = 0, half_len = 0, nz = 0, mel_mode = 0, dct_mode = 0;
     Tables t{};
     std::vector<float> host_tables;
     float* d_tables = nullptr;
@@ -410,6 +519,49 @@ int cmoop_mfcc_create(const cmoop_mfcc_config* cfg, cmoop_mfcc_handle* out) {
         for (int k = 0; k < count[b]; ++k) taps.push_back((float)w[first[b] + k]);
     }
 
+    // mel_mode 1 tables: per-bin (rising weight for band s, falling weight for band s-1) with s the mel
+    // segment [hz[s], hz[s+1]) that holds the bin; lanes own 17 consecutive bins and flush a partial at
+    // every segment end.  Falls back to the per-band sparse taps (mel_mode 0) if the layout does not fit.
+    std::vector<int> seg(32 * kChunk, -1);
+    std::vector<float> wt(2 * 32 * kChunk, 0.f);
+    for (int k = 0; k < kBins; ++k) {
+        const double fk = 0.5 * cfg->sample_rate * k / (kBins - 1);
+        int sfound = -1;
+        for (int sidx = 0; sidx <= n_mels; ++sidx)
+            if (fk >= hz[sidx] && fk < hz[sidx + 1]) sfound = sidx;
+        seg[k] = sfound;
+        if (sfound < 0) continue;
+        const double width = hz[sfound + 1] - hz[sfound];
+        if (sfound < n_mels) wt[2 * k] = (float)((fk - hz[sfound]) / width * (2.0 / (hz[sfound + 2] - hz[sfound])));
+        if (sfound >= 1) wt[2 * k + 1] = (float)((hz[sfound + 1] - fk) / width * (2.0 / (hz[sfound + 1] - hz[sfound - 1])));
+    }
+    std::vector<unsigned> flush(32, 0u);
+    // run[s] = (first lane, flush index in that lane, number of lanes) of the partials of segment s
+    std::vector<int> run_lane(n_mels + 1, 0), run_k(n_mels + 1, 0), run_n(n_mels + 1, 0);
+    bool mel_fast = true;
+    for (int l = 0; l < 32 && mel_fast; ++l) {
+        int nfl = 0;
+        for (int i = 0; i < kChunk; ++i) {
+            const int k = l * kChunk + i;
+            const bool last = (i == kChunk - 1) || seg[k + 1] != seg[k];
+            if (!last) continue;
+            flush[l] |= 1u << i;
+            const int sidx = seg[k];
+            if (sidx >= 0) {
+                if (run_n[sidx] == 0) {
+                    run_lane[sidx] = l;
+                    run_k[sidx] = nfl;
+                } else if (nfl != 0 || run_lane[sidx] + run_n[sidx] != l) {
+                    mel_fast = false;      // a continuation must be the next lane's first partial
+                }
+                run_n[sidx] += 1;
+            }
+            ++nfl;
+        }
+        if (nfl > kMaxFlush) mel_fast = false;
+    }
+    const bool dct_fast = (n_mels % 2 == 0);
+
     Tables& t = h->t;
     int off = 0;
     auto take = [&](int floats) {
@@ -420,13 +572,26 @@ int cmoop_mfcc_create(const cmoop_mfcc_config* cfg, cmoop_mfcc_handle* out) {
     t.window2 = take(2 * h->half_len);
     t.tw512 = take(2 * 16 * 32);
     t.tw1024 = take(2 * 256);
-    t.mel_w = take((int)taps.size());
-    t.mel_meta = take(2 * n_mels);
-    t.mel_cnt = take(n_mels);
-    t.dct = take(n_mels * n_out);
+    t.mel_w = t.mel_meta = t.mel_cnt = t.mel_wt = t.mel_flush = t.mel_comb = 0;
+    if (mel_fast) {
+        t.mel_wt = take(2 * 32 * kChunk);
+        t.mel_flush = take(32);
+        t.mel_comb = take(2 * n_mels);
+    } else {
+        t.mel_w = take((int)taps.size());
+        t.mel_meta = take(2 * n_mels);
+        t.mel_cnt = take(n_mels);
+    }
+    t.dct = t.dcth = 0;
+    if (dct_fast)
+        t.dcth = take((n_mels / 2) * n_out);
+    else
+        t.dct = take(n_mels * n_out);
     t.mean = take(n_out);
     t.inv_scale = take(n_out);
     t.total = off;
+    h->mel_mode = mel_fast ? 1 : 0;
+    h->dct_mode = dct_fast ? 1 : 0;
     h->host_tables.assign(off, 0.f);
     float* T = h->host_tables.data();
     for (int n = 0; n < cfg->frame_length; ++n)
@@ -442,19 +607,30 @@ int cmoop_mfcc_create(const cmoop_mfcc_config* cfg, cmoop_mfcc_handle* out) {
         T[t.tw1024 + 2 * k] = (float)cos(ang);
         T[t.tw1024 + 2 * k + 1] = (float)sin(ang);
     }
-    for (size_t i = 0; i < taps.size(); ++i) T[t.mel_w + i] = taps[i];
-    int* meta = reinterpret_cast<int*>(T + t.mel_meta);
-    int* cnt = reinterpret_cast<int*>(T + t.mel_cnt);
-    for (int b = 0; b < n_mels; ++b) {
-        meta[2 * b] = first[b];
-        meta[2 * b + 1] = t.mel_w + offset[b] - t.mel_w;   // tap offset relative to mel_w
-        cnt[b] = count[b];
+    if (mel_fast) {
+        for (size_t i = 0; i < wt.size(); ++i) T[t.mel_wt + i] = wt[i];
+        unsigned* fm = reinterpret_cast<unsigned*>(T + t.mel_flush);
+        for (int l = 0; l < 32; ++l) fm[l] = flush[l];
+        int* comb = reinterpret_cast<int*>(T + t.mel_comb);
+        for (int b = 0; b < n_mels; ++b) {
+            comb[2 * b] = run_lane[b] | (run_k[b] << 8) | (run_n[b] << 16);                    // rising: segment b
+            comb[2 * b + 1] = run_lane[b + 1] | (run_k[b + 1] << 8) | (run_n[b + 1] << 16);    // falling: segment b+1
+        }
+    } else {
+        for (size_t i = 0; i < taps.size(); ++i) T[t.mel_w + i] = taps[i];
+        int* meta = reinterpret_cast<int*>(T + t.mel_meta);
+        int* cnt = reinterpret_cast<int*>(T + t.mel_cnt);
+        for (int b = 0; b < n_mels; ++b) {
+            meta[2 * b] = first[b];
+            meta[2 * b + 1] = offset[b];
+            cnt[b] = count[b];
+        }
     }
-    for (int b = 0; b < n_mels; ++b)
+    for (int b = 0; b < (dct_fast ? n_mels / 2 : n_mels); ++b)
         for (int c = 0; c < n_out; ++c) {
             double v = cos(pi * c * (2 * b + 1) / (2.0 * n_mels)) * sqrt(2.0 / n_mels);
             if (c == 0) v *= sqrt(0.5);
-            T[t.dct + b * n_out + c] = (float)v;
+            T[(dct_fast ? t.dcth : t.dct) + b * n_out + c] = (float)v;
         }
     for (int c = 0; c < n_out; ++c) {
         T[t.mean + c] = 0.f;
@@ -518,6 +694,8 @@ int cmoop_mfcc_fwd_dev(cmoop_mfcc_handle h, const float* wave, int64_t n_clips, 
     p.n_mels = h->cfg.n_mels;
     p.n_out = h->n_out;
     p.use_dct = h->cfg.n_mfcc > 0;
+    p.mel_mode = h->mel_mode;
+    p.dct_mode = h->dct_mode;
     p.vec2 = (n_samples % 2 == 0) && (h->cfg.hop % 2 == 0) && (((uintptr_t)wave & 7u) == 0);
     p.log_floor = h->cfg.log_floor;
     const long long blocks_needed = (p.n_frames_total + kWarps - 1) / kWarps;
