@@ -63,6 +63,16 @@ SIGNATURES = {
     "cmoop_mfcc_fwd_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "cmoop_mfcc_fwd_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "cmoop_mfcc_set_standardise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cmoop_cnn_dataset_create_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                                C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "cmoop_cnn_dataset_destroy": (C.c_int, [C.c_void_p]),
+    "cmoop_cnn_param_count": (C.c_longlong, [C.c_void_p, C.c_void_p]),
+    "cmoop_cnn_pop_train_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]),
+    "cmoop_cnn_debug_init_params": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "cmoop_cnn_debug_permutation": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.c_void_p]),
+    "cmoop_cnn_debug_train_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,161 @@
+// Population-batched candidate-CNN training / scoring: device task descriptors shared by the
+// kernels (kernels.cu, conv_tc.cu) and the host executor (engine.cu).
+//
+// Replaces build_model / evaluate_individual / compute_objectives_and_constraints
+// (nsga_penalty.py:225-442, sa_nsga_penalty.py:137-253).  Every launch is GROUPED: one grid covers
+// the same stage of every active candidate (heterogeneous genotypes), blockIdx.x is mapped to a
+// (candidate task, tile) pair through the tasks' tile_begin prefix.
+// Layout: activations NHWC fp32, conv kernels HWIO (= GEMM B matrix [K][Cout]) immediately followed by
+// the bias row in the flat parameter buffer, so bias is the (K+1)-th row of the GEMM ("ones column").
+#pragma once
+#include <stdint.h>
+
+namespace cmoop_cnn {
+
+constexpr int kBatch = 64;
+
+struct ConvTask {
+    const float* x;        // input activations (or dataset base)
+    const int* gather;     // per-step sample indices into x rows (stem conv on the dataset), or null
+    const float* w;        // [K (+1 bias row)][Cout]
+    float* y;              // output
+    float* stat_part;      // [tiles_m][2][Cout] per-tile column sums of y and y^2 (BN batch stats), or null
+    long long x_step;      // elements added to x per step (eval: contiguous batches of the split)
+    long long gather_step; // elements added to gather per step
+    int H, W, Cin, Ho, Wo, Cout, k, stride, pad;
+    int relu;              // ReLU in the epilogue
+    int use_bias;          // append the virtual ones column (K_ext = K + 1)
+    int out_h, out_w, out_s;  // scattered destination grid (strided-conv dgrad); out_s == 0 -> dense [M][Cout]
+    int accumulate;        // y += result
+    int tiles_n, tile_begin;
+};
+
+struct WgradTask {
+    const float* x;        // forward input of the conv (same addressing as ConvTask)
+    const int* gather;
+    const float* dy;       // [M][Cout] gradient of the conv output
+    float* out;            // grad buffer [K+1][Cout] (splits == 1) or workspace [splits][K+1][Cout]
+    long long x_step, gather_step;
+    int H, W, Cin, Ho, Wo, Cout, k, stride, pad;
+    int splits, m_chunk;   // rows of M per split (multiple of 16)
+    int tiles_k, tiles_n, tile_begin;
+};
+
+struct ReduceTask {       // out[i] = sum_s part[s][i]
+    const float* part;
+    float* out;
+    int n, splits, block_begin;
+};
+
+struct WtTask {           // dgrad weights: wt[(k-1-kh, k-1-kw, co)][ci] = w[(kh,kw,ci)][co]
+    const float* w;
+    float* wt;
+    int k, Cin, Cout, block_begin;
+};
+
+struct PostTask {
+    const float* u;        // conv output [n,H,W,C]
+    float* v;              // unit output [n,Ho,Wo,C]
+    const float* skip;     // residual branch [n,Ho,Wo,C] or null
+    uint8_t* idx;          // 2x2 pool argmax code per output element, or null
+    const float* gamma;    // BN parameters (null when the unit has no BN)
+    const float* beta;
+    float* mov_mean;
+    float* mov_var;
+    const float* stat_part;   // forward partial sums written by the conv epilogue
+    float* bn;             // [6][C]: mean, invstd, scale, shift, mean_g, mean_gx
+    const float* dv;       // backward: gradient of v
+    float* du;             // gradient of u (dense, [n,H,W,C])
+    float* dskip;          // gradient of the residual branch [n,Ho,Wo,C] or null
+    float* dgamma;
+    float* dbeta;
+    float* bwd_part;       // [rows][2][C] partial sums of g and g*xhat
+    int H, W, C, Ho, Wo;
+    int pool, relu_mid, add_skip, relu_in, has_bn;
+    int stat_tiles, bwd_rows;
+    int block_begin;       // grouped offset for the elementwise kernels (forward / backward-apply)
+    int block_begin_bwd;   // grouped offset for the backward reduce kernel
+};
+
+struct HeadTask {
+    const float* v;        // last feature map [n,Hf,Wf,C]
+    float* gap;            // [n,C]
+    const float* dgap;     // [n,C]
+    float* dv;             // [n,Hf,Wf,C]
+    int Hf, Wf, C, block_begin;
+};
+
+struct DropTask {          // dense ReLU output u -> v = u*keep/(1-rate); backward dz = dv*keep/(1-rate)*(u>0)
+    const float* u;
+    float* v;
+    const float* dv;
+    float* dz;
+    unsigned seed;
+    int layer, units, use_dropout, block_begin;
+};
+
+struct CeTask {
+    const float* logits;   // [n,C]
+    const int* labels;     // dataset labels
+    const int* gather;     // sample indices for this step or null (eval: contiguous)
+    long long label_step, gather_step;
+    float* dlogits;        // [n,C] (training)
+    double* acc;           // [4]: loss sum, sample count, correct count, (unused)
+    int* pred;             // [n_split] argmax predictions (eval/predict) or null
+    int* confusion;        // [C][C] (predict) or null
+    int n_classes, y_true_zero;
+};
+
+struct AdamTask {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    int n, block_begin;
+};
+
+struct InitTask {          // Glorot-uniform / constant initialisation of one tensor
+    float* p;
+    int n, tensor, kind;   // kind 0: uniform(-limit, limit), 1: constant value
+    float limit, value;
+    unsigned seed;
+    int block_begin;
+};
+
+// dropout / init hash shared with oracle/cnn_ref.py (dropout_keep_mask)
+__host__ __device__ inline unsigned fmix32(unsigned h) {
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+__host__ __device__ inline float hash_uniform(unsigned seed, unsigned stream, unsigned step, unsigned elem) {
+    unsigned h = fmix32(seed + 0x9E3779B9u * (stream + 1u));
+    h = fmix32(h ^ step);
+    h = fmix32(h ^ elem);
+    return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+
+// launchers (kernels.cu); every function returns cudaGetLastError()
+struct Launch {
+    static int conv(const ConvTask* tasks, int n_tasks, int total_tiles, int n_b, int step, void* stream);
+    static int wgrad(const WgradTask* tasks, int n_tasks, int total_tiles, int n_b, int step, void* stream);
+    static int reduce(const ReduceTask* tasks, int n_tasks, int total_blocks, void* stream);
+    static int wt(const WtTask* tasks, int n_tasks, int total_blocks, void* stream);
+    static int bn_finalize(const PostTask* tasks, int n_tasks, int n_b, int training, float momentum, float eps, void* stream);
+    static int post_fwd(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
+    static int post_bwd_reduce(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
+    static int bn_bwd_finalize(const PostTask* tasks, int n_tasks, int n_b, void* stream);
+    static int post_bwd_apply(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
+    static int gap_fwd(const HeadTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
+    static int gap_bwd(const HeadTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
+    static int drop_fwd(const DropTask* tasks, int n_tasks, int total_blocks, int n_b, int step, int training, float rate, void* stream);
+    static int drop_bwd(const DropTask* tasks, int n_tasks, int total_blocks, int n_b, int step, float rate, void* stream);
+    static int ce(const CeTask* tasks, int n_tasks, int n_b, int step, int training, void* stream);
+    static int adam(const AdamTask* tasks, int n_tasks, int total_blocks, float alpha, float b1, float b2, float eps, void* stream);
+    static int init(const InitTask* tasks, int n_tasks, int total_blocks, void* stream);
+};
+
+}  // namespace cmoop_cnn

@@ -1,0 +1,976 @@
+// Host executor of the population-batched candidate-CNN training/scoring path and its C ABI.
+//
+// Replaces the serial `for ind in population: evaluate_individual(ind)` loop of
+// compute_objectives_and_constraints (nsga_penalty.py:418-442; sa_nsga_penalty.py:231-253) together with
+// build_model / model.fit / model.evaluate / model.predict / calculate_fpr / compute_model_size_mb
+// (nsga_penalty.py:225-395).  One process drives one GPU; candidates are packed into "waves" that fit
+// the activation arena, and every kernel launch of a training / evaluation step covers the same stage
+// of every still-active candidate of the wave (grouped launch, cnn.cuh).
+//
+// Canonical stage order (a valid topological order for every genotype of both variants):
+//   0 stem1 | 1 stem2 (variant A) | per block b: 2+3b skip (1x1/s2), 3+3b conv1, 4+3b conv2 (variant A)
+//   | GAP | 11..14 fc0..fc3 | 15 output layer | cross-entropy
+// Backward walks the same list in reverse; gradients w.r.t. unit outputs live in buffer A, gradients
+// w.r.t. conv outputs in buffer B, the residual-branch gradient in S (see run_backward).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../common.cuh"
+#include "cnn.cuh"
+
+using namespace cmoop_cnn;
+
+struct cmoop_cnn_dataset {
+    float* x_train = nullptr;
+    int* y_train = nullptr;
+    float* x_val = nullptr;
+    int* y_val = nullptr;
+    int n_train = 0, n_val = 0, H = 0, W = 0;
+};
+
+namespace {
+
+constexpr int N_STAGES = 16, ST_FC0 = 11, ST_OUT = 15;
+const int kFcUnits[5][4] = {{0, 0, 0, 0}, {64, 0, 0, 0}, {128, 64, 0, 0}, {256, 128, 64, 0}, {512, 256, 128, 64}};
+
+struct Unit {
+    int stage = 0, cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
+    int H = 1, W = 1, Ho = 1, Wo = 1, Po = 1, Qo = 1;   // input grid, conv-output grid, unit-output grid
+    bool dense = false, is_skip = false, has_bn = false, relu_epi = false, relu_mid = false, pool = false;
+    bool add_skip = false, post_fwd = false, need_dgrad = true, use_dropout = false;
+    int input = -1;        // producing unit, -1 = dataset, -2 = GAP output
+    int skip_unit = -1;
+    int fc_index = -1;
+    long long w_off = 0, bn_off = -1;
+    long long u_elems = 0, v_elems = 0;
+    int stat_tiles = 0, bwd_rows = 0, wg_splits = 1, wg_chunk = 0;
+    float* U = nullptr;
+    float* V = nullptr;
+    float* stat = nullptr;
+    float* bn = nullptr;
+    float* bwd_part = nullptr;
+    float* wt = nullptr;
+    uint8_t* idx = nullptr;
+};
+
+struct Cand {
+    cmoop_genotype g{};
+    uint64_t seed = 0;
+    int index = 0;
+    std::vector<Unit> units;
+    int last_conv = 0, n_fc = 0;
+    long long n_params = 0;
+    size_t arena_bytes = 0;
+    float *p = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr, *best = nullptr;
+    float *gA = nullptr, *gB = nullptr, *gS = nullptr, *gG = nullptr, *gap = nullptr, *dlogits = nullptr, *wg_ws = nullptr;
+    int* perm = nullptr;
+    double* acc = nullptr;     // [3][4]: train, val, predict accumulators
+    int* pred = nullptr;
+    int* confusion = nullptr;
+    // early-stopping state (keras.callbacks.EarlyStopping semantics, see oracle/cnn_ref.py)
+    bool active = true, has_best = false;
+    int epochs_run = 0, wait = 0;
+    double best_loss = INFINITY, last_val_loss = NAN, last_val_acc = NAN, final_acc = NAN, fpr = NAN;
+};
+
+long long conv_params(int cin, int cout, int k) { return (long long)k * k * cin * cout + cout; }
+
+// Builds the unit list + flat parameter layout of one genotype (order == oracle/cnn_ref.layer_specs).
+void build_units(Cand& c, const cmoop_cnn_config& cfg, int H, int W, int batch) {
+    c.units.clear();
+    const bool A = cfg.variant == 0;
+    const bool bn = c.g.use_bn != 0;
+    long long off = 0;
+    int f = c.g.filters, k = c.g.kernel_size;
+    int h = H, w = W;
+    auto add_conv = [&](int stage, int cin, int cout, int ks, int stride, int hin, int win, bool with_bn) -> int {
+        Unit u;
+        u.stage = stage;
+        u.cin = cin;
+        u.cout = cout;
+        u.k = ks;
+        u.stride = stride;
+        u.pad = stride == 1 ? (ks - 1) / 2 : 0;
+        u.H = hin;
+        u.W = win;
+        u.Ho = stride == 1 ? hin : (hin + 1) / 2;
+        u.Wo = stride == 1 ? win : (win + 1) / 2;
+        u.Po = u.Ho;
+        u.Qo = u.Wo;
+        u.has_bn = with_bn;
+        u.w_off = off;
+        off += conv_params(cin, cout, ks);
+        if (with_bn) {
+            u.bn_off = off;
+            off += 4LL * cout;
+        }
+        c.units.push_back(u);
+        return (int)c.units.size() - 1;
+    };
+    auto set_pool = [&](Unit& u) {
+        u.pool = true;
+        u.Po = (u.Ho + 1) / 2;
+        u.Qo = (u.Wo + 1) / 2;
+    };
+    int prev;
+    if (A) {
+        int s1 = add_conv(0, 1, f, k, 1, h, w, bn);
+        c.units[s1].input = -1;
+        c.units[s1].need_dgrad = false;
+        c.units[s1].relu_epi = !bn;
+        c.units[s1].relu_mid = bn;
+        c.units[s1].post_fwd = bn;
+        int s2 = add_conv(1, f, f, k, 1, h, w, bn);
+        c.units[s2].input = s1;
+        c.units[s2].relu_epi = !bn;
+        c.units[s2].relu_mid = bn;
+        set_pool(c.units[s2]);
+        c.units[s2].post_fwd = true;
+        prev = s2;
+    } else {
+        int s1 = add_conv(0, 1, f, k, 1, h, w, bn);
+        c.units[s1].input = -1;
+        c.units[s1].need_dgrad = false;
+        c.units[s1].relu_epi = true;
+        set_pool(c.units[s1]);
+        c.units[s1].post_fwd = true;
+        prev = s1;
+    }
+    h = c.units[prev].Po;
+    w = c.units[prev].Qo;
+    for (int b = 0; b < c.g.residual_blocks; ++b) {
+        int sk = add_conv(2 + 3 * b, f, 2 * f, 1, 2, h, w, false);
+        c.units[sk].input = prev;
+        c.units[sk].is_skip = true;
+        int last;
+        if (A) {
+            int c1 = add_conv(3 + 3 * b, f, 2 * f, k, 1, h, w, bn);
+            c.units[c1].input = prev;
+            c.units[c1].relu_epi = !bn;
+            c.units[c1].relu_mid = bn;
+            c.units[c1].post_fwd = bn;
+            int c2 = add_conv(4 + 3 * b, 2 * f, 2 * f, k, 1, h, w, bn);
+            c.units[c2].input = c1;
+            set_pool(c.units[c2]);
+            c.units[c2].add_skip = true;
+            c.units[c2].skip_unit = sk;
+            c.units[c2].post_fwd = true;
+            last = c2;
+        } else {
+            int c1 = add_conv(3 + 3 * b, f, 2 * f, k, 1, h, w, bn);
+            c.units[c1].input = prev;
+            c.units[c1].relu_epi = true;
+            set_pool(c.units[c1]);
+            c.units[c1].add_skip = true;
+            c.units[c1].skip_unit = sk;
+            c.units[c1].post_fwd = true;
+            last = c1;
+        }
+        prev = last;
+        f *= 2;
+        h = c.units[prev].Po;
+        w = c.units[prev].Qo;
+    }
+    c.last_conv = prev;
+    int width = f;
+    c.n_fc = c.g.fc_layers;
+    int in_unit = -2;
+    for (int i = 0; i < c.n_fc; ++i) {
+        const int units = kFcUnits[c.g.fc_layers][i];
+        int d = add_conv(ST_FC0 + i, width, units, 1, 1, 1, 1, false);
+        Unit& u = c.units[d];
+        u.dense = true;
+        u.relu_epi = true;
+        u.input = in_unit;
+        u.fc_index = i;
+        u.use_dropout = c.g.use_dropout != 0;
+        in_unit = d;
+        width = units;
+    }
+    int o = add_conv(ST_OUT, width, cfg.n_classes, 1, 1, 1, 1, false);
+    c.units[o].dense = true;
+    c.units[o].input = in_unit;
+    c.n_params = off;
+    for (Unit& u : c.units) {
+        u.u_elems = (long long)batch * u.Ho * u.Wo * u.cout;
+        u.v_elems = (long long)batch * u.Po * u.Qo * u.cout;
+        const long long M = (long long)batch * u.Ho * u.Wo;
+        u.stat_tiles = (int)((M + 63) / 64);
+        const long long npix = (long long)batch * u.Po * u.Qo;
+        const int cb = u.cout < 128 ? u.cout : 128;
+        u.bwd_rows = (int)(((npix + 127) / 128) * (128 / cb));
+        int splits = (int)std::min<long long>(32, std::max<long long>(1, M / 2048));
+        int chunk = (int)((M + splits - 1) / splits);
+        chunk = (chunk + 15) / 16 * 16;
+        splits = (int)((M + chunk - 1) / chunk);
+        u.wg_splits = splits;
+        u.wg_chunk = chunk;
+    }
+}
+
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, off = 0;
+    bool dry = false;
+    void* take(size_t bytes) {
+        const size_t at = off;
+        off += (bytes + 255) / 256 * 256;
+        if (dry) return nullptr;
+        return off <= cap ? base + at : nullptr;
+    }
+};
+
+// Assigns (or, in a dry run, just sizes) all device buffers of one candidate.
+void place(Cand& c, Arena& a, const cmoop_cnn_config& cfg, int n_train, int n_val, int batch) {
+    const size_t f4 = sizeof(float);
+    c.p = (float*)a.take(c.n_params * f4);
+    c.grad = (float*)a.take(c.n_params * f4);
+    c.m = (float*)a.take(c.n_params * f4);
+    c.v = (float*)a.take(c.n_params * f4);
+    c.best = cfg.restore_best_weights ? (float*)a.take(c.n_params * f4) : nullptr;
+    long long maxV = (long long)batch * 1, maxU = 1, maxS = 1, maxWs = 1;
+    for (Unit& u : c.units) {
+        u.U = (float*)a.take(u.u_elems * f4);
+        const bool separate_v = u.post_fwd || (u.dense && u.use_dropout);
+        u.V = separate_v ? (float*)a.take(u.v_elems * f4) : u.U;
+        u.idx = u.pool ? (uint8_t*)a.take(u.v_elems) : nullptr;
+        if (u.has_bn) {
+            u.stat = (float*)a.take((size_t)u.stat_tiles * 2 * u.cout * f4);
+            u.bn = (float*)a.take((size_t)6 * u.cout * f4);
+            u.bwd_part = (float*)a.take((size_t)u.bwd_rows * 2 * u.cout * f4);
+        }
+        u.wt = u.need_dgrad ? (float*)a.take((size_t)u.k * u.k * u.cin * u.cout * f4) : nullptr;
+        maxV = std::max(maxV, u.v_elems);
+        maxV = std::max(maxV, (long long)batch * u.H * u.W * u.cin);
+        maxU = std::max(maxU, u.u_elems);
+        if (u.is_skip) maxS = std::max(maxS, u.u_elems);
+        if (u.wg_splits > 1)
+            maxWs = std::max(maxWs, (long long)u.wg_splits * ((long long)u.k * u.k * u.cin + 1) * u.cout);
+    }
+    const Unit& lc = c.units[c.last_conv];
+    c.gA = (float*)a.take(maxV * f4);
+    c.gB = (float*)a.take(maxU * f4);
+    c.gS = (float*)a.take(maxS * f4);
+    c.gG = (float*)a.take((size_t)batch * lc.cout * f4);
+    c.gap = (float*)a.take((size_t)batch * lc.cout * f4);
+    c.dlogits = (float*)a.take((size_t)batch * cfg.n_classes * f4);
+    c.wg_ws = (float*)a.take(maxWs * f4);
+    c.perm = (int*)a.take((size_t)n_train * sizeof(int));
+    c.acc = (double*)a.take(12 * sizeof(double));
+    c.pred = (int*)a.take((size_t)n_val * sizeof(int));
+    c.confusion = (int*)a.take((size_t)cfg.n_classes * cfg.n_classes * sizeof(int));
+}
+
+template <class T>
+struct DevList {
+    std::vector<T> h;
+    T* d = nullptr;
+    int total = 0;   // tiles / blocks of the grouped grid
+    size_t blob_off = 0;
+};
+
+struct StageLists {
+    DevList<ConvTask> conv, conv_eval, dgrad;
+    DevList<PostTask> post_fwd, post_bn, post_bwd;
+    DevList<WgradTask> wgrad;
+    DevList<ReduceTask> wreduce;
+    DevList<DropTask> drop_fwd, drop_bwd;
+};
+
+struct Wave {
+    std::vector<Cand*> cands;
+    StageLists st[N_STAGES];
+    DevList<HeadTask> head;
+    DevList<CeTask> ce_train, ce_val, ce_pred;
+    DevList<AdamTask> adam;
+    DevList<WtTask> wt;
+    char* d_blob = nullptr;
+    size_t blob_cap = 0;
+};
+
+template <class T>
+void blob_add(std::vector<char>& blob, DevList<T>& l) {
+    l.blob_off = (blob.size() + 255) / 256 * 256;
+    blob.resize(l.blob_off + l.h.size() * sizeof(T));
+    if (!l.h.empty()) memcpy(blob.data() + l.blob_off, l.h.data(), l.h.size() * sizeof(T));
+}
+
+inline int blocks_for(long long elems) { return (int)((elems + 255) / 256); }
+
+struct Engine {
+    const cmoop_cnn_dataset* data;
+    cmoop_cnn_config cfg;
+    int batch;
+    cudaStream_t stream;
+    int global_step = 0;   // dropout hash stream
+
+    // ---- task-list construction for the currently active candidates of a wave
+    int build_lists(Wave& wv) {
+        for (int s = 0; s < N_STAGES; ++s) wv.st[s] = StageLists();
+        wv.head = DevList<HeadTask>();
+        wv.ce_train = wv.ce_val = wv.ce_pred = DevList<CeTask>();
+        wv.adam = DevList<AdamTask>();
+        wv.wt = DevList<WtTask>();
+        const long long img = (long long)data->H * data->W;
+        for (Cand* cp : wv.cands) {
+            Cand& c = *cp;
+            if (!c.active) continue;
+            for (size_t ui = 0; ui < c.units.size(); ++ui) {
+                Unit& u = c.units[ui];
+                StageLists& S = wv.st[u.stage];
+                const float* xin = u.input == -1 ? data->x_train : (u.input == -2 ? (c.n_fc ? c.gap : c.gap) : c.units[u.input].V);
+                // ---- forward conv
+                ConvTask t{};
+                t.x = xin;
+                t.w = c.p + u.w_off;
+                t.y = u.U;
+                t.stat_part = u.has_bn ? u.stat : nullptr;
+                t.H = u.H; t.W = u.W; t.Cin = u.cin; t.Ho = u.Ho; t.Wo = u.Wo; t.Cout = u.cout;
+                t.k = u.k; t.stride = u.stride; t.pad = u.pad;
+                t.relu = u.relu_epi;
+                t.use_bias = 1;
+                t.tiles_n = (u.cout + 63) / 64;
+                t.tile_begin = S.conv.total;
+                if (u.input == -1) {
+                    t.gather = c.perm;
+                    t.gather_step = batch;
+                    ConvTask e = t;
+                    e.x = data->x_val;
+                    e.gather = nullptr;
+                    e.gather_step = 0;
+                    e.x_step = (long long)batch * img;
+                    e.tile_begin = S.conv_eval.total;
+                    S.conv_eval.h.push_back(e);
+                    S.conv_eval.total += u.stat_tiles * t.tiles_n;
+                }
+                S.conv.h.push_back(t);
+                S.conv.total += u.stat_tiles * t.tiles_n;
+                // ---- post stage (forward / BN / backward lists)
+                if (!u.dense && !u.is_skip) {
+                    PostTask p{};
+                    p.u = u.U; p.v = u.V;
+                    p.skip = u.add_skip ? c.units[u.skip_unit].U : nullptr;
+                    p.idx = u.idx;
+                    if (u.has_bn) {
+                        float* bnp = c.p + u.bn_off;
+                        p.gamma = bnp; p.beta = bnp + u.cout; p.mov_mean = bnp + 2 * u.cout; p.mov_var = bnp + 3 * u.cout;
+                        p.dgamma = c.grad + u.bn_off; p.dbeta = c.grad + u.bn_off + u.cout;
+                        p.stat_part = u.stat; p.bn = u.bn; p.bwd_part = u.bwd_part;
+                    }
+                    p.dv = c.gA; p.du = c.gB;
+                    p.dskip = u.add_skip ? c.gS : nullptr;
+                    p.H = u.Ho; p.W = u.Wo; p.C = u.cout; p.Ho = u.Po; p.Wo = u.Qo;
+                    p.pool = u.pool; p.relu_mid = u.relu_mid; p.add_skip = u.add_skip; p.relu_in = u.relu_epi;
+                    p.has_bn = u.has_bn;
+                    p.stat_tiles = u.stat_tiles; p.bwd_rows = u.bwd_rows;
+                    if (u.post_fwd) {
+                        PostTask q = p;
+                        q.block_begin = S.post_fwd.total;
+                        S.post_fwd.h.push_back(q);
+                        S.post_fwd.total += blocks_for(u.v_elems);
+                    }
+                    if (u.has_bn) {
+                        PostTask q = p;
+                        q.block_begin_bwd = S.post_bn.total;
+                        S.post_bn.h.push_back(q);
+                        S.post_bn.total += (int)(((long long)batch * u.Po * u.Qo + 127) / 128);
+                    }
+                    PostTask q = p;
+                    q.block_begin = S.post_bwd.total;
+                    S.post_bwd.h.push_back(q);
+                    S.post_bwd.total += blocks_for(u.u_elems);
+                }
+                // ---- dense ReLU / dropout
+                if (u.dense && u.fc_index >= 0) {
+                    DropTask d{};
+                    d.u = u.U; d.v = u.V; d.dv = c.gA; d.dz = c.gB;
+                    d.seed = (unsigned)(c.seed & 0xffffffffu);
+                    d.layer = u.fc_index; d.units = u.cout; d.use_dropout = u.use_dropout;
+                    if (u.use_dropout) {
+                        d.block_begin = S.drop_fwd.total;
+                        S.drop_fwd.h.push_back(d);
+                        S.drop_fwd.total += blocks_for((long long)batch * u.cout);
+                    }
+                    d.block_begin = S.drop_bwd.total;
+                    S.drop_bwd.h.push_back(d);
+                    S.drop_bwd.total += blocks_for((long long)batch * u.cout);
+                }
+                // ---- weight gradient (+ bias row)
+                {
+                    const bool to_ws = u.wg_splits > 1;
+                    const int kext = u.k * u.k * u.cin + 1;
+                    WgradTask g{};
+                    g.x = xin;
+                    if (u.input == -1) { g.gather = c.perm; g.gather_step = batch; }
+                    g.dy = u.is_skip ? c.gS : (u.stage == ST_OUT ? c.dlogits : c.gB);
+                    g.out = to_ws ? c.wg_ws : c.grad + u.w_off;
+                    g.H = u.H; g.W = u.W; g.Cin = u.cin; g.Ho = u.Ho; g.Wo = u.Wo; g.Cout = u.cout;
+                    g.k = u.k; g.stride = u.stride; g.pad = u.pad;
+                    g.splits = u.wg_splits; g.m_chunk = u.wg_chunk;
+                    g.tiles_k = (kext + 63) / 64; g.tiles_n = (u.cout + 63) / 64;
+                    g.tile_begin = S.wgrad.total;
+                    S.wgrad.h.push_back(g);
+                    S.wgrad.total += g.tiles_k * g.tiles_n * g.splits;
+                    if (to_ws) {
+                        ReduceTask r{};
+                        r.part = c.wg_ws; r.out = c.grad + u.w_off; r.n = kext * u.cout; r.splits = u.wg_splits;
+                        r.block_begin = S.wreduce.total;
+                        S.wreduce.h.push_back(r);
+                        S.wreduce.total += blocks_for(r.n);
+                    }
+                }
+                // ---- data gradient: conv of dy with flipped/transposed weights into buffer A (or gG below the first FC)
+                if (u.need_dgrad) {
+                    WtTask w{};
+                    w.w = c.p + u.w_off; w.wt = u.wt; w.k = u.k; w.Cin = u.cin; w.Cout = u.cout;
+                    w.block_begin = wv.wt.total;
+                    wv.wt.h.push_back(w);
+                    wv.wt.total += blocks_for((long long)u.k * u.k * u.cin * u.cout);
+                    ConvTask d{};
+                    d.x = u.is_skip ? c.gS : (u.stage == ST_OUT ? c.dlogits : c.gB);
+                    d.w = u.wt;
+                    d.y = u.input == -2 ? c.gG : c.gA;
+                    d.Cin = u.cout; d.Cout = u.cin; d.k = u.k;
+                    d.H = u.Ho; d.W = u.Wo; d.Ho = u.Ho; d.Wo = u.Wo;
+                    d.stride = 1; d.pad = u.pad;
+                    if (u.is_skip) {
+                        d.pad = 0;
+                        d.out_h = u.H; d.out_w = u.W; d.out_s = 2;
+                        d.accumulate = 1;
+                    }
+                    d.tiles_n = (u.cin + 63) / 64;
+                    d.tile_begin = S.dgrad.total;
+                    S.dgrad.h.push_back(d);
+                    S.dgrad.total += u.stat_tiles * d.tiles_n;
+                }
+            }
+            const Unit& lc = c.units[c.last_conv];
+            HeadTask hd{};
+            hd.v = lc.V; hd.gap = c.gap; hd.dgap = c.gG; hd.dv = c.gA;
+            hd.Hf = lc.Po; hd.Wf = lc.Qo; hd.C = lc.cout;
+            hd.block_begin = wv.head.total;
+            wv.head.h.push_back(hd);
+            wv.head.total += blocks_for((long long)batch * lc.Po * lc.Qo * lc.cout);
+            const Unit& ou = c.units.back();
+            CeTask ce{};
+            ce.logits = ou.U; ce.dlogits = c.dlogits; ce.n_classes = cfg.n_classes;
+            ce.labels = data->y_train; ce.gather = c.perm; ce.gather_step = batch; ce.acc = c.acc;
+            wv.ce_train.h.push_back(ce);
+            ce.labels = data->y_val; ce.gather = nullptr; ce.gather_step = 0; ce.label_step = batch; ce.acc = c.acc + 4;
+            wv.ce_val.h.push_back(ce);
+            ce.acc = c.acc + 8; ce.pred = c.pred; ce.confusion = c.confusion; ce.y_true_zero = cfg.y_true_zero;
+            wv.ce_pred.h.push_back(ce);
+            AdamTask ad{};
+            ad.p = c.p; ad.g = c.grad; ad.m = c.m; ad.v = c.v; ad.n = (int)c.n_params;
+            ad.block_begin = wv.adam.total;
+            wv.adam.h.push_back(ad);
+            wv.adam.total += blocks_for(c.n_params);
+        }
+        // ---- one blob upload, then fix the device pointers
+        std::vector<char> blob;
+        for (int s = 0; s < N_STAGES; ++s) {
+            StageLists& S = wv.st[s];
+            blob_add(blob, S.conv); blob_add(blob, S.conv_eval); blob_add(blob, S.dgrad);
+            blob_add(blob, S.post_fwd); blob_add(blob, S.post_bn); blob_add(blob, S.post_bwd);
+            blob_add(blob, S.wgrad); blob_add(blob, S.wreduce); blob_add(blob, S.drop_fwd); blob_add(blob, S.drop_bwd);
+        }
+        blob_add(blob, wv.head); blob_add(blob, wv.ce_train); blob_add(blob, wv.ce_val); blob_add(blob, wv.ce_pred);
+        blob_add(blob, wv.adam); blob_add(blob, wv.wt);
+        if (blob.size() > wv.blob_cap) {
+            if (wv.d_blob) {
+                CMOOP_CUDA_OK(cudaStreamSynchronize(stream));
+                CMOOP_CUDA_OK(cudaFree(wv.d_blob));
+            }
+            wv.blob_cap = blob.size() * 2 + 4096;
+            CMOOP_CUDA_OK(cudaMalloc((void**)&wv.d_blob, wv.blob_cap));
+        }
+        CMOOP_CUDA_OK(cudaStreamSynchronize(stream));   // previous launches may still read the old lists
+        CMOOP_CUDA_OK(cudaMemcpy(wv.d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+        auto fix = [&](auto& l) { l.d = reinterpret_cast<decltype(l.d)>(wv.d_blob + l.blob_off); };
+        for (int s = 0; s < N_STAGES; ++s) {
+            StageLists& S = wv.st[s];
+            fix(S.conv); fix(S.conv_eval); fix(S.dgrad); fix(S.post_fwd); fix(S.post_bn); fix(S.post_bwd);
+            fix(S.wgrad); fix(S.wreduce); fix(S.drop_fwd); fix(S.drop_bwd);
+        }
+        fix(wv.head); fix(wv.ce_train); fix(wv.ce_val); fix(wv.ce_pred); fix(wv.adam); fix(wv.wt);
+        return CMOOP_OK;
+    }
+
+#define CNN_LAUNCH(expr)                                                                           \
+    do {                                                                                           \
+        int _e = (expr);                                                                           \
+        cmoop::count_launch();                                                                     \
+        if (_e != 0) {                                                                             \
+            cmoop::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString((cudaError_t)_e)); \
+            return CMOOP_ERR_CUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+    // mode 0: training batch from the permutation; 1: validation loss/accuracy; 2: final predict (+confusion)
+    int run_forward(Wave& wv, int mode, int step, int n_b) {
+        const int training = mode == 0;
+        for (int s = 0; s < N_STAGES; ++s) {
+            StageLists& S = wv.st[s];
+            if (s == ST_FC0) CNN_LAUNCH(Launch::gap_fwd(wv.head.d, (int)wv.head.h.size(), wv.head.total, n_b, stream));
+            if (S.conv.h.empty()) continue;
+            DevList<ConvTask>& cl = (s == 0 && !training) ? S.conv_eval : S.conv;
+            CNN_LAUNCH(Launch::conv(cl.d, (int)cl.h.size(), cl.total, n_b, step, stream));
+            if (!S.post_bn.h.empty())
+                CNN_LAUNCH(Launch::bn_finalize(S.post_bn.d, (int)S.post_bn.h.size(), n_b, training, cfg.bn_momentum,
+                                               cfg.bn_eps, stream));
+            if (!S.post_fwd.h.empty())
+                CNN_LAUNCH(Launch::post_fwd(S.post_fwd.d, (int)S.post_fwd.h.size(), S.post_fwd.total, n_b, stream));
+            if (!S.drop_fwd.h.empty())
+                CNN_LAUNCH(Launch::drop_fwd(S.drop_fwd.d, (int)S.drop_fwd.h.size(), S.drop_fwd.total, n_b, global_step,
+                                            training, cfg.dropout_rate, stream));
+        }
+        DevList<CeTask>& ce = mode == 0 ? wv.ce_train : (mode == 1 ? wv.ce_val : wv.ce_pred);
+        CNN_LAUNCH(Launch::ce(ce.d, (int)ce.h.size(), n_b, step, training, stream));
+        return CMOOP_OK;
+    }
+
+    int run_backward(Wave& wv, int step, int n_b) {
+        CNN_LAUNCH(Launch::wt(wv.wt.d, (int)wv.wt.h.size(), wv.wt.total, stream));
+        for (int s = N_STAGES - 1; s >= 0; --s) {
+            StageLists& S = wv.st[s];
+            if (s == ST_FC0 - 1) CNN_LAUNCH(Launch::gap_bwd(wv.head.d, (int)wv.head.h.size(), wv.head.total, n_b, stream));
+            if (S.conv.h.empty()) continue;
+            if (!S.drop_bwd.h.empty())      // dense: A (grad of the layer output) -> B (grad of the pre-activation)
+                CNN_LAUNCH(Launch::drop_bwd(S.drop_bwd.d, (int)S.drop_bwd.h.size(), S.drop_bwd.total, n_b, global_step,
+                                            cfg.dropout_rate, stream));
+            if (!S.post_bn.h.empty()) {
+                CNN_LAUNCH(Launch::post_bwd_reduce(S.post_bn.d, (int)S.post_bn.h.size(), S.post_bn.total, n_b, stream));
+                CNN_LAUNCH(Launch::bn_bwd_finalize(S.post_bn.d, (int)S.post_bn.h.size(), n_b, stream));
+            }
+            if (!S.post_bwd.h.empty())
+                CNN_LAUNCH(Launch::post_bwd_apply(S.post_bwd.d, (int)S.post_bwd.h.size(), S.post_bwd.total, n_b, stream));
+            CNN_LAUNCH(Launch::wgrad(S.wgrad.d, (int)S.wgrad.h.size(), S.wgrad.total, n_b, step, stream));
+            if (!S.wreduce.h.empty())
+                CNN_LAUNCH(Launch::reduce(S.wreduce.d, (int)S.wreduce.h.size(), S.wreduce.total, stream));
+            if (!S.dgrad.h.empty())
+                CNN_LAUNCH(Launch::conv(S.dgrad.d, (int)S.dgrad.h.size(), S.dgrad.total, n_b, 0, stream));
+        }
+        return CMOOP_OK;
+    }
+
+    int adam_step(Wave& wv, int t) {
+        const double b1 = cfg.beta1, b2 = cfg.beta2;
+        const double alpha = cfg.learning_rate * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t));
+        CNN_LAUNCH(Launch::adam(wv.adam.d, (int)wv.adam.h.size(), wv.adam.total, (float)alpha, cfg.beta1, cfg.beta2,
+                                cfg.adam_eps, stream));
+        return CMOOP_OK;
+    }
+
+    int init_params(const std::vector<Cand*>& cands) {
+        std::vector<InitTask> tasks;
+        int total = 0;
+        for (Cand* cp : cands) {
+            Cand& c = *cp;
+            int tensor = 0;
+            auto add = [&](float* p, long long n, int kind, float limit, float value) {
+                InitTask t{};
+                t.p = p; t.n = (int)n; t.tensor = tensor++; t.kind = kind; t.limit = limit; t.value = value;
+                t.seed = (unsigned)(c.seed & 0xffffffffu) ^ (unsigned)(c.seed >> 32);
+                t.block_begin = total;
+                total += blocks_for(n);
+                tasks.push_back(t);
+            };
+            for (const Unit& u : c.units) {
+                const double fan_in = (double)u.k * u.k * u.cin, fan_out = (double)u.k * u.k * u.cout;
+                add(c.p + u.w_off, (long long)u.k * u.k * u.cin * u.cout, 0, (float)sqrt(6.0 / (fan_in + fan_out)), 0.f);
+                add(c.p + u.w_off + (long long)u.k * u.k * u.cin * u.cout, u.cout, 1, 0.f, 0.f);
+                if (u.has_bn) {
+                    add(c.p + u.bn_off, u.cout, 1, 0.f, 1.f);
+                    add(c.p + u.bn_off + u.cout, u.cout, 1, 0.f, 0.f);
+                    add(c.p + u.bn_off + 2 * u.cout, u.cout, 1, 0.f, 0.f);
+                    add(c.p + u.bn_off + 3 * u.cout, u.cout, 1, 0.f, 1.f);
+                }
+            }
+            CMOOP_CUDA_OK(cudaMemsetAsync(c.grad, 0, c.n_params * sizeof(float), stream));
+            CMOOP_CUDA_OK(cudaMemsetAsync(c.m, 0, c.n_params * sizeof(float), stream));
+            CMOOP_CUDA_OK(cudaMemsetAsync(c.v, 0, c.n_params * sizeof(float), stream));
+            CMOOP_CUDA_OK(cudaMemsetAsync(c.acc, 0, 12 * sizeof(double), stream));
+        }
+        InitTask* d = nullptr;
+        CMOOP_CUDA_OK(cudaMalloc((void**)&d, tasks.size() * sizeof(InitTask)));
+        CMOOP_CUDA_OK(cudaMemcpyAsync(d, tasks.data(), tasks.size() * sizeof(InitTask), cudaMemcpyHostToDevice, stream));
+        int rc = Launch::init(d, (int)tasks.size(), total, stream);
+        cmoop::count_launch();
+        CMOOP_CUDA_OK(cudaStreamSynchronize(stream));
+        cudaFree(d);
+        if (rc != 0) {
+            cmoop::set_error("init kernel: %s", cudaGetErrorString((cudaError_t)rc));
+            return CMOOP_ERR_CUDA;
+        }
+        return CMOOP_OK;
+    }
+};
+
+// Deterministic Fisher-Yates driven by the fmix32 hash (the harness-imposed "Keras shuffle").
+void make_permutation(uint64_t seed, int epoch, int n, int* out) {
+    for (int i = 0; i < n; ++i) out[i] = i;
+    const unsigned s = fmix32((unsigned)(seed & 0xffffffffu) ^ 0x5bd1e995u * (unsigned)(epoch + 1)) ^ (unsigned)(seed >> 32);
+    for (int i = n - 1; i > 0; --i) {
+        const unsigned r = fmix32(fmix32(s ^ 0x27d4eb2fu) ^ (unsigned)i);
+        const int j = (int)(r % (unsigned)(i + 1));
+        const int t = out[i];
+        out[i] = out[j];
+        out[j] = t;
+    }
+}
+
+int check_config(const cmoop_genotype* g, int n, const cmoop_cnn_config* cfg) {
+    CMOOP_REQUIRE(cfg != nullptr, "cnn: null config");
+    CMOOP_REQUIRE(cfg->variant == 0 || cfg->variant == 1, "cnn: variant must be 0 (A) or 1 (B)");
+    CMOOP_REQUIRE(cfg->n_classes >= 2 && cfg->n_classes <= 4096, "cnn: n_classes=%d outside [2,4096]", cfg->n_classes);
+    CMOOP_REQUIRE(cfg->batch_size >= 1 && cfg->batch_size <= kBatch, "cnn: batch_size=%d outside [1,%d]", cfg->batch_size,
+                  kBatch);
+    CMOOP_REQUIRE(cfg->max_epochs >= 1 && cfg->patience >= 0, "cnn: bad epochs/patience");
+    if (cfg->precision != 0) {
+        cmoop::set_error("cnn: precision=%d not available in this build (0 = fp32 SIMT)", cfg->precision);
+        return CMOOP_ERR_UNSUPPORTED;
+    }
+    for (int i = 0; i < n; ++i) {
+        CMOOP_REQUIRE(g[i].filters >= 4 && g[i].filters <= 256 && g[i].filters % 4 == 0,
+                      "cnn: genotype %d filters=%d must be a multiple of 4 in [4,256]", i, g[i].filters);
+        CMOOP_REQUIRE(g[i].kernel_size == 1 || g[i].kernel_size == 3 || g[i].kernel_size == 5 || g[i].kernel_size == 7,
+                      "cnn: genotype %d kernel_size=%d must be odd and <= 7", i, g[i].kernel_size);
+        CMOOP_REQUIRE(g[i].residual_blocks >= 0 && g[i].residual_blocks <= 3, "cnn: genotype %d residual_blocks=%d", i,
+                      g[i].residual_blocks);
+        CMOOP_REQUIRE(g[i].fc_layers >= 1 && g[i].fc_layers <= 4, "cnn: genotype %d fc_layers=%d outside [1,4]", i,
+                      g[i].fc_layers);
+    }
+    return CMOOP_OK;
+}
+
+double fpr_from_confusion(const std::vector<int>& cm, int C, bool filtered) {
+    long long total = 0;
+    std::vector<long long> row(C, 0), col(C, 0);
+    for (int i = 0; i < C; ++i)
+        for (int j = 0; j < C; ++j) {
+            const int v = cm[(size_t)i * C + j];
+            total += v;
+            row[i] += v;
+            col[j] += v;
+        }
+    double sum = 0.0;
+    int cnt = 0;
+    for (int i = 0; i < C; ++i) {
+        const long long fp = col[i] - cm[(size_t)i * C + i];
+        const long long denom = total - row[i];
+        if (denom > 0) {
+            sum += (double)fp / (double)denom;
+            ++cnt;
+        } else if (!filtered) {
+            ++cnt;
+        }
+    }
+    return cnt ? sum / cnt : 0.0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cmoop_cnn_dataset_destroy(cmoop_cnn_dataset_handle h) {
+    if (!h) return CMOOP_OK;
+    cudaFree(h->x_train);
+    cudaFree(h->y_train);
+    cudaFree(h->x_val);
+    cudaFree(h->y_val);
+    delete h;
+    return CMOOP_OK;
+}
+
+int cmoop_cnn_dataset_create_host(const float* x_train, const int* y_train, int n_train, const float* x_val,
+                                  const int* y_val, int n_val, int height, int width, cmoop_cnn_dataset_handle* out) {
+    CMOOP_REQUIRE(out && x_train && y_train && x_val && y_val, "cnn_dataset: null pointer");
+    CMOOP_REQUIRE(n_train > 0 && n_val > 0 && height > 0 && width > 0, "cnn_dataset: empty split or bad shape");
+    *out = nullptr;
+    if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
+    cmoop_cnn_dataset* d = new cmoop_cnn_dataset();
+    d->n_train = n_train; d->n_val = n_val; d->H = height; d->W = width;
+    const size_t img = (size_t)height * width * sizeof(float);
+    if (cudaMalloc((void**)&d->x_train, img * n_train) != cudaSuccess || cudaMalloc((void**)&d->y_train, sizeof(int) * n_train) != cudaSuccess ||
+        cudaMalloc((void**)&d->x_val, img * n_val) != cudaSuccess || cudaMalloc((void**)&d->y_val, sizeof(int) * n_val) != cudaSuccess) {
+        cmoop::set_error("cnn_dataset: cudaMalloc failed");
+        cmoop_cnn_dataset_destroy(d);
+        return CMOOP_ERR_CUDA;
+    }
+    CMOOP_CUDA_OK(cudaMemcpy(d->x_train, x_train, img * n_train, cudaMemcpyHostToDevice));
+    CMOOP_CUDA_OK(cudaMemcpy(d->y_train, y_train, sizeof(int) * n_train, cudaMemcpyHostToDevice));
+    CMOOP_CUDA_OK(cudaMemcpy(d->x_val, x_val, img * n_val, cudaMemcpyHostToDevice));
+    CMOOP_CUDA_OK(cudaMemcpy(d->y_val, y_val, sizeof(int) * n_val, cudaMemcpyHostToDevice));
+    *out = d;
+    return CMOOP_OK;
+}
+
+long long cmoop_cnn_param_count(const cmoop_genotype* g, const cmoop_cnn_config* cfg) {
+    if (!g || check_config(g, 1, cfg) != CMOOP_OK) return -1;
+    Cand c;
+    c.g = *g;
+    build_units(c, *cfg, 49, 40, cfg->batch_size);
+    return c.n_params;
+}
+
+int cmoop_cnn_debug_permutation(uint64_t seed, int epoch, int n, int* out) {
+    CMOOP_REQUIRE(out && n >= 0, "debug_permutation: bad arguments");
+    make_permutation(seed, epoch, n, out);
+    return CMOOP_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// Trains and scores one wave of candidates to completion.
+int run_wave(Engine& eng, Wave& wv, double* out, double* history, int debug_steps, float* dbg_losses, float* dbg_grads,
+             float* dbg_params) {
+    const cmoop_cnn_dataset* data = eng.data;
+    const cmoop_cnn_config& cfg = eng.cfg;
+    const int batch = eng.batch;
+    cudaStream_t st = eng.stream;
+    int rc = eng.init_params(wv.cands);
+    if (rc != CMOOP_OK) return rc;
+    rc = eng.build_lists(wv);
+    if (rc != CMOOP_OK) return rc;
+    const int steps_per_epoch = (data->n_train + batch - 1) / batch;
+    const int val_steps = (data->n_val + batch - 1) / batch;
+    std::vector<int> perm(data->n_train);
+    std::vector<double> acc(12);
+    int t_adam = 0;
+    const int max_epochs = debug_steps > 0 ? 1 : cfg.max_epochs;
+    for (int epoch = 0; epoch < max_epochs; ++epoch) {
+        bool any = false;
+        for (Cand* c : wv.cands) {
+            if (!c->active) continue;
+            any = true;
+            make_permutation(c->seed, epoch, data->n_train, perm.data());
+            CMOOP_CUDA_OK(cudaMemcpyAsync(c->perm, perm.data(), sizeof(int) * data->n_train, cudaMemcpyHostToDevice, st));
+            CMOOP_CUDA_OK(cudaStreamSynchronize(st));     // perm is a reused pageable staging buffer
+            CMOOP_CUDA_OK(cudaMemsetAsync(c->acc, 0, 8 * sizeof(double), st));
+        }
+        if (!any) break;
+        const int n_steps = debug_steps > 0 ? std::min(debug_steps, steps_per_epoch) : steps_per_epoch;
+        for (int s = 0; s < n_steps; ++s) {
+            const int n_b = std::min(batch, data->n_train - s * batch);
+            if ((rc = eng.run_forward(wv, 0, s, n_b)) != CMOOP_OK) return rc;
+            if ((rc = eng.run_backward(wv, s, n_b)) != CMOOP_OK) return rc;
+            if (debug_steps > 0) {
+                Cand* c = wv.cands[0];
+                if (s == 0 && dbg_grads)
+                    CMOOP_CUDA_OK(cudaMemcpyAsync(dbg_grads, c->grad, c->n_params * sizeof(float), cudaMemcpyDeviceToHost, st));
+                if (dbg_losses) {
+                    double a[4];
+                    CMOOP_CUDA_OK(cudaMemcpyAsync(a, c->acc, sizeof(a), cudaMemcpyDeviceToHost, st));
+                    CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+                    dbg_losses[s] = (float)(a[0] / a[1]);
+                    CMOOP_CUDA_OK(cudaMemsetAsync(c->acc, 0, 4 * sizeof(double), st));
+                }
+            }
+            ++t_adam;
+            if ((rc = eng.adam_step(wv, t_adam)) != CMOOP_OK) return rc;
+            ++eng.global_step;
+        }
+        if (debug_steps > 0) {
+            Cand* c = wv.cands[0];
+            if (dbg_params)
+                CMOOP_CUDA_OK(cudaMemcpyAsync(dbg_params, c->p, c->n_params * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+            return CMOOP_OK;
+        }
+        for (int s = 0; s < val_steps; ++s) {
+            const int n_b = std::min(batch, data->n_val - s * batch);
+            if ((rc = eng.run_forward(wv, 1, s, n_b)) != CMOOP_OK) return rc;
+        }
+        bool changed = false;
+        for (Cand* c : wv.cands) {
+            if (!c->active) continue;
+            CMOOP_CUDA_OK(cudaMemcpyAsync(acc.data(), c->acc, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+            const double train_loss = acc[0] / acc[1], val_loss = acc[4] / acc[5], val_acc = acc[6] / acc[5];
+            c->epochs_run = epoch + 1;
+            c->last_val_loss = val_loss;
+            c->last_val_acc = val_acc;
+            if (history) {
+                double* hrow = history + ((size_t)c->index * cfg.max_epochs + epoch) * 3;
+                hrow[0] = train_loss; hrow[1] = val_loss; hrow[2] = val_acc;
+            }
+            // keras.callbacks.EarlyStopping(monitor='val_loss', patience, restore_best_weights)
+            if (cfg.restore_best_weights && !c->has_best) {
+                CMOOP_CUDA_OK(cudaMemcpyAsync(c->best, c->p, c->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                c->has_best = true;
+            }
+            c->wait += 1;
+            if (val_loss < c->best_loss) {
+                c->best_loss = val_loss;
+                c->wait = 0;
+                if (cfg.restore_best_weights)
+                    CMOOP_CUDA_OK(cudaMemcpyAsync(c->best, c->p, c->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            } else if (c->wait >= cfg.patience && epoch > 0) {
+                c->active = false;
+                changed = true;
+            }
+        }
+        if (changed) {
+            bool left = false;
+            for (Cand* c : wv.cands) left = left || c->active;
+            if (!left) break;
+            if ((rc = eng.build_lists(wv)) != CMOOP_OK) return rc;
+        }
+    }
+    // ---- final scoring: [restore best] -> predict on the validation split -> accuracy / confusion / FPR
+    for (Cand* c : wv.cands) {
+        c->active = true;
+        if (cfg.restore_best_weights && c->has_best)
+            CMOOP_CUDA_OK(cudaMemcpyAsync(c->p, c->best, c->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CMOOP_CUDA_OK(cudaMemsetAsync(c->acc + 8, 0, 4 * sizeof(double), st));
+        CMOOP_CUDA_OK(cudaMemsetAsync(c->confusion, 0, sizeof(int) * cfg.n_classes * cfg.n_classes, st));
+    }
+    if ((rc = eng.build_lists(wv)) != CMOOP_OK) return rc;
+    for (int s = 0; s < val_steps; ++s) {
+        const int n_b = std::min(batch, data->n_val - s * batch);
+        if ((rc = eng.run_forward(wv, 2, s, n_b)) != CMOOP_OK) return rc;
+    }
+    std::vector<int> cm((size_t)cfg.n_classes * cfg.n_classes);
+    for (Cand* c : wv.cands) {
+        CMOOP_CUDA_OK(cudaMemcpyAsync(acc.data(), c->acc + 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CMOOP_CUDA_OK(cudaMemcpyAsync(cm.data(), c->confusion, cm.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+        const double acc_eval = acc[2] / acc[1];
+        c->final_acc = cfg.acc_from_history ? c->last_val_acc : acc_eval;
+        c->fpr = fpr_from_confusion(cm, cfg.n_classes, cfg.fpr_filtered != 0);
+        double* o = out + (size_t)c->index * 6;
+        o[0] = c->final_acc;
+        o[1] = (double)c->n_params * 4.0 / (1024.0 * 1024.0);
+        o[2] = c->fpr;
+        o[3] = (double)c->epochs_run;
+        o[4] = c->last_val_loss;
+        o[5] = c->best_loss;
+    }
+    return CMOOP_OK;
+}
+
+int run_population(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotypes, const uint64_t* seeds, int P,
+                   const cmoop_cnn_config* cfg, double* out, double* history, int debug_steps, float* dbg_losses,
+                   float* dbg_grads, float* dbg_params) {
+    CMOOP_REQUIRE(data && genotypes && (out || debug_steps > 0), "cnn: null pointer");
+    int rc = check_config(genotypes, P, cfg);
+    if (rc != CMOOP_OK) return rc;
+    if (P == 0) return CMOOP_OK;
+    if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
+    Engine eng;
+    eng.data = data;
+    eng.cfg = *cfg;
+    eng.batch = cfg->batch_size;
+    eng.stream = cmoop::internal_stream();
+    std::vector<Cand> cands(P);
+    for (int i = 0; i < P; ++i) {
+        cands[i].g = genotypes[i];
+        cands[i].seed = seeds ? seeds[i] : (uint64_t)i;
+        cands[i].index = i;
+        build_units(cands[i], *cfg, data->H, data->W, eng.batch);
+        Arena dry;
+        dry.dry = true;
+        place(cands[i], dry, *cfg, data->n_train, data->n_val, eng.batch);
+        cands[i].arena_bytes = dry.off;
+    }
+    if (history)
+        for (size_t i = 0; i < (size_t)P * cfg->max_epochs * 3; ++i) history[i] = NAN;
+    size_t free_b = 0, total_b = 0;
+    CMOOP_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = cfg->memory_budget_bytes > 0 ? (size_t)cfg->memory_budget_bytes : (size_t)(0.6 * (double)free_b);
+    // ---- waves: consecutive candidates while they fit the arena
+    int next = 0;
+    Wave wv;
+    char* arena_base = nullptr;
+    size_t arena_cap = 0;
+    while (next < P) {
+        size_t need = 0;
+        int end = next;
+        while (end < P && (end == next || need + cands[end].arena_bytes <= budget)) need += cands[end++].arena_bytes;
+        if (need > arena_cap) {
+            if (arena_base) CMOOP_CUDA_OK(cudaFree(arena_base));
+            arena_base = nullptr;
+            if (cudaMalloc((void**)&arena_base, need) != cudaSuccess) {
+                (void)cudaGetLastError();
+                cmoop::set_error("cnn: cannot allocate a %.2f GB arena for candidates [%d,%d)", need / 1e9, next, end);
+                return CMOOP_ERR_CUDA;
+            }
+            arena_cap = need;
+        }
+        Arena a;
+        a.base = arena_base;
+        a.cap = arena_cap;
+        wv.cands.clear();
+        for (int i = next; i < end; ++i) {
+            place(cands[i], a, *cfg, data->n_train, data->n_val, eng.batch);
+            wv.cands.push_back(&cands[i]);
+        }
+        rc = run_wave(eng, wv, out, history, debug_steps, dbg_losses, dbg_grads, dbg_params);
+        if (rc != CMOOP_OK) break;
+        next = end;
+    }
+    cudaStreamSynchronize(eng.stream);
+    if (arena_base) cudaFree(arena_base);
+    if (wv.d_blob) cudaFree(wv.d_blob);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cmoop_cnn_pop_train_eval(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotypes, const uint64_t* seeds,
+                             int n_candidates, const cmoop_cnn_config* cfg, double* out, double* history) {
+    CMOOP_REQUIRE(n_candidates >= 0, "cnn: negative population");
+    return run_population(data, genotypes, seeds, n_candidates, cfg, out, history, 0, nullptr, nullptr, nullptr);
+}
+
+int cmoop_cnn_debug_train_steps(cmoop_cnn_dataset_handle data, const cmoop_genotype* g, uint64_t seed,
+                                const cmoop_cnn_config* cfg, int n_steps, float* losses, float* grads_first,
+                                float* params_out) {
+    CMOOP_REQUIRE(n_steps >= 1, "debug_train_steps: n_steps must be >= 1");
+    return run_population(data, g, &seed, 1, cfg, nullptr, nullptr, n_steps, losses, grads_first, params_out);
+}
+
+int cmoop_cnn_debug_init_params(const cmoop_genotype* g, uint64_t seed, const cmoop_cnn_config* cfg, float* out) {
+    CMOOP_REQUIRE(g && out, "debug_init_params: null pointer");
+    int rc = check_config(g, 1, cfg);
+    if (rc != CMOOP_OK) return rc;
+    if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
+    Engine eng;
+    cmoop_cnn_dataset dummy;
+    eng.data = &dummy;
+    eng.cfg = *cfg;
+    eng.batch = cfg->batch_size;
+    eng.stream = cmoop::internal_stream();
+    Cand c;
+    c.g = *g;
+    c.seed = seed;
+    build_units(c, *cfg, 49, 40, eng.batch);
+    float* buf = nullptr;
+    CMOOP_CUDA_OK(cudaMalloc((void**)&buf, (size_t)c.n_params * 4 * sizeof(float) + 12 * sizeof(double) + 1024));
+    c.p = buf;
+    c.grad = buf + c.n_params;
+    c.m = buf + 2 * c.n_params;
+    c.v = buf + 3 * c.n_params;
+    c.acc = (double*)(((uintptr_t)(buf + 4 * c.n_params) + 255) / 256 * 256);
+    std::vector<Cand*> one{&c};
+    rc = eng.init_params(one);
+    if (rc == CMOOP_OK) {
+        cudaError_t e = cudaMemcpy(out, c.p, c.n_params * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            cmoop::set_error("debug_init_params: %s", cudaGetErrorString(e));
+            rc = CMOOP_ERR_CUDA;
+        }
+    }
+    cudaFree(buf);
+    return rc;
+}
+
+}  // extern "C"

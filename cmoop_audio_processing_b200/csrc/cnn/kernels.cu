@@ -1,0 +1,747 @@
+// fp32 SIMT kernels of the population-batched candidate CNN (exact path): grouped implicit-GEMM
+// convolution (forward, data-gradient via pre-transposed weights, weight-gradient with deterministic
+// split-M), BatchNorm statistics / apply / backward, ReLU / 2x2 'same' max-pool / residual add,
+// global average pooling, dropout, Keras-style sparse cross-entropy, Adam, initialisation.
+//
+// Semantics follow the reference call sites nsga_penalty.py:250-332 (variant A),
+// sa_nsga_penalty.py:150-176 (variant B) and the recipe nsga_penalty.py:377-386 with Keras-default
+// numerics (see oracle/cnn_ref.py, which is the CPU statement these kernels are tested against).
+// Every kernel is grouped over candidates (cnn.cuh) and deterministic: no floating-point atomics.
+#include <cuda_runtime.h>
+
+#include "cnn.cuh"
+
+namespace cmoop_cnn {
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+template <class T, class F>
+__device__ __forceinline__ int find_task(const T* tasks, int n, int block, F begin_of) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (begin_of(tasks[mid]) <= block)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ------------------------------------------------------------------------------------------------
+// y[M][Cout] = im2col(x)[M][K(+1)] * w[K(+1)][Cout]   (M = n_b*Ho*Wo, bias = last row of w)
+__global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvTask* __restrict__ tasks, int n_tasks, int n_b,
+                                                        int step) {
+    __shared__ ConvTask T;
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    if (tid == 0) T = tasks[find_task(tasks, n_tasks, blockIdx.x, [](const ConvTask& t) { return t.tile_begin; })];
+    __syncthreads();
+    const int local = blockIdx.x - T.tile_begin;
+    const int tm = local / T.tiles_n, tn = local - tm * T.tiles_n;
+    const int HoWo = T.Ho * T.Wo, M = n_b * HoWo, m0 = tm * BM, n0 = tn * BN;
+    if (m0 >= M) return;
+    const int K = T.k * T.k * T.Cin, Kext = K + T.use_bias;
+    const float* xbase = T.x + T.x_step * step;
+    const int* gather = T.gather ? T.gather + T.gather_step * step : nullptr;
+
+    const int row = tid & 63, kq = tid >> 6;
+    const int m = m0 + row;
+    const bool mvalid = m < M;
+    int hi0 = 0, wi0 = 0;
+    const float* xin = xbase;
+    if (mvalid) {
+        const int n = m / HoWo, r = m - n * HoWo;
+        const int ho = r / T.Wo, wo = r - ho * T.Wo;
+        hi0 = ho * T.stride - T.pad;
+        wi0 = wo * T.stride - T.pad;
+        xin = xbase + (long long)(gather ? gather[n] : n) * ((long long)T.H * T.W * T.Cin);
+    }
+    const bool vec_a = (T.Cin & 3) == 0 && aligned16(xbase);
+    const int bk = tid >> 4, bn4 = (tid & 15) * 4;
+    const bool vec_b = (T.Cout & 3) == 0 && aligned16(T.w);
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < Kext; k0 += BK) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        const int kb = k0 + kq * 4;
+        if (mvalid) {
+            if (vec_a && kb + 3 < K) {
+                const int kk = kb / T.Cin, ci = kb - kk * T.Cin;
+                const int kh = kk / T.k, kw = kk - kh * T.k;
+                const int hi = hi0 + kh, wi = wi0 + kw;
+                if ((unsigned)hi < (unsigned)T.H && (unsigned)wi < (unsigned)T.W) {
+                    const float4 v = *reinterpret_cast<const float4*>(xin + ((long long)hi * T.W + wi) * T.Cin + ci);
+                    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int kj = kb + j;
+                    if (kj < K) {
+                        const int kk = kj / T.Cin, ci = kj - kk * T.Cin;
+                        const int kh = kk / T.k, kw = kk - kh * T.k;
+                        const int hi = hi0 + kh, wi = wi0 + kw;
+                        if ((unsigned)hi < (unsigned)T.H && (unsigned)wi < (unsigned)T.W)
+                            a[j] = xin[((long long)hi * T.W + wi) * T.Cin + ci];
+                    } else if (kj == K && T.use_bias) {
+                        a[j] = 1.f;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) As[kq * 4 + j][row] = a[j];
+        float b[4] = {0.f, 0.f, 0.f, 0.f};
+        const int kB = k0 + bk;
+        if (kB < Kext) {
+            const float* wr = T.w + (long long)kB * T.Cout + n0 + bn4;
+            if (vec_b && n0 + bn4 + 3 < T.Cout) {
+                const float4 v = *reinterpret_cast<const float4*>(wr);
+                b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n0 + bn4 + j < T.Cout) b[j] = wr[j];
+            }
+        }
+        *reinterpret_cast<float4*>(&Bs[bk][bn4]) = make_float4(b[0], b[1], b[2], b[3]);
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int mi = m0 + ty * 4 + i;
+        if (mi >= M) continue;
+        long long base;
+        if (T.out_s == 0) {
+            base = (long long)mi * T.Cout;
+        } else {
+            const int n = mi / HoWo, r = mi - n * HoWo;
+            const int ho = r / T.Wo, wo = r - ho * T.Wo;
+            base = (((long long)n * T.out_h + ho * T.out_s) * T.out_w + wo * T.out_s) * T.Cout;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = n0 + tx * 4 + j;
+            if (col >= T.Cout) continue;
+            float v = acc[i][j];
+            if (T.relu) v = fmaxf(v, 0.f);
+            if (T.accumulate)
+                T.y[base + col] += v;
+            else
+                T.y[base + col] = v;
+            s1[j] += v;
+            s2[j] = fmaf(v, v, s2[j]);
+        }
+    }
+    if (T.stat_part) {
+        float(*red1)[BM + 4] = As;
+        float(*red2)[BN + 4] = Bs;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            red1[ty][tx * 4 + j] = s1[j];
+            red2[ty][tx * 4 + j] = s2[j];
+        }
+        __syncthreads();
+        if (tid < BN && n0 + tid < T.Cout) {
+            float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                a1 += red1[r][tid];
+                a2 += red2[r][tid];
+            }
+            T.stat_part[((long long)tm * 2 + 0) * T.Cout + n0 + tid] = a1;
+            T.stat_part[((long long)tm * 2 + 1) * T.Cout + n0 + tid] = a2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[split][K+1][Cout] = sum_{m in split} im2col(x)[m][K+1]^T * dy[m][Cout]   (row K = bias gradient)
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradTask* __restrict__ tasks, int n_tasks, int n_b,
+                                                         int step) {
+    __shared__ WgradTask T;
+    __shared__ __align__(16) float As[BK][BM + 4];   // [m][kk]
+    __shared__ __align__(16) float Bs[BK][BN + 4];   // [m][co]
+    const int tid = threadIdx.x;
+    if (tid == 0) T = tasks[find_task(tasks, n_tasks, blockIdx.x, [](const WgradTask& t) { return t.tile_begin; })];
+    __syncthreads();
+    int local = blockIdx.x - T.tile_begin;
+    const int per_split = T.tiles_k * T.tiles_n;
+    const int split = local / per_split;
+    local -= split * per_split;
+    const int tk = local / T.tiles_n, tn = local - tk * T.tiles_n;
+    const int HoWo = T.Ho * T.Wo, M = n_b * HoWo;
+    const int K = T.k * T.k * T.Cin, Kext = K + 1;
+    const int kk0 = tk * BM, n0 = tn * BN;
+    const int m_begin = split * T.m_chunk;
+    const int m_end = min(M, m_begin + T.m_chunk);
+    const float* xbase = T.x + T.x_step * step;
+    const int* gather = T.gather ? T.gather + T.gather_step * step : nullptr;
+    const long long img = (long long)T.H * T.W * T.Cin;
+
+    const int mm = tid >> 4, q4 = (tid & 15) * 4;
+    // fixed per thread: the four kk it loads
+    const int kb = kk0 + q4;
+    const bool vec_a = (T.Cin & 3) == 0 && aligned16(xbase) && kb + 3 < K;
+    int kh[4], kw[4], ci[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int kj = kb + j;
+        if (kj < K) {
+            const int kk = kj / T.Cin;
+            ci[j] = kj - kk * T.Cin;
+            kh[j] = kk / T.k;
+            kw[j] = kk - kh[j] * T.k;
+        } else {
+            kh[j] = kw[j] = 0;
+            ci[j] = (kj == K) ? -1 : -2;     // -1: ones column, -2: outside
+        }
+    }
+    const bool vec_b = (T.Cout & 3) == 0 && aligned16(T.dy);
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int ms = m_begin; ms < m_end; ms += BK) {
+        const int m = ms + mm;
+        float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+        if (m < m_end) {
+            const int n = m / HoWo, r = m - n * HoWo;
+            const int ho = r / T.Wo, wo = r - ho * T.Wo;
+            const int hi0 = ho * T.stride - T.pad, wi0 = wo * T.stride - T.pad;
+            const float* xin = xbase + (long long)(gather ? gather[n] : n) * img;
+            if (vec_a) {
+                const int hi = hi0 + kh[0], wi = wi0 + kw[0];
+                if ((unsigned)hi < (unsigned)T.H && (unsigned)wi < (unsigned)T.W) {
+                    const float4 v = *reinterpret_cast<const float4*>(xin + ((long long)hi * T.W + wi) * T.Cin + ci[0]);
+                    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (ci[j] >= 0) {
+                        const int hi = hi0 + kh[j], wi = wi0 + kw[j];
+                        if ((unsigned)hi < (unsigned)T.H && (unsigned)wi < (unsigned)T.W)
+                            a[j] = xin[((long long)hi * T.W + wi) * T.Cin + ci[j]];
+                    } else if (ci[j] == -1) {
+                        a[j] = 1.f;
+                    }
+                }
+            }
+            const float* dr = T.dy + (long long)m * T.Cout + n0 + q4;
+            if (vec_b && n0 + q4 + 3 < T.Cout) {
+                const float4 v = *reinterpret_cast<const float4*>(dr);
+                b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n0 + q4 + j < T.Cout) b[j] = dr[j];
+            }
+        }
+        *reinterpret_cast<float4*>(&As[mm][q4]) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4*>(&Bs[mm][q4]) = make_float4(b[0], b[1], b[2], b[3]);
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < BK; ++r) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[r][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[r][tx * 4]);
+            const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* out = T.out + (long long)split * Kext * T.Cout;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int kk = kk0 + ty * 4 + i;
+        if (kk >= Kext) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = n0 + tx * 4 + j;
+            if (col < T.Cout) out[(long long)kk * T.Cout + col] = acc[i][j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) reduce_kernel(const ReduceTask* __restrict__ tasks, int n_tasks) {
+    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const ReduceTask& r) { return r.block_begin; });
+    const ReduceTask T = tasks[t];
+    const int i = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
+    if (i >= T.n) return;
+    float s = 0.f;
+    for (int k = 0; k < T.splits; ++k) s += T.part[(long long)k * T.n + i];
+    T.out[i] = s;
+}
+
+__global__ void __launch_bounds__(256) wt_kernel(const WtTask* __restrict__ tasks, int n_tasks) {
+    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const WtTask& r) { return r.block_begin; });
+    const WtTask T = tasks[t];
+    const int e = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
+    const int total = T.k * T.k * T.Cin * T.Cout;
+    if (e >= total) return;
+    const int ci = e % T.Cin;
+    int r = e / T.Cin;
+    const int co = r % T.Cout;
+    r /= T.Cout;
+    const int kw = r % T.k, kh = r / T.k;
+    const int src = (((T.k - 1 - kh) * T.k + (T.k - 1 - kw)) * T.Cin + ci) * T.Cout + co;
+    T.wt[e] = T.w[src];
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm statistics -> (mean, invstd, scale, shift); one CTA per task
+__global__ void __launch_bounds__(128) bn_finalize_kernel(const PostTask* __restrict__ tasks, int n_b, int training,
+                                                          float momentum, float eps) {
+    const PostTask T = tasks[blockIdx.x];
+    if (!T.has_bn) return;
+    const double count = (double)n_b * T.H * T.W;
+    for (int c = threadIdx.x; c < T.C; c += blockDim.x) {
+        float mean, var;
+        if (training) {
+            double s1 = 0.0, s2 = 0.0;
+            const int tiles = (n_b * T.H * T.W + BM - 1) / BM;    // tiles the conv epilogue wrote for THIS batch size
+            for (int t = 0; t < tiles; ++t) {
+                s1 += (double)T.stat_part[((long long)t * 2 + 0) * T.C + c];
+                s2 += (double)T.stat_part[((long long)t * 2 + 1) * T.C + c];
+            }
+            const double mu = s1 / count;
+            double vv = s2 / count - mu * mu;
+            vv = vv > 0.0 ? vv : 0.0;
+            mean = (float)mu;
+            var = (float)vv;
+            T.mov_mean[c] = T.mov_mean[c] * momentum + mean * (1.f - momentum);
+            T.mov_var[c] = T.mov_var[c] * momentum + var * (1.f - momentum);
+        } else {
+            mean = T.mov_mean[c];
+            var = T.mov_var[c];
+        }
+        const float invstd = rsqrtf(var + eps);
+        const float scale = T.gamma[c] * invstd;
+        T.bn[0 * T.C + c] = mean;
+        T.bn[1 * T.C + c] = invstd;
+        T.bn[2 * T.C + c] = scale;
+        T.bn[3 * T.C + c] = T.beta[c] - mean * scale;
+    }
+}
+
+// [BN] -> [ReLU] -> [2x2/s2 'same' max-pool] -> [+skip, ReLU]
+__global__ void __launch_bounds__(256) post_fwd_kernel(const PostTask* __restrict__ tasks, int n_tasks, int n_b) {
+    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin; });
+    const PostTask T = tasks[t];
+    const long long e = (long long)(blockIdx.x - T.block_begin) * 256 + threadIdx.x;
+    const long long total = (long long)n_b * T.Ho * T.Wo * T.C;
+    if (e >= total) return;
+    const int c = (int)(e % T.C);
+    long long pix = e / T.C;
+    const int wo = (int)(pix % T.Wo);
+    pix /= T.Wo;
+    const int ho = (int)(pix % T.Ho);
+    const int n = (int)(pix / T.Ho);
+    const float scale = T.has_bn ? T.bn[2 * T.C + c] : 1.f;
+    const float shift = T.has_bn ? T.bn[3 * T.C + c] : 0.f;
+    float z;
+    if (T.pool) {
+        z = 0.f;
+        int code = 0;
+        bool first = true;
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+            for (int dw = 0; dw < 2; ++dw) {
+                const int hi = 2 * ho + dh, wi = 2 * wo + dw;
+                if (hi < T.H && wi < T.W) {
+                    float v = T.u[(((long long)n * T.H + hi) * T.W + wi) * T.C + c];
+                    if (T.has_bn) v = fmaf(v, scale, shift);
+                    if (T.relu_mid) v = fmaxf(v, 0.f);
+                    if (first || v > z) {
+                        z = v;
+                        code = dh * 2 + dw;
+                        first = false;
+                    }
+                }
+            }
+        T.idx[e] = (uint8_t)code;
+    } else {
+        z = T.u[e];
+        if (T.has_bn) z = fmaf(z, scale, shift);
+        if (T.relu_mid) z = fmaxf(z, 0.f);
+    }
+    if (T.add_skip) z = fmaxf(z + T.skip[e], 0.f);
+    T.v[e] = z;
+}
+
+// BN backward, pass 1: per-channel partial sums of g and g*xhat over the unit's output elements
+__global__ void __launch_bounds__(128) post_bwd_reduce_kernel(const PostTask* __restrict__ tasks, int n_tasks,
+                                                              int n_b) {
+    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin_bwd; });
+    const PostTask T = tasks[t];
+    const int blk = blockIdx.x - T.block_begin_bwd;
+    const int cb = T.C < 128 ? T.C : 128;
+    const int lanes = 128 / cb;
+    const int p_lane = threadIdx.x / cb, c_lane = threadIdx.x - p_lane * cb;
+    if (p_lane >= lanes) return;
+    const long long n_pix = (long long)n_b * T.Ho * T.Wo;
+    const long long pix0 = (long long)blk * 128, pix1 = pix0 + 128 < n_pix ? pix0 + 128 : n_pix;
+    for (int c = c_lane; c < T.C; c += cb) {
+        const float mean = T.bn[0 * T.C + c], invstd = T.bn[1 * T.C + c];
+        const float scale = T.bn[2 * T.C + c], shift = T.bn[3 * T.C + c];
+        float sg = 0.f, sgx = 0.f;
+        for (long long pix = pix0 + p_lane; pix < pix1; pix += lanes) {
+            const long long e = pix * T.C + c;
+            float g = T.dv[e];
+            if (T.add_skip && !(T.v[e] > 0.f)) g = 0.f;
+            long long ue = e;
+            if (T.pool) {
+                const int wo = (int)(pix % T.Wo);
+                const long long r = pix / T.Wo;
+                const int ho = (int)(r % T.Ho);
+                const int n = (int)(r / T.Ho);
+                const int code = T.idx[e];
+                ue = (((long long)n * T.H + 2 * ho + (code >> 1)) * T.W + 2 * wo + (code & 1)) * T.C + c;
+            }
+            const float u = T.u[ue];
+            if (T.relu_mid && !(fmaf(u, scale, shift) > 0.f)) g = 0.f;
+            sg += g;
+            sgx = fmaf(g, (u - mean) * invstd, sgx);
+        }
+        const long long rowi = (long long)blk * lanes + p_lane;
+        T.bwd_part[(rowi * 2 + 0) * T.C + c] = sg;
+        T.bwd_part[(rowi * 2 + 1) * T.C + c] = sgx;
+    }
+}
+
+__global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const PostTask* __restrict__ tasks, int n_b) {
+    const PostTask T = tasks[blockIdx.x];
+    if (!T.has_bn) return;
+    const int cb = T.C < 128 ? T.C : 128;
+    const int lanes = 128 / cb;
+    const long long n_pix = (long long)n_b * T.Ho * T.Wo;
+    const long long rows = ((n_pix + 127) / 128) * lanes;
+    const double count = (double)n_b * T.H * T.W;
+    for (int c = threadIdx.x; c < T.C; c += blockDim.x) {
+        double sg = 0.0, sgx = 0.0;
+        for (long long r = 0; r < rows; ++r) {
+            sg += (double)T.bwd_part[(r * 2 + 0) * T.C + c];
+            sgx += (double)T.bwd_part[(r * 2 + 1) * T.C + c];
+        }
+        T.dbeta[c] = (float)sg;
+        T.dgamma[c] = (float)sgx;
+        T.bn[4 * T.C + c] = (float)(sg / count);
+        T.bn[5 * T.C + c] = (float)(sgx / count);
+    }
+}
+
+// backward of the whole post stage, dense over the conv-output grid
+__global__ void __launch_bounds__(256) post_bwd_apply_kernel(const PostTask* __restrict__ tasks, int n_tasks, int n_b) {
+    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin; });
+    const PostTask T = tasks[t];
+    const long long e = (long long)(blockIdx.x - T.block_begin) * 256 + threadIdx.x;
+    const long long total = (long long)n_b * T.H * T.W * T.C;
+    if (e >= total) return;
+    const int c = (int)(e % T.C);
+    long long pix = e / T.C;
+    const int wi = (int)(pix % T.W);
+    pix /= T.W;
+    const int hi = (int)(pix % T.H);
+    const int n = (int)(pix / T.H);
+    long long oe = e;
+    bool origin = true, routed = true;
+    if (T.pool) {
+        const int ho = hi >> 1, wo = wi >> 1;
+        oe = (((long long)n * T.Ho + ho) * T.Wo + wo) * T.C + c;
+        origin = ((hi & 1) == 0) && ((wi & 1) == 0);
+        routed = T.idx[oe] == (uint8_t)((hi & 1) * 2 + (wi & 1));
+    }
+    float g = T.dv[oe];
+    if (T.add_skip) {
+        if (!(T.v[oe] > 0.f)) g = 0.f;
+        if (origin && T.dskip) T.dskip[oe] = g;
+    }
+    if (!routed) g = 0.f;
+    const float u = T.u[e];
+    float du;
+    if (T.has_bn) {
+        const float mean = T.bn[0 * T.C + c], invstd = T.bn[1 * T.C + c];
+        const float scale = T.bn[2 * T.C + c], shift = T.bn[3 * T.C + c];
+        if (T.relu_mid && !(fmaf(u, scale, shift) > 0.f)) g = 0.f;
+        const float xhat = (u - mean) * invstd;
+        du = scale * (g - T.bn[4 * T.C + c] - xhat * T.bn[5 * T.C + c]);
+    } else {
+        if (T.relu_mid && !(u > 0.f)) g = 0.f;
+        du = g;
+    }
+    if (T.relu_in && !(u > 0.f)) du = 0.f;
+    T.du[e] = du;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gap_fwd_kernel(const HeadTask* __restrict__ tasks, int n_tasks, int n_b) {
+    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const HeadTask& r) { return r.block_begin; });
+    const HeadTask T = tasks[t];
+    const int e = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
+    if (e >= n_b * T.C) return;
+    const int c = e % T.C, n = e / T.C;
+    const int hw = T.Hf * T.Wf;
+    float s = 0.f;
+    for (int p = 0; p < hw; ++p) s += T.v[((long long)n * hw + p) * T.C + c];
+    T.gap[e] = s / (float)hw;
+}
+
+__global__ void __launch_bounds__(256) gap_bwd_kernel(const HeadTask* __restrict__ tasks, int n_tasks, int n_b) {
+    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const HeadTask& r) { return r.block_begin; });
+    const HeadTask T = tasks[t];
+    const long long e = (long long)(blockIdx.x - T.block_begin) * 256 + threadIdx.x;
+    const int hw = T.Hf * T.Wf;
+    if (e >= (long long)n_b * hw * T.C) return;
+    const int c = (int)(e % T.C);
+    const int n = (int)(e / ((long long)hw * T.C));
+    T.dv[e] = T.dgap[n * T.C + c] / (float)hw;
+}
+
+__global__ void __launch_bounds__(256) drop_fwd_kernel(const DropTask* __restrict__ tasks, int n_tasks, int n_b, int step,
+                                                       int training, float rate) {
+    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const DropTask& r) { return r.block_begin; });
+    const DropTask T = tasks[t];
+    const int e = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
+    if (e >= n_b * T.units) return;
+    float v = T.u[e];
+    if (training && T.use_dropout) {
+        const bool keep = hash_uniform(T.seed, (unsigned)T.layer, (unsigned)step, (unsigned)e) >= rate;
+        v = keep ? v / (1.f - rate) : 0.f;
+    }
+    T.v[e] = v;
+}
+
+__global__ void __launch_bounds__(256) drop_bwd_kernel(const DropTask* __restrict__ tasks, int n_tasks, int n_b, int step,
+                                                       float rate) {
+    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const DropTask& r) { return r.block_begin; });
+    const DropTask T = tasks[t];
+    const int e = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
+    if (e >= n_b * T.units) return;
+    float g = T.dv[e];
+    if (T.use_dropout) {
+        const bool keep = hash_uniform(T.seed, (unsigned)T.layer, (unsigned)step, (unsigned)e) >= rate;
+        g = keep ? g / (1.f - rate) : 0.f;
+    }
+    if (!(T.u[e] > 0.f)) g = 0.f;
+    T.dz[e] = g;
+}
+
+// Keras sparse_categorical_crossentropy on softmax probabilities (clip 1e-7) + gradient w.r.t. logits.
+// One CTA per candidate, one warp per sample (8 warps x 8 rounds); losses are summed in sample order.
+__global__ void __launch_bounds__(256) ce_kernel(const CeTask* __restrict__ tasks, int n_b, int step, int training) {
+    const CeTask T = tasks[blockIdx.x];
+    __shared__ float s_loss[kBatch];
+    __shared__ int s_ok[kBatch];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = T.n_classes;
+    const float lo = 1e-7f, hi = 1.f - 1e-7f;
+    for (int r = warp; r < n_b; r += 8) {
+        const int sidx = T.gather ? T.gather[T.gather_step * step + r] : (int)(T.label_step * step) + r;
+        const int y = T.labels[sidx];
+        const float* z = T.logits + (long long)r * C;
+        float mx = -3.4e38f;
+        int arg = 0x7fffffff;
+        for (int j = lane; j < C; j += 32) {
+            const float v = z[j];
+            if (v > mx) {
+                mx = v;
+                arg = j;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (om > mx || (om == mx && oa < arg)) {
+                mx = om;
+                arg = oa;
+            }
+        }
+        float se = 0.f;
+        for (int j = lane; j < C; j += 32) se += expf(z[j] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+        const float inv = 1.f / se;
+        float sc = 0.f, sgp = 0.f;   // sum of clipped probs ; sum_j G_j p_j
+        for (int j = lane; j < C; j += 32) sc += fminf(fmaxf(expf(z[j] - mx) * inv, lo), hi);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+        if (training) {
+            for (int j = lane; j < C; j += 32) {
+                const float p = expf(z[j] - mx) * inv;
+                const float pc = fminf(fmaxf(p, lo), hi);
+                const bool inside = p >= lo && p <= hi;
+                const float G = inside ? (pc / sc - (j == y ? 1.f : 0.f)) / pc : 0.f;
+                sgp = fmaf(G, p, sgp);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sgp += __shfl_xor_sync(0xffffffffu, sgp, o);
+            const float invn = 1.f / (float)n_b;
+            for (int j = lane; j < C; j += 32) {
+                const float p = expf(z[j] - mx) * inv;
+                const float pc = fminf(fmaxf(p, lo), hi);
+                const bool inside = p >= lo && p <= hi;
+                const float G = inside ? (pc / sc - (j == y ? 1.f : 0.f)) / pc : 0.f;
+                T.dlogits[(long long)r * C + j] = p * (G - sgp) * invn;
+            }
+        }
+        if (lane == 0) {
+            const float py = fminf(fmaxf(expf(z[y] - mx) * inv, lo), hi);
+            s_loss[r] = -(logf(py) - logf(sc));
+            s_ok[r] = (arg == y) ? 1 : 0;
+            if (T.pred) T.pred[sidx] = arg;
+            if (T.confusion) atomicAdd(&T.confusion[(T.y_true_zero ? 0 : y) * C + arg], 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ls = 0.0;
+        int ok = 0;
+        for (int r = 0; r < n_b; ++r) {
+            ls += (double)s_loss[r];
+            ok += s_ok[r];
+        }
+        T.acc[0] += ls;
+        T.acc[1] += (double)n_b;
+        T.acc[2] += (double)ok;
+    }
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(const AdamTask* __restrict__ tasks, int n_tasks, float alpha, float b1,
+                                                   float b2, float eps) {
+    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const AdamTask& r) { return r.block_begin; });
+    const AdamTask T = tasks[t];
+    const int i = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
+    if (i >= T.n) return;
+    const float g = T.g[i];
+    const float m = b1 * T.m[i] + (1.f - b1) * g;
+    const float v = b2 * T.v[i] + (1.f - b2) * g * g;
+    T.m[i] = m;
+    T.v[i] = v;
+    T.p[i] -= alpha * m / (sqrtf(v) + eps);
+}
+
+__global__ void __launch_bounds__(256) init_kernel(const InitTask* __restrict__ tasks, int n_tasks) {
+    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const InitTask& r) { return r.block_begin; });
+    const InitTask T = tasks[t];
+    const int i = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
+    if (i >= T.n) return;
+    T.p[i] = T.kind == 0 ? (2.f * hash_uniform(T.seed, (unsigned)T.tensor, 0u, (unsigned)i) - 1.f) * T.limit : T.value;
+}
+
+inline int check() { return (int)cudaGetLastError(); }
+
+}  // namespace
+
+int Launch::conv(const ConvTask* tasks, int n, int tiles, int n_b, int step, void* st) {
+    if (n == 0 || tiles == 0) return 0;
+    conv_gemm_kernel<<<tiles, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b, step);
+    return check();
+}
+int Launch::wgrad(const WgradTask* tasks, int n, int tiles, int n_b, int step, void* st) {
+    if (n == 0 || tiles == 0) return 0;
+    conv_wgrad_kernel<<<tiles, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b, step);
+    return check();
+}
+int Launch::reduce(const ReduceTask* tasks, int n, int blocks, void* st) {
+    if (n == 0 || blocks == 0) return 0;
+    reduce_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n);
+    return check();
+}
+int Launch::wt(const WtTask* tasks, int n, int blocks, void* st) {
+    if (n == 0 || blocks == 0) return 0;
+    wt_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n);
+    return check();
+}
+int Launch::bn_finalize(const PostTask* tasks, int n, int n_b, int training, float momentum, float eps, void* st) {
+    if (n == 0) return 0;
+    bn_finalize_kernel<<<n, 128, 0, (cudaStream_t)st>>>(tasks, n_b, training, momentum, eps);
+    return check();
+}
+int Launch::post_fwd(const PostTask* tasks, int n, int blocks, int n_b, void* st) {
+    if (n == 0 || blocks == 0) return 0;
+    post_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b);
+    return check();
+}
+int Launch::post_bwd_reduce(const PostTask* tasks, int n, int blocks, int n_b, void* st) {
+    if (n == 0 || blocks == 0) return 0;
+    post_bwd_reduce_kernel<<<blocks, 128, 0, (cudaStream_t)st>>>(tasks, n, n_b);
+    return check();
+}
+int Launch::bn_bwd_finalize(const PostTask* tasks, int n, int n_b, void* st) {
+    if (n == 0) return 0;
+    bn_bwd_finalize_kernel<<<n, 128, 0, (cudaStream_t)st>>>(tasks, n_b);
+    return check();
+}
+int Launch::post_bwd_apply(const PostTask* tasks, int n, int blocks, int n_b, void* st) {
+    if (n == 0 || blocks == 0) return 0;
+    post_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b);
+    return check();
+}
+int Launch::gap_fwd(const HeadTask* tasks, int n, int blocks, int n_b, void* st) {
+    if (n == 0 || blocks == 0) return 0;
+    gap_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b);
+    return check();
+}
+int Launch::gap_bwd(const HeadTask* tasks, int n, int blocks, int n_b, void* st) {
+    if (n == 0 || blocks == 0) return 0;
+    gap_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b);
+    return check();
+}
+int Launch::drop_fwd(const DropTask* tasks, int n, int blocks, int n_b, int step, int training, float rate, void* st) {
+    if (n == 0 || blocks == 0) return 0;
+    drop_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b, step, training, rate);
+    return check();
+}
+int Launch::drop_bwd(const DropTask* tasks, int n, int blocks, int n_b, int step, float rate, void* st) {
+    if (n == 0 || blocks == 0) return 0;
+    drop_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b, step, rate);
+    return check();
+}
+int Launch::ce(const CeTask* tasks, int n, int n_b, int step, int training, void* st) {
+    if (n == 0) return 0;
+    ce_kernel<<<n, 256, 0, (cudaStream_t)st>>>(tasks, n_b, step, training);
+    return check();
+}
+int Launch::adam(const AdamTask* tasks, int n, int blocks, float alpha, float b1, float b2, float eps, void* st) {
+    if (n == 0 || blocks == 0) return 0;
+    adam_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, alpha, b1, b2, eps);
+    return check();
+}
+int Launch::init(const InitTask* tasks, int n, int blocks, void* st) {
+    if (n == 0 || blocks == 0) return 0;
+    init_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n);
+    return check();
+}
+
+}  // namespace cmoop_cnn

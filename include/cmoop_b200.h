@@ -159,6 +159,60 @@ int cmoop_mfcc_fwd_host(cmoop_mfcc_handle h, const float* wave, int64_t n_clips,
  * out = (out - mean[f]) / scale[f]; pass NULL/NULL to disable. mean/scale are host fp32 [n_out]. */
 int cmoop_mfcc_set_standardise(cmoop_mfcc_handle h, const float* mean, const float* scale);
 
+/* ------------------------------------------------------------------ (2) candidate-CNN train + score
+ * Replaces build_model / evaluate_individual / the serial loop of compute_objectives_and_constraints
+ *   nsga_penalty.py:225-442 (variant A), sa_nsga_penalty.py:137-253 (variant B),
+ *   mobo_penalty.py:128-247, ablation_study/*.py copies.
+ * A whole population is trained and scored in one call; every kernel launch is grouped over the
+ * candidates that are still training.  The reference is unseeded; here seeds[i] fixes candidate i's
+ * Glorot-uniform initialisation, its per-epoch shuffles and its dropout masks.
+ * out[i] = { accuracy, size_mb, fpr, epochs_run, last_val_loss, best_val_loss }.
+ * history (optional) [P][max_epochs][3] = { train_loss, val_loss, val_accuracy } per epoch, NaN after the stop.
+ */
+typedef struct {
+    int filters;          /* 16 | 32 | 64 */
+    int kernel_size;      /* 3 | 5 */
+    int use_bn;
+    int residual_blocks;  /* 1..3 */
+    int fc_layers;        /* 1..4 */
+    int use_dropout;
+} cmoop_genotype;
+
+typedef struct {
+    int variant;               /* 0 = A (nsga_penalty.py / mobo_penalty.py), 1 = B (sa_nsga_*.py) */
+    int n_classes;
+    int batch_size;            /* 64 (nsga_penalty.py:178); at most 64 */
+    int max_epochs;            /* 300 */
+    int patience;              /* 5 */
+    int restore_best_weights;  /* EarlyStopping(restore_best_weights=...) */
+    int acc_from_history;      /* 1: history['val_accuracy'][-1] (nsga_penalty.py:384); 0: model.evaluate after restore */
+    int y_true_zero;           /* 1: reproduce argmax(y_val, axis=1) == 0 of nsga_penalty.py:387 */
+    int fpr_filtered;          /* 1: mean over classes with FP+TN > 0 (sa_nsga_local.py:138-141) */
+    float learning_rate;       /* 1e-3 (Keras Adam default) */
+    float beta1, beta2, adam_eps;   /* 0.9, 0.999, 1e-7 */
+    float bn_momentum, bn_eps;      /* 0.99, 1e-3 */
+    float dropout_rate;        /* 0.3 */
+    int precision;             /* 0: fp32 SIMT (exact path), 1: bf16 tcgen05 implicit GEMM for Cin >= 16 convolutions */
+    double memory_budget_bytes;/* activation arena per wave of candidates; 0 = 60% of free device memory */
+} cmoop_cnn_config;
+
+typedef struct cmoop_cnn_dataset* cmoop_cnn_dataset_handle;
+/* x_* [n][height][width] fp32 (single channel, already standardised), y_* [n] int32 class ids; copied to the device */
+int cmoop_cnn_dataset_create_host(const float* x_train, const int* y_train, int n_train, const float* x_val,
+                                  const int* y_val, int n_val, int height, int width,
+                                  cmoop_cnn_dataset_handle* out);
+int cmoop_cnn_dataset_destroy(cmoop_cnn_dataset_handle h);
+long long cmoop_cnn_param_count(const cmoop_genotype* g, const cmoop_cnn_config* cfg);
+int cmoop_cnn_pop_train_eval(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotypes, const uint64_t* seeds,
+                             int n_candidates, const cmoop_cnn_config* cfg, double* out, double* history);
+/* test hooks: the harness-imposed random streams, so the CPU oracle can train on identical inputs */
+int cmoop_cnn_debug_init_params(const cmoop_genotype* g, uint64_t seed, const cmoop_cnn_config* cfg, float* out);
+int cmoop_cnn_debug_permutation(uint64_t seed, int epoch, int n, int* out);
+/* run n_steps Adam steps of epoch 0 for one candidate; losses [n_steps]; grads_first / params_out [param_count] may be NULL */
+int cmoop_cnn_debug_train_steps(cmoop_cnn_dataset_handle data, const cmoop_genotype* g, uint64_t seed,
+                                const cmoop_cnn_config* cfg, int n_steps, float* losses, float* grads_first,
+                                float* params_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,174 @@
+"""GPU parity: population-batched candidate-CNN training / scoring vs the torch-CPU fp32 oracle
+(oracle/cnn_ref.py) under shared initial parameters, shuffles and dropout masks.
+
+Stated tolerances (fp32 SIMT path): gradients of one step rtol 2e-3 (+ atol 2e-5 * max|g|); per-step loss
+over 6 Adam steps 2e-3 relative; after a short fixed-seed training run |d accuracy| <= 0.03,
+|d FPR| <= 0.01 and |d val_loss| <= 0.05 (chaotic divergence of fp32 summation orders, not an error model).
+"""
+import numpy as np
+import pytest
+
+from oracle import cnn_ref, nsga_ref
+
+pytestmark = pytest.mark.gpu
+
+N_CLASSES = 12
+
+
+def make_data(n_train=320, n_val=160, h=49, w=40, seed=0):
+    """Class-dependent blobs + noise on a 49x40 'log-mel' grid, already standardised."""
+    rng = np.random.default_rng(seed)
+    def split(n):
+        y = rng.integers(0, N_CLASSES, size=n)
+        x = rng.standard_normal((n, h, w)).astype(np.float32) * 0.7
+        for i, c in enumerate(y):
+            r0, c0 = (c * 4) % (h - 8), (c * 3) % (w - 8)
+            x[i, r0:r0 + 8, c0:c0 + 8] += 2.0
+        return x[..., None], y.astype(np.int64)
+    xt, yt = split(n_train)
+    xv, yv = split(n_val)
+    return xt, yt, xv, yv
+
+
+def unflatten(flat, hp, variant):
+    out, off = {}, 0
+    for name, shape in cnn_ref.param_shapes(hp, N_CLASSES, variant):
+        n = int(np.prod(shape))
+        out[name] = flat[off:off + n].reshape(shape).copy()
+        off += n
+    assert off == len(flat)
+    return out
+
+
+def flat_grads(model, hp, variant):
+    parts = []
+    for name, shape in cnn_ref.param_shapes(hp, N_CLASSES, variant):
+        g = model.p[name].grad
+        parts.append(np.zeros(int(np.prod(shape)), np.float32) if g is None else g.detach().numpy().ravel())
+    return np.concatenate(parts)
+
+
+GENOTYPES = [
+    ("A", dict(filters=16, kernel_size=3, use_bn=False, residual_blocks=1, fc_layers=1, use_dropout=False)),
+    ("A", dict(filters=16, kernel_size=5, use_bn=True, residual_blocks=2, fc_layers=2, use_dropout=True)),
+    ("B", dict(filters=16, kernel_size=3, use_bn=True, residual_blocks=3, fc_layers=3, use_dropout=True)),
+    ("B", dict(filters=32, kernel_size=5, use_bn=False, residual_blocks=1, fc_layers=4, use_dropout=False)),
+    ("A", dict(filters=32, kernel_size=3, use_bn=True, residual_blocks=3, fc_layers=1, use_dropout=False)),
+]
+
+
+@pytest.mark.parametrize("variant,hp", GENOTYPES)
+def test_first_step_gradients_and_loss_trajectory(variant, hp):
+    import torch
+    from cmoop_audio_processing_b200.problem import FitnessProblem, TrainConfig, param_count
+    torch.manual_seed(0)
+    xt, yt, xv, yv = make_data()
+    prob = FitnessProblem(xt, yt, xv, yv, classes=N_CLASSES, config=TrainConfig(variant=variant, epochs=2))
+    seed = 1234
+    init = prob.debug_init_params(hp, seed)
+    assert len(init) == param_count(hp, N_CLASSES, variant) == nsga_ref.param_count(hp, N_CLASSES, variant)
+    perm = prob.debug_permutation(seed, 0)
+    assert sorted(perm.tolist()) == list(range(len(xt)))
+    n_steps = 5                                              # 320 / 64: the whole first epoch
+    losses, grads, params = prob.debug_train_steps(hp, seed, n_steps)
+
+    # gradients of the first step: fp64 statement of the oracle is the reference, its own fp32 run calibrates
+    # how much of the difference is summation-order noise (deep BN stacks amplify it)
+    idx = perm[:64]
+    g = {}
+    for dtype in (torch.float64, torch.float32):
+        model = cnn_ref.RefModel(hp, N_CLASSES, variant, unflatten(init, hp, variant), dtype=dtype)
+        p = model.forward(torch.from_numpy(xt[idx]), training=True, drop_ctx=(seed & 0xFFFFFFFF, 0))
+        loss0 = cnn_ref.keras_sparse_ce(p, torch.from_numpy(yt[idx]).long()).mean()
+        loss0.backward()
+        g[dtype] = flat_grads(model, hp, variant).astype(np.float64)
+    g_ref = g[torch.float64]
+    assert losses[0] == pytest.approx(float(loss0.detach()), rel=2e-4)
+    scale = np.abs(g_ref).max()
+    err_ours = np.abs(grads - g_ref)
+    err_torch32 = np.abs(g[torch.float32] - g_ref)
+    assert err_ours.max() <= 4e-3 * scale                                   # absolute, relative to the largest gradient
+    assert np.linalg.norm(grads - g_ref) <= 2e-3 * np.linalg.norm(g_ref)   # relative L2
+    assert err_ours.max() <= max(6 * err_torch32.max(), 1e-4 * scale)      # same order as torch's own fp32 noise
+    big = np.abs(g_ref) > 0.05 * scale
+    np.testing.assert_allclose(grads[big], g_ref[big], rtol=2e-2)
+    # loss trajectory + parameters after the epoch (fresh model, same streams)
+    model = cnn_ref.RefModel(hp, N_CLASSES, variant, unflatten(init, hp, variant))
+    ref_losses, _ = cnn_ref.train_steps(model, xt, yt, perm, n_steps, seed=seed & 0xFFFFFFFF)
+    np.testing.assert_allclose(losses, ref_losses, rtol=2e-3)
+    ref_params = np.concatenate([model.p[name].detach().numpy().ravel()
+                                 for name, _ in cnn_ref.param_shapes(hp, N_CLASSES, variant)])
+    # Adam moves every weight by <= ~lr per step in the direction of sign(g): a near-zero gradient whose sign
+    # differs in the last bit costs up to 2*lr per step, so bound the tail and require the bulk to agree closely
+    diff = np.abs(params - ref_params)
+    assert diff.max() < 2 * 1e-3 * n_steps
+    assert np.mean(diff < 3e-4) > 0.9 and np.median(diff) < 2e-4
+
+
+def test_population_batching_is_invariant():
+    """Grouped launches over heterogeneous candidates give exactly the numbers of one-at-a-time evaluation."""
+    from cmoop_audio_processing_b200.problem import FitnessProblem, TrainConfig
+    xt, yt, xv, yv = make_data(192, 96)
+    cfg = TrainConfig(variant="B", epochs=2, restore_best_weights=True, acc_from="evaluate")
+    prob = FitnessProblem(xt, yt, xv, yv, classes=N_CLASSES, config=cfg)
+    hps = [hp for _, hp in GENOTYPES]
+    seeds = [11, 12, 13, 14, 15]
+    together, hist = prob.train_eval(hps, seeds, want_history=True)
+    for i, hp in enumerate(hps):
+        alone, h1 = prob.train_eval([hp], [seeds[i]], want_history=True)
+        np.testing.assert_array_equal(together[i], alone[0])
+        np.testing.assert_array_equal(hist[i], h1[0])
+    for i, hp in enumerate(hps):
+        assert together[i, 1] == nsga_ref.model_size_mb(hp, N_CLASSES, "B")       # size objective is exact
+
+
+@pytest.mark.parametrize("variant,restore,acc_from,quirk", [("A", False, "history", "argmax_quirk"),
+                                                           ("B", True, "evaluate", "flatten")])
+def test_evaluate_individual_matches_oracle_after_training(variant, restore, acc_from, quirk):
+    from cmoop_audio_processing_b200.problem import FitnessProblem, TrainConfig
+    xt, yt, xv, yv = make_data(384, 192)
+    hp = dict(filters=16, kernel_size=3, use_bn=True, residual_blocks=1, fc_layers=2, use_dropout=True)
+    epochs = 4
+    cfg = TrainConfig(variant=variant, epochs=epochs, patience=2, restore_best_weights=restore, acc_from=acc_from,
+                      y_true_mode=quirk)
+    prob = FitnessProblem(xt, yt, xv, yv, classes=N_CLASSES, config=cfg, seed=77)
+    out, hist = prob.train_eval([hp], [77], want_history=True)
+    init = prob.debug_init_params(hp, 77)
+    perms = [prob.debug_permutation(77, e) for e in range(epochs)]
+    ref = cnn_ref.evaluate_individual(hp, (xt, yt, xv, yv), unflatten(init, hp, variant), perms, n_classes=N_CLASSES,
+                                      variant=variant, seed=77, epochs=epochs, patience=2,
+                                      restore_best_weights=restore, acc_from=acc_from, y_true_mode=quirk)
+    assert int(out[0, 3]) == ref["epochs_run"]
+    assert out[0, 1] == ref["size_mb"]
+    assert abs(out[0, 0] - ref["acc"]) <= 0.03
+    assert abs(out[0, 2] - ref["fpr"]) <= 0.01
+    e = ref["epochs_run"]
+    np.testing.assert_allclose(hist[0, :e, 1], ref["history"]["val_loss"], atol=0.05)
+    np.testing.assert_allclose(hist[0, :e, 0], ref["history"]["loss"], atol=0.05)
+    assert np.isnan(hist[0, e:, :]).all()
+
+
+def test_drop_in_records_and_early_stopping():
+    from cmoop_audio_processing_b200.problem import FitnessProblem, TrainConfig
+    xt, yt, xv, yv = make_data(256, 128)
+    prob = FitnessProblem.sa_nsga_local(xt, yt, xv, yv, classes=N_CLASSES,
+                                        config=TrainConfig(variant="B", epochs=12, patience=1, restore_best_weights=True,
+                                                           acc_from="evaluate", fpr_mode="filtered"))
+    pop = [hp for _, hp in GENOTYPES[:3]]
+    recs = prob.compute_objectives_and_constraints(pop)
+    assert [r["hparams"] is hp for r, hp in zip(recs, pop)] == [True] * 3
+    for r, hp in zip(recs, pop):
+        assert len(r["objs"]) == 3 and all(isinstance(v, float) for v in r["objs"]) and isinstance(r["CV"], float)
+        acc, size, fpr = -r["objs"][0], r["objs"][1], r["objs"][2]
+        assert size == nsga_ref.model_size_mb(hp, N_CLASSES, "B")
+        assert r["CV"] == nsga_ref.constraint_violation(acc, size, fpr, 0.90, 2.5, 0.09)
+        assert 0.0 <= acc <= 1.0 and 0.0 <= fpr <= 1.0
+    det = prob.last_details
+    assert (det[:, 3] >= 2).all() and (det[:, 3] <= 12).all()
+    assert (det[:, 5] <= det[:, 4] + 1e-12).all()              # best val loss <= last val loss
+    acc1, size1, fpr1 = prob.evaluate_individual(pop[0])
+    assert size1 == recs[0]["objs"][1] and prob.evaluations == 4
+    bi = FitnessProblem(prob.data, None, None, None, classes=N_CLASSES, objectives=("neg_acc", "fpr"),
+                        config=TrainConfig(variant="A", epochs=1))
+    rec = bi.compute_objectives_and_constraints(pop[:1])[0]
+    assert len(rec["objs"]) == 2 and "size_metric" in rec
