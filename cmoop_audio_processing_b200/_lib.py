@@ -100,6 +100,14 @@ def load() -> C.CDLL:
     return lib
 
 
+def bind_device() -> None:
+    """Make the library use the device torch has selected for this process (one process per GPU)."""
+    import sys
+    torch = sys.modules.get("torch")
+    if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
+        check(load().cmoop_set_device(int(torch.cuda.current_device())), "cmoop_set_device")
+
+
 def check(status: int, what: str) -> None:
     if status != 0:
         msg = load().cmoop_last_error().decode("utf-8", "replace")

@@ -32,6 +32,7 @@ class MfccConfig:
 class MfccFrontEnd:
     def __init__(self, config: MfccConfig = MfccConfig()):
         self._lib = _lib.load()
+        _lib.bind_device()
         self.config = config
         c = _lib.MfccConfig(config.sample_rate, config.frame_length, config.hop, config.n_fft, config.n_mels,
                             config.n_mfcc, config.f_min, config.f_max, config.log_floor)

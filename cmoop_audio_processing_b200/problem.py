@@ -121,6 +121,7 @@ class DeviceDataset:
 
     def __init__(self, x_train, y_train, x_val, y_val):
         self._lib = _lib.load()
+        _lib.bind_device()
         xt = np.ascontiguousarray(np.asarray(x_train, np.float32).reshape(len(x_train), *np.shape(x_train)[1:3]))
         xv = np.ascontiguousarray(np.asarray(x_val, np.float32).reshape(len(x_val), *np.shape(x_val)[1:3]))
         yt = np.ascontiguousarray(np.asarray(y_train).reshape(-1), np.int32)

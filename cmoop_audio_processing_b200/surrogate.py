@@ -64,6 +64,7 @@ class DeviceGPGroup:
         """specs: dicts with x_train [n,d], alpha [n], chol_lower [n,n] or None, amplitude,
         length_scale, nu, noise, y_scale, y_shift."""
         self._lib = _lib.load()
+        _lib.bind_device()
         self.n_models = len(specs)
         self.dim = int(np.asarray(specs[0]["x_train"]).shape[1])
         self._keep = []

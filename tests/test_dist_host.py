@@ -1,0 +1,61 @@
+"""N>1 host logic on CPU: LPT candidate assignment and the gloo all-gather of objective rows (world_size 2)."""
+import os
+
+import numpy as np
+import pytest
+
+from cmoop_audio_processing_b200.dist import assign_lpt
+
+
+def test_assign_lpt_balances_and_is_deterministic():
+    costs = [100, 1, 1, 1, 50, 49, 2, 98]
+    owner = assign_lpt(costs, 2)
+    loads = [sum(c for c, o in zip(costs, owner) if o == r) for r in range(2)]
+    assert abs(loads[0] - loads[1]) <= 2
+    assert owner == assign_lpt(list(costs), 2)
+    assert assign_lpt([], 4) == []
+    assert sorted(set(assign_lpt([5] * 8, 8))) == list(range(8))
+
+
+def _worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from types import SimpleNamespace
+    from cmoop_audio_processing_b200.problem import FitnessProblem, TrainConfig, compute_model_size_mb
+    prob = object.__new__(FitnessProblem)
+    prob.data = SimpleNamespace(height=49, width=40)
+    prob.classes, prob.config, prob.seed, prob.evaluations = 12, TrainConfig(variant="B"), 5, 0
+    prob.min_accuracy, prob.max_model_size, prob.max_fpr = 0.9, 2.5, 0.09
+    prob.objectives = ("neg_acc", "size", "fpr")
+    calls = []
+
+    def fake_train_eval(hps, seeds=None, want_history=False):
+        calls.append(list(seeds))
+        out = np.zeros((len(hps), 6))
+        for i, (hp, s) in enumerate(zip(hps, seeds)):
+            out[i] = [0.5 + 0.001 * hp["filters"] + 1e-4 * s, compute_model_size_mb(hp, 12, "B"), 0.01 * hp["fc_layers"],
+                      3, 1.0, 0.9]
+        return out, None
+
+    prob.train_eval = fake_train_eval
+    pop = [dict(filters=f, kernel_size=k, use_bn=True, residual_blocks=r, fc_layers=fc, use_dropout=False)
+           for f in (16, 64) for k in (3, 5) for r in (1, 3) for fc in (1, 4)][:13]
+    recs = prob.compute_objectives_and_constraints(pop)
+    np.save(os.path.join(tmp, f"r{rank}.npy"), np.array([r["objs"] + [r["CV"]] for r in recs]))
+    np.save(os.path.join(tmp, f"n{rank}.npy"), np.array([len(c) for c in calls]))
+    dist.destroy_process_group()
+
+
+def test_sharded_evaluation_all_gathers_rows_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "r0.npy"), np.load(tmp_path / "r1.npy")
+    np.testing.assert_array_equal(a, b)                       # every rank holds the full, identically ordered result
+    assert a.shape == (13, 4) and np.all(a[:, 1] > 0)
+    n0, n1 = int(np.load(tmp_path / "n0.npy").sum()), int(np.load(tmp_path / "n1.npy").sum())
+    assert n0 + n1 == 13 and n0 > 0 and n1 > 0               # disjoint shards cover the population
+    # seeds follow the global candidate index, so results do not depend on the world size
+    expect = [0.5 + 0.001 * (16 if i < 8 else 64) + 1e-4 * (5 + i) for i in range(13)]
+    np.testing.assert_allclose(-a[:, 0], expect, rtol=0, atol=1e-12)
