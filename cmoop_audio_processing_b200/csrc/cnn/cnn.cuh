@@ -8,6 +8,7 @@
 // Layout: activations NHWC fp32, conv kernels HWIO (= GEMM B matrix [K][Cout]) immediately followed by
 // the bias row in the flat parameter buffer, so bias is the (K+1)-th row of the GEMM ("ones column").
 #pragma once
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 namespace cmoop_cnn {
@@ -28,6 +29,34 @@ struct ConvTask {
     int out_h, out_w, out_s;  // scattered destination grid (strided-conv dgrad); out_s == 0 -> dense [M][Cout]
     int accumulate;        // y += result
     int tiles_n, tile_begin;
+};
+
+// tcgen05 implicit GEMM (conv_tc.cu): bf16 operands, fp32 accumulation in TMEM
+struct TcConvTask {
+    const float* x;              // fp32 NHWC input (converted to bf16 while staging)
+    const __nv_bfloat16* wt;     // bf16 weights, K-major [Cout][K_pad]
+    const float* bias;           // fp32 [Cout] or null
+    float* y;
+    long long x_step;
+    int H, W, Cin, Ho, Wo, Cout, k, stride, pad;
+    int K_pad;                   // K rounded up to a multiple of 64
+    int bn;                      // N tile (UMMA N): min(Cout, 128)
+    int relu;
+    int out_h, out_w, out_s, accumulate;
+    int tiles_n, tile_begin;
+};
+
+struct WtBf16Task {
+    const float* w;              // fp32 HWIO master weights
+    __nv_bfloat16* out;
+    int k, Cin, Cout, K_pad, mode;   // mode 0: forward copy, 1: flipped/transposed copy for the data gradient
+    int block_begin;
+};
+
+struct StatTask {               // BN batch statistics of a conv output produced by the tensor-core path
+    const float* y;
+    float* part;
+    int C, rows_per_sample, block_begin;
 };
 
 struct WgradTask {
@@ -156,6 +185,9 @@ struct Launch {
     static int ce(const CeTask* tasks, int n_tasks, int n_b, int step, int training, void* stream);
     static int adam(const AdamTask* tasks, int n_tasks, int total_blocks, float alpha, float b1, float b2, float eps, void* stream);
     static int init(const InitTask* tasks, int n_tasks, int total_blocks, void* stream);
+    static int conv_tc(const TcConvTask* tasks, int n_tasks, int total_tiles, int n_b, int step, void* stream);
+    static int wt_bf16(const WtBf16Task* tasks, int n_tasks, int total_blocks, void* stream);
+    static int bn_stats(const StatTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
 };
 
 }  // namespace cmoop_cnn

@@ -973,4 +973,91 @@ int cmoop_cnn_debug_init_params(const cmoop_genotype* g, uint64_t seed, const cm
     return rc;
 }
 
+
+// Test hook: one convolution (mode 0: forward y = conv(x, w) + b; mode 1: data gradient dx = conv^T(dy, w)) through
+// the fp32 SIMT kernel (use_tc = 0) or the tcgen05 kernel (use_tc = 1).  Host pointers.
+int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, const float* bias, int n, int H, int W,
+                         int Cin, int Cout, int k, int stride, int relu, float* out) {
+    CMOOP_REQUIRE(in && w && out, "debug_conv: null pointer");
+    CMOOP_REQUIRE(n >= 1 && n <= kBatch && (stride == 1 || (stride == 2 && k == 1)), "debug_conv: unsupported shape");
+    CMOOP_REQUIRE(!use_tc || (Cin % 16 == 0 && Cout % 16 == 0), "debug_conv: tensor-core path needs Cin, Cout multiples of 16");
+    if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
+    cudaStream_t st = cmoop::internal_stream();
+    const int pad = stride == 1 ? (k - 1) / 2 : 0;
+    const int Ho = stride == 1 ? H : (H + 1) / 2, Wo = stride == 1 ? W : (W + 1) / 2;
+    const long long n_x = (long long)n * H * W * Cin, n_y = (long long)n * Ho * Wo * Cout;
+    const long long n_w = (long long)k * k * Cin * Cout;
+    const long long n_in = mode == 0 ? n_x : n_y, n_out = mode == 0 ? n_y : n_x;
+    const int gi = mode == 0 ? Cin : Cout, go = mode == 0 ? Cout : Cin;      // GEMM input / output channels
+    const int K = k * k * gi, K_pad = (K + 63) / 64 * 64;
+    float *d_in, *d_w, *d_out, *d_wt;
+    __nv_bfloat16* d_wb;
+    void* d_task;
+    CMOOP_CUDA_OK(cudaMalloc((void**)&d_in, n_in * 4));
+    CMOOP_CUDA_OK(cudaMalloc((void**)&d_w, (n_w + Cout) * 4));
+    CMOOP_CUDA_OK(cudaMalloc((void**)&d_out, n_out * 4));
+    CMOOP_CUDA_OK(cudaMalloc((void**)&d_wt, n_w * 4));
+    CMOOP_CUDA_OK(cudaMalloc((void**)&d_wb, (size_t)go * K_pad * 2));
+    CMOOP_CUDA_OK(cudaMalloc(&d_task, 1024));
+    CMOOP_CUDA_OK(cudaMemcpyAsync(d_in, in, n_in * 4, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cudaMemcpyAsync(d_w, w, n_w * 4, cudaMemcpyHostToDevice, st));
+    if (bias)
+        CMOOP_CUDA_OK(cudaMemcpyAsync(d_w + n_w, bias, Cout * 4, cudaMemcpyHostToDevice, st));
+    else
+        CMOOP_CUDA_OK(cudaMemsetAsync(d_w + n_w, 0, Cout * 4, st));
+    CMOOP_CUDA_OK(cudaMemsetAsync(d_out, 0, n_out * 4, st));
+    const int tiles_m64 = (int)(((long long)n * Ho * Wo + 63) / 64), tiles_m128 = (int)(((long long)n * Ho * Wo + 127) / 128);
+    int rc = 0;
+    if (!use_tc) {
+        ConvTask t{};
+        t.x = d_in; t.y = d_out;
+        t.Ho = Ho; t.Wo = Wo; t.k = k;
+        if (mode == 0) {
+            t.w = d_w; t.use_bias = 1; t.relu = relu;
+            t.H = H; t.W = W; t.Cin = Cin; t.Cout = Cout; t.stride = stride; t.pad = pad;
+        } else {
+            WtTask wt{};
+            wt.w = d_w; wt.wt = d_wt; wt.k = k; wt.Cin = Cin; wt.Cout = Cout;
+            CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &wt, sizeof(wt), cudaMemcpyHostToDevice, st));
+            rc = Launch::wt((const WtTask*)d_task, 1, (int)((n_w + 255) / 256), st);
+            CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+            t.w = d_wt; t.use_bias = 0;
+            t.H = Ho; t.W = Wo; t.Cin = Cout; t.Cout = Cin; t.stride = 1; t.pad = stride == 1 ? pad : 0;
+            if (stride == 2) { t.out_h = H; t.out_w = W; t.out_s = 2; t.accumulate = 1; }
+        }
+        t.tiles_n = (t.Cout + 63) / 64;
+        CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &t, sizeof(t), cudaMemcpyHostToDevice, st));
+        if (rc == 0) rc = Launch::conv((const ConvTask*)d_task, 1, tiles_m64 * t.tiles_n, n, 0, st);
+    } else {
+        WtBf16Task wb{};
+        wb.w = d_w; wb.out = d_wb; wb.k = k; wb.Cin = Cin; wb.Cout = Cout; wb.K_pad = K_pad; wb.mode = mode;
+        CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &wb, sizeof(wb), cudaMemcpyHostToDevice, st));
+        rc = Launch::wt_bf16((const WtBf16Task*)d_task, 1, (int)(((long long)go * K_pad + 255) / 256), st);
+        CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+        TcConvTask t{};
+        t.x = d_in; t.wt = d_wb; t.y = d_out; t.k = k; t.K_pad = K_pad;
+        t.Ho = Ho; t.Wo = Wo;
+        if (mode == 0) {
+            t.bias = d_w + n_w; t.relu = relu;
+            t.H = H; t.W = W; t.Cin = Cin; t.Cout = Cout; t.stride = stride; t.pad = pad;
+        } else {
+            t.H = Ho; t.W = Wo; t.Cin = Cout; t.Cout = Cin; t.stride = 1; t.pad = stride == 1 ? pad : 0;
+            if (stride == 2) { t.out_h = H; t.out_w = W; t.out_s = 2; t.accumulate = 1; }
+        }
+        t.bn = t.Cout < 128 ? t.Cout : 128;
+        t.tiles_n = (t.Cout + t.bn - 1) / t.bn;
+        CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &t, sizeof(t), cudaMemcpyHostToDevice, st));
+        if (rc == 0) rc = Launch::conv_tc((const TcConvTask*)d_task, 1, tiles_m128 * t.tiles_n, n, 0, st);
+    }
+    cmoop::count_launch();
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == 0 && e == cudaSuccess) e = cudaMemcpy(out, d_out, n_out * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_w); cudaFree(d_out); cudaFree(d_wt); cudaFree(d_wb); cudaFree(d_task);
+    if (rc != 0 || e != cudaSuccess) {
+        cmoop::set_error("debug_conv: %s", cudaGetErrorString(rc != 0 ? (cudaError_t)rc : e));
+        return CMOOP_ERR_CUDA;
+    }
+    return CMOOP_OK;
+}
+
 }  // extern "C"

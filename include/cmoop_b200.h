@@ -213,6 +213,12 @@ int cmoop_cnn_debug_train_steps(cmoop_cnn_dataset_handle data, const cmoop_genot
                                 const cmoop_cnn_config* cfg, int n_steps, float* losses, float* grads_first,
                                 float* params_out);
 
+/* one convolution through the fp32 SIMT kernel (use_tc = 0) or the tcgen05 kernel (use_tc = 1); host pointers.
+ * mode 0: out[n][Ho][Wo][Cout] = conv(in[n][H][W][Cin], w[k][k][Cin][Cout]) + bias (optional ReLU)
+ * mode 1: out[n][H][W][Cin] = data gradient of that convolution for in = dy[n][Ho][Wo][Cout] */
+int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, const float* bias, int n, int H,
+                         int W, int Cin, int Cout, int k, int stride, int relu, float* out);
+
 #ifdef __cplusplus
 }
 #endif

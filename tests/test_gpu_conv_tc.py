@@ -1,0 +1,69 @@
+"""GPU: the tcgen05 implicit-GEMM convolution (forward + data gradient) against torch on bf16-rounded operands
+(products are then exact in fp32, so the tolerance only covers accumulation order) and against the fp32 SIMT kernel."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def run_conv(mode, use_tc, inp, w, bias, n, H, W, Cin, Cout, k, stride, relu):
+    from cmoop_audio_processing_b200 import _lib
+    lib = _lib.load()
+    Ho, Wo = (H, W) if stride == 1 else ((H + 1) // 2, (W + 1) // 2)
+    out = np.zeros((n, Ho, Wo, Cout) if mode == 0 else (n, H, W, Cin), np.float32)
+    _lib.check(lib.cmoop_cnn_debug_conv(mode, use_tc, _lib.ptr(inp), _lib.ptr(w), _lib.ptr(bias), n, H, W, Cin, Cout, k,
+                                        stride, relu, _lib.ptr(out)), "cmoop_cnn_debug_conv")
+    return out
+
+
+def bf16_round(a):
+    import torch
+    return torch.from_numpy(a).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+CASES = [  # n, H, W, Cin, Cout, k, stride
+    (3, 9, 8, 16, 16, 3, 1),
+    (64, 49, 40, 16, 16, 3, 1),      # stem2, F=16: K=144 -> one padded K block of 3
+    (8, 25, 20, 32, 64, 5, 1),       # K=800 -> 13 K blocks (ring wraps 4x), N tile 64
+    (5, 13, 10, 64, 128, 3, 1),
+    (4, 7, 5, 128, 256, 3, 1),       # two N tiles
+    (7, 25, 20, 32, 64, 1, 2),       # residual skip projection 1x1 / stride 2 (odd height)
+    (2, 49, 40, 64, 64, 5, 1),
+]
+
+
+@pytest.mark.parametrize("n,H,W,Cin,Cout,k,stride", CASES)
+def test_forward_and_dgrad(n, H, W, Cin, Cout, k, stride):
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(n * 1000 + Cin + Cout + k)
+    x = rng.standard_normal((n, H, W, Cin)).astype(np.float32)
+    w = (rng.standard_normal((k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    pad = (k - 1) // 2 if stride == 1 else 0
+    xt = torch.from_numpy(bf16_round(x)).permute(0, 3, 1, 2).double()
+    wt = torch.from_numpy(bf16_round(w)).permute(3, 2, 0, 1).double()
+    ref = F.conv2d(xt, wt, torch.from_numpy(b).double(), stride=stride, padding=pad).permute(0, 2, 3, 1).numpy()
+    for relu in (0, 1):
+        want = np.maximum(ref, 0) if relu else ref
+        got = run_conv(0, 1, x, w, b, n, H, W, Cin, Cout, k, stride, relu)
+        np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-4)
+    simt = run_conv(0, 0, x, w, b, n, H, W, Cin, Cout, k, stride, 0)
+    full = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2).double(), torch.from_numpy(w).permute(3, 2, 0, 1).double(),
+                    torch.from_numpy(b).double(), stride=stride, padding=pad).permute(0, 2, 3, 1).numpy()
+    np.testing.assert_allclose(simt, full, rtol=1e-4, atol=1e-4)                     # fp32 SIMT path is the exact one
+    assert np.abs(got if not relu else run_conv(0, 1, x, w, b, n, H, W, Cin, Cout, k, stride, 0) - full).max() < 0.05
+    # data gradient
+    Ho, Wo = ref.shape[1:3]
+    dy = rng.standard_normal((n, Ho, Wo, Cout)).astype(np.float32)
+    dyt = torch.from_numpy(bf16_round(dy)).permute(0, 3, 1, 2).double()
+    xin = torch.zeros((n, Cin, H, W), dtype=torch.float64, requires_grad=True)
+    F.conv2d(xin, wt, None, stride=stride, padding=pad).backward(dyt)
+    want_dx = xin.grad.permute(0, 2, 3, 1).numpy()
+    got_dx = run_conv(1, 1, dy, w, None, n, H, W, Cin, Cout, k, stride, 0)
+    np.testing.assert_allclose(got_dx, want_dx, rtol=2e-4, atol=2e-4)
+    xin2 = torch.zeros((n, Cin, H, W), dtype=torch.float64, requires_grad=True)
+    F.conv2d(xin2, torch.from_numpy(w).permute(3, 2, 0, 1).double(), None, stride=stride, padding=pad).backward(
+        torch.from_numpy(dy).permute(0, 3, 1, 2).double())
+    np.testing.assert_allclose(run_conv(1, 0, dy, w, None, n, H, W, Cin, Cout, k, stride, 0),
+                               xin2.grad.permute(0, 2, 3, 1).numpy(), rtol=1e-4, atol=1e-4)
