@@ -55,6 +55,10 @@ struct Unit {
     float* bwd_part = nullptr;
     float* wt = nullptr;
     uint8_t* idx = nullptr;
+    bool tc = false;                 // convolution runs on the tcgen05 path (bf16 operands)
+    int kpad_f = 0, kpad_d = 0;      // padded K of the forward / data-gradient GEMM
+    __nv_bfloat16* wtb = nullptr;    // bf16 [cout][kpad_f]
+    __nv_bfloat16* wtd = nullptr;    // bf16 [cin][kpad_d]
 };
 
 struct Cand {
@@ -196,6 +200,9 @@ void build_units(Cand& c, const cmoop_cnn_config& cfg, int H, int W, int batch) 
     c.units[o].input = in_unit;
     c.n_params = off;
     for (Unit& u : c.units) {
+        u.tc = cfg.precision == 1 && !u.dense && u.cin % 16 == 0 && u.cout % 16 == 0;
+        u.kpad_f = (u.k * u.k * u.cin + 63) / 64 * 64;
+        u.kpad_d = (u.k * u.k * u.cout + 63) / 64 * 64;
         u.u_elems = (long long)batch * u.Ho * u.Wo * u.cout;
         u.v_elems = (long long)batch * u.Po * u.Qo * u.cout;
         const long long M = (long long)batch * u.Ho * u.Wo;
@@ -243,7 +250,11 @@ void place(Cand& c, Arena& a, const cmoop_cnn_config& cfg, int n_train, int n_va
             u.bn = (float*)a.take((size_t)6 * u.cout * f4);
             u.bwd_part = (float*)a.take((size_t)u.bwd_rows * 2 * u.cout * f4);
         }
-        u.wt = u.need_dgrad ? (float*)a.take((size_t)u.k * u.k * u.cin * u.cout * f4) : nullptr;
+        u.wt = (u.need_dgrad && !u.tc) ? (float*)a.take((size_t)u.k * u.k * u.cin * u.cout * f4) : nullptr;
+        if (u.tc) {
+            u.wtb = (__nv_bfloat16*)a.take((size_t)u.cout * u.kpad_f * 2);
+            u.wtd = u.need_dgrad ? (__nv_bfloat16*)a.take((size_t)u.cin * u.kpad_d * 2) : nullptr;
+        }
         maxV = std::max(maxV, u.v_elems);
         maxV = std::max(maxV, (long long)batch * u.H * u.W * u.cin);
         maxU = std::max(maxU, u.u_elems);
@@ -275,6 +286,9 @@ struct DevList {
 
 struct StageLists {
     DevList<ConvTask> conv, conv_eval, dgrad;
+    DevList<TcConvTask> conv_tc, dgrad_tc;
+    DevList<StatTask> stat;
+    bool any = false;
     DevList<PostTask> post_fwd, post_bn, post_bwd;
     DevList<WgradTask> wgrad;
     DevList<ReduceTask> wreduce;
@@ -288,6 +302,8 @@ struct Wave {
     DevList<CeTask> ce_train, ce_val, ce_pred;
     DevList<AdamTask> adam;
     DevList<WtTask> wt;
+    DevList<WtBf16Task> wt_bf16;
+    bool weights_dirty = true;
     char* d_blob = nullptr;
     size_t blob_cap = 0;
 };
@@ -315,6 +331,8 @@ struct Engine {
         wv.ce_train = wv.ce_val = wv.ce_pred = DevList<CeTask>();
         wv.adam = DevList<AdamTask>();
         wv.wt = DevList<WtTask>();
+        wv.wt_bf16 = DevList<WtBf16Task>();
+        wv.weights_dirty = true;
         const long long img = (long long)data->H * data->W;
         for (Cand* cp : wv.cands) {
             Cand& c = *cp;
@@ -324,31 +342,58 @@ struct Engine {
                 StageLists& S = wv.st[u.stage];
                 const float* xin = u.input == -1 ? data->x_train : (u.input == -2 ? (c.n_fc ? c.gap : c.gap) : c.units[u.input].V);
                 // ---- forward conv
-                ConvTask t{};
-                t.x = xin;
-                t.w = c.p + u.w_off;
-                t.y = u.U;
-                t.stat_part = u.has_bn ? u.stat : nullptr;
-                t.H = u.H; t.W = u.W; t.Cin = u.cin; t.Ho = u.Ho; t.Wo = u.Wo; t.Cout = u.cout;
-                t.k = u.k; t.stride = u.stride; t.pad = u.pad;
-                t.relu = u.relu_epi;
-                t.use_bias = 1;
-                t.tiles_n = (u.cout + 63) / 64;
-                t.tile_begin = S.conv.total;
-                if (u.input == -1) {
-                    t.gather = c.perm;
-                    t.gather_step = batch;
-                    ConvTask e = t;
-                    e.x = data->x_val;
-                    e.gather = nullptr;
-                    e.gather_step = 0;
-                    e.x_step = (long long)batch * img;
-                    e.tile_begin = S.conv_eval.total;
-                    S.conv_eval.h.push_back(e);
-                    S.conv_eval.total += u.stat_tiles * t.tiles_n;
+                S.any = true;
+                if (u.tc) {
+                    TcConvTask t{};
+                    t.x = xin; t.wt = u.wtb; t.bias = c.p + u.w_off + (long long)u.k * u.k * u.cin * u.cout; t.y = u.U;
+                    t.H = u.H; t.W = u.W; t.Cin = u.cin; t.Ho = u.Ho; t.Wo = u.Wo; t.Cout = u.cout;
+                    t.k = u.k; t.stride = u.stride; t.pad = u.pad; t.K_pad = u.kpad_f;
+                    t.bn = u.cout < 128 ? u.cout : 128;
+                    t.relu = u.relu_epi;
+                    t.tiles_n = (u.cout + t.bn - 1) / t.bn;
+                    t.tile_begin = S.conv_tc.total;
+                    S.conv_tc.h.push_back(t);
+                    S.conv_tc.total += (int)(((long long)batch * u.Ho * u.Wo + 127) / 128) * t.tiles_n;
+                    if (u.has_bn) {
+                        StatTask sk{};
+                        sk.y = u.U; sk.part = u.stat; sk.C = u.cout; sk.rows_per_sample = u.Ho * u.Wo;
+                        sk.block_begin = S.stat.total;
+                        S.stat.h.push_back(sk);
+                        S.stat.total += u.stat_tiles;
+                    }
+                    WtBf16Task wb{};
+                    wb.w = c.p + u.w_off; wb.out = u.wtb; wb.k = u.k; wb.Cin = u.cin; wb.Cout = u.cout;
+                    wb.K_pad = u.kpad_f; wb.mode = 0;
+                    wb.block_begin = wv.wt_bf16.total;
+                    wv.wt_bf16.h.push_back(wb);
+                    wv.wt_bf16.total += blocks_for((long long)u.cout * u.kpad_f);
+                } else {
+                    ConvTask t{};
+                    t.x = xin;
+                    t.w = c.p + u.w_off;
+                    t.y = u.U;
+                    t.stat_part = u.has_bn ? u.stat : nullptr;
+                    t.H = u.H; t.W = u.W; t.Cin = u.cin; t.Ho = u.Ho; t.Wo = u.Wo; t.Cout = u.cout;
+                    t.k = u.k; t.stride = u.stride; t.pad = u.pad;
+                    t.relu = u.relu_epi;
+                    t.use_bias = 1;
+                    t.tiles_n = (u.cout + 63) / 64;
+                    t.tile_begin = S.conv.total;
+                    if (u.input == -1) {
+                        t.gather = c.perm;
+                        t.gather_step = batch;
+                        ConvTask e = t;
+                        e.x = data->x_val;
+                        e.gather = nullptr;
+                        e.gather_step = 0;
+                        e.x_step = (long long)batch * img;
+                        e.tile_begin = S.conv_eval.total;
+                        S.conv_eval.h.push_back(e);
+                        S.conv_eval.total += u.stat_tiles * t.tiles_n;
+                    }
+                    S.conv.h.push_back(t);
+                    S.conv.total += u.stat_tiles * t.tiles_n;
                 }
-                S.conv.h.push_back(t);
-                S.conv.total += u.stat_tiles * t.tiles_n;
                 // ---- post stage (forward / BN / backward lists)
                 if (!u.dense && !u.is_skip) {
                     PostTask p{};
@@ -424,7 +469,31 @@ struct Engine {
                     }
                 }
                 // ---- data gradient: conv of dy with flipped/transposed weights into buffer A (or gG below the first FC)
-                if (u.need_dgrad) {
+                if (u.need_dgrad && u.tc) {
+                    WtBf16Task wb{};
+                    wb.w = c.p + u.w_off; wb.out = u.wtd; wb.k = u.k; wb.Cin = u.cin; wb.Cout = u.cout;
+                    wb.K_pad = u.kpad_d; wb.mode = 1;
+                    wb.block_begin = wv.wt_bf16.total;
+                    wv.wt_bf16.h.push_back(wb);
+                    wv.wt_bf16.total += blocks_for((long long)u.cin * u.kpad_d);
+                    TcConvTask d{};
+                    d.x = u.is_skip ? c.gS : c.gB;
+                    d.wt = u.wtd;
+                    d.y = c.gA;
+                    d.Cin = u.cout; d.Cout = u.cin; d.k = u.k; d.K_pad = u.kpad_d;
+                    d.H = u.Ho; d.W = u.Wo; d.Ho = u.Ho; d.Wo = u.Wo;
+                    d.stride = 1; d.pad = u.pad;
+                    if (u.is_skip) {
+                        d.pad = 0;
+                        d.out_h = u.H; d.out_w = u.W; d.out_s = 2;
+                        d.accumulate = 1;
+                    }
+                    d.bn = u.cin < 128 ? u.cin : 128;
+                    d.tiles_n = (u.cin + d.bn - 1) / d.bn;
+                    d.tile_begin = S.dgrad_tc.total;
+                    S.dgrad_tc.h.push_back(d);
+                    S.dgrad_tc.total += (int)(((long long)batch * u.Ho * u.Wo + 127) / 128) * d.tiles_n;
+                } else if (u.need_dgrad) {
                     WtTask w{};
                     w.w = c.p + u.w_off; w.wt = u.wt; w.k = u.k; w.Cin = u.cin; w.Cout = u.cout;
                     w.block_begin = wv.wt.total;
@@ -475,11 +544,12 @@ struct Engine {
         for (int s = 0; s < N_STAGES; ++s) {
             StageLists& S = wv.st[s];
             blob_add(blob, S.conv); blob_add(blob, S.conv_eval); blob_add(blob, S.dgrad);
+            blob_add(blob, S.conv_tc); blob_add(blob, S.dgrad_tc); blob_add(blob, S.stat);
             blob_add(blob, S.post_fwd); blob_add(blob, S.post_bn); blob_add(blob, S.post_bwd);
             blob_add(blob, S.wgrad); blob_add(blob, S.wreduce); blob_add(blob, S.drop_fwd); blob_add(blob, S.drop_bwd);
         }
         blob_add(blob, wv.head); blob_add(blob, wv.ce_train); blob_add(blob, wv.ce_val); blob_add(blob, wv.ce_pred);
-        blob_add(blob, wv.adam); blob_add(blob, wv.wt);
+        blob_add(blob, wv.adam); blob_add(blob, wv.wt); blob_add(blob, wv.wt_bf16);
         if (blob.size() > wv.blob_cap) {
             if (wv.d_blob) {
                 CMOOP_CUDA_OK(cudaStreamSynchronize(stream));
@@ -494,9 +564,10 @@ struct Engine {
         for (int s = 0; s < N_STAGES; ++s) {
             StageLists& S = wv.st[s];
             fix(S.conv); fix(S.conv_eval); fix(S.dgrad); fix(S.post_fwd); fix(S.post_bn); fix(S.post_bwd);
+            fix(S.conv_tc); fix(S.dgrad_tc); fix(S.stat);
             fix(S.wgrad); fix(S.wreduce); fix(S.drop_fwd); fix(S.drop_bwd);
         }
-        fix(wv.head); fix(wv.ce_train); fix(wv.ce_val); fix(wv.ce_pred); fix(wv.adam); fix(wv.wt);
+        fix(wv.head); fix(wv.ce_train); fix(wv.ce_val); fix(wv.ce_pred); fix(wv.adam); fix(wv.wt); fix(wv.wt_bf16);
         return CMOOP_OK;
     }
 
@@ -513,12 +584,21 @@ struct Engine {
     // mode 0: training batch from the permutation; 1: validation loss/accuracy; 2: final predict (+confusion)
     int run_forward(Wave& wv, int mode, int step, int n_b) {
         const int training = mode == 0;
+        if (wv.weights_dirty && !wv.wt_bf16.h.empty()) {
+            CNN_LAUNCH(Launch::wt_bf16(wv.wt_bf16.d, (int)wv.wt_bf16.h.size(), wv.wt_bf16.total, stream));
+        }
+        wv.weights_dirty = false;
         for (int s = 0; s < N_STAGES; ++s) {
             StageLists& S = wv.st[s];
             if (s == ST_FC0) CNN_LAUNCH(Launch::gap_fwd(wv.head.d, (int)wv.head.h.size(), wv.head.total, n_b, stream));
-            if (S.conv.h.empty()) continue;
+            if (!S.any) continue;
             DevList<ConvTask>& cl = (s == 0 && !training) ? S.conv_eval : S.conv;
-            CNN_LAUNCH(Launch::conv(cl.d, (int)cl.h.size(), cl.total, n_b, step, stream));
+            if (!cl.h.empty()) CNN_LAUNCH(Launch::conv(cl.d, (int)cl.h.size(), cl.total, n_b, step, stream));
+            if (!S.conv_tc.h.empty()) {
+                CNN_LAUNCH(Launch::conv_tc(S.conv_tc.d, (int)S.conv_tc.h.size(), S.conv_tc.total, n_b, step, stream));
+                if (!S.stat.h.empty() && training)
+                    CNN_LAUNCH(Launch::bn_stats(S.stat.d, (int)S.stat.h.size(), S.stat.total, n_b, stream));
+            }
             if (!S.post_bn.h.empty())
                 CNN_LAUNCH(Launch::bn_finalize(S.post_bn.d, (int)S.post_bn.h.size(), n_b, training, cfg.bn_momentum,
                                                cfg.bn_eps, stream));
@@ -534,11 +614,11 @@ struct Engine {
     }
 
     int run_backward(Wave& wv, int step, int n_b) {
-        CNN_LAUNCH(Launch::wt(wv.wt.d, (int)wv.wt.h.size(), wv.wt.total, stream));
+        if (!wv.wt.h.empty()) CNN_LAUNCH(Launch::wt(wv.wt.d, (int)wv.wt.h.size(), wv.wt.total, stream));
         for (int s = N_STAGES - 1; s >= 0; --s) {
             StageLists& S = wv.st[s];
             if (s == ST_FC0 - 1) CNN_LAUNCH(Launch::gap_bwd(wv.head.d, (int)wv.head.h.size(), wv.head.total, n_b, stream));
-            if (S.conv.h.empty()) continue;
+            if (!S.any) continue;
             if (!S.drop_bwd.h.empty())      // dense: A (grad of the layer output) -> B (grad of the pre-activation)
                 CNN_LAUNCH(Launch::drop_bwd(S.drop_bwd.d, (int)S.drop_bwd.h.size(), S.drop_bwd.total, n_b, global_step,
                                             cfg.dropout_rate, stream));
@@ -553,6 +633,8 @@ struct Engine {
                 CNN_LAUNCH(Launch::reduce(S.wreduce.d, (int)S.wreduce.h.size(), S.wreduce.total, stream));
             if (!S.dgrad.h.empty())
                 CNN_LAUNCH(Launch::conv(S.dgrad.d, (int)S.dgrad.h.size(), S.dgrad.total, n_b, 0, stream));
+            if (!S.dgrad_tc.h.empty())
+                CNN_LAUNCH(Launch::conv_tc(S.dgrad_tc.d, (int)S.dgrad_tc.h.size(), S.dgrad_tc.total, n_b, 0, stream));
         }
         return CMOOP_OK;
     }
@@ -562,6 +644,7 @@ struct Engine {
         const double alpha = cfg.learning_rate * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t));
         CNN_LAUNCH(Launch::adam(wv.adam.d, (int)wv.adam.h.size(), wv.adam.total, (float)alpha, cfg.beta1, cfg.beta2,
                                 cfg.adam_eps, stream));
+        wv.weights_dirty = true;
         return CMOOP_OK;
     }
 
@@ -630,8 +713,8 @@ int check_config(const cmoop_genotype* g, int n, const cmoop_cnn_config* cfg) {
     CMOOP_REQUIRE(cfg->batch_size >= 1 && cfg->batch_size <= kBatch, "cnn: batch_size=%d outside [1,%d]", cfg->batch_size,
                   kBatch);
     CMOOP_REQUIRE(cfg->max_epochs >= 1 && cfg->patience >= 0, "cnn: bad epochs/patience");
-    if (cfg->precision != 0) {
-        cmoop::set_error("cnn: precision=%d not available in this build (0 = fp32 SIMT)", cfg->precision);
+    if (cfg->precision != 0 && cfg->precision != 1) {
+        cmoop::set_error("cnn: precision=%d unknown (0 = fp32 SIMT, 1 = bf16 tcgen05)", cfg->precision);
         return CMOOP_ERR_UNSUPPORTED;
     }
     for (int i = 0; i < n; ++i) {

@@ -172,3 +172,53 @@ def test_drop_in_records_and_early_stopping():
                         config=TrainConfig(variant="A", epochs=1))
     rec = bi.compute_objectives_and_constraints(pop[:1])[0]
     assert len(rec["objs"]) == 2 and "size_metric" in rec
+
+
+@pytest.mark.parametrize("variant,hp", [GENOTYPES[1], GENOTYPES[2], GENOTYPES[3], GENOTYPES[4]])
+def test_bf16_tensor_core_path_tracks_the_oracle(variant, hp):
+    """precision='bf16': convolutions with Cin >= 16 run on tcgen05 (bf16 operands, fp32 accumulation in TMEM).
+    The kernel itself is checked exactly in test_gpu_conv_tc.py.  Here, against the oracle with the SAME rounding
+    points (bf16_convs=True): loss 1e-3, dense-head gradients (downstream of no rounding) 2e-3; conv-stack gradients
+    only to 8e-2 relative L2 because a 1e-6 accumulation-order difference flips ~2.5e-4 of the bf16 roundings
+    (each a 0.4 % step), which in turn flips a few ReLU masks / pool argmaxes -- measured 2-5 %.  Against the
+    unrounded fp64 oracle: cosine similarity of the full gradient >= 0.99."""
+    import torch
+    from cmoop_audio_processing_b200.problem import FitnessProblem, TrainConfig
+    xt, yt, xv, yv = make_data()
+    seed = 4321
+    prob = FitnessProblem(xt, yt, xv, yv, classes=N_CLASSES, config=TrainConfig(variant=variant, epochs=2, precision="bf16"))
+    init = prob.debug_init_params(hp, seed)
+    perm = prob.debug_permutation(seed, 0)
+    losses, grads, _ = prob.debug_train_steps(hp, seed, 5)
+    idx = perm[:64]
+    g, l0 = {}, {}
+    for mirror in (True, False):
+        model = cnn_ref.RefModel(hp, N_CLASSES, variant, unflatten(init, hp, variant), dtype=torch.float64, bf16_convs=mirror)
+        p = model.forward(torch.from_numpy(xt[idx]), training=True, drop_ctx=(seed & 0xFFFFFFFF, 0))
+        loss0 = cnn_ref.keras_sparse_ce(p, torch.from_numpy(yt[idx]).long()).mean()
+        loss0.backward()
+        g[mirror], l0[mirror] = flat_grads(model, hp, variant).astype(np.float64), float(loss0.detach())
+    assert losses[0] == pytest.approx(l0[True], rel=1e-3)
+    assert np.linalg.norm(grads - g[True]) <= 8e-2 * np.linalg.norm(g[True])
+    n_head = N_CLASSES * 64 + N_CLASSES                               # output layer: exact fp32 path on both sides
+    assert np.linalg.norm(grads[-n_head:] - g[True][-n_head:]) <= 2e-3 * np.linalg.norm(g[True][-n_head:])
+    cos = float(np.dot(grads, g[False]) / (np.linalg.norm(grads) * np.linalg.norm(g[False])))
+    assert cos >= 0.99
+    assert losses[0] == pytest.approx(l0[False], rel=2e-2)
+    model = cnn_ref.RefModel(hp, N_CLASSES, variant, unflatten(init, hp, variant), bf16_convs=True)
+    ref_losses, _ = cnn_ref.train_steps(model, xt, yt, perm, 5, seed=seed & 0xFFFFFFFF)
+    np.testing.assert_allclose(losses, ref_losses, rtol=1e-2)
+
+
+def test_bf16_and_fp32_paths_agree_after_training():
+    from cmoop_audio_processing_b200.problem import FitnessProblem, TrainConfig
+    xt, yt, xv, yv = make_data(384, 192)
+    hps = [hp for _, hp in GENOTYPES]
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        cfg = TrainConfig(variant="B", epochs=4, patience=4, restore_best_weights=True, acc_from="evaluate", precision=prec)
+        prob = FitnessProblem(xt, yt, xv, yv, classes=N_CLASSES, config=cfg)
+        outs[prec], _ = prob.train_eval(hps, [5, 6, 7, 8, 9])
+    np.testing.assert_array_equal(outs["fp32"][:, 1], outs["bf16"][:, 1])          # size is exact in both
+    assert np.abs(outs["fp32"][:, 0] - outs["bf16"][:, 0]).max() <= 0.08          # accuracy after 4 epochs
+    assert np.abs(outs["fp32"][:, 5] - outs["bf16"][:, 5]).max() <= 0.15          # best validation loss
