@@ -144,6 +144,83 @@ def time_cpu_port(target_seconds: float, threads_note: bool = True) -> dict:
                       "(oracle/c/mfcc_oracle.c; the reference has no feature-extraction code to time)"}
 
 
+def cnn_generation_extra(args, rank: int, world: int) -> dict:
+    """Secondary measurement (BASELINE metric part 1): true candidate evaluations per second for one
+    compute_objectives_and_constraints call on synthetic GSC-shaped features (SA-NSGA-II infill batch, CNN variant B,
+    12 classes), next to the torch-CPU oracle timed on a bounded sample.  Not the headline `value`."""
+    import random
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from cmoop_audio_processing_b200.nsga import HPARAM_SPACE
+    from cmoop_audio_processing_b200.problem import FitnessProblem, TrainConfig, forward_macs
+
+    n_train, n_val, epochs, pop = args.cnn_train, 768, args.cnn_epochs, args.cnn_pop * world
+    rng = np.random.default_rng(1234)
+    xt = rng.standard_normal((n_train, 49, 40, 1)).astype(np.float32)
+    yt = rng.integers(0, 12, n_train)
+    xv = rng.standard_normal((n_val, 49, 40, 1)).astype(np.float32)
+    yv = rng.integers(0, 12, n_val)
+    pyr = random.Random(0)
+    hps = [{k: pyr.choice(v) for k, v in HPARAM_SPACE.items()} for _ in range(pop)]
+    out = {}
+    for prec in ("bf16", "fp32"):
+        cfg = TrainConfig(variant="B", epochs=epochs, patience=epochs, restore_best_weights=True, acc_from="evaluate",
+                          precision=prec)
+        prob = FitnessProblem(xt, yt, xv, yv, classes=12, config=cfg)
+        prob.train_eval(hps[:1], [0])
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        recs = prob.compute_objectives_and_constraints(hps)          # sharded over ranks + all-gather when world > 1
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt[0])
+        macs = [forward_macs(hp, 49, 40, 12, "B") for hp in hps]
+        flops = sum(epochs * (6 * m * n_train + 2 * m * n_val) + 2 * m * n_val for m in macs)
+        out[prec] = {"evals_per_sec": pop / dt, "seconds": dt, "analytic_tflops": flops / dt / 1e12,
+                     "records": len(recs)}
+        prob.data.close()
+    res = {"workload": f"{pop} random genotypes (variant B), {n_train} train / {n_val} val 49x40 features, {epochs} epochs "
+                       "fixed, batch 64, Adam; one compute_objectives_and_constraints call",
+           "gpu": out}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cnn_ref
+        hp = sorted(zip(macs, range(pop)))[pop // 2][1]
+        hp = hps[hp]
+        m = forward_macs(hp, 49, 40, 12, "B")
+        torch.set_num_threads(os.cpu_count() or 1)
+        shapes = cnn_ref.param_shapes(hp, 12, "B")
+        prng = np.random.default_rng(0)
+        params = {}
+        for name, shape in shapes:
+            if name.endswith(".w"):
+                params[name] = (prng.standard_normal(shape) * 0.05).astype(np.float32)
+            elif name.endswith((".gamma", ".var")):
+                params[name] = np.ones(shape, np.float32)
+            else:
+                params[name] = np.zeros(shape, np.float32)
+        model = cnn_ref.RefModel(hp, 12, "B", params)
+        steps = 6
+        cnn_ref.train_steps(model, xt, yt, np.arange(n_train), 1)
+        t0 = time.perf_counter()
+        cnn_ref.train_steps(model, xt, yt, np.arange(n_train), steps, start_step=1)
+        dt = time.perf_counter() - t0
+        cpu_flops = 6 * m * 64 * steps / dt
+        total_flops = sum(epochs * (6 * mm * n_train + 2 * mm * n_val) + 2 * mm * n_val for mm in macs)
+        res["cpu_baseline"] = {"kind": "port", "cores": os.cpu_count(),
+                               "sample": f"{steps} Adam steps (batch 64) of the median-cost genotype with the torch-CPU fp32 "
+                                         "oracle (TensorFlow is not installable here), extrapolated by analytic FLOPs",
+                               "cpu_tflops": cpu_flops / 1e12,
+                               "evals_per_sec": pop / (total_flops / cpu_flops)}
+    return res
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -281,6 +358,17 @@ def run_ours(args) -> None:
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = time_cpu_port(args.cpu_seconds)
+    extra = None
+    if not args.no_cnn:
+        del wave, out, h_wave, h_out, np_wave, np_out
+        torch.cuda.empty_cache()
+        try:
+            extra = cnn_generation_extra(args, rank, world)
+        except Exception as exc:                                   # the headline line must still be printed
+            extra = {"error": repr(exc)}
+    if rank == 0:
+        if extra is not None:
+            line["candidate_evaluation"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -295,6 +383,10 @@ def main() -> None:
     ap.add_argument("--clips", type=int, default=65536, help="clips per GPU (BASELINE configs[1]: 65 536)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size in seconds of work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cnn", action="store_true", help="skip the secondary candidate-evaluation measurement")
+    ap.add_argument("--cnn-pop", type=int, default=32, help="candidates per GPU for the secondary measurement")
+    ap.add_argument("--cnn-train", type=int, default=3072)
+    ap.add_argument("--cnn-epochs", type=int, default=2)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                            # timing rule: W >= 3

@@ -167,6 +167,8 @@ struct Params {
     long long n_frames_total;
     int n_samples, frames_per_clip, frame_length, hop, half_len;
     int n_mels, n_out, use_dct, vec2, mel_mode, dct_mode;
+    int runs_per_clip, frames_per_run;   // FAST path: a warp walks a run of consecutive frames of one clip
+    long long total_runs;
     float log_floor;
 };
 
@@ -175,10 +177,17 @@ static_assert(2 * 16 * kTileStride >= 2 * kZPlane, "natural-order planes must fi
 static_assert(2 * 16 * kTileStride >= 2 * kMaxFlush * 32 + 2 * kMaxMel, "mel partials + logmel + folded input must fit in the tile");
 static_assert(kPowFloats >= kBins, "power buffer too small");
 
-template <int NZ>
-__global__ void __launch_bounds__(kWarps * 32, 3) mfcc_kernel(Params p) {
+// FAST = 0: any supported configuration, one independent frame per warp iteration.
+// FAST = 1 / 2: the default 640/320/40-mel configuration without / with the 40-point DCT, everything that
+// depends on the configuration folded at compile time; a warp walks consecutive frames of one clip, keeps the
+// overlapping half frame in registers (frame t+1 re-uses rows a+5 of frame t as its rows a) and prefetches the
+// next half frame while the current FFT runs, so every sample is loaded exactly once and never waited for.
+template <int NZ, int FAST>
+__global__ void __launch_bounds__(kWarps * 32, FAST ? 2 : 3) mfcc_kernel(Params p) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_mels = FAST ? 40 : p.n_mels, n_out = FAST ? 40 : p.n_out;
+    const int use_dct = FAST ? (FAST == 2) : p.use_dct, mel_mode = FAST ? 1 : p.mel_mode, dct_mode = FAST ? 1 : p.dct_mode;
     // ---- stage tables once per CTA
     for (int i = threadIdx.x; i < p.t.total; i += blockDim.x) smem[i] = p.tables[i];
     __syncthreads();
@@ -192,7 +201,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) mfcc_kernel(Params p) {
     const int2* s_comb = reinterpret_cast<const int2*>(smem + p.t.mel_comb);
     const float* s_dct = smem + p.t.dct;
     const float* s_dcth = smem + p.t.dcth;
-    const unsigned flush_mask = p.mel_mode ? reinterpret_cast<const unsigned*>(smem + p.t.mel_flush)[lane] : 0u;
+    const unsigned flush_mask = mel_mode ? reinterpret_cast<const unsigned*>(smem + p.t.mel_flush)[lane] : 0u;
     const float* s_mean = smem + p.t.mean;
     const float* s_inv = smem + p.t.inv_scale;
     float* w_base = smem + ((p.t.total + 3) & ~3) + warp * kWarpFloats;
@@ -209,34 +218,10 @@ __global__ void __launch_bounds__(kWarps * 32, 3) mfcc_kernel(Params p) {
 
     const int h = lane & 1, k1o = lane >> 1;
     const long long stride = (long long)gridDim.x * kWarps;
-    for (long long f = (long long)blockIdx.x * kWarps + warp; f < p.n_frames_total; f += stride) {
-        const long long clip = f / p.frames_per_clip;
-        const int t = (int)(f - clip * p.frames_per_clip);
-        const float* src = p.wave + (size_t)clip * p.n_samples + (size_t)t * p.hop;
+    const long long first = (long long)blockIdx.x * kWarps + warp;
 
-        // ---- load + window: lane holds z[32a + lane]
-        float2 v[16];
-#pragma unroll
-        for (int a = 0; a < 16; ++a) {
-            if (a < NZ) {
-                const int n = 32 * a + lane;
-                float2 x = make_float2(0.f, 0.f);
-                if (n < p.half_len) {
-                    if (p.vec2) {
-                        x = __ldg(reinterpret_cast<const float2*>(src) + n);
-                    } else {
-                        x.x = __ldg(src + 2 * n);
-                        x.y = __ldg(src + 2 * n + 1);
-                    }
-                    const float2 w = s_win[n];
-                    x.x *= w.x;
-                    x.y *= w.y;
-                }
-                v[a] = x;
-            } else {
-                v[a] = make_float2(0.f, 0.f);
-            }
-        }
+    // everything after the (windowed) samples are in registers: FFT -> power -> mel -> log -> [DCT] -> store
+    auto compute = [&](float2 (&v)[16], long long f) {
         // ---- radix-16 over a, W512 twiddle, transpose
         dft16<NZ>(v);
         static_for<0, 16>([&](auto ic) {
@@ -293,7 +278,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) mfcc_kernel(Params p) {
         }
         __syncwarp();
         // ---- mel + log
-        if (p.mel_mode) {
+        if (mel_mode) {
             // lane owns bins [17*lane, 17*lane+17): conflict-free; every bin feeds the rising edge of band s and
             // the falling edge of band s-1 (s = its mel segment); partial sums are flushed at segment ends
             float accr = 0.f, accf = 0.f;
@@ -305,13 +290,12 @@ __global__ void __launch_bounds__(kWarps * 32, 3) mfcc_kernel(Params p) {
                 const float2 w = s_melwt[k0 + i];
                 accr = fmaf(w.x, pw, accr);
                 accf = fmaf(w.y, pw, accf);
-                if (flush_mask & (1u << i)) {
-                    part_r[nfl * 32 + lane] = accr;
-                    part_f[nfl * 32 + lane] = accf;
-                    accr = 0.f;
-                    accf = 0.f;
-                    ++nfl;
-                }
+                const bool fl = (flush_mask >> i) & 1u;
+                if (fl) part_r[nfl * 32 + lane] = accr;
+                if (fl) part_f[nfl * 32 + lane] = accf;
+                accr = fl ? 0.f : accr;
+                accf = fl ? 0.f : accf;
+                nfl += fl ? 1 : 0;
             }
             __syncwarp();
             float mel[2];
@@ -319,7 +303,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) mfcc_kernel(Params p) {
             for (int rnd = 0; rnd < 2; ++rnd) {
                 const int b = lane + 32 * rnd;
                 float acc = 0.f;
-                if (b < p.n_mels) {
+                if (b < n_mels) {
                     const int2 cb = s_comb[b];
                     int n = cb.x >> 16;
                     if (n) {
@@ -340,10 +324,10 @@ __global__ void __launch_bounds__(kWarps * 32, 3) mfcc_kernel(Params p) {
 #pragma unroll
             for (int rnd = 0; rnd < 2; ++rnd) {
                 const int b = lane + 32 * rnd;
-                if (b < p.n_mels) s_lm[b] = 10.f * log10f(fmaxf(mel[rnd], p.log_floor));
+                if (b < n_mels) s_lm[b] = 10.f * log10f(fmaxf(mel[rnd], p.log_floor));
             }
         } else {
-            for (int b = lane; b < p.n_mels; b += 32) {
+            for (int b = lane; b < n_mels; b += 32) {
                 const int2 meta = s_meta[b];
                 const int cnt = s_cnt[b];
                 float acc = 0.f;
@@ -353,49 +337,49 @@ __global__ void __launch_bounds__(kWarps * 32, 3) mfcc_kernel(Params p) {
         }
         __syncwarp();
         // ---- DCT / standardise / store
-        float* dst = p.out + (size_t)f * p.n_out;
-        if (p.use_dct && p.dct_mode) {
+        float* dst = p.out + (size_t)f * n_out;
+        if (use_dct && dct_mode) {
             // D[c][n-1-b] = (-1)^c D[c][b]: fold the input once, halve the multiply-adds
-            const int half = p.n_mels >> 1;
+            const int half = n_mels >> 1;
             for (int b = lane; b < half; b += 32) {
-                const float a = s_lm[b], z = s_lm[p.n_mels - 1 - b];
+                const float a = s_lm[b], z = s_lm[n_mels - 1 - b];
                 s_sd[b] = a + z;
                 s_sd[half + b] = a - z;
             }
             __syncwarp();
-            if (lane < p.n_out) {
+            if (lane < n_out) {
                 const float* sd = s_sd + (lane & 1) * half;
                 float acc = 0.f;
-                for (int b = 0; b < half; ++b) acc = fmaf(s_dcth[b * p.n_out + lane], sd[b], acc);
+                for (int b = 0; b < half; ++b) acc = fmaf(s_dcth[b * n_out + lane], sd[b], acc);
                 dst[lane] = (acc - s_mean[lane]) * s_inv[lane];
             }
-            const int rem = p.n_out - 32;
+            const int rem = n_out - 32;
             if (rem > 0 && rem <= 8) {
                 // the last <= 8 coefficients: 4 lanes per coefficient, strided terms, two shuffles
                 const int c = 32 + (lane >> 2), part = lane & 3;
                 float acc = 0.f;
-                if (c < p.n_out) {
+                if (c < n_out) {
                     const float* sd = s_sd + (c & 1) * half;
-                    for (int b = part; b < half; b += 4) acc = fmaf(s_dcth[b * p.n_out + c], sd[b], acc);
+                    for (int b = part; b < half; b += 4) acc = fmaf(s_dcth[b * n_out + c], sd[b], acc);
                 }
                 acc += __shfl_xor_sync(0xffffffffu, acc, 1);
                 acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                if (part == 0 && c < p.n_out) dst[c] = (acc - s_mean[c]) * s_inv[c];
+                if (part == 0 && c < n_out) dst[c] = (acc - s_mean[c]) * s_inv[c];
             } else if (rem > 0) {
                 const int c = 32 + lane;
-                if (c < p.n_out) {
+                if (c < n_out) {
                     const float* sd = s_sd + (c & 1) * half;
                     float acc = 0.f;
-                    for (int b = 0; b < half; ++b) acc = fmaf(s_dcth[b * p.n_out + c], sd[b], acc);
+                    for (int b = 0; b < half; ++b) acc = fmaf(s_dcth[b * n_out + c], sd[b], acc);
                     dst[c] = (acc - s_mean[c]) * s_inv[c];
                 }
             }
         } else {
-            for (int c = lane; c < p.n_out; c += 32) {
+            for (int c = lane; c < n_out; c += 32) {
                 float acc;
-                if (p.use_dct) {
+                if (use_dct) {
                     acc = 0.f;
-                    for (int b = 0; b < p.n_mels; ++b) acc = fmaf(s_dct[b * p.n_out + c], s_lm[b], acc);
+                    for (int b = 0; b < n_mels; ++b) acc = fmaf(s_dct[b * n_out + c], s_lm[b], acc);
                 } else {
                     acc = s_lm[c];
                 }
@@ -403,6 +387,72 @@ __global__ void __launch_bounds__(kWarps * 32, 3) mfcc_kernel(Params p) {
             }
         }
         __syncwarp();
+    };
+
+    if constexpr (FAST == 0) {
+        for (long long f = first; f < p.n_frames_total; f += stride) {
+            const long long clip = f / p.frames_per_clip;
+            const int t = (int)(f - clip * p.frames_per_clip);
+            const float* src = p.wave + (size_t)clip * p.n_samples + (size_t)t * p.hop;
+            // ---- load + window: lane holds z[32a + lane]
+            float2 v[16];
+#pragma unroll
+            for (int a = 0; a < 16; ++a) {
+                if (a < NZ) {
+                    const int n = 32 * a + lane;
+                    float2 x = make_float2(0.f, 0.f);
+                    if (n < p.half_len) {
+                        if (p.vec2) {
+                            x = __ldg(reinterpret_cast<const float2*>(src) + n);
+                        } else {
+                            x.x = __ldg(src + 2 * n);
+                            x.y = __ldg(src + 2 * n + 1);
+                        }
+                        const float2 w = s_win[n];
+                        x.x *= w.x;
+                        x.y *= w.y;
+                    }
+                    v[a] = x;
+                } else {
+                    v[a] = make_float2(0.f, 0.f);
+                }
+            }
+            compute(v, f);
+        }
+    } else {
+        constexpr int HZ = NZ / 2;            // rows of 32 float2 per hop (hop == frame_length / 2 == 64 * HZ samples)
+        for (long long run = first; run < p.total_runs; run += stride) {
+            const long long clip = run / p.runs_per_clip;
+            const int part = (int)(run - clip * p.runs_per_clip);
+            const int t0 = part * p.frames_per_run;
+            const int t1 = min(p.frames_per_clip, t0 + p.frames_per_run);
+            if (t0 >= t1) continue;
+            const float2* src = reinterpret_cast<const float2*>(p.wave + (size_t)clip * p.n_samples + (size_t)t0 * p.hop);
+            float2 keep[HZ], nxt[HZ];
+#pragma unroll
+            for (int a = 0; a < HZ; ++a) {
+                keep[a] = __ldg(src + 32 * a + lane);
+                nxt[a] = __ldg(src + 32 * (a + HZ) + lane);
+            }
+            for (int t = t0; t < t1; ++t) {
+                float2 v[16];
+#pragma unroll
+                for (int a = 0; a < HZ; ++a) {
+                    const float2 w0 = s_win[32 * a + lane], w1 = s_win[32 * (a + HZ) + lane];
+                    v[a] = make_float2(keep[a].x * w0.x, keep[a].y * w0.y);
+                    v[a + HZ] = make_float2(nxt[a].x * w1.x, nxt[a].y * w1.y);
+                    keep[a] = nxt[a];
+                }
+#pragma unroll
+                for (int a = NZ; a < 16; ++a) v[a] = make_float2(0.f, 0.f);
+                if (t + 1 < t1) {
+                    const float2* nsrc = src + (size_t)(t + 1 - t0) * (32 * HZ);
+#pragma unroll
+                    for (int a = 0; a < HZ; ++a) nxt[a] = __ldg(nsrc + 32 * (a + HZ) + lane);
+                }
+                compute(v, clip * p.frames_per_clip + t);
+            }
+        }
     }
 }
 
@@ -438,14 +488,14 @@ int upload_tables(cmoop_mfcc* h) {
     return CMOOP_OK;
 }
 
-template <int NZ>
+template <int NZ, int FAST = 0>
 int launch_nz(const Params& p, int grid, size_t smem, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        CMOOP_CUDA_OK(cudaFuncSetAttribute(mfcc_kernel<NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CMOOP_CUDA_OK(cudaFuncSetAttribute(mfcc_kernel<NZ, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
-    mfcc_kernel<NZ><<<grid, kWarps * 32, smem, st>>>(p);
+    mfcc_kernel<NZ, FAST><<<grid, kWarps * 32, smem, st>>>(p);
     cmoop::count_launch();
     CMOOP_CUDA_OK(cudaGetLastError());
     return CMOOP_OK;
@@ -698,10 +748,26 @@ int cmoop_mfcc_fwd_dev(cmoop_mfcc_handle h, const float* wave, int64_t n_clips, 
     p.dct_mode = h->dct_mode;
     p.vec2 = (n_samples % 2 == 0) && (h->cfg.hop % 2 == 0) && (((uintptr_t)wave & 7u) == 0);
     p.log_floor = h->cfg.log_floor;
+    cudaStream_t st = (cudaStream_t)stream;
+    const auto& c = h->cfg;
+    const bool fast = c.frame_length == 640 && c.hop == 320 && c.n_mels == 40 && (c.n_mfcc == 0 || c.n_mfcc == 40) &&
+                      h->mel_mode == 1 && h->dct_mode == 1 && p.vec2;
+    if (fast) {
+        // runs of consecutive frames: about two runs per resident warp, at most one clip per run
+        const long long warps = (long long)h->sm_count * 2 * kWarps;
+        long long rpc = (2 * warps + n_clips - 1) / n_clips;
+        rpc = rpc < 1 ? 1 : (rpc > frames ? frames : rpc);
+        p.frames_per_run = (int)((frames + rpc - 1) / rpc);
+        p.runs_per_clip = (frames + p.frames_per_run - 1) / p.frames_per_run;
+        p.total_runs = (long long)n_clips * p.runs_per_clip;
+        const long long blocks_needed = (p.total_runs + kWarps - 1) / kWarps;
+        const long long persistent = (long long)h->sm_count * 2;
+        const int grid = (int)(blocks_needed < persistent ? blocks_needed : persistent);
+        return c.n_mfcc == 0 ? launch_nz<10, 1>(p, grid, h->smem_bytes, st) : launch_nz<10, 2>(p, grid, h->smem_bytes, st);
+    }
     const long long blocks_needed = (p.n_frames_total + kWarps - 1) / kWarps;
     const long long persistent = (long long)h->sm_count * 3;
     const int grid = (int)(blocks_needed < persistent ? blocks_needed : persistent);
-    cudaStream_t st = (cudaStream_t)stream;
     switch (h->nz) {
         case 1: case 2: case 3: case 4: case 5: case 6: case 7: case 8:
             return launch_nz<8>(p, grid, h->smem_bytes, st);
