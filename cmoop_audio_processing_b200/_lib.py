@@ -73,6 +73,8 @@ SIGNATURES = {
     "cmoop_cnn_debug_permutation": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.c_void_p]),
     "cmoop_cnn_debug_conv": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "cmoop_cnn_debug_wgrad": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cmoop_cnn_debug_train_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p,
                                               C.c_void_p, C.c_void_p]),
 }

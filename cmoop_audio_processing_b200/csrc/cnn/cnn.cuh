@@ -46,6 +46,15 @@ struct TcConvTask {
     int tiles_n, tile_begin;
 };
 
+struct TcWgradTask {
+    const float* x;              // forward input of the conv (fp32 NHWC)
+    const float* dy;             // [M][Cout] fp32
+    float* out;                  // grad [K+1][Cout] (splits == 1) or workspace [splits][K+1][Cout]
+    int H, W, Cin, Ho, Wo, Cout, k, stride, pad;
+    int splits, m_chunk;         // m_chunk multiple of 64
+    int bn, tiles_k, tiles_n, tile_begin;
+};
+
 struct WtBf16Task {
     const float* w;              // fp32 HWIO master weights
     __nv_bfloat16* out;
@@ -186,6 +195,7 @@ struct Launch {
     static int adam(const AdamTask* tasks, int n_tasks, int total_blocks, float alpha, float b1, float b2, float eps, void* stream);
     static int init(const InitTask* tasks, int n_tasks, int total_blocks, void* stream);
     static int conv_tc(const TcConvTask* tasks, int n_tasks, int total_tiles, int n_b, int step, void* stream);
+    static int wgrad_tc(const TcWgradTask* tasks, int n_tasks, int total_tiles, int n_b, void* stream);
     static int wt_bf16(const WtBf16Task* tasks, int n_tasks, int total_blocks, void* stream);
     static int bn_stats(const StatTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
 };

@@ -289,6 +289,193 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcConvTask
     }
 }
 
+// MN-major, SWIZZLE_128B descriptor: 64-element (128-byte) groups along M/N `lbo` bytes apart, 8-row groups
+// along K 1024 bytes apart (rows = K index, 128 bytes each).
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Weight gradient on tcgen05:  dW[kk][co] (+ bias row kk == K) = sum_m im2col(x)[m][kk] * dy[m][co].
+// The reduction runs over pixels, so both operands are MN-major: a stage holds 64 pixels (UMMA K) as rows of
+// 128 bytes -- A: two 64-wide kk groups (UMMA M = 128), B: bn/64 co groups -- which is exactly the natural
+// [pixel][channel] order of the im2col row and of dy.  Split-M partials are written per split (deterministic).
+__global__ void __launch_bounds__(TC_THREADS, 2) wgrad_tc_kernel(const TcWgradTask* __restrict__ tasks, int n_tasks,
+                                                                 int n_b) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ TcWgradTask T;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        int lo = 0, hi = n_tasks - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (tasks[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+        }
+        T = tasks[lo];
+    }
+    __syncthreads();
+    int local = blockIdx.x - T.tile_begin;
+    const int per_split = T.tiles_k * T.tiles_n;
+    const int split = local / per_split;
+    local -= split * per_split;
+    const int tk = local / T.tiles_n, tn = local - tk * T.tiles_n;
+    const int HoWo = T.Ho * T.Wo, M = n_b * HoWo;
+    const int K = T.k * T.k * T.Cin, Kext = K + 1;
+    const int kk0 = tk * 128, n0 = tn * T.bn;
+    const int m_begin = split * T.m_chunk;
+    const int m_end = min(M, m_begin + T.m_chunk);
+    float* out = T.out + (long long)split * Kext * T.Cout;
+    const int num_st = m_end > m_begin ? (m_end - m_begin + 63) / 64 : 0;
+    if (num_st == 0) {                      // empty split (partial last batch): its partial must still be zero
+        for (int e = tid; e < 128 * T.bn; e += TC_THREADS) {
+            const int r = e / T.bn, c = e - r * T.bn;
+            if (kk0 + r < Kext) out[(long long)(kk0 + r) * T.Cout + n0 + c] = 0.f;
+        }
+        return;
+    }
+
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_smem = base;
+    uint8_t* b_smem = base + TC_STAGES * TC_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + TC_STAGES * (TC_A_BYTES + TC_B_BYTES));
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + TC_STAGES;
+    uint64_t* accum_bar = bars + 2 * TC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&full_bar[s], 128);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ---- producers: thread owns chunk column c16 (8 consecutive kk / co) and rows r_lo + 8 i of the stage
+        const int c16 = tid & 15, r_lo = tid >> 4;
+        const long long img = (long long)T.H * T.W * T.Cin;
+        const int kk = kk0 + c16 * 8;
+        int kh = 0, kw = 0, ci = 0, a_kind;             // a_kind 0: zeros, 1: im2col taps, 2: chunk containing the ones column
+        if (kk + 7 < K) {
+            a_kind = 1;
+            const int pos = kk / T.Cin;
+            ci = kk - pos * T.Cin;
+            kh = pos / T.k;
+            kw = pos - kh * T.k;
+        } else {
+            a_kind = (kk <= K && K < kk + 8) ? 2 : 0;   // K is a multiple of 8, so the ones column starts a chunk
+        }
+        const bool b_on = c16 * 8 < T.bn;
+        const uint32_t a_off = (uint32_t)(c16 >> 3) * 8192u, a_chunk = (uint32_t)(c16 & 7);
+        for (int st = 0; st < num_st; ++st) {
+            const int s = st % TC_STAGES;
+            const uint32_t ph = (uint32_t)(st / TC_STAGES) & 1u;
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            uint8_t* a_st = a_smem + s * TC_A_BYTES;
+            uint8_t* b_st = b_smem + s * TC_B_BYTES;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = r_lo + 8 * i;
+                const int m = m_begin + st * 64 + r;
+                uint4 va = make_uint4(0u, 0u, 0u, 0u), vb = make_uint4(0u, 0u, 0u, 0u);
+                if (m < m_end) {
+                    if (a_kind == 1) {
+                        const int n = m / HoWo, rr = m - n * HoWo;
+                        const int ho = rr / T.Wo, wo = rr - ho * T.Wo;
+                        const int hi = ho * T.stride - T.pad + kh, wi = wo * T.stride - T.pad + kw;
+                        if ((unsigned)hi < (unsigned)T.H && (unsigned)wi < (unsigned)T.W) {
+                            const float4* src = reinterpret_cast<const float4*>(T.x + (long long)n * img + ((long long)hi * T.W + wi) * T.Cin + ci);
+                            const float4 f0 = __ldg(src), f1 = __ldg(src + 1);
+                            va.x = pack_bf16(f0.x, f0.y); va.y = pack_bf16(f0.z, f0.w);
+                            va.z = pack_bf16(f1.x, f1.y); va.w = pack_bf16(f1.z, f1.w);
+                        }
+                    } else if (a_kind == 2) {
+                        va.x = 0x00003F80u;             // bf16(1.0) in the first element: the bias-gradient row
+                    }
+                    if (b_on) {
+                        const float4* src = reinterpret_cast<const float4*>(T.dy + (long long)m * T.Cout + n0 + c16 * 8);
+                        const float4 f0 = __ldg(src), f1 = __ldg(src + 1);
+                        vb.x = pack_bf16(f0.x, f0.y); vb.y = pack_bf16(f0.z, f0.w);
+                        vb.z = pack_bf16(f1.x, f1.y); vb.w = pack_bf16(f1.z, f1.w);
+                    }
+                }
+                const uint32_t row_off = (uint32_t)r * 128u + ((a_chunk ^ (uint32_t)(r & 7)) << 4);
+                *reinterpret_cast<uint4*>(a_st + a_off + row_off) = va;
+                if (b_on) *reinterpret_cast<uint4*>(b_st + a_off + row_off) = vb;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&full_bar[s]);
+        }
+        // ---- epilogue: D rows = kk, columns = co
+        mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = warp * 32 + lane;
+        const int krow = kk0 + row;
+        for (int c0 = 0; c0 < T.bn; c0 += 16) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (krow < Kext) {
+                float* dst = out + (long long)krow * T.Cout + n0 + c0;
+#pragma unroll
+                for (int q = 0; q < 16; q += 4)
+                    *reinterpret_cast<float4*>(dst + q) = make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]),
+                                                                      __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        if (lane == 0) {
+            uint32_t idesc = make_idesc_bf16(T.bn);
+            idesc |= (1u << 15) | (1u << 16);            // A and B are MN-major
+            for (int st = 0; st < num_st; ++st) {
+                const int s = st % TC_STAGES;
+                const uint32_t ph = (uint32_t)(st / TC_STAGES) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = smem_u32(a_smem + s * TC_A_BYTES);
+                const uint32_t b_addr = smem_u32(b_smem + s * TC_B_BYTES);
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {           // 16 pixels (rows) per MMA: 2 KiB further down
+                    const uint64_t ad = make_desc_mn_sw128(a_addr + k4 * 2048, 8192);
+                    const uint64_t bd = make_desc_mn_sw128(b_addr + k4 * 2048, 8192);
+                    umma_bf16(tmem_base, ad, bd, idesc, (st | k4) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(accum_bar);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // bf16 K-major weight copies: mode 0 forward [Cout][K_pad], mode 1 data-gradient [Cin][K'_pad]
 __global__ void __launch_bounds__(256) wt_bf16_kernel(const WtBf16Task* __restrict__ tasks, int n_tasks) {
     int lo = 0, hi = n_tasks - 1;
@@ -369,6 +556,17 @@ int Launch::conv_tc(const TcConvTask* tasks, int n, int tiles, int n_b, int step
         configured = true;
     }
     conv_tc_kernel<<<tiles, TC_THREADS, TC_SMEM, (cudaStream_t)st>>>(tasks, n, n_b, step);
+    return (int)cudaGetLastError();
+}
+int Launch::wgrad_tc(const TcWgradTask* tasks, int n, int tiles, int n_b, void* st) {
+    if (n == 0 || tiles == 0) return 0;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    wgrad_tc_kernel<<<tiles, TC_THREADS, TC_SMEM, (cudaStream_t)st>>>(tasks, n, n_b);
     return (int)cudaGetLastError();
 }
 int Launch::wt_bf16(const WtBf16Task* tasks, int n, int blocks, void* st) {

@@ -212,7 +212,8 @@ void build_units(Cand& c, const cmoop_cnn_config& cfg, int H, int W, int batch) 
         u.bwd_rows = (int)(((npix + 127) / 128) * (128 / cb));
         int splits = (int)std::min<long long>(32, std::max<long long>(1, M / 2048));
         int chunk = (int)((M + splits - 1) / splits);
-        chunk = (chunk + 15) / 16 * 16;
+        const int gran = u.tc ? 64 : 16;
+        chunk = (chunk + gran - 1) / gran * gran;
         splits = (int)((M + chunk - 1) / chunk);
         u.wg_splits = splits;
         u.wg_chunk = chunk;
@@ -287,6 +288,7 @@ struct DevList {
 struct StageLists {
     DevList<ConvTask> conv, conv_eval, dgrad;
     DevList<TcConvTask> conv_tc, dgrad_tc;
+    DevList<TcWgradTask> wgrad_tc;
     DevList<StatTask> stat;
     bool any = false;
     DevList<PostTask> post_fwd, post_bn, post_bwd;
@@ -448,18 +450,33 @@ struct Engine {
                 {
                     const bool to_ws = u.wg_splits > 1;
                     const int kext = u.k * u.k * u.cin + 1;
-                    WgradTask g{};
-                    g.x = xin;
-                    if (u.input == -1) { g.gather = c.perm; g.gather_step = batch; }
-                    g.dy = u.is_skip ? c.gS : (u.stage == ST_OUT ? c.dlogits : c.gB);
-                    g.out = to_ws ? c.wg_ws : c.grad + u.w_off;
-                    g.H = u.H; g.W = u.W; g.Cin = u.cin; g.Ho = u.Ho; g.Wo = u.Wo; g.Cout = u.cout;
-                    g.k = u.k; g.stride = u.stride; g.pad = u.pad;
-                    g.splits = u.wg_splits; g.m_chunk = u.wg_chunk;
-                    g.tiles_k = (kext + 63) / 64; g.tiles_n = (u.cout + 63) / 64;
-                    g.tile_begin = S.wgrad.total;
-                    S.wgrad.h.push_back(g);
-                    S.wgrad.total += g.tiles_k * g.tiles_n * g.splits;
+                    const float* dy = u.is_skip ? c.gS : (u.stage == ST_OUT ? c.dlogits : c.gB);
+                    float* dst = to_ws ? c.wg_ws : c.grad + u.w_off;
+                    if (u.tc) {
+                        TcWgradTask g{};
+                        g.x = xin; g.dy = dy; g.out = dst;
+                        g.H = u.H; g.W = u.W; g.Cin = u.cin; g.Ho = u.Ho; g.Wo = u.Wo; g.Cout = u.cout;
+                        g.k = u.k; g.stride = u.stride; g.pad = u.pad;
+                        g.splits = u.wg_splits; g.m_chunk = u.wg_chunk;
+                        g.bn = u.cout < 128 ? u.cout : 128;
+                        g.tiles_k = (kext + 127) / 128; g.tiles_n = (u.cout + g.bn - 1) / g.bn;
+                        g.tile_begin = S.wgrad_tc.total;
+                        S.wgrad_tc.h.push_back(g);
+                        S.wgrad_tc.total += g.tiles_k * g.tiles_n * g.splits;
+                    } else {
+                        WgradTask g{};
+                        g.x = xin;
+                        if (u.input == -1) { g.gather = c.perm; g.gather_step = batch; }
+                        g.dy = dy;
+                        g.out = dst;
+                        g.H = u.H; g.W = u.W; g.Cin = u.cin; g.Ho = u.Ho; g.Wo = u.Wo; g.Cout = u.cout;
+                        g.k = u.k; g.stride = u.stride; g.pad = u.pad;
+                        g.splits = u.wg_splits; g.m_chunk = u.wg_chunk;
+                        g.tiles_k = (kext + 63) / 64; g.tiles_n = (u.cout + 63) / 64;
+                        g.tile_begin = S.wgrad.total;
+                        S.wgrad.h.push_back(g);
+                        S.wgrad.total += g.tiles_k * g.tiles_n * g.splits;
+                    }
                     if (to_ws) {
                         ReduceTask r{};
                         r.part = c.wg_ws; r.out = c.grad + u.w_off; r.n = kext * u.cout; r.splits = u.wg_splits;
@@ -544,7 +561,7 @@ struct Engine {
         for (int s = 0; s < N_STAGES; ++s) {
             StageLists& S = wv.st[s];
             blob_add(blob, S.conv); blob_add(blob, S.conv_eval); blob_add(blob, S.dgrad);
-            blob_add(blob, S.conv_tc); blob_add(blob, S.dgrad_tc); blob_add(blob, S.stat);
+            blob_add(blob, S.conv_tc); blob_add(blob, S.dgrad_tc); blob_add(blob, S.stat); blob_add(blob, S.wgrad_tc);
             blob_add(blob, S.post_fwd); blob_add(blob, S.post_bn); blob_add(blob, S.post_bwd);
             blob_add(blob, S.wgrad); blob_add(blob, S.wreduce); blob_add(blob, S.drop_fwd); blob_add(blob, S.drop_bwd);
         }
@@ -564,7 +581,7 @@ struct Engine {
         for (int s = 0; s < N_STAGES; ++s) {
             StageLists& S = wv.st[s];
             fix(S.conv); fix(S.conv_eval); fix(S.dgrad); fix(S.post_fwd); fix(S.post_bn); fix(S.post_bwd);
-            fix(S.conv_tc); fix(S.dgrad_tc); fix(S.stat);
+            fix(S.conv_tc); fix(S.dgrad_tc); fix(S.stat); fix(S.wgrad_tc);
             fix(S.wgrad); fix(S.wreduce); fix(S.drop_fwd); fix(S.drop_bwd);
         }
         fix(wv.head); fix(wv.ce_train); fix(wv.ce_val); fix(wv.ce_pred); fix(wv.adam); fix(wv.wt); fix(wv.wt_bf16);
@@ -628,7 +645,10 @@ struct Engine {
             }
             if (!S.post_bwd.h.empty())
                 CNN_LAUNCH(Launch::post_bwd_apply(S.post_bwd.d, (int)S.post_bwd.h.size(), S.post_bwd.total, n_b, stream));
-            CNN_LAUNCH(Launch::wgrad(S.wgrad.d, (int)S.wgrad.h.size(), S.wgrad.total, n_b, step, stream));
+            if (!S.wgrad.h.empty())
+                CNN_LAUNCH(Launch::wgrad(S.wgrad.d, (int)S.wgrad.h.size(), S.wgrad.total, n_b, step, stream));
+            if (!S.wgrad_tc.h.empty())
+                CNN_LAUNCH(Launch::wgrad_tc(S.wgrad_tc.d, (int)S.wgrad_tc.h.size(), S.wgrad_tc.total, n_b, stream));
             if (!S.wreduce.h.empty())
                 CNN_LAUNCH(Launch::reduce(S.wreduce.d, (int)S.wreduce.h.size(), S.wreduce.total, stream));
             if (!S.dgrad.h.empty())
@@ -1138,6 +1158,69 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
     cudaFree(d_in); cudaFree(d_w); cudaFree(d_out); cudaFree(d_wt); cudaFree(d_wb); cudaFree(d_task);
     if (rc != 0 || e != cudaSuccess) {
         cmoop::set_error("debug_conv: %s", cudaGetErrorString(rc != 0 ? (cudaError_t)rc : e));
+        return CMOOP_ERR_CUDA;
+    }
+    return CMOOP_OK;
+}
+
+
+// Test hook: weight (+bias) gradient out[K+1][Cout] of one convolution from x[n][H][W][Cin] and dy[n][Ho][Wo][Cout].
+int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, int H, int W, int Cin, int Cout, int k,
+                          int stride, int splits, float* out) {
+    CMOOP_REQUIRE(x && dy && out, "debug_wgrad: null pointer");
+    CMOOP_REQUIRE(n >= 1 && n <= kBatch && (stride == 1 || (stride == 2 && k == 1)) && splits >= 1 && splits <= 32,
+                  "debug_wgrad: unsupported shape");
+    CMOOP_REQUIRE(!use_tc || (Cin % 16 == 0 && Cout % 16 == 0), "debug_wgrad: tensor-core path needs Cin, Cout multiples of 16");
+    if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
+    cudaStream_t st = cmoop::internal_stream();
+    const int pad = stride == 1 ? (k - 1) / 2 : 0;
+    const int Ho = stride == 1 ? H : (H + 1) / 2, Wo = stride == 1 ? W : (W + 1) / 2;
+    const long long n_x = (long long)n * H * W * Cin, n_y = (long long)n * Ho * Wo * Cout;
+    const int kext = k * k * Cin + 1;
+    const long long n_o = (long long)kext * Cout;
+    const long long M = (long long)n * Ho * Wo;
+    const int gran = use_tc ? 64 : 16;
+    int chunk = (int)((M + splits - 1) / splits);
+    chunk = (chunk + gran - 1) / gran * gran;
+    float *d_x, *d_y, *d_ws, *d_o;
+    void* d_task;
+    CMOOP_CUDA_OK(cudaMalloc((void**)&d_x, n_x * 4));
+    CMOOP_CUDA_OK(cudaMalloc((void**)&d_y, n_y * 4));
+    CMOOP_CUDA_OK(cudaMalloc((void**)&d_ws, n_o * 4 * splits));
+    CMOOP_CUDA_OK(cudaMalloc((void**)&d_o, n_o * 4));
+    CMOOP_CUDA_OK(cudaMalloc(&d_task, 1024));
+    CMOOP_CUDA_OK(cudaMemcpyAsync(d_x, x, n_x * 4, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cudaMemcpyAsync(d_y, dy, n_y * 4, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cudaMemsetAsync(d_ws, 0xff, n_o * 4 * splits, st));       // poison: every partial must be written
+    int rc;
+    if (use_tc) {
+        TcWgradTask g{};
+        g.x = d_x; g.dy = d_y; g.out = d_ws; g.H = H; g.W = W; g.Cin = Cin; g.Ho = Ho; g.Wo = Wo; g.Cout = Cout;
+        g.k = k; g.stride = stride; g.pad = pad; g.splits = splits; g.m_chunk = chunk;
+        g.bn = Cout < 128 ? Cout : 128; g.tiles_k = (kext + 127) / 128; g.tiles_n = (Cout + g.bn - 1) / g.bn;
+        CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &g, sizeof(g), cudaMemcpyHostToDevice, st));
+        rc = Launch::wgrad_tc((const TcWgradTask*)d_task, 1, g.tiles_k * g.tiles_n * splits, n, st);
+    } else {
+        WgradTask g{};
+        g.x = d_x; g.dy = d_y; g.out = d_ws; g.H = H; g.W = W; g.Cin = Cin; g.Ho = Ho; g.Wo = Wo; g.Cout = Cout;
+        g.k = k; g.stride = stride; g.pad = pad; g.splits = splits; g.m_chunk = chunk;
+        g.tiles_k = (kext + 63) / 64; g.tiles_n = (Cout + 63) / 64;
+        CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &g, sizeof(g), cudaMemcpyHostToDevice, st));
+        rc = Launch::wgrad((const WgradTask*)d_task, 1, g.tiles_k * g.tiles_n * splits, n, 0, st);
+    }
+    cmoop::count_launch();
+    CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+    if (rc == 0) {
+        ReduceTask r{};
+        r.part = d_ws; r.out = d_o; r.n = (int)n_o; r.splits = splits;
+        CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &r, sizeof(r), cudaMemcpyHostToDevice, st));
+        rc = Launch::reduce((const ReduceTask*)d_task, 1, (int)((n_o + 255) / 256), st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == 0 && e == cudaSuccess) e = cudaMemcpy(out, d_o, n_o * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_x); cudaFree(d_y); cudaFree(d_ws); cudaFree(d_o); cudaFree(d_task);
+    if (rc != 0 || e != cudaSuccess) {
+        cmoop::set_error("debug_wgrad: %s", cudaGetErrorString(rc != 0 ? (cudaError_t)rc : e));
         return CMOOP_ERR_CUDA;
     }
     return CMOOP_OK;

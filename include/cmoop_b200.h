@@ -219,6 +219,10 @@ int cmoop_cnn_debug_train_steps(cmoop_cnn_dataset_handle data, const cmoop_genot
 int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, const float* bias, int n, int H,
                          int W, int Cin, int Cout, int k, int stride, int relu, float* out);
 
+/* weight (+ bias, last row) gradient out[k*k*Cin + 1][Cout] of one convolution; `splits` deterministic split-M partials */
+int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, int H, int W, int Cin, int Cout, int k,
+                          int stride, int splits, float* out);
+
 #ifdef __cplusplus
 }
 #endif

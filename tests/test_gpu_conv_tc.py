@@ -67,3 +67,39 @@ def test_forward_and_dgrad(n, H, W, Cin, Cout, k, stride):
         torch.from_numpy(dy).permute(0, 3, 1, 2).double())
     np.testing.assert_allclose(run_conv(1, 0, dy, w, None, n, H, W, Cin, Cout, k, stride, 0),
                                xin2.grad.permute(0, 2, 3, 1).numpy(), rtol=1e-4, atol=1e-4)
+
+
+def run_wgrad(use_tc, x, dy, n, H, W, Cin, Cout, k, stride, splits):
+    from cmoop_audio_processing_b200 import _lib
+    lib = _lib.load()
+    out = np.zeros((k * k * Cin + 1, Cout), np.float32)
+    _lib.check(lib.cmoop_cnn_debug_wgrad(use_tc, _lib.ptr(x), _lib.ptr(dy), n, H, W, Cin, Cout, k, stride, splits,
+                                         _lib.ptr(out)), "cmoop_cnn_debug_wgrad")
+    return out
+
+
+@pytest.mark.parametrize("n,H,W,Cin,Cout,k,stride", CASES)
+@pytest.mark.parametrize("splits", [1, 5])
+def test_weight_gradient(n, H, W, Cin, Cout, k, stride, splits):
+    """dW (HWIO rows) and db (last row) on tcgen05 with MN-major operands vs torch on bf16-rounded operands; the fp32
+    SIMT kernel vs torch on the unrounded operands."""
+    import torch
+    rng = np.random.default_rng(7 + n + Cin + Cout + k + splits)
+    x = rng.standard_normal((n, H, W, Cin)).astype(np.float32)
+    Ho, Wo = (H, W) if stride == 1 else ((H + 1) // 2, (W + 1) // 2)
+    dy = rng.standard_normal((n, Ho, Wo, Cout)).astype(np.float32)
+    pad = (k - 1) // 2 if stride == 1 else 0
+
+    def ref(xa, ya):
+        xt = torch.from_numpy(xa).permute(0, 3, 1, 2).double()
+        yt = torch.from_numpy(ya).permute(0, 3, 1, 2).double()
+        gw = torch.nn.grad.conv2d_weight(xt, (Cout, Cin, k, k), yt, stride=stride, padding=pad)      # OIHW
+        return np.concatenate([gw.permute(2, 3, 1, 0).reshape(k * k * Cin, Cout).numpy(), yt.sum(dim=(0, 2, 3)).numpy()[None]])
+
+    want = ref(bf16_round(x), bf16_round(dy))
+    got = run_wgrad(1, x, dy, n, H, W, Cin, Cout, k, stride, splits)
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(got, want, rtol=1e-3, atol=2e-4 * scale)
+    want32 = ref(x, dy)
+    got32 = run_wgrad(0, x, dy, n, H, W, Cin, Cout, k, stride, splits)
+    np.testing.assert_allclose(got32, want32, rtol=1e-3, atol=2e-4 * np.abs(want32).max())
