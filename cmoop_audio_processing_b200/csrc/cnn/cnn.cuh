@@ -20,6 +20,7 @@ struct ConvTask {
     const int* gather;     // per-step sample indices into x rows (stem conv on the dataset), or null
     const float* w;        // [K (+1 bias row)][Cout]
     float* y;              // output
+    __nv_bfloat16* yh;     // optional bf16 shadow of y for a tensor-core consumer
     float* stat_part;      // [tiles_m][2][Cout] per-tile column sums of y and y^2 (BN batch stats), or null
     long long x_step;      // elements added to x per step (eval: contiguous batches of the split)
     long long gather_step; // elements added to gather per step
@@ -33,10 +34,11 @@ struct ConvTask {
 
 // tcgen05 implicit GEMM (conv_tc.cu): bf16 operands, fp32 accumulation in TMEM
 struct TcConvTask {
-    const float* x;              // fp32 NHWC input (converted to bf16 while staging)
+    const __nv_bfloat16* xh;     // bf16 NHWC input (shadow copy written by the producing kernel)
     const __nv_bfloat16* wt;     // bf16 weights, K-major [Cout][K_pad]
     const float* bias;           // fp32 [Cout] or null
     float* y;
+    __nv_bfloat16* yh;           // optional bf16 shadow of y (when y feeds another tensor-core GEMM directly)
     long long x_step;
     int H, W, Cin, Ho, Wo, Cout, k, stride, pad;
     int K_pad;                   // K rounded up to a multiple of 64
@@ -47,8 +49,8 @@ struct TcConvTask {
 };
 
 struct TcWgradTask {
-    const float* x;              // forward input of the conv (fp32 NHWC)
-    const float* dy;             // [M][Cout] fp32
+    const __nv_bfloat16* xh;     // forward input of the conv (bf16 NHWC shadow)
+    const __nv_bfloat16* dyh;    // [M][Cout] bf16 shadow of the output gradient
     float* out;                  // grad [K+1][Cout] (splits == 1) or workspace [splits][K+1][Cout]
     int H, W, Cin, Ho, Wo, Cout, k, stride, pad;
     int splits, m_chunk;         // m_chunk multiple of 64
@@ -94,6 +96,9 @@ struct WtTask {           // dgrad weights: wt[(k-1-kh, k-1-kw, co)][ci] = w[(kh
 struct PostTask {
     const float* u;        // conv output [n,H,W,C]
     float* v;              // unit output [n,Ho,Wo,C]
+    __nv_bfloat16* vh;     // optional bf16 shadow of v
+    __nv_bfloat16* duh;    // optional bf16 shadow of du
+    __nv_bfloat16* dskiph; // optional bf16 shadow of dskip
     const float* skip;     // residual branch [n,Ho,Wo,C] or null
     uint8_t* idx;          // 2x2 pool argmax code per output element, or null
     const float* gamma;    // BN parameters (null when the unit has no BN)

@@ -4,8 +4,8 @@
 // model.predict (nsga_penalty.py:255-330, 383-386) with a hand-written sm_100a kernel:
 //   D[128 x BN] (fp32, TMEM) += A[128 x 64] (bf16, smem, K-major, SWIZZLE_128B) * B[BN x 64]^T (bf16, smem)
 //   * A = im2col tile: 128 output pixels x 64 consecutive (kh,kw,ci) taps, gathered from the fp32 NHWC
-//     activations by 4 producer warps (8 x 16-byte chunks per row, coalesced 256-B row segments),
-//     converted to bf16 and written with the 128-byte XOR swizzle the UMMA descriptor expects
+//     shadow copy of the activations by 4 producer warps with 16-byte cp.async (zero-fill for padding), two
+//     stages in flight per thread, written with the 128-byte XOR swizzle the UMMA descriptor expects
 //   * B = pre-transposed bf16 weights [Cout][K_pad] (refreshed once per optimiser step by wt_bf16_kernel;
 //     the data-gradient uses the spatially flipped, channel-transposed copy [Cin][K'_pad])
 //   * one elected thread of warp 4 issues tcgen05.mma (UMMA 128 x BN x 16, cta_group::1), stages are
@@ -91,6 +91,18 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// 16-byte asynchronous global->shared copy; src_bytes == 0 zero-fills (padding / out-of-range rows)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+constexpr int TC_LOOKAHEAD = 2;   // stages whose copies are in flight per producer thread
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -146,12 +158,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcConvTask
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        // ================= producers: im2col gather (fp32 -> bf16) + weight tile =================
-        const float* xbase = T.x + T.x_step * step;
+        // ================= producers: im2col gather + weight tile, cp.async straight into the swizzled stage ====
+        const __nv_bfloat16* xbase = T.xh + T.x_step * step;
         const int j = tid & 7;                 // 16-byte chunk (8 bf16) inside the 64-wide K block
         const int r_lo = tid >> 3;             // rows r_lo + 16*i
         const long long img = (long long)T.H * T.W * T.Cin;
-        const float* xrow[8];
+        const __nv_bfloat16* xrow[8];
         int hi0[8], wi0[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -168,45 +180,48 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcConvTask
             }
         }
         const int b_rows = T.bn / 16;          // weight rows handled per thread
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % TC_STAGES;
-            const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
-            mbar_wait(&empty_bar[s], ph ^ 1u);
-            uint8_t* a_st = a_smem + s * TC_A_BYTES;
-            uint8_t* b_st = b_smem + s * TC_B_BYTES;
-            const int k = kb * TC_BK + j * 8;
-            int kh = 0, kw = 0, ci = 0;
-            const bool kvalid = k < K;
-            if (kvalid) {
-                const int pos = k / T.Cin;
-                ci = k - pos * T.Cin;
-                kh = pos / T.k;
-                kw = pos - kh * T.k;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = r_lo + 16 * i;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (kvalid && xrow[i] != nullptr) {
-                    const int hi = hi0[i] + kh, wi = wi0[i] + kw;
-                    if ((unsigned)hi < (unsigned)T.H && (unsigned)wi < (unsigned)T.W) {
-                        const float4* src = reinterpret_cast<const float4*>(xrow[i] + ((long long)hi * T.W + wi) * T.Cin + ci);
-                        const float4 f0 = __ldg(src), f1 = __ldg(src + 1);
-                        v.x = pack_bf16(f0.x, f0.y);
-                        v.y = pack_bf16(f0.z, f0.w);
-                        v.z = pack_bf16(f1.x, f1.y);
-                        v.w = pack_bf16(f1.z, f1.w);
-                    }
+        for (int kb = 0; kb < num_kb + TC_LOOKAHEAD; ++kb) {
+            if (kb < num_kb) {
+                const int s = kb % TC_STAGES;
+                const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                uint8_t* a_st = a_smem + s * TC_A_BYTES;
+                uint8_t* b_st = b_smem + s * TC_B_BYTES;
+                const int k = kb * TC_BK + j * 8;
+                int kh = 0, kw = 0, ci = 0;
+                const bool kvalid = k < K;
+                if (kvalid) {
+                    const int pos = k / T.Cin;
+                    ci = k - pos * T.Cin;
+                    kh = pos / T.k;
+                    kw = pos - kh * T.k;
                 }
-                *reinterpret_cast<uint4*>(a_st + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)) = v;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = r_lo + 16 * i;
+                    const __nv_bfloat16* src = xbase;
+                    uint32_t bytes = 0;
+                    if (kvalid && xrow[i] != nullptr) {
+                        const int hi = hi0[i] + kh, wi = wi0[i] + kw;
+                        if ((unsigned)hi < (unsigned)T.H && (unsigned)wi < (unsigned)T.W) {
+                            src = xrow[i] + ((long long)hi * T.W + wi) * T.Cin + ci;
+                            bytes = 16;
+                        }
+                    }
+                    cp_async16(a_st + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4), src, bytes);
+                }
+                for (int i = 0; i < b_rows; ++i) {
+                    const int r = r_lo + 16 * i;
+                    cp_async16(b_st + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4),
+                               T.wt + (long long)(n0 + r) * T.K_pad + kb * TC_BK + j * 8, 16);
+                }
             }
-            for (int i = 0; i < b_rows; ++i) {
-                const int r = r_lo + 16 * i;
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(T.wt + (long long)(n0 + r) * T.K_pad + kb * TC_BK + j * 8));
-                *reinterpret_cast<uint4*>(b_st + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)) = v;
+            cp_async_commit();
+            if (kb >= TC_LOOKAHEAD) {
+                cp_async_wait<TC_LOOKAHEAD>();                               // the copies of stage kb - LOOKAHEAD have landed
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // ... and are visible to the MMA (async proxy)
+                mbar_arrive(&full_bar[(kb - TC_LOOKAHEAD) % TC_STAGES]);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
-            mbar_arrive(&full_bar[s]);
         }
         // ================= epilogue: TMEM -> registers -> global =================
         mbar_wait(accum_bar, 0);
@@ -255,6 +270,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcConvTask
                         o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
                     }
                     *d4 = o;
+                    if (T.yh)
+                        *reinterpret_cast<uint2*>(T.yh + obase + n0 + c0 + q) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
                 }
             }
         }
@@ -383,44 +400,45 @@ __global__ void __launch_bounds__(TC_THREADS, 2) wgrad_tc_kernel(const TcWgradTa
         }
         const bool b_on = c16 * 8 < T.bn;
         const uint32_t a_off = (uint32_t)(c16 >> 3) * 8192u, a_chunk = (uint32_t)(c16 & 7);
-        for (int st = 0; st < num_st; ++st) {
-            const int s = st % TC_STAGES;
-            const uint32_t ph = (uint32_t)(st / TC_STAGES) & 1u;
-            mbar_wait(&empty_bar[s], ph ^ 1u);
-            uint8_t* a_st = a_smem + s * TC_A_BYTES;
-            uint8_t* b_st = b_smem + s * TC_B_BYTES;
+        for (int st = 0; st < num_st + TC_LOOKAHEAD; ++st) {
+            if (st < num_st) {
+                const int s = st % TC_STAGES;
+                const uint32_t ph = (uint32_t)(st / TC_STAGES) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                uint8_t* a_st = a_smem + s * TC_A_BYTES;
+                uint8_t* b_st = b_smem + s * TC_B_BYTES;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = r_lo + 8 * i;
-                const int m = m_begin + st * 64 + r;
-                uint4 va = make_uint4(0u, 0u, 0u, 0u), vb = make_uint4(0u, 0u, 0u, 0u);
-                if (m < m_end) {
-                    if (a_kind == 1) {
+                for (int i = 0; i < 8; ++i) {
+                    const int r = r_lo + 8 * i;
+                    const int m = m_begin + st * 64 + r;
+                    const uint32_t row_off = (uint32_t)r * 128u + ((a_chunk ^ (uint32_t)(r & 7)) << 4);
+                    const __nv_bfloat16* asrc = T.xh;
+                    uint32_t abytes = 0;
+                    const bool mvalid = m < m_end;
+                    if (mvalid && a_kind == 1) {
                         const int n = m / HoWo, rr = m - n * HoWo;
                         const int ho = rr / T.Wo, wo = rr - ho * T.Wo;
                         const int hi = ho * T.stride - T.pad + kh, wi = wo * T.stride - T.pad + kw;
                         if ((unsigned)hi < (unsigned)T.H && (unsigned)wi < (unsigned)T.W) {
-                            const float4* src = reinterpret_cast<const float4*>(T.x + (long long)n * img + ((long long)hi * T.W + wi) * T.Cin + ci);
-                            const float4 f0 = __ldg(src), f1 = __ldg(src + 1);
-                            va.x = pack_bf16(f0.x, f0.y); va.y = pack_bf16(f0.z, f0.w);
-                            va.z = pack_bf16(f1.x, f1.y); va.w = pack_bf16(f1.z, f1.w);
+                            asrc = T.xh + (long long)n * img + ((long long)hi * T.W + wi) * T.Cin + ci;
+                            abytes = 16;
                         }
-                    } else if (a_kind == 2) {
-                        va.x = 0x00003F80u;             // bf16(1.0) in the first element: the bias-gradient row
                     }
-                    if (b_on) {
-                        const float4* src = reinterpret_cast<const float4*>(T.dy + (long long)m * T.Cout + n0 + c16 * 8);
-                        const float4 f0 = __ldg(src), f1 = __ldg(src + 1);
-                        vb.x = pack_bf16(f0.x, f0.y); vb.y = pack_bf16(f0.z, f0.w);
-                        vb.z = pack_bf16(f1.x, f1.y); vb.w = pack_bf16(f1.z, f1.w);
-                    }
+                    if (a_kind == 2)       // the ones column (bias-gradient row): bf16(1.0) in the first element
+                        *reinterpret_cast<uint4*>(a_st + a_off + row_off) = make_uint4(mvalid ? 0x00003F80u : 0u, 0u, 0u, 0u);
+                    else
+                        cp_async16(a_st + a_off + row_off, asrc, abytes);
+                    if (b_on)
+                        cp_async16(b_st + a_off + row_off, mvalid ? T.dyh + (long long)m * T.Cout + n0 + c16 * 8 : T.dyh,
+                                   mvalid ? 16u : 0u);
                 }
-                const uint32_t row_off = (uint32_t)r * 128u + ((a_chunk ^ (uint32_t)(r & 7)) << 4);
-                *reinterpret_cast<uint4*>(a_st + a_off + row_off) = va;
-                if (b_on) *reinterpret_cast<uint4*>(b_st + a_off + row_off) = vb;
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&full_bar[s]);
+            cp_async_commit();
+            if (st >= TC_LOOKAHEAD) {
+                cp_async_wait<TC_LOOKAHEAD>();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&full_bar[(st - TC_LOOKAHEAD) % TC_STAGES]);
+            }
         }
         // ---- epilogue: D rows = kk, columns = co
         mbar_wait(accum_bar, 0);

@@ -57,6 +57,8 @@ struct Unit {
     uint8_t* idx = nullptr;
     bool tc = false;                 // convolution runs on the tcgen05 path (bf16 operands)
     int kpad_f = 0, kpad_d = 0;      // padded K of the forward / data-gradient GEMM
+    bool need_vh = false;            // a tensor-core unit consumes this unit's output
+    __nv_bfloat16* Vh = nullptr;     // bf16 shadow of V
     __nv_bfloat16* wtb = nullptr;    // bf16 [cout][kpad_f]
     __nv_bfloat16* wtd = nullptr;    // bf16 [cin][kpad_d]
 };
@@ -71,6 +73,7 @@ struct Cand {
     size_t arena_bytes = 0;
     float *p = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr, *best = nullptr;
     float *gA = nullptr, *gB = nullptr, *gS = nullptr, *gG = nullptr, *gap = nullptr, *dlogits = nullptr, *wg_ws = nullptr;
+    __nv_bfloat16 *gBh = nullptr, *gSh = nullptr;   // bf16 shadows of B / S for the tensor-core dgrad / wgrad
     int* perm = nullptr;
     double* acc = nullptr;     // [3][4]: train, val, predict accumulators
     int* pred = nullptr;
@@ -218,6 +221,8 @@ void build_units(Cand& c, const cmoop_cnn_config& cfg, int H, int W, int batch) 
         u.wg_splits = splits;
         u.wg_chunk = chunk;
     }
+    for (Unit& u : c.units)
+        if (u.tc && u.input >= 0) c.units[u.input].need_vh = true;
 }
 
 struct Arena {
@@ -246,6 +251,7 @@ void place(Cand& c, Arena& a, const cmoop_cnn_config& cfg, int n_train, int n_va
         const bool separate_v = u.post_fwd || (u.dense && u.use_dropout);
         u.V = separate_v ? (float*)a.take(u.v_elems * f4) : u.U;
         u.idx = u.pool ? (uint8_t*)a.take(u.v_elems) : nullptr;
+        u.Vh = u.need_vh ? (__nv_bfloat16*)a.take(u.v_elems * 2) : nullptr;
         if (u.has_bn) {
             u.stat = (float*)a.take((size_t)u.stat_tiles * 2 * u.cout * f4);
             u.bn = (float*)a.take((size_t)6 * u.cout * f4);
@@ -267,6 +273,8 @@ void place(Cand& c, Arena& a, const cmoop_cnn_config& cfg, int n_train, int n_va
     c.gA = (float*)a.take(maxV * f4);
     c.gB = (float*)a.take(maxU * f4);
     c.gS = (float*)a.take(maxS * f4);
+    c.gBh = cfg.precision == 1 ? (__nv_bfloat16*)a.take(maxU * 2) : nullptr;
+    c.gSh = cfg.precision == 1 ? (__nv_bfloat16*)a.take(maxS * 2) : nullptr;
     c.gG = (float*)a.take((size_t)batch * lc.cout * f4);
     c.gap = (float*)a.take((size_t)batch * lc.cout * f4);
     c.dlogits = (float*)a.take((size_t)batch * cfg.n_classes * f4);
@@ -347,7 +355,9 @@ struct Engine {
                 S.any = true;
                 if (u.tc) {
                     TcConvTask t{};
-                    t.x = xin; t.wt = u.wtb; t.bias = c.p + u.w_off + (long long)u.k * u.k * u.cin * u.cout; t.y = u.U;
+                    t.xh = c.units[u.input].Vh; t.wt = u.wtb; t.bias = c.p + u.w_off + (long long)u.k * u.k * u.cin * u.cout;
+                    t.y = u.U;
+                    t.yh = (!u.post_fwd && u.need_vh) ? u.Vh : nullptr;
                     t.H = u.H; t.W = u.W; t.Cin = u.cin; t.Ho = u.Ho; t.Wo = u.Wo; t.Cout = u.cout;
                     t.k = u.k; t.stride = u.stride; t.pad = u.pad; t.K_pad = u.kpad_f;
                     t.bn = u.cout < 128 ? u.cout : 128;
@@ -374,6 +384,7 @@ struct Engine {
                     t.x = xin;
                     t.w = c.p + u.w_off;
                     t.y = u.U;
+                    t.yh = (!u.post_fwd && u.need_vh) ? u.Vh : nullptr;
                     t.stat_part = u.has_bn ? u.stat : nullptr;
                     t.H = u.H; t.W = u.W; t.Cin = u.cin; t.Ho = u.Ho; t.Wo = u.Wo; t.Cout = u.cout;
                     t.k = u.k; t.stride = u.stride; t.pad = u.pad;
@@ -410,6 +421,9 @@ struct Engine {
                     }
                     p.dv = c.gA; p.du = c.gB;
                     p.dskip = u.add_skip ? c.gS : nullptr;
+                    p.vh = u.post_fwd ? u.Vh : nullptr;
+                    p.duh = u.tc ? c.gBh : nullptr;
+                    p.dskiph = (u.add_skip && c.units[u.skip_unit].tc) ? c.gSh : nullptr;
                     p.H = u.Ho; p.W = u.Wo; p.C = u.cout; p.Ho = u.Po; p.Wo = u.Qo;
                     p.pool = u.pool; p.relu_mid = u.relu_mid; p.add_skip = u.add_skip; p.relu_in = u.relu_epi;
                     p.has_bn = u.has_bn;
@@ -454,7 +468,7 @@ struct Engine {
                     float* dst = to_ws ? c.wg_ws : c.grad + u.w_off;
                     if (u.tc) {
                         TcWgradTask g{};
-                        g.x = xin; g.dy = dy; g.out = dst;
+                        g.xh = c.units[u.input].Vh; g.dyh = u.is_skip ? c.gSh : c.gBh; g.out = dst;
                         g.H = u.H; g.W = u.W; g.Cin = u.cin; g.Ho = u.Ho; g.Wo = u.Wo; g.Cout = u.cout;
                         g.k = u.k; g.stride = u.stride; g.pad = u.pad;
                         g.splits = u.wg_splits; g.m_chunk = u.wg_chunk;
@@ -494,7 +508,7 @@ struct Engine {
                     wv.wt_bf16.h.push_back(wb);
                     wv.wt_bf16.total += blocks_for((long long)u.cin * u.kpad_d);
                     TcConvTask d{};
-                    d.x = u.is_skip ? c.gS : c.gB;
+                    d.xh = u.is_skip ? c.gSh : c.gBh;
                     d.wt = u.wtd;
                     d.y = c.gA;
                     d.Cin = u.cout; d.Cout = u.cin; d.k = u.k; d.K_pad = u.kpad_d;
@@ -1094,8 +1108,12 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
     const int gi = mode == 0 ? Cin : Cout, go = mode == 0 ? Cout : Cin;      // GEMM input / output channels
     const int K = k * k * gi, K_pad = (K + 63) / 64 * 64;
     float *d_in, *d_w, *d_out, *d_wt;
-    __nv_bfloat16* d_wb;
+    __nv_bfloat16 *d_wb, *d_inh;
     void* d_task;
+    std::vector<__nv_bfloat16> in_h((size_t)n_in);
+    for (long long i = 0; i < n_in; ++i) in_h[i] = __float2bfloat16_rn(in[i]);
+    CMOOP_CUDA_OK(cudaMalloc((void**)&d_inh, n_in * 2));
+    CMOOP_CUDA_OK(cudaMemcpyAsync(d_inh, in_h.data(), n_in * 2, cudaMemcpyHostToDevice, st));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_in, n_in * 4));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_w, (n_w + Cout) * 4));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_out, n_out * 4));
@@ -1138,7 +1156,7 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
         rc = Launch::wt_bf16((const WtBf16Task*)d_task, 1, (int)(((long long)go * K_pad + 255) / 256), st);
         CMOOP_CUDA_OK(cudaStreamSynchronize(st));
         TcConvTask t{};
-        t.x = d_in; t.wt = d_wb; t.y = d_out; t.k = k; t.K_pad = K_pad;
+        t.xh = d_inh; t.wt = d_wb; t.y = d_out; t.k = k; t.K_pad = K_pad;
         t.Ho = Ho; t.Wo = Wo;
         if (mode == 0) {
             t.bias = d_w + n_w; t.relu = relu;
@@ -1155,7 +1173,7 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
     cmoop::count_launch();
     cudaError_t e = cudaStreamSynchronize(st);
     if (rc == 0 && e == cudaSuccess) e = cudaMemcpy(out, d_out, n_out * 4, cudaMemcpyDeviceToHost);
-    cudaFree(d_in); cudaFree(d_w); cudaFree(d_out); cudaFree(d_wt); cudaFree(d_wb); cudaFree(d_task);
+    cudaFree(d_in); cudaFree(d_w); cudaFree(d_out); cudaFree(d_wt); cudaFree(d_wb); cudaFree(d_task); cudaFree(d_inh);
     if (rc != 0 || e != cudaSuccess) {
         cmoop::set_error("debug_conv: %s", cudaGetErrorString(rc != 0 ? (cudaError_t)rc : e));
         return CMOOP_ERR_CUDA;
@@ -1183,7 +1201,15 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
     int chunk = (int)((M + splits - 1) / splits);
     chunk = (chunk + gran - 1) / gran * gran;
     float *d_x, *d_y, *d_ws, *d_o;
+    __nv_bfloat16 *d_xh, *d_yh;
     void* d_task;
+    std::vector<__nv_bfloat16> xh((size_t)n_x), yh((size_t)n_y);
+    for (long long i = 0; i < n_x; ++i) xh[i] = __float2bfloat16_rn(x[i]);
+    for (long long i = 0; i < n_y; ++i) yh[i] = __float2bfloat16_rn(dy[i]);
+    CMOOP_CUDA_OK(cudaMalloc((void**)&d_xh, n_x * 2));
+    CMOOP_CUDA_OK(cudaMalloc((void**)&d_yh, n_y * 2));
+    CMOOP_CUDA_OK(cudaMemcpyAsync(d_xh, xh.data(), n_x * 2, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cudaMemcpyAsync(d_yh, yh.data(), n_y * 2, cudaMemcpyHostToDevice, st));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_x, n_x * 4));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_y, n_y * 4));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_ws, n_o * 4 * splits));
@@ -1195,7 +1221,7 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
     int rc;
     if (use_tc) {
         TcWgradTask g{};
-        g.x = d_x; g.dy = d_y; g.out = d_ws; g.H = H; g.W = W; g.Cin = Cin; g.Ho = Ho; g.Wo = Wo; g.Cout = Cout;
+        g.xh = d_xh; g.dyh = d_yh; g.out = d_ws; g.H = H; g.W = W; g.Cin = Cin; g.Ho = Ho; g.Wo = Wo; g.Cout = Cout;
         g.k = k; g.stride = stride; g.pad = pad; g.splits = splits; g.m_chunk = chunk;
         g.bn = Cout < 128 ? Cout : 128; g.tiles_k = (kext + 127) / 128; g.tiles_n = (Cout + g.bn - 1) / g.bn;
         CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &g, sizeof(g), cudaMemcpyHostToDevice, st));
@@ -1218,7 +1244,7 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
     }
     cudaError_t e = cudaStreamSynchronize(st);
     if (rc == 0 && e == cudaSuccess) e = cudaMemcpy(out, d_o, n_o * 4, cudaMemcpyDeviceToHost);
-    cudaFree(d_x); cudaFree(d_y); cudaFree(d_ws); cudaFree(d_o); cudaFree(d_task);
+    cudaFree(d_x); cudaFree(d_y); cudaFree(d_ws); cudaFree(d_o); cudaFree(d_task); cudaFree(d_xh); cudaFree(d_yh);
     if (rc != 0 || e != cudaSuccess) {
         cmoop::set_error("debug_wgrad: %s", cudaGetErrorString(rc != 0 ? (cudaError_t)rc : e));
         return CMOOP_ERR_CUDA;

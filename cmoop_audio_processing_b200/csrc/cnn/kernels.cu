@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvTask* __restri
                 T.y[base + col] += v;
             else
                 T.y[base + col] = v;
+            if (T.yh) T.yh[base + col] = __float2bfloat16_rn(v);
             s1[j] += v;
             s2[j] = fmaf(v, v, s2[j]);
         }
@@ -397,6 +398,7 @@ __global__ void __launch_bounds__(256) post_fwd_kernel(const PostTask* __restric
     }
     if (T.add_skip) z = fmaxf(z + T.skip[e], 0.f);
     T.v[e] = z;
+    if (T.vh) T.vh[e] = __float2bfloat16_rn(z);
 }
 
 // BN backward, pass 1: per-channel partial sums of g and g*xhat over the unit's output elements
@@ -484,7 +486,10 @@ __global__ void __launch_bounds__(256) post_bwd_apply_kernel(const PostTask* __r
     float g = T.dv[oe];
     if (T.add_skip) {
         if (!(T.v[oe] > 0.f)) g = 0.f;
-        if (origin && T.dskip) T.dskip[oe] = g;
+        if (origin && T.dskip) {
+            T.dskip[oe] = g;
+            if (T.dskiph) T.dskiph[oe] = __float2bfloat16_rn(g);
+        }
     }
     if (!routed) g = 0.f;
     const float u = T.u[e];
@@ -501,6 +506,7 @@ __global__ void __launch_bounds__(256) post_bwd_apply_kernel(const PostTask* __r
     }
     if (T.relu_in && !(u > 0.f)) du = 0.f;
     T.du[e] = du;
+    if (T.duh) T.duh[e] = __float2bfloat16_rn(du);
 }
 
 // ------------------------------------------------------------------------------------------------
