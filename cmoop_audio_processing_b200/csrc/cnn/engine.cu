@@ -211,7 +211,7 @@ void build_units(Cand& c, const cmoop_cnn_config& cfg, int H, int W, int batch) 
         const long long M = (long long)batch * u.Ho * u.Wo;
         u.stat_tiles = (int)((M + 63) / 64);
         const long long npix = (long long)batch * u.Po * u.Qo;
-        const int cb = u.cout < 128 ? u.cout : 128;
+        const int cb = (u.cout / 4) < 128 ? (u.cout / 4) : 128;     // post_bwd_reduce: 4 channels per thread
         u.bwd_rows = (int)(((npix + 127) / 128) * (128 / cb));
         int splits = (int)std::min<long long>(32, std::max<long long>(1, M / 2048));
         int chunk = (int)((M + splits - 1) / splits);
@@ -432,7 +432,7 @@ struct Engine {
                         PostTask q = p;
                         q.block_begin = S.post_fwd.total;
                         S.post_fwd.h.push_back(q);
-                        S.post_fwd.total += blocks_for(u.v_elems);
+                        S.post_fwd.total += blocks_for(u.v_elems / 4);
                     }
                     if (u.has_bn) {
                         PostTask q = p;
@@ -443,7 +443,7 @@ struct Engine {
                     PostTask q = p;
                     q.block_begin = S.post_bwd.total;
                     S.post_bwd.h.push_back(q);
-                    S.post_bwd.total += blocks_for(u.u_elems);
+                    S.post_bwd.total += blocks_for(u.u_elems / 4);
                 }
                 // ---- dense ReLU / dropout
                 if (u.dense && u.fc_index >= 0) {

@@ -319,60 +319,88 @@ __global__ void __launch_bounds__(256) wt_kernel(const WtTask* __restrict__ task
 }
 
 // ------------------------------------------------------------------------------------------------
-// BatchNorm statistics -> (mean, invstd, scale, shift); one CTA per task
+// BatchNorm statistics -> (mean, invstd, scale, shift); one CTA per task, tile partials summed in double by
+// (128 / C) lanes per channel and combined in lane order (deterministic)
 __global__ void __launch_bounds__(128) bn_finalize_kernel(const PostTask* __restrict__ tasks, int n_b, int training,
                                                           float momentum, float eps) {
+    __shared__ double red[2][128];
     const PostTask T = tasks[blockIdx.x];
     if (!T.has_bn) return;
     const double count = (double)n_b * T.H * T.W;
-    for (int c = threadIdx.x; c < T.C; c += blockDim.x) {
-        float mean, var;
-        if (training) {
-            double s1 = 0.0, s2 = 0.0;
-            const int tiles = (n_b * T.H * T.W + BM - 1) / BM;    // tiles the conv epilogue wrote for THIS batch size
-            for (int t = 0; t < tiles; ++t) {
+    const int tiles = (n_b * T.H * T.W + BM - 1) / BM;    // tiles the conv epilogue / bn_stats wrote for THIS batch size
+    const int cb = T.C < 128 ? T.C : 128;
+    const int lanes = 128 / cb;
+    const int t_lane = threadIdx.x / cb, c_lane = threadIdx.x - t_lane * cb;
+    for (int c0 = 0; c0 < T.C; c0 += cb) {
+        const int c = c0 + c_lane;
+        double s1 = 0.0, s2 = 0.0;
+        if (training && t_lane < lanes && c < T.C)
+            for (int t = t_lane; t < tiles; t += lanes) {
                 s1 += (double)T.stat_part[((long long)t * 2 + 0) * T.C + c];
                 s2 += (double)T.stat_part[((long long)t * 2 + 1) * T.C + c];
             }
-            const double mu = s1 / count;
-            double vv = s2 / count - mu * mu;
-            vv = vv > 0.0 ? vv : 0.0;
-            mean = (float)mu;
-            var = (float)vv;
-            T.mov_mean[c] = T.mov_mean[c] * momentum + mean * (1.f - momentum);
-            T.mov_var[c] = T.mov_var[c] * momentum + var * (1.f - momentum);
-        } else {
-            mean = T.mov_mean[c];
-            var = T.mov_var[c];
+        red[0][threadIdx.x] = s1;
+        red[1][threadIdx.x] = s2;
+        __syncthreads();
+        if (t_lane == 0 && c < T.C) {
+            float mean, var;
+            if (training) {
+                double a1 = 0.0, a2 = 0.0;
+                for (int l = 0; l < lanes; ++l) {
+                    a1 += red[0][l * cb + c_lane];
+                    a2 += red[1][l * cb + c_lane];
+                }
+                const double mu = a1 / count;
+                double vv = a2 / count - mu * mu;
+                vv = vv > 0.0 ? vv : 0.0;
+                mean = (float)mu;
+                var = (float)vv;
+                T.mov_mean[c] = T.mov_mean[c] * momentum + mean * (1.f - momentum);
+                T.mov_var[c] = T.mov_var[c] * momentum + var * (1.f - momentum);
+            } else {
+                mean = T.mov_mean[c];
+                var = T.mov_var[c];
+            }
+            const float invstd = rsqrtf(var + eps);
+            const float scale = T.gamma[c] * invstd;
+            T.bn[0 * T.C + c] = mean;
+            T.bn[1 * T.C + c] = invstd;
+            T.bn[2 * T.C + c] = scale;
+            T.bn[3 * T.C + c] = T.beta[c] - mean * scale;
         }
-        const float invstd = rsqrtf(var + eps);
-        const float scale = T.gamma[c] * invstd;
-        T.bn[0 * T.C + c] = mean;
-        T.bn[1 * T.C + c] = invstd;
-        T.bn[2 * T.C + c] = scale;
-        T.bn[3 * T.C + c] = T.beta[c] - mean * scale;
+        __syncthreads();
     }
 }
 
-// [BN] -> [ReLU] -> [2x2/s2 'same' max-pool] -> [+skip, ReLU]
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ uint2 bf16x4(float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    return make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+
+// [BN] -> [ReLU] -> [2x2/s2 'same' max-pool] -> [+skip, ReLU]; one thread = 4 consecutive channels of one output pixel
 __global__ void __launch_bounds__(256) post_fwd_kernel(const PostTask* __restrict__ tasks, int n_tasks, int n_b) {
     const int t = find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin; });
     const PostTask T = tasks[t];
-    const long long e = (long long)(blockIdx.x - T.block_begin) * 256 + threadIdx.x;
-    const long long total = (long long)n_b * T.Ho * T.Wo * T.C;
-    if (e >= total) return;
-    const int c = (int)(e % T.C);
-    long long pix = e / T.C;
+    const int C4 = T.C >> 2;
+    const long long e4 = (long long)(blockIdx.x - T.block_begin) * 256 + threadIdx.x;
+    if (e4 >= (long long)n_b * T.Ho * T.Wo * C4) return;
+    const int c = (int)(e4 % C4) * 4;
+    long long pix = e4 / C4;
+    const long long e = pix * T.C + c;
     const int wo = (int)(pix % T.Wo);
     pix /= T.Wo;
     const int ho = (int)(pix % T.Ho);
     const int n = (int)(pix / T.Ho);
-    const float scale = T.has_bn ? T.bn[2 * T.C + c] : 1.f;
-    const float shift = T.has_bn ? T.bn[3 * T.C + c] : 0.f;
-    float z;
+    float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+    if (T.has_bn) {
+        const float4 a = ld4(T.bn + 2 * T.C + c), b = ld4(T.bn + 3 * T.C + c);
+        sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w;
+        sh[0] = b.x; sh[1] = b.y; sh[2] = b.z; sh[3] = b.w;
+    }
+    float z[4];
     if (T.pool) {
-        z = 0.f;
-        int code = 0;
+        int code[4] = {0, 0, 0, 0};
         bool first = true;
 #pragma unroll
         for (int dh = 0; dh < 2; ++dh)
@@ -380,133 +408,218 @@ __global__ void __launch_bounds__(256) post_fwd_kernel(const PostTask* __restric
             for (int dw = 0; dw < 2; ++dw) {
                 const int hi = 2 * ho + dh, wi = 2 * wo + dw;
                 if (hi < T.H && wi < T.W) {
-                    float v = T.u[(((long long)n * T.H + hi) * T.W + wi) * T.C + c];
-                    if (T.has_bn) v = fmaf(v, scale, shift);
-                    if (T.relu_mid) v = fmaxf(v, 0.f);
-                    if (first || v > z) {
-                        z = v;
-                        code = dh * 2 + dw;
-                        first = false;
+                    const float4 uv = ld4(T.u + (((long long)n * T.H + hi) * T.W + wi) * T.C + c);
+                    const float v[4] = {uv.x, uv.y, uv.z, uv.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float x = v[q];
+                        if (T.has_bn) x = fmaf(x, sc[q], sh[q]);
+                        if (T.relu_mid) x = fmaxf(x, 0.f);
+                        if (first || x > z[q]) {
+                            z[q] = x;
+                            code[q] = dh * 2 + dw;
+                        }
                     }
+                    first = false;
                 }
             }
-        T.idx[e] = (uint8_t)code;
+        *reinterpret_cast<uchar4*>(T.idx + e) = make_uchar4((unsigned char)code[0], (unsigned char)code[1],
+                                                             (unsigned char)code[2], (unsigned char)code[3]);
     } else {
-        z = T.u[e];
-        if (T.has_bn) z = fmaf(z, scale, shift);
-        if (T.relu_mid) z = fmaxf(z, 0.f);
+        const float4 uv = ld4(T.u + e);
+        const float v[4] = {uv.x, uv.y, uv.z, uv.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float x = v[q];
+            if (T.has_bn) x = fmaf(x, sc[q], sh[q]);
+            if (T.relu_mid) x = fmaxf(x, 0.f);
+            z[q] = x;
+        }
     }
-    if (T.add_skip) z = fmaxf(z + T.skip[e], 0.f);
-    T.v[e] = z;
-    if (T.vh) T.vh[e] = __float2bfloat16_rn(z);
+    if (T.add_skip) {
+        const float4 sk = ld4(T.skip + e);
+        z[0] = fmaxf(z[0] + sk.x, 0.f);
+        z[1] = fmaxf(z[1] + sk.y, 0.f);
+        z[2] = fmaxf(z[2] + sk.z, 0.f);
+        z[3] = fmaxf(z[3] + sk.w, 0.f);
+    }
+    const float4 out = make_float4(z[0], z[1], z[2], z[3]);
+    *reinterpret_cast<float4*>(T.v + e) = out;
+    if (T.vh) *reinterpret_cast<uint2*>(T.vh + e) = bf16x4(out);
 }
 
-// BN backward, pass 1: per-channel partial sums of g and g*xhat over the unit's output elements
+// BN backward, pass 1: per-channel partial sums of g and g*xhat over the unit's output elements.
+// A CTA covers 128 output pixels; thread = (pixel lane, 4 channels); one partial row per (CTA, pixel lane).
 __global__ void __launch_bounds__(128) post_bwd_reduce_kernel(const PostTask* __restrict__ tasks, int n_tasks,
                                                               int n_b) {
     const int t = find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin_bwd; });
     const PostTask T = tasks[t];
     const int blk = blockIdx.x - T.block_begin_bwd;
-    const int cb = T.C < 128 ? T.C : 128;
+    const int C4 = T.C >> 2;
+    const int cb = C4 < 128 ? C4 : 128;
     const int lanes = 128 / cb;
     const int p_lane = threadIdx.x / cb, c_lane = threadIdx.x - p_lane * cb;
     if (p_lane >= lanes) return;
     const long long n_pix = (long long)n_b * T.Ho * T.Wo;
     const long long pix0 = (long long)blk * 128, pix1 = pix0 + 128 < n_pix ? pix0 + 128 : n_pix;
-    for (int c = c_lane; c < T.C; c += cb) {
-        const float mean = T.bn[0 * T.C + c], invstd = T.bn[1 * T.C + c];
-        const float scale = T.bn[2 * T.C + c], shift = T.bn[3 * T.C + c];
-        float sg = 0.f, sgx = 0.f;
+    for (int c4 = c_lane; c4 < C4; c4 += cb) {
+        const int c = c4 * 4;
+        const float4 mean = ld4(T.bn + 0 * T.C + c), invstd = ld4(T.bn + 1 * T.C + c);
+        const float4 scale = ld4(T.bn + 2 * T.C + c), shift = ld4(T.bn + 3 * T.C + c);
+        const float mu[4] = {mean.x, mean.y, mean.z, mean.w}, is[4] = {invstd.x, invstd.y, invstd.z, invstd.w};
+        const float sc[4] = {scale.x, scale.y, scale.z, scale.w}, sh[4] = {shift.x, shift.y, shift.z, shift.w};
+        float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};
         for (long long pix = pix0 + p_lane; pix < pix1; pix += lanes) {
             const long long e = pix * T.C + c;
-            float g = T.dv[e];
-            if (T.add_skip && !(T.v[e] > 0.f)) g = 0.f;
-            long long ue = e;
+            const float4 gv = ld4(T.dv + e);
+            float g[4] = {gv.x, gv.y, gv.z, gv.w};
+            if (T.add_skip) {
+                const float4 vv = ld4(T.v + e);
+                if (!(vv.x > 0.f)) g[0] = 0.f;
+                if (!(vv.y > 0.f)) g[1] = 0.f;
+                if (!(vv.z > 0.f)) g[2] = 0.f;
+                if (!(vv.w > 0.f)) g[3] = 0.f;
+            }
+            float u[4];
             if (T.pool) {
                 const int wo = (int)(pix % T.Wo);
                 const long long r = pix / T.Wo;
                 const int ho = (int)(r % T.Ho);
                 const int n = (int)(r / T.Ho);
-                const int code = T.idx[e];
-                ue = (((long long)n * T.H + 2 * ho + (code >> 1)) * T.W + 2 * wo + (code & 1)) * T.C + c;
+                const uchar4 cd = *reinterpret_cast<const uchar4*>(T.idx + e);
+                const unsigned char code[4] = {cd.x, cd.y, cd.z, cd.w};
+                const long long base = (((long long)n * T.H + 2 * ho) * T.W + 2 * wo) * T.C + c;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    u[q] = T.u[base + ((long long)(code[q] >> 1) * T.W + (code[q] & 1)) * T.C + q];
+            } else {
+                const float4 uv = ld4(T.u + e);
+                u[0] = uv.x; u[1] = uv.y; u[2] = uv.z; u[3] = uv.w;
             }
-            const float u = T.u[ue];
-            if (T.relu_mid && !(fmaf(u, scale, shift) > 0.f)) g = 0.f;
-            sg += g;
-            sgx = fmaf(g, (u - mean) * invstd, sgx);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float gq = g[q];
+                if (T.relu_mid && !(fmaf(u[q], sc[q], sh[q]) > 0.f)) gq = 0.f;
+                sg[q] += gq;
+                sgx[q] = fmaf(gq, (u[q] - mu[q]) * is[q], sgx[q]);
+            }
         }
         const long long rowi = (long long)blk * lanes + p_lane;
-        T.bwd_part[(rowi * 2 + 0) * T.C + c] = sg;
-        T.bwd_part[(rowi * 2 + 1) * T.C + c] = sgx;
+        *reinterpret_cast<float4*>(T.bwd_part + (rowi * 2 + 0) * T.C + c) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+        *reinterpret_cast<float4*>(T.bwd_part + (rowi * 2 + 1) * T.C + c) = make_float4(sgx[0], sgx[1], sgx[2], sgx[3]);
     }
 }
 
 __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const PostTask* __restrict__ tasks, int n_b) {
+    __shared__ double red[2][128];
     const PostTask T = tasks[blockIdx.x];
     if (!T.has_bn) return;
+    const int C4 = T.C >> 2;
+    const int lanes_w = 128 / (C4 < 128 ? C4 : 128);          // partial rows per CTA written by post_bwd_reduce
+    const long long n_pix = (long long)n_b * T.Ho * T.Wo;
+    const long long rows = ((n_pix + 127) / 128) * lanes_w;
+    const double count = (double)n_b * T.H * T.W;
     const int cb = T.C < 128 ? T.C : 128;
     const int lanes = 128 / cb;
-    const long long n_pix = (long long)n_b * T.Ho * T.Wo;
-    const long long rows = ((n_pix + 127) / 128) * lanes;
-    const double count = (double)n_b * T.H * T.W;
-    for (int c = threadIdx.x; c < T.C; c += blockDim.x) {
+    const int r_lane = threadIdx.x / cb, c_lane = threadIdx.x - r_lane * cb;
+    for (int c0 = 0; c0 < T.C; c0 += cb) {
+        const int c = c0 + c_lane;
         double sg = 0.0, sgx = 0.0;
-        for (long long r = 0; r < rows; ++r) {
-            sg += (double)T.bwd_part[(r * 2 + 0) * T.C + c];
-            sgx += (double)T.bwd_part[(r * 2 + 1) * T.C + c];
+        if (r_lane < lanes && c < T.C)
+            for (long long r = r_lane; r < rows; r += lanes) {
+                sg += (double)T.bwd_part[(r * 2 + 0) * T.C + c];
+                sgx += (double)T.bwd_part[(r * 2 + 1) * T.C + c];
+            }
+        red[0][threadIdx.x] = sg;
+        red[1][threadIdx.x] = sgx;
+        __syncthreads();
+        if (r_lane == 0 && c < T.C) {
+            double a1 = 0.0, a2 = 0.0;
+            for (int l = 0; l < lanes; ++l) {
+                a1 += red[0][l * cb + c_lane];
+                a2 += red[1][l * cb + c_lane];
+            }
+            T.dbeta[c] = (float)a1;
+            T.dgamma[c] = (float)a2;
+            T.bn[4 * T.C + c] = (float)(a1 / count);
+            T.bn[5 * T.C + c] = (float)(a2 / count);
         }
-        T.dbeta[c] = (float)sg;
-        T.dgamma[c] = (float)sgx;
-        T.bn[4 * T.C + c] = (float)(sg / count);
-        T.bn[5 * T.C + c] = (float)(sgx / count);
+        __syncthreads();
     }
 }
 
-// backward of the whole post stage, dense over the conv-output grid
+// backward of the whole post stage, dense over the conv-output grid; one thread = 4 channels of one input pixel
 __global__ void __launch_bounds__(256) post_bwd_apply_kernel(const PostTask* __restrict__ tasks, int n_tasks, int n_b) {
     const int t = find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin; });
     const PostTask T = tasks[t];
-    const long long e = (long long)(blockIdx.x - T.block_begin) * 256 + threadIdx.x;
-    const long long total = (long long)n_b * T.H * T.W * T.C;
-    if (e >= total) return;
-    const int c = (int)(e % T.C);
-    long long pix = e / T.C;
+    const int C4 = T.C >> 2;
+    const long long e4 = (long long)(blockIdx.x - T.block_begin) * 256 + threadIdx.x;
+    if (e4 >= (long long)n_b * T.H * T.W * C4) return;
+    const int c = (int)(e4 % C4) * 4;
+    long long pix = e4 / C4;
+    const long long e = pix * T.C + c;
     const int wi = (int)(pix % T.W);
     pix /= T.W;
     const int hi = (int)(pix % T.H);
     const int n = (int)(pix / T.H);
     long long oe = e;
-    bool origin = true, routed = true;
+    bool origin = true;
+    bool routed[4] = {true, true, true, true};
     if (T.pool) {
         const int ho = hi >> 1, wo = wi >> 1;
         oe = (((long long)n * T.Ho + ho) * T.Wo + wo) * T.C + c;
         origin = ((hi & 1) == 0) && ((wi & 1) == 0);
-        routed = T.idx[oe] == (uint8_t)((hi & 1) * 2 + (wi & 1));
+        const uchar4 cd = *reinterpret_cast<const uchar4*>(T.idx + oe);
+        const unsigned char me = (unsigned char)((hi & 1) * 2 + (wi & 1));
+        routed[0] = cd.x == me; routed[1] = cd.y == me; routed[2] = cd.z == me; routed[3] = cd.w == me;
     }
-    float g = T.dv[oe];
+    const float4 gv = ld4(T.dv + oe);
+    float g[4] = {gv.x, gv.y, gv.z, gv.w};
     if (T.add_skip) {
-        if (!(T.v[oe] > 0.f)) g = 0.f;
+        const float4 vv = ld4(T.v + oe);
+        if (!(vv.x > 0.f)) g[0] = 0.f;
+        if (!(vv.y > 0.f)) g[1] = 0.f;
+        if (!(vv.z > 0.f)) g[2] = 0.f;
+        if (!(vv.w > 0.f)) g[3] = 0.f;
         if (origin && T.dskip) {
-            T.dskip[oe] = g;
-            if (T.dskiph) T.dskiph[oe] = __float2bfloat16_rn(g);
+            const float4 gs = make_float4(g[0], g[1], g[2], g[3]);
+            *reinterpret_cast<float4*>(T.dskip + oe) = gs;
+            if (T.dskiph) *reinterpret_cast<uint2*>(T.dskiph + oe) = bf16x4(gs);
         }
     }
-    if (!routed) g = 0.f;
-    const float u = T.u[e];
-    float du;
+    const float4 uv = ld4(T.u + e);
+    const float u[4] = {uv.x, uv.y, uv.z, uv.w};
+    float du[4];
     if (T.has_bn) {
-        const float mean = T.bn[0 * T.C + c], invstd = T.bn[1 * T.C + c];
-        const float scale = T.bn[2 * T.C + c], shift = T.bn[3 * T.C + c];
-        if (T.relu_mid && !(fmaf(u, scale, shift) > 0.f)) g = 0.f;
-        const float xhat = (u - mean) * invstd;
-        du = scale * (g - T.bn[4 * T.C + c] - xhat * T.bn[5 * T.C + c]);
+        const float4 mean = ld4(T.bn + 0 * T.C + c), invstd = ld4(T.bn + 1 * T.C + c);
+        const float4 scale = ld4(T.bn + 2 * T.C + c), shift = ld4(T.bn + 3 * T.C + c);
+        const float4 mg = ld4(T.bn + 4 * T.C + c), mgx = ld4(T.bn + 5 * T.C + c);
+        const float mu[4] = {mean.x, mean.y, mean.z, mean.w}, is[4] = {invstd.x, invstd.y, invstd.z, invstd.w};
+        const float sc[4] = {scale.x, scale.y, scale.z, scale.w}, sh[4] = {shift.x, shift.y, shift.z, shift.w};
+        const float a4[4] = {mg.x, mg.y, mg.z, mg.w}, b4[4] = {mgx.x, mgx.y, mgx.z, mgx.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float gq = routed[q] ? g[q] : 0.f;
+            if (T.relu_mid && !(fmaf(u[q], sc[q], sh[q]) > 0.f)) gq = 0.f;
+            const float xhat = (u[q] - mu[q]) * is[q];
+            du[q] = sc[q] * (gq - a4[q] - xhat * b4[q]);
+        }
     } else {
-        if (T.relu_mid && !(u > 0.f)) g = 0.f;
-        du = g;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float gq = routed[q] ? g[q] : 0.f;
+            if (T.relu_mid && !(u[q] > 0.f)) gq = 0.f;
+            du[q] = gq;
+        }
     }
-    if (T.relu_in && !(u > 0.f)) du = 0.f;
-    T.du[e] = du;
-    if (T.duh) T.duh[e] = __float2bfloat16_rn(du);
+    if (T.relu_in) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (!(u[q] > 0.f)) du[q] = 0.f;
+    }
+    const float4 out = make_float4(du[0], du[1], du[2], du[3]);
+    *reinterpret_cast<float4*>(T.du + e) = out;
+    if (T.duh) *reinterpret_cast<uint2*>(T.duh + e) = bf16x4(out);
 }
 
 // ------------------------------------------------------------------------------------------------
