@@ -9,8 +9,8 @@
 //   * B = pre-transposed bf16 weights [Cout][K_pad] (refreshed once per optimiser step by wt_bf16_kernel;
 //     the data-gradient uses the spatially flipped, channel-transposed copy [Cin][K'_pad])
 //   * one elected thread of warp 4 issues tcgen05.mma (UMMA 128 x BN x 16, cta_group::1), stages are
-//     recycled through tcgen05.commit -> mbarrier; 3-stage ring, 2 CTAs per SM
-//   * epilogue: the producer warps read their 32 TMEM lanes with tcgen05.ld (32x32b.x16), add the fp32
+//     recycled through tcgen05.commit -> mbarrier; 3-stage ring, 2 CTAs per SM, 8 producer warps per CTA
+//   * epilogue: the 8 producer warps (lane group = warp % 4, column half = warp / 4) read TMEM with tcgen05.ld (32x32b.x16), add the fp32
 //     bias, apply ReLU and store fp32 rows (optionally strided/accumulating for the 1x1/s2 skip dgrad)
 // Grouped over candidates exactly like the SIMT kernels (cnn.cuh): blockIdx.x -> (task, tile).
 #include <cuda_bf16.h>
@@ -25,7 +25,8 @@ constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;        // 16 KiB
 constexpr int TC_B_BYTES = 128 * TC_BK * 2;          // 16 KiB (BN <= 128)
 constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int TC_THREADS = 160;
+constexpr int TC_PRODUCERS = 256;          // 8 producer / epilogue warps
+constexpr int TC_THREADS = TC_PRODUCERS + 32;   // + the MMA-issuing warp
 constexpr uint32_t TMEM_COLS = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -140,13 +141,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcConvTask
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(&full_bar[s], 128);
+            mbar_init(&full_bar[s], TC_PRODUCERS);
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == TC_PRODUCERS / 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(TMEM_COLS)
                      : "memory");
@@ -157,17 +158,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcConvTask
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < TC_PRODUCERS / 32) {
         // ================= producers: im2col gather + weight tile, cp.async straight into the swizzled stage ====
         const __nv_bfloat16* xbase = T.xh + T.x_step * step;
         const int j = tid & 7;                 // 16-byte chunk (8 bf16) inside the 64-wide K block
-        const int r_lo = tid >> 3;             // rows r_lo + 16*i
+        const int r_lo = tid >> 3;             // rows r_lo + 32*i
         const long long img = (long long)T.H * T.W * T.Cin;
-        const __nv_bfloat16* xrow[8];
-        int hi0[8], wi0[8];
+        const __nv_bfloat16* xrow[4];
+        int hi0[4], wi0[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int m = m0 + r_lo + 16 * i;
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + r_lo + 32 * i;
             if (m < M) {
                 const int n = m / HoWo, r = m - n * HoWo;
                 const int ho = r / T.Wo, wo = r - ho * T.Wo;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcConvTask
                 hi0[i] = wi0[i] = 0;
             }
         }
-        const int b_rows = T.bn / 16;          // weight rows handled per thread
+        const int b_rows = (T.bn + 31) / 32;   // weight rows handled per thread (rows r_lo + 32*i < bn)
         for (int kb = 0; kb < num_kb + TC_LOOKAHEAD; ++kb) {
             if (kb < num_kb) {
                 const int s = kb % TC_STAGES;
@@ -197,8 +198,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcConvTask
                     kw = pos - kh * T.k;
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = r_lo + 16 * i;
+                for (int i = 0; i < 4; ++i) {
+                    const int r = r_lo + 32 * i;
                     const __nv_bfloat16* src = xbase;
                     uint32_t bytes = 0;
                     if (kvalid && xrow[i] != nullptr) {
@@ -211,9 +212,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcConvTask
                     cp_async16(a_st + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4), src, bytes);
                 }
                 for (int i = 0; i < b_rows; ++i) {
-                    const int r = r_lo + 16 * i;
-                    cp_async16(b_st + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4),
-                               T.wt + (long long)(n0 + r) * T.K_pad + kb * TC_BK + j * 8, 16);
+                    const int r = r_lo + 32 * i;
+                    if (r < T.bn)
+                        cp_async16(b_st + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4),
+                                   T.wt + (long long)(n0 + r) * T.K_pad + kb * TC_BK + j * 8, 16);
                 }
             }
             cp_async_commit();
@@ -226,7 +228,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcConvTask
         // ================= epilogue: TMEM -> registers -> global =================
         mbar_wait(accum_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = warp * 32 + lane;
+        const int lane_grp = warp & 3;                          // TMEM lanes 32*lane_grp .. +31 (warp-id mod 4 rule)
+        const int c_begin = T.bn >= 32 ? (warp >> 2) * (T.bn / 2) : 0;
+        const int c_end = T.bn >= 32 ? c_begin + T.bn / 2 : ((warp >> 2) == 0 ? T.bn : 0);
+        const int row = lane_grp * 32 + lane;
         const int mi = m0 + row;
         long long obase = 0;
         if (mi < M) {
@@ -238,9 +243,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcConvTask
                 obase = (((long long)n * T.out_h + ho * T.out_s) * T.out_w + wo * T.out_s) * T.Cout;
             }
         }
-        for (int c0 = 0; c0 < T.bn; c0 += 16) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
             uint32_t v[16];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcConvTask
         __syncwarp();
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == TC_PRODUCERS / 32) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
@@ -366,13 +371,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) wgrad_tc_kernel(const TcWgradTa
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(&full_bar[s], 128);
+            mbar_init(&full_bar[s], TC_PRODUCERS);
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == TC_PRODUCERS / 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(TMEM_COLS)
                      : "memory");
@@ -383,9 +388,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) wgrad_tc_kernel(const TcWgradTa
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < TC_PRODUCERS / 32) {
         // ---- producers: thread owns chunk column c16 (8 consecutive kk / co) and rows r_lo + 8 i of the stage
-        const int c16 = tid & 15, r_lo = tid >> 4;
+        const int c16 = tid & 15, r_lo = tid >> 4;      // rows r_lo + 16*i
         const long long img = (long long)T.H * T.W * T.Cin;
         const int kk = kk0 + c16 * 8;
         int kh = 0, kw = 0, ci = 0, a_kind;             // a_kind 0: zeros, 1: im2col taps, 2: chunk containing the ones column
@@ -408,8 +413,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) wgrad_tc_kernel(const TcWgradTa
                 uint8_t* a_st = a_smem + s * TC_A_BYTES;
                 uint8_t* b_st = b_smem + s * TC_B_BYTES;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = r_lo + 8 * i;
+                for (int i = 0; i < 4; ++i) {
+                    const int r = r_lo + 16 * i;
                     const int m = m_begin + st * 64 + r;
                     const uint32_t row_off = (uint32_t)r * 128u + ((a_chunk ^ (uint32_t)(r & 7)) << 4);
                     const __nv_bfloat16* asrc = T.xh;
@@ -443,11 +448,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) wgrad_tc_kernel(const TcWgradTa
         // ---- epilogue: D rows = kk, columns = co
         mbar_wait(accum_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = warp * 32 + lane;
+        const int lane_grp = warp & 3;
+        const int c_begin = T.bn >= 32 ? (warp >> 2) * (T.bn / 2) : 0;
+        const int c_end = T.bn >= 32 ? c_begin + T.bn / 2 : ((warp >> 2) == 0 ? T.bn : 0);
+        const int row = lane_grp * 32 + lane;
         const int krow = kk0 + row;
-        for (int c0 = 0; c0 < T.bn; c0 += 16) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
             uint32_t v[16];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -488,7 +496,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) wgrad_tc_kernel(const TcWgradTa
         __syncwarp();
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == TC_PRODUCERS / 32) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
