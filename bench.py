@@ -170,7 +170,12 @@ def cnn_generation_extra(args, rank: int, world: int) -> dict:
         cfg = TrainConfig(variant="B", epochs=epochs, patience=epochs, restore_best_weights=True, acc_from="evaluate",
                           precision=prec)
         prob = FitnessProblem(xt, yt, xv, yv, classes=12, config=cfg)
-        prob.train_eval(hps[:1], [0])
+        # warm-up: the whole population for one epoch on a 128-sample slice, so the persistent activation arena
+        # is allocated (tens of GB of cudaMalloc) and every kernel is loaded before the timed call
+        warm = FitnessProblem(xt[:128], yt[:128], xv[:64], yv[:64], classes=12,
+                              config=TrainConfig(variant="B", epochs=1, patience=1, precision=prec))
+        warm.compute_objectives_and_constraints(hps)
+        warm.data.close()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

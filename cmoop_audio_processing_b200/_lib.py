@@ -27,7 +27,7 @@ class GpModel(C.Structure):
 class MfccConfig(C.Structure):
     _fields_ = [("sample_rate", C.c_int), ("frame_length", C.c_int), ("hop", C.c_int), ("n_fft", C.c_int),
                 ("n_mels", C.c_int), ("n_mfcc", C.c_int), ("f_min", C.c_float), ("f_max", C.c_float),
-                ("log_floor", C.c_float)]
+                ("log_floor", C.c_float), ("center", C.c_int)]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check every symbol of the header.

@@ -187,10 +187,10 @@ struct Launch {
     static int wgrad(const WgradTask* tasks, int n_tasks, int total_tiles, int n_b, int step, void* stream);
     static int reduce(const ReduceTask* tasks, int n_tasks, int total_blocks, void* stream);
     static int wt(const WtTask* tasks, int n_tasks, int total_blocks, void* stream);
-    static int bn_finalize(const PostTask* tasks, int n_tasks, int n_b, int training, float momentum, float eps, void* stream);
+    static int bn_finalize(const PostTask* tasks, int n_tasks, int max_c, int n_b, int training, float momentum, float eps, void* stream);
     static int post_fwd(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
     static int post_bwd_reduce(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
-    static int bn_bwd_finalize(const PostTask* tasks, int n_tasks, int n_b, void* stream);
+    static int bn_bwd_finalize(const PostTask* tasks, int n_tasks, int max_c, int n_b, void* stream);
     static int post_bwd_apply(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
     static int gap_fwd(const HeadTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
     static int gap_bwd(const HeadTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);

@@ -299,6 +299,7 @@ struct StageLists {
     DevList<TcWgradTask> wgrad_tc;
     DevList<StatTask> stat;
     bool any = false;
+    int max_bn_c = 0;                // widest BN unit of the stage (grid.y of the finalize kernels)
     DevList<PostTask> post_fwd, post_bn, post_bwd;
     DevList<WgradTask> wgrad;
     DevList<ReduceTask> wreduce;
@@ -435,6 +436,7 @@ struct Engine {
                         S.post_fwd.total += blocks_for(u.v_elems / 4);
                     }
                     if (u.has_bn) {
+                        S.max_bn_c = std::max(S.max_bn_c, u.cout);
                         PostTask q = p;
                         q.block_begin_bwd = S.post_bn.total;
                         S.post_bn.h.push_back(q);
@@ -631,7 +633,7 @@ struct Engine {
                     CNN_LAUNCH(Launch::bn_stats(S.stat.d, (int)S.stat.h.size(), S.stat.total, n_b, stream));
             }
             if (!S.post_bn.h.empty())
-                CNN_LAUNCH(Launch::bn_finalize(S.post_bn.d, (int)S.post_bn.h.size(), n_b, training, cfg.bn_momentum,
+                CNN_LAUNCH(Launch::bn_finalize(S.post_bn.d, (int)S.post_bn.h.size(), S.max_bn_c, n_b, training, cfg.bn_momentum,
                                                cfg.bn_eps, stream));
             if (!S.post_fwd.h.empty())
                 CNN_LAUNCH(Launch::post_fwd(S.post_fwd.d, (int)S.post_fwd.h.size(), S.post_fwd.total, n_b, stream));
@@ -655,7 +657,7 @@ struct Engine {
                                             cfg.dropout_rate, stream));
             if (!S.post_bn.h.empty()) {
                 CNN_LAUNCH(Launch::post_bwd_reduce(S.post_bn.d, (int)S.post_bn.h.size(), S.post_bn.total, n_b, stream));
-                CNN_LAUNCH(Launch::bn_bwd_finalize(S.post_bn.d, (int)S.post_bn.h.size(), n_b, stream));
+                CNN_LAUNCH(Launch::bn_bwd_finalize(S.post_bn.d, (int)S.post_bn.h.size(), S.max_bn_c, n_b, stream));
             }
             if (!S.post_bwd.h.empty())
                 CNN_LAUNCH(Launch::post_bwd_apply(S.post_bwd.d, (int)S.post_bwd.h.size(), S.post_bwd.total, n_b, stream));
@@ -857,19 +859,25 @@ int run_wave(Engine& eng, Wave& wv, double* out, double* history, int debug_step
     if (rc != CMOOP_OK) return rc;
     const int steps_per_epoch = (data->n_train + batch - 1) / batch;
     const int val_steps = (data->n_val + batch - 1) / batch;
-    std::vector<int> perm(data->n_train);
     std::vector<double> acc(12);
     int t_adam = 0;
     const int max_epochs = debug_steps > 0 ? 1 : cfg.max_epochs;
     for (int epoch = 0; epoch < max_epochs; ++epoch) {
         bool any = false;
-        for (Cand* c : wv.cands) {
-            if (!c->active) continue;
-            any = true;
-            make_permutation(c->seed, epoch, data->n_train, perm.data());
-            CMOOP_CUDA_OK(cudaMemcpyAsync(c->perm, perm.data(), sizeof(int) * data->n_train, cudaMemcpyHostToDevice, st));
-            CMOOP_CUDA_OK(cudaStreamSynchronize(st));     // perm is a reused pageable staging buffer
-            CMOOP_CUDA_OK(cudaMemsetAsync(c->acc, 0, 8 * sizeof(double), st));
+        {
+            int n_active = 0;
+            for (Cand* c : wv.cands) n_active += c->active ? 1 : 0;
+            int* stage = (int*)cmoop::pinned_scratch(5, (size_t)std::max(1, n_active) * data->n_train * sizeof(int));
+            if (!stage) return CMOOP_ERR_CUDA;
+            int slot = 0;
+            for (Cand* c : wv.cands) {
+                if (!c->active) continue;
+                any = true;
+                int* dst = stage + (size_t)slot++ * data->n_train;
+                make_permutation(c->seed, epoch, data->n_train, dst);
+                CMOOP_CUDA_OK(cudaMemcpyAsync(c->perm, dst, sizeof(int) * data->n_train, cudaMemcpyHostToDevice, st));
+                CMOOP_CUDA_OK(cudaMemsetAsync(c->acc, 0, 8 * sizeof(double), st));
+            }
         }
         if (!any) break;
         const int n_steps = debug_steps > 0 ? std::min(debug_steps, steps_per_epoch) : steps_per_epoch;
@@ -1004,8 +1012,9 @@ int run_population(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotype
     // ---- waves: consecutive candidates while they fit the arena
     int next = 0;
     Wave wv;
-    char* arena_base = nullptr;
-    size_t arena_cap = 0;
+    static char* arena_base = nullptr;        // grow-only, kept across calls (one process drives one GPU)
+    static size_t arena_cap = 0;
+    if (arena_cap > 0 && !(cfg->memory_budget_bytes > 0)) budget += arena_cap;   // already ours, not in the free figure
     while (next < P) {
         size_t need = 0;
         int end = next;
@@ -1013,6 +1022,7 @@ int run_population(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotype
         if (need > arena_cap) {
             if (arena_base) CMOOP_CUDA_OK(cudaFree(arena_base));
             arena_base = nullptr;
+            arena_cap = 0;
             if (cudaMalloc((void**)&arena_base, need) != cudaSuccess) {
                 (void)cudaGetLastError();
                 cmoop::set_error("cnn: cannot allocate a %.2f GB arena for candidates [%d,%d)", need / 1e9, next, end);
@@ -1033,7 +1043,6 @@ int run_population(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotype
         next = end;
     }
     cudaStreamSynchronize(eng.stream);
-    if (arena_base) cudaFree(arena_base);
     if (wv.d_blob) cudaFree(wv.d_blob);
     return rc;
 }

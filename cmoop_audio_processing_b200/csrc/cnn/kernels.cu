@@ -319,56 +319,51 @@ __global__ void __launch_bounds__(256) wt_kernel(const WtTask* __restrict__ task
 }
 
 // ------------------------------------------------------------------------------------------------
-// BatchNorm statistics -> (mean, invstd, scale, shift); one CTA per task, tile partials summed in double by
-// (128 / C) lanes per channel and combined in lane order (deterministic)
+// BatchNorm statistics -> (mean, invstd, scale, shift); grid (task, 8-channel chunk): 16 tile lanes x 8 channels sum
+// the tile partials in double and are combined in lane order (deterministic)
 __global__ void __launch_bounds__(128) bn_finalize_kernel(const PostTask* __restrict__ tasks, int n_b, int training,
                                                           float momentum, float eps) {
     __shared__ double red[2][128];
     const PostTask T = tasks[blockIdx.x];
-    if (!T.has_bn) return;
+    const int c = blockIdx.y * 8 + (threadIdx.x & 7);
+    if (!T.has_bn || blockIdx.y * 8 >= T.C) return;
+    const int t_lane = threadIdx.x >> 3;
     const double count = (double)n_b * T.H * T.W;
     const int tiles = (n_b * T.H * T.W + BM - 1) / BM;    // tiles the conv epilogue / bn_stats wrote for THIS batch size
-    const int cb = T.C < 128 ? T.C : 128;
-    const int lanes = 128 / cb;
-    const int t_lane = threadIdx.x / cb, c_lane = threadIdx.x - t_lane * cb;
-    for (int c0 = 0; c0 < T.C; c0 += cb) {
-        const int c = c0 + c_lane;
-        double s1 = 0.0, s2 = 0.0;
-        if (training && t_lane < lanes && c < T.C)
-            for (int t = t_lane; t < tiles; t += lanes) {
-                s1 += (double)T.stat_part[((long long)t * 2 + 0) * T.C + c];
-                s2 += (double)T.stat_part[((long long)t * 2 + 1) * T.C + c];
-            }
-        red[0][threadIdx.x] = s1;
-        red[1][threadIdx.x] = s2;
-        __syncthreads();
-        if (t_lane == 0 && c < T.C) {
-            float mean, var;
-            if (training) {
-                double a1 = 0.0, a2 = 0.0;
-                for (int l = 0; l < lanes; ++l) {
-                    a1 += red[0][l * cb + c_lane];
-                    a2 += red[1][l * cb + c_lane];
-                }
-                const double mu = a1 / count;
-                double vv = a2 / count - mu * mu;
-                vv = vv > 0.0 ? vv : 0.0;
-                mean = (float)mu;
-                var = (float)vv;
-                T.mov_mean[c] = T.mov_mean[c] * momentum + mean * (1.f - momentum);
-                T.mov_var[c] = T.mov_var[c] * momentum + var * (1.f - momentum);
-            } else {
-                mean = T.mov_mean[c];
-                var = T.mov_var[c];
-            }
-            const float invstd = rsqrtf(var + eps);
-            const float scale = T.gamma[c] * invstd;
-            T.bn[0 * T.C + c] = mean;
-            T.bn[1 * T.C + c] = invstd;
-            T.bn[2 * T.C + c] = scale;
-            T.bn[3 * T.C + c] = T.beta[c] - mean * scale;
+    double s1 = 0.0, s2 = 0.0;
+    if (training && c < T.C)
+        for (int t = t_lane; t < tiles; t += 16) {
+            s1 += (double)T.stat_part[((long long)t * 2 + 0) * T.C + c];
+            s2 += (double)T.stat_part[((long long)t * 2 + 1) * T.C + c];
         }
-        __syncthreads();
+    red[0][threadIdx.x] = s1;
+    red[1][threadIdx.x] = s2;
+    __syncthreads();
+    if (t_lane == 0 && c < T.C) {
+        float mean, var;
+        if (training) {
+            double a1 = 0.0, a2 = 0.0;
+            for (int l = 0; l < 16; ++l) {
+                a1 += red[0][l * 8 + (threadIdx.x & 7)];
+                a2 += red[1][l * 8 + (threadIdx.x & 7)];
+            }
+            const double mu = a1 / count;
+            double vv = a2 / count - mu * mu;
+            vv = vv > 0.0 ? vv : 0.0;
+            mean = (float)mu;
+            var = (float)vv;
+            T.mov_mean[c] = T.mov_mean[c] * momentum + mean * (1.f - momentum);
+            T.mov_var[c] = T.mov_var[c] * momentum + var * (1.f - momentum);
+        } else {
+            mean = T.mov_mean[c];
+            var = T.mov_var[c];
+        }
+        const float invstd = rsqrtf(var + eps);
+        const float scale = T.gamma[c] * invstd;
+        T.bn[0 * T.C + c] = mean;
+        T.bn[1 * T.C + c] = invstd;
+        T.bn[2 * T.C + c] = scale;
+        T.bn[3 * T.C + c] = T.beta[c] - mean * scale;
     }
 }
 
@@ -513,38 +508,33 @@ __global__ void __launch_bounds__(128) post_bwd_reduce_kernel(const PostTask* __
 __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const PostTask* __restrict__ tasks, int n_b) {
     __shared__ double red[2][128];
     const PostTask T = tasks[blockIdx.x];
-    if (!T.has_bn) return;
+    const int c = blockIdx.y * 8 + (threadIdx.x & 7);
+    if (!T.has_bn || blockIdx.y * 8 >= T.C) return;
+    const int r_lane = threadIdx.x >> 3;
     const int C4 = T.C >> 2;
     const int lanes_w = 128 / (C4 < 128 ? C4 : 128);          // partial rows per CTA written by post_bwd_reduce
     const long long n_pix = (long long)n_b * T.Ho * T.Wo;
     const long long rows = ((n_pix + 127) / 128) * lanes_w;
     const double count = (double)n_b * T.H * T.W;
-    const int cb = T.C < 128 ? T.C : 128;
-    const int lanes = 128 / cb;
-    const int r_lane = threadIdx.x / cb, c_lane = threadIdx.x - r_lane * cb;
-    for (int c0 = 0; c0 < T.C; c0 += cb) {
-        const int c = c0 + c_lane;
-        double sg = 0.0, sgx = 0.0;
-        if (r_lane < lanes && c < T.C)
-            for (long long r = r_lane; r < rows; r += lanes) {
-                sg += (double)T.bwd_part[(r * 2 + 0) * T.C + c];
-                sgx += (double)T.bwd_part[(r * 2 + 1) * T.C + c];
-            }
-        red[0][threadIdx.x] = sg;
-        red[1][threadIdx.x] = sgx;
-        __syncthreads();
-        if (r_lane == 0 && c < T.C) {
-            double a1 = 0.0, a2 = 0.0;
-            for (int l = 0; l < lanes; ++l) {
-                a1 += red[0][l * cb + c_lane];
-                a2 += red[1][l * cb + c_lane];
-            }
-            T.dbeta[c] = (float)a1;
-            T.dgamma[c] = (float)a2;
-            T.bn[4 * T.C + c] = (float)(a1 / count);
-            T.bn[5 * T.C + c] = (float)(a2 / count);
+    double sg = 0.0, sgx = 0.0;
+    if (c < T.C)
+        for (long long r = r_lane; r < rows; r += 16) {
+            sg += (double)T.bwd_part[(r * 2 + 0) * T.C + c];
+            sgx += (double)T.bwd_part[(r * 2 + 1) * T.C + c];
         }
-        __syncthreads();
+    red[0][threadIdx.x] = sg;
+    red[1][threadIdx.x] = sgx;
+    __syncthreads();
+    if (r_lane == 0 && c < T.C) {
+        double a1 = 0.0, a2 = 0.0;
+        for (int l = 0; l < 16; ++l) {
+            a1 += red[0][l * 8 + (threadIdx.x & 7)];
+            a2 += red[1][l * 8 + (threadIdx.x & 7)];
+        }
+        T.dbeta[c] = (float)a1;
+        T.dgamma[c] = (float)a2;
+        T.bn[4 * T.C + c] = (float)(a1 / count);
+        T.bn[5 * T.C + c] = (float)(a2 / count);
     }
 }
 
@@ -802,9 +792,9 @@ int Launch::wt(const WtTask* tasks, int n, int blocks, void* st) {
     wt_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n);
     return check();
 }
-int Launch::bn_finalize(const PostTask* tasks, int n, int n_b, int training, float momentum, float eps, void* st) {
+int Launch::bn_finalize(const PostTask* tasks, int n, int max_c, int n_b, int training, float momentum, float eps, void* st) {
     if (n == 0) return 0;
-    bn_finalize_kernel<<<n, 128, 0, (cudaStream_t)st>>>(tasks, n_b, training, momentum, eps);
+    bn_finalize_kernel<<<dim3(n, (max_c + 7) / 8), 128, 0, (cudaStream_t)st>>>(tasks, n_b, training, momentum, eps);
     return check();
 }
 int Launch::post_fwd(const PostTask* tasks, int n, int blocks, int n_b, void* st) {
@@ -817,9 +807,9 @@ int Launch::post_bwd_reduce(const PostTask* tasks, int n, int blocks, int n_b, v
     post_bwd_reduce_kernel<<<blocks, 128, 0, (cudaStream_t)st>>>(tasks, n, n_b);
     return check();
 }
-int Launch::bn_bwd_finalize(const PostTask* tasks, int n, int n_b, void* st) {
+int Launch::bn_bwd_finalize(const PostTask* tasks, int n, int max_c, int n_b, void* st) {
     if (n == 0) return 0;
-    bn_bwd_finalize_kernel<<<n, 128, 0, (cudaStream_t)st>>>(tasks, n_b);
+    bn_bwd_finalize_kernel<<<dim3(n, (max_c + 7) / 8), 128, 0, (cudaStream_t)st>>>(tasks, n_b);
     return check();
 }
 int Launch::post_bwd_apply(const PostTask* tasks, int n, int blocks, int n_b, void* st) {

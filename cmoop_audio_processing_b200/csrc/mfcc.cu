@@ -34,6 +34,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "mfcc_generic.cuh"
 
 namespace {
 
@@ -471,6 +472,7 @@ double mel_to_hz(double m) {
 }  // namespace
 
 struct cmoop_mfcc {
+    cmoop::GenericMfcc* generic = nullptr;   // set when the configuration runs on the generic kernel
     cmoop_mfcc_config cfg;
     int n_out = 0, half_len = 0, nz = 0, mel_mode = 0, dct_mode = 0;
     Tables t{};
@@ -507,6 +509,7 @@ extern "C" {
 
 int cmoop_mfcc_destroy(cmoop_mfcc_handle h) {
     if (!h) return CMOOP_OK;
+    if (h->generic) cmoop::generic_mfcc_destroy(h->generic);
     if (h->d_tables) cudaFree(h->d_tables);
     delete h;
     return CMOOP_OK;
@@ -515,20 +518,28 @@ int cmoop_mfcc_destroy(cmoop_mfcc_handle h) {
 int cmoop_mfcc_create(const cmoop_mfcc_config* cfg, cmoop_mfcc_handle* out) {
     CMOOP_REQUIRE(cfg && out, "mfcc_create: null pointer");
     *out = nullptr;
-    if (cfg->n_fft != kNfft) {
-        cmoop::set_error("mfcc_create: n_fft=%d not implemented (only 1024)", cfg->n_fft);
-        return CMOOP_ERR_UNSUPPORTED;
-    }
-    CMOOP_REQUIRE(cfg->frame_length > 0 && cfg->frame_length <= kNfft && cfg->frame_length % 2 == 0,
-                  "mfcc_create: frame_length=%d must be even and in (0,%d]", cfg->frame_length, kNfft);
     CMOOP_REQUIRE(cfg->hop > 0, "mfcc_create: hop must be positive");
-    CMOOP_REQUIRE(cfg->n_mels > 0 && cfg->n_mels <= kMaxMel, "mfcc_create: n_mels=%d outside [1,%d]", cfg->n_mels,
-                  kMaxMel);
     CMOOP_REQUIRE(cfg->n_mfcc >= 0 && cfg->n_mfcc <= cfg->n_mels, "mfcc_create: n_mfcc=%d outside [0,n_mels]",
                   cfg->n_mfcc);
     CMOOP_REQUIRE(cfg->sample_rate > 0 && cfg->f_min >= 0.f && cfg->f_max > cfg->f_min &&
                       cfg->f_max <= 0.5f * cfg->sample_rate,
                   "mfcc_create: need 0 <= f_min < f_max <= sample_rate/2");
+    const bool specialised = cfg->n_fft == kNfft && !cfg->center && cfg->n_mels <= kMaxMel && cfg->frame_length % 2 == 0;
+    if (!specialised) {
+        if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
+        cmoop::GenericMfcc* g = nullptr;
+        int rc = cmoop::generic_mfcc_create(cfg, &g);
+        if (rc != CMOOP_OK) return rc;
+        cmoop_mfcc* h = new cmoop_mfcc();
+        h->cfg = *cfg;
+        h->generic = g;
+        h->n_out = cmoop::generic_mfcc_n_out(g);
+        *out = h;
+        return CMOOP_OK;
+    }
+    CMOOP_REQUIRE(cfg->frame_length > 0 && cfg->frame_length <= kNfft,
+                  "mfcc_create: frame_length=%d must be in (0,%d]", cfg->frame_length, kNfft);
+    CMOOP_REQUIRE(cfg->n_mels > 0, "mfcc_create: n_mels must be positive");
     if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
 
     cmoop_mfcc* h = new cmoop_mfcc();
@@ -705,6 +716,7 @@ int cmoop_mfcc_create(const cmoop_mfcc_config* cfg, cmoop_mfcc_handle* out) {
 }
 
 int cmoop_mfcc_n_frames(cmoop_mfcc_handle h, int n_samples) {
+    if (h && h->generic) return cmoop::generic_mfcc_n_frames(h->generic, n_samples);
     if (!h || n_samples < h->cfg.frame_length) return 0;
     return 1 + (n_samples - h->cfg.frame_length) / h->cfg.hop;
 }
@@ -714,6 +726,7 @@ int cmoop_mfcc_n_out(cmoop_mfcc_handle h) { return h ? h->n_out : 0; }
 int cmoop_mfcc_set_standardise(cmoop_mfcc_handle h, const float* mean, const float* scale) {
     CMOOP_REQUIRE(h != nullptr, "mfcc_set_standardise: null handle");
     CMOOP_REQUIRE((mean == nullptr) == (scale == nullptr), "mfcc_set_standardise: pass both or neither");
+    if (h->generic) return cmoop::generic_mfcc_set_standardise(h->generic, mean, scale);
     float* T = h->host_tables.data();
     for (int c = 0; c < h->n_out; ++c) {
         T[h->t.mean + c] = mean ? mean[c] : 0.f;
@@ -730,6 +743,7 @@ int cmoop_mfcc_fwd_dev(cmoop_mfcc_handle h, const float* wave, int64_t n_clips, 
     const int frames = cmoop_mfcc_n_frames(h, n_samples);
     if (n_clips == 0 || frames == 0) return CMOOP_OK;
     CMOOP_REQUIRE(wave && out, "mfcc_fwd: null pointer");
+    if (h->generic) return cmoop::generic_mfcc_fwd(h->generic, wave, n_clips, n_samples, out, stream);
     Params p{};
     p.wave = wave;
     p.out = out;

@@ -27,6 +27,7 @@ class MfccConfig:
     f_min: float = 0.0
     f_max: float = 8000.0
     log_floor: float = 1e-10
+    center: bool = False      # librosa-style reflect-padded centring (frame_length must equal n_fft)
 
 
 class MfccFrontEnd:
@@ -35,7 +36,7 @@ class MfccFrontEnd:
         _lib.bind_device()
         self.config = config
         c = _lib.MfccConfig(config.sample_rate, config.frame_length, config.hop, config.n_fft, config.n_mels,
-                            config.n_mfcc, config.f_min, config.f_max, config.log_floor)
+                            config.n_mfcc, config.f_min, config.f_max, config.log_floor, int(config.center))
         handle = C.c_void_p()
         _lib.check(self._lib.cmoop_mfcc_create(C.byref(c), C.byref(handle)), "cmoop_mfcc_create")
         self._handle = handle

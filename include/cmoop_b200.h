@@ -130,6 +130,8 @@ int cmoop_coverage_host(const double* a, int na, const double* b, int nb, int m,
 /* ------------------------------------------------------------------ (1) log-mel / MFCC front-end
  * No reference code exists for this stage (features are loaded pre-computed:
  * nsga_penalty.py:64-71, sa_nsga_penalty.py:42-63); the spec is oracle/mfcc_ref.py.
+ * n_fft == 1024 without centring and n_mels <= 64 runs the specialised warp-per-frame kernel (mfcc.cu); any other
+ * power-of-two n_fft in [64, 4096] / centring / up to 256 bands runs the generic CTA-per-frame kernel.
  * wave [n_clips][n_samples] fp32 ; out [n_clips][n_frames][n_out] fp32 with
  * n_out = n_mfcc if n_mfcc > 0 else n_mels  -- the (N, T, F) layout prepare_dataset
  * expects (nsga_penalty.py:104-114).
@@ -144,6 +146,8 @@ typedef struct {
     float f_min;       /* 0    */
     float f_max;       /* 8000 */
     float log_floor;   /* 1e-10 */
+    int center;        /* 0: frames start at t*hop (default); 1: librosa-style centring with reflect padding
+                          (needs frame_length == n_fft), e.g. BirdCLEF-shaped 32 kHz / 2048 / 512 / 128 mel */
 } cmoop_mfcc_config;
 
 typedef struct cmoop_mfcc* cmoop_mfcc_handle;

@@ -40,8 +40,11 @@ class MfccSpec:
     f_min: float = 0.0
     f_max: float = 8000.0
     log_floor: float = 1e-10
+    center: bool = False      # librosa stft(center=True): reflect-pad n_fft//2 on both sides (frame_length == n_fft)
 
     def n_frames(self, n_samples: int) -> int:
+        if self.center:
+            return 1 + n_samples // self.hop if n_samples > self.n_fft // 2 else 0
         if n_samples < self.frame_length:
             return 0
         return 1 + (n_samples - self.frame_length) // self.hop
@@ -102,6 +105,9 @@ def power_spectrogram(wave: np.ndarray, spec: MfccSpec) -> np.ndarray:
     """(B, T, n_fft//2+1) fp64."""
     wave = np.atleast_2d(np.asarray(wave, np.float64))
     t = spec.n_frames(wave.shape[1])
+    if spec.center:
+        assert spec.frame_length == spec.n_fft
+        wave = np.pad(wave, ((0, 0), (spec.n_fft // 2, spec.n_fft // 2)), mode="reflect")
     idx = np.arange(spec.frame_length)[None, :] + spec.hop * np.arange(t)[:, None]
     frames = wave[:, idx] * hann_periodic(spec.frame_length)
     spectrum = np.fft.rfft(frames, n=spec.n_fft, axis=-1)

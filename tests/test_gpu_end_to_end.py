@@ -72,3 +72,20 @@ def test_sa_nsga2_with_surrogate_and_local_search(kws_features):
     assert hv > 0.0
     m = quality.front_metrics(front, front)
     assert m["gd"] == 0.0 and m["igd"] == 0.0
+
+
+def test_run_mobo_loop(kws_features):
+    """mobo_penalty.py flow: 4 GPs (Matern 2.5, normalize_y) on the GPU posterior, 500 random candidates, penalised sum."""
+    from cmoop_audio_processing_b200 import drivers
+    from cmoop_audio_processing_b200.problem import FitnessProblem, TrainConfig
+    xt, yt, xv, yv, n_cls = kws_features
+    cfg = TrainConfig(variant="A", epochs=2, patience=2, restore_best_weights=True, acc_from="history", precision="bf16")
+    prob = FitnessProblem.mobo_penalty(xt, yt, xv, yv, classes=n_cls, config=cfg)
+    random.seed(2)
+    np.random.seed(2)
+    pareto, (x_vec, y_objs, y_cv) = drivers.run_mobo(5, 3, 500, prob)
+    assert x_vec.shape == (8, 6) and y_objs.shape == (8, 3) and y_cv.shape == (8, 1)
+    assert prob.evaluations == 8
+    assert np.all((x_vec >= 0) & (x_vec <= 1))
+    for hp, objs, cv in pareto:
+        assert cv <= 1e-8

@@ -108,7 +108,9 @@ def test_mfcc_shapes_edges_and_standardise():
     fe.set_standardise(None, None)
     _check_features(fe(wave), base)
     with pytest.raises(RuntimeError):
-        MfccFrontEnd(MfccConfig(n_fft=2048))
+        MfccFrontEnd(MfccConfig(n_fft=1000))                       # not a power of two
+    with pytest.raises(RuntimeError):
+        MfccFrontEnd(MfccConfig(n_fft=2048, frame_length=640, center=True))   # centring needs frame_length == n_fft
 
 
 def test_mfcc_full_size_properties():
@@ -128,3 +130,31 @@ def test_mfcc_full_size_properties():
     assert torch.equal(c, a[perm])
     sub = wave[:64].cpu().numpy()
     _check_features(a[:64].cpu().numpy(), mfcc_ref.log_mel(sub, mfcc_ref.MfccSpec(n_mfcc=0)))
+
+
+def test_generic_front_end_birdclef_shape_and_other_fft_sizes():
+    """Generic CTA-per-frame kernel: BirdCLEF-shaped 32 kHz / n_fft 2048 / hop 512 / centred / 128 mel (313 frames for
+    5 s, BASELINE configs[3]), plus a 512-point and a zero-padded 2048-point configuration."""
+    import torch
+    from cmoop_audio_processing_b200 import synth
+    from cmoop_audio_processing_b200.features import MfccConfig, MfccFrontEnd
+    wave, _ = synth.make_clips(3, 12, sample_rate=32000, seconds=5.0, seed=11)
+    assert wave.shape == (3, 160000)
+    cfg = dict(sample_rate=32000, frame_length=2048, hop=512, n_fft=2048, n_mels=128, n_mfcc=0, f_max=16000.0, center=True)
+    fe = MfccFrontEnd(MfccConfig(**cfg))
+    assert fe.n_frames(160000) == 313 and fe.n_out == 128
+    want = mfcc_ref.log_mel(wave, mfcc_ref.MfccSpec(**cfg))
+    got = fe(wave)
+    assert got.shape == (3, 313, 128)
+    _check_features(got, want)
+    np.testing.assert_array_equal(fe(torch.from_numpy(wave).cuda()).cpu().numpy(), got)
+    small, _ = synth.make_clips(4, 12, seed=3)
+    for cfg in (dict(frame_length=400, hop=160, n_fft=512, n_mels=40, n_mfcc=13),
+                dict(frame_length=640, hop=320, n_fft=2048, n_mels=64, n_mfcc=20),
+                dict(frame_length=1024, hop=256, n_fft=1024, n_mels=80, n_mfcc=0, center=True),
+                dict(frame_length=401, hop=160, n_fft=1024, n_mels=40, n_mfcc=0)):
+        fe = MfccFrontEnd(MfccConfig(**cfg))
+        want = mfcc_ref.mfcc(small, mfcc_ref.MfccSpec(**cfg))
+        got = fe(small)
+        assert got.shape == want.shape
+        _check_features(got, want)
