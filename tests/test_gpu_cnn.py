@@ -222,3 +222,29 @@ def test_bf16_and_fp32_paths_agree_after_training():
     np.testing.assert_array_equal(outs["fp32"][:, 1], outs["bf16"][:, 1])          # size is exact in both
     assert np.abs(outs["fp32"][:, 0] - outs["bf16"][:, 0]).max() <= 0.08          # accuracy after 4 epochs
     assert np.abs(outs["fp32"][:, 5] - outs["bf16"][:, 5]).max() <= 0.15          # best validation loss
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ragged_last_batches(precision):
+    """n_train and n_val that are not multiples of 64 (Keras keeps the last partial batch): per-step losses over a full
+    epoch incl. the 8-sample tail batch, then the validation loss / accuracy of the ragged validation split."""
+    import torch
+    from cmoop_audio_processing_b200.problem import FitnessProblem, TrainConfig
+    xt, yt, xv, yv = make_data(200, 77)
+    variant, hp = GENOTYPES[1]
+    seed = 99
+    cfg = TrainConfig(variant=variant, epochs=1, patience=1, precision=precision, acc_from="evaluate")
+    prob = FitnessProblem(xt, yt, xv, yv, classes=N_CLASSES, config=cfg)
+    init = prob.debug_init_params(hp, seed)
+    perm = prob.debug_permutation(seed, 0)
+    losses, _, _ = prob.debug_train_steps(hp, seed, 4)                  # 64 + 64 + 64 + 8 samples
+    mirror = precision == "bf16"
+    model = cnn_ref.RefModel(hp, N_CLASSES, variant, unflatten(init, hp, variant), bf16_convs=mirror)
+    ref_losses, _ = cnn_ref.train_steps(model, xt, yt, perm, 4, seed=seed & 0xFFFFFFFF)
+    np.testing.assert_allclose(losses, ref_losses, rtol=2e-3 if not mirror else 1e-2)
+    out, hist = prob.train_eval([hp], [seed], want_history=True)
+    ref = cnn_ref.evaluate_individual(hp, (xt, yt, xv, yv), unflatten(init, hp, variant), [perm], n_classes=N_CLASSES,
+                                      variant=variant, seed=seed, epochs=1, patience=1, acc_from="evaluate")
+    assert hist[0, 0, 0] == pytest.approx(ref["history"]["loss"][0], rel=2e-3 if not mirror else 2e-2)
+    assert hist[0, 0, 1] == pytest.approx(ref["history"]["val_loss"][0], rel=5e-3 if not mirror else 3e-2)
+    assert abs(out[0, 0] - ref["acc"]) <= 2.0 / 77
