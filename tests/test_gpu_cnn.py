@@ -248,3 +248,21 @@ def test_ragged_last_batches(precision):
     assert hist[0, 0, 0] == pytest.approx(ref["history"]["loss"][0], rel=2e-3 if not mirror else 2e-2)
     assert hist[0, 0, 1] == pytest.approx(ref["history"]["val_loss"][0], rel=5e-3 if not mirror else 3e-2)
     assert abs(out[0, 0] - ref["acc"]) <= 2.0 / 77
+
+
+def test_waves_and_bf16_batching_invariance():
+    """A tiny activation-arena budget forces several waves of candidates; results must be bit-identical to the
+    single-wave run, also on the tensor-core path (deterministic kernels, no cross-candidate state)."""
+    from cmoop_audio_processing_b200.problem import FitnessProblem, TrainConfig
+    xt, yt, xv, yv = make_data(128, 64)
+    hps = [hp for _, hp in GENOTYPES] + [dict(filters=64, kernel_size=3, use_bn=True, residual_blocks=2, fc_layers=2,
+                                              use_dropout=True)]
+    seeds = list(range(21, 21 + len(hps)))
+    outs = []
+    for budget in (0.0, 1.2e8):     # 120 MB: at most one or two of these candidates per wave
+        cfg = TrainConfig(variant="B", epochs=2, patience=2, precision="bf16", memory_budget_bytes=budget)
+        prob = FitnessProblem(xt, yt, xv, yv, classes=N_CLASSES, config=cfg)
+        outs.append(prob.train_eval(hps, seeds, want_history=True))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    assert np.isfinite(outs[0][0]).all()
