@@ -29,6 +29,7 @@
 // Bound: HBM by contract (71 840 B/clip) but ~1.6 MFLOP/clip of fp32 butterflies puts
 // it between the HBM and the fp32-pipe roofs; bench.py reports the HBM fraction.
 #include <math.h>
+#include <stdlib.h>
 
 #include <type_traits>
 #include <vector>
@@ -457,6 +458,422 @@ __global__ void __launch_bounds__(kWarps * 32, FAST ? 2 : 3) mfcc_kernel(Params 
     }
 }
 
+// =====================================================================================================
+// Frame-pair kernel (default 640/320/40-mel configuration).  The v3 kernel above sits on the shared-memory
+// data pipe (406 wavefronts per frame, 1 wavefront/clk/SM; shuffles share that pipe) and on instruction issue.
+// Here a warp processes frames (t, t+1) of one clip together as packed f32x2 values (.x = frame t, .y = frame
+// t+1): every butterfly is one FADD2/FMUL2/FFMA2 (twiddle constants are broadcast immediates), every
+// shared-memory exchange is a 64-bit access, and every table read (window, mel weights, DCT) is shared by the
+// two frames.  Exchanges that v3 made through shared memory and that can be made cheaper are:
+//   * W512 twiddles: power tree (depth <= 4) from W512^lane instead of a 15-row table
+//   * real-FFT unpack: partner bins fetched with shuffles (32 per frame instead of 80 wavefronts);
+//     lane = k1o + 16 h holds Z[k1o + 16 Q + 256 h]; the partner 512 - k is register 15 - Q of lane
+//     ((16 - k1o) & 15) + 16 (1 - h); lanes with k1o == 0 pair their own register Q + 1 instead (SEL) and keep
+//     the self-paired bins 0 / 256 / 512 for the last round; W1024^k = W1024^kb(lane) * W64^Q (immediates)
+//   * the power spectrum aliases the transpose tile; mel/log/DCT as in v3, on packed values
+//   * waveform rows reach shared memory by 1-D bulk TMA (cp.async.bulk + mbarrier, one 3 840-B copy per pair issued
+//     by lane 0 as soon as the previous pair's rows are windowed), so the next pair's samples land during the
+//     whole FFT/mel/DCT of the current one without holding registers (a register prefetch was spilled by ptxas)
+// tools/fft_pair_model.py is the NumPy model of the index maps.  Everything is kept at twice the true
+// amplitude until the power spectrum (the 1/2 of the unpack is folded into the window while staging it).
+// =====================================================================================================
+typedef float2 P;   // (frame t, frame t+1)
+
+__device__ __forceinline__ uint32_t pair_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pair_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(pair_smem_u32(bar)), "r"(parity) : "memory");
+}
+// one lane: arm the barrier with the byte count and start the bulk copy global -> shared
+__device__ __forceinline__ void pair_tma_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic-proxy reads of dst are done
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pair_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(pair_smem_u32(dst)), "l"(src), "r"(bytes), "r"(pair_smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ P padd(P a, P b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ P pneg(P a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ P psub(P a, P b) { return __fadd2_rn(a, pneg(b)); }
+__device__ __forceinline__ P pmul(P a, P b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ P pfma(P a, P b, P c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ P pdup(float c) { return make_float2(c, c); }
+
+struct PC {   // packed complex
+    P re, im;
+};
+__device__ __forceinline__ PC pc_add(PC a, PC b) { return {padd(a.re, b.re), padd(a.im, b.im)}; }
+__device__ __forceinline__ PC pc_sub(PC a, PC b) { return {psub(a.re, b.re), psub(a.im, b.im)}; }
+// a * (wr + i wi), wr / wi duplicated pairs
+__device__ __forceinline__ PC pc_mul(PC a, P wr, P wi) {
+    return {pfma(a.re, wr, pneg(pmul(a.im, wi))), pfma(a.re, wi, pmul(a.im, wr))};
+}
+
+// a * exp(-2*pi*i*J/32), J a compile-time constant in [0,16)
+template <int J>
+__device__ __forceinline__ PC pc_mul_w32(PC a) {
+    if constexpr (J == 0) {
+        return a;
+    } else if constexpr (J == 8) {
+        return {a.im, pneg(a.re)};
+    } else if constexpr (J == 4) {
+        constexpr float s = 0.70710678118654757f;
+        return {pmul(padd(a.re, a.im), pdup(s)), pmul(psub(a.im, a.re), pdup(s))};
+    } else if constexpr (J == 12) {
+        constexpr float s = 0.70710678118654757f;
+        return {pmul(psub(a.im, a.re), pdup(s)), pmul(padd(a.re, a.im), pdup(-s))};
+    } else {
+        constexpr float c = cos32(J), s = sin32(J);      // w = c - i s
+        return {pfma(a.im, pdup(s), pmul(a.re, pdup(c))), pfma(a.re, pdup(-s), pmul(a.im, pdup(c)))};
+    }
+}
+
+template <int NZ>
+__device__ __forceinline__ void pc_dft16(PC (&v)[16]) {
+    static_for<0, 8>([&](auto jc) {
+        constexpr int J = decltype(jc)::value;
+        if constexpr (J + 8 < NZ) {
+            const PC u = v[J], t = v[J + 8];
+            v[J] = pc_add(u, t);
+            v[J + 8] = pc_mul_w32<2 * J>(pc_sub(u, t));
+        } else {
+            v[J + 8] = pc_mul_w32<2 * J>(v[J]);
+        }
+    });
+    static_for<0, 2>([&](auto bc) {
+        constexpr int B = decltype(bc)::value * 8;
+        static_for<0, 4>([&](auto jc) {
+            constexpr int J = decltype(jc)::value;
+            const PC u = v[B + J], t = v[B + J + 4];
+            v[B + J] = pc_add(u, t);
+            v[B + J + 4] = pc_mul_w32<4 * J>(pc_sub(u, t));
+        });
+    });
+    static_for<0, 4>([&](auto bc) {
+        constexpr int B = decltype(bc)::value * 4;
+        static_for<0, 2>([&](auto jc) {
+            constexpr int J = decltype(jc)::value;
+            const PC u = v[B + J], t = v[B + J + 2];
+            v[B + J] = pc_add(u, t);
+            v[B + J + 2] = pc_mul_w32<8 * J>(pc_sub(u, t));
+        });
+    });
+    static_for<0, 8>([&](auto bc) {
+        constexpr int B = decltype(bc)::value * 2;
+        const PC u = v[B], t = v[B + 1];
+        v[B] = pc_add(u, t);
+        v[B + 1] = pc_sub(u, t);
+    });
+}
+
+__host__ __device__ constexpr float cos64(int q) {
+    constexpr float t[16] = {1.f, 0.99518472667219693f, 0.98078528040323043f, 0.95694033573220882f,
+                             0.92387953251128674f, 0.88192126434835505f, 0.83146961230254524f, 0.77301045336273699f,
+                             0.70710678118654757f, 0.63439328416364549f, 0.55557023301960229f, 0.47139673682599781f,
+                             0.38268343236508984f, 0.29028467725446239f, 0.19509032201612833f, 0.09801714032956077f};
+    return t[q];
+}
+__host__ __device__ constexpr float sin64(int q) {
+    constexpr float t[16] = {0.f, 0.09801714032956060f, 0.19509032201612825f, 0.29028467725446233f,
+                             0.38268343236508978f, 0.47139673682599764f, 0.55557023301960218f, 0.63439328416364549f,
+                             0.70710678118654746f, 0.77301045336273699f, 0.83146961230254524f, 0.88192126434835494f,
+                             0.92387953251128674f, 0.95694033573220894f, 0.98078528040323043f, 0.99518472667219682f};
+    return t[q];
+}
+
+constexpr int kPairWarps = 12;                    // warps per CTA, one CTA per SM
+constexpr int kPTile = 33;                        // transpose tile stride in P units (odd: conflict-free 64-bit reads)
+constexpr int kPairTileP = 2 * 16 * kPTile;       // re + im planes; the power spectrum (32 * 17 P) aliases them
+constexpr int kPairMiscP = 2 * kMaxFlush * 32 + 2 * 40;   // mel partials (R, F) | log-mel | folded DCT input
+constexpr int kPairStageP = 3 * 5 * 32;            // 15 rows of 32 float2: the samples of one frame pair, landed by TMA
+constexpr int kPairWarpP = kPairTileP + kPairMiscP + kPairStageP;
+static_assert(kPairTileP >= kPowFloats, "power spectrum must fit in the transpose tile");
+
+template <int DCT>
+__global__ void __launch_bounds__(kPairWarps * 32, 1) mfcc_pair_kernel(Params p) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int NZ = 10, HZ = 5, n_mels = 40, n_out = 40, half = 20;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // ---- stage tables once per CTA (window scaled by 1/2: the unpack below works at twice the amplitude)
+    for (int i = threadIdx.x; i < p.t.total; i += blockDim.x) {
+        const float s = (i >= p.t.window2 && i < p.t.window2 + 2 * p.half_len) ? 0.5f : 1.f;
+        smem[i] = p.tables[i] * s;
+    }
+    __syncthreads();
+    const float2* s_win = reinterpret_cast<const float2*>(smem + p.t.window2);
+    const float2* s_tw512 = reinterpret_cast<const float2*>(smem + p.t.tw512);
+    const float2* s_tw1024 = reinterpret_cast<const float2*>(smem + p.t.tw1024);
+    const float2* s_melwt = reinterpret_cast<const float2*>(smem + p.t.mel_wt);
+    const int2* s_comb = reinterpret_cast<const int2*>(smem + p.t.mel_comb);
+    const float* s_dcth = smem + p.t.dcth;
+    const unsigned flush_mask = reinterpret_cast<const unsigned*>(smem + p.t.mel_flush)[lane];
+    P* w_base = reinterpret_cast<P*>(smem + ((p.t.total + 3) & ~3)) + warp * kPairWarpP;
+    P* t_re = w_base;
+    P* t_im = w_base + 16 * kPTile;
+    P* s_pow = w_base;                                   // aliases the tile (dead once stage 2 has read it)
+    P* part_r = w_base + kPairTileP;                     // [kMaxFlush][32]
+    P* part_f = part_r + kMaxFlush * 32;
+    P* s_lm = part_f + kMaxFlush * 32;                   // [40]
+    P* s_sd = s_lm + 40;                                 // [40]
+    const float2* s_stage = s_sd + 40;                   // [15][32] samples of the current pair
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + ((p.t.total + 3) & ~3) + 2 * kPairWarps * kPairWarpP) + warp;
+    if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pair_smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    uint32_t phase = 0;
+
+    const int k1o = lane & 15, h = lane >> 4;
+    const bool edge = (k1o == 0);                        // lanes that own the self-paired bins
+    const int src_lane = ((16 - k1o) & 15) + 16 * (1 - h);
+    const int kb = (edge ? 16 : k1o) + 256 * h;          // first bin this lane unpacks (own register 0, or 1 on edge lanes)
+    const int k15 = edge ? 256 * h : kb + 240;           // bin of the last round
+    float cb, sb;                                        // W1024^kb = cb - i sb
+    {
+        const float2 w = s_tw1024[kb & 255];             // (cos, -sin) of 2 pi k / 1024
+        cb = h ? w.y : w.x;                              // +pi/2: cos -> -sin, sin -> cos
+        sb = h ? w.x : -w.y;
+    }
+    const P sg = pdup(h ? -1.f : 1.f);
+    float mean0 = smem[p.t.mean + lane], inv0 = smem[p.t.inv_scale + lane];
+    float mean1 = 0.f, inv1 = 1.f;
+    if (lane < 4 * (n_out - 32)) {
+        mean1 = smem[p.t.mean + 32 + (lane >> 2)];
+        inv1 = smem[p.t.inv_scale + 32 + (lane >> 2)];
+    }
+
+    const long long stride = (long long)gridDim.x * kPairWarps;
+    for (long long run = (long long)blockIdx.x * kPairWarps + warp; run < p.total_runs; run += stride) {
+        const long long clip = run / p.runs_per_clip;
+        const int part = (int)(run - clip * p.runs_per_clip);
+        const int t0 = part * p.frames_per_run;                       // frames_per_run is even
+        const int t1 = min(p.frames_per_clip, t0 + p.frames_per_run);
+        if (t0 >= t1) continue;
+        const float2* clip_src = reinterpret_cast<const float2*>(p.wave + (size_t)clip * p.n_samples);
+        // rows of 32 float2 (64 samples): frame t starts at row 5 t; the pair (t, t+1) needs rows 5t .. 5t+14
+        auto issue_rows = [&](int t) {
+            const bool has_b = (t + 1 < p.frames_per_clip);                // never read past the clip
+            pair_tma_load(const_cast<float2*>(s_stage), clip_src + (size_t)t * (32 * HZ),
+                          (has_b ? 3 * HZ : 2 * HZ) * 32 * (uint32_t)sizeof(float2), mbar);
+        };
+        if (lane == 0) issue_rows(t0);
+        for (int t = t0; t < t1; t += 2) {
+            pair_mbar_wait(mbar, phase);
+            phase ^= 1u;
+            PC v[16];
+#pragma unroll
+            for (int a = 0; a < NZ; ++a) {
+                const float2 w = s_win[32 * a + lane];
+                const float2 xa = s_stage[32 * a + lane], xb = s_stage[32 * (a + HZ) + lane];
+                v[a].re = make_float2(xa.x * w.x, xb.x * w.x);
+                v[a].im = make_float2(xa.y * w.y, xb.y * w.y);
+            }
+            __syncwarp();
+            if (lane == 0 && t + 2 < t1) issue_rows(t + 2);
+#pragma unroll
+            for (int a = NZ; a < 16; ++a) v[a] = {pdup(0.f), pdup(0.f)};
+            // ---- radix-16 over a, W512^(lane*k1) twiddle (power tree), transpose
+            pc_dft16<NZ>(v);
+            {
+                const float2 w1s = s_tw512[32 + lane];
+                P wr[16], wi[16];
+                wr[1] = pdup(w1s.x);
+                wi[1] = pdup(w1s.y);
+                auto cm = [&](int a, int b, int c) {
+                    wr[c] = pfma(wr[a], wr[b], pneg(pmul(wi[a], wi[b])));
+                    wi[c] = pfma(wr[a], wi[b], pmul(wi[a], wr[b]));
+                };
+                cm(1, 1, 2); cm(2, 1, 3); cm(2, 2, 4); cm(4, 1, 5); cm(4, 2, 6); cm(4, 3, 7); cm(4, 4, 8);
+                cm(8, 1, 9); cm(8, 2, 10); cm(8, 3, 11); cm(8, 4, 12); cm(8, 5, 13); cm(8, 6, 14); cm(8, 7, 15);
+                static_for<0, 16>([&](auto ic) {
+                    constexpr int I = decltype(ic)::value;
+                    constexpr int K1 = brev4(I);
+                    PC y = v[I];
+                    if constexpr (K1 != 0) y = pc_mul(y, wr[K1], wi[K1]);
+                    t_re[K1 * kPTile + lane] = y.re;
+                    t_im[K1 * kPTile + lane] = y.im;
+                });
+            }
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                v[m].re = t_re[k1o * kPTile + h + 2 * m];
+                v[m].im = t_im[k1o * kPTile + h + 2 * m];
+            }
+            __syncwarp();
+            // ---- radix-16 over m, W32 combine with lane ^ 16: z[Q] = Z[k1o + 16 Q + 256 h]
+            pc_dft16<16>(v);
+            PC z[16];
+            static_for<0, 16>([&](auto ic) {
+                constexpr int I = decltype(ic)::value;
+                constexpr int Q = brev4(I);
+                PC s = v[I];
+                if (h) s = pc_mul_w32<Q>(s);
+                PC r;
+                r.re.x = __shfl_xor_sync(0xffffffffu, s.re.x, 16);
+                r.re.y = __shfl_xor_sync(0xffffffffu, s.re.y, 16);
+                r.im.x = __shfl_xor_sync(0xffffffffu, s.im.x, 16);
+                r.im.y = __shfl_xor_sync(0xffffffffu, s.im.y, 16);
+                z[Q].re = pfma(sg, s.re, r.re);
+                z[Q].im = pfma(sg, s.im, r.im);
+            });
+            // ---- real-FFT unpack with shuffles -> power spectrum (aliases the tile)
+            const P cb2 = pdup(cb), sb2 = pdup(sb);
+            static_for<0, 16>([&](auto qc) {
+                constexpr int Q = decltype(qc)::value;
+                PC own = z[Q];
+                if (edge) own = z[(Q + 1) & 15];
+                PC rcv;
+                rcv.re.x = __shfl_sync(0xffffffffu, z[15 - Q].re.x, src_lane);
+                rcv.re.y = __shfl_sync(0xffffffffu, z[15 - Q].re.y, src_lane);
+                rcv.im.x = __shfl_sync(0xffffffffu, z[15 - Q].im.x, src_lane);
+                rcv.im.y = __shfl_sync(0xffffffffu, z[15 - Q].im.y, src_lane);
+                // W1024^(kb + 16 Q) = (cb - i sb)(cq - i sq)
+                constexpr float cq = cos64(Q), sq = sin64(Q);
+                P c2 = pfma(sb2, pdup(-sq), pmul(cb2, pdup(cq)));
+                P s2 = pfma(cb2, pdup(sq), pmul(sb2, pdup(cq)));
+                if constexpr (Q == 15) {
+                    if (edge) {
+                        rcv = own;
+                        c2 = pdup(h ? 0.f : 1.f);
+                        s2 = pdup(h ? 1.f : 0.f);
+                    }
+                }
+                const P er = padd(own.re, rcv.re), ei = psub(own.im, rcv.im);
+                const P od = padd(own.im, rcv.im), oi = psub(rcv.re, own.re);
+                const P xr = pfma(c2, od, pfma(s2, oi, er));
+                const P xi = pfma(c2, oi, pfma(pneg(s2), od, ei));
+                const P pw = pfma(xr, xr, pmul(xi, xi));
+                if constexpr (Q == 15) {
+                    s_pow[k15] = pw;
+                    if (lane == 0) {
+                        const P d = psub(er, od);
+                        s_pow[512] = pmul(d, d);
+                    }
+                } else {
+                    s_pow[kb + 16 * Q] = pw;
+                }
+            });
+            __syncwarp();
+            // ---- mel: lane owns bins [17 lane, 17 lane + 17)
+            {
+                P accr = pdup(0.f), accf = pdup(0.f);
+                int nfl = 0;
+                const int k0 = kChunk * lane;
+#pragma unroll
+                for (int i = 0; i < kChunk; ++i) {
+                    const P pw = s_pow[k0 + i];
+                    const float2 w = s_melwt[k0 + i];
+                    accr = make_float2(fmaf(w.x, pw.x, accr.x), fmaf(w.x, pw.y, accr.y));
+                    accf = make_float2(fmaf(w.y, pw.x, accf.x), fmaf(w.y, pw.y, accf.y));
+                    const bool fl = (flush_mask >> i) & 1u;
+                    if (fl) {
+                        part_r[nfl * 32 + lane] = accr;
+                        part_f[nfl * 32 + lane] = accf;
+                        accr = pdup(0.f);
+                        accf = pdup(0.f);
+                        ++nfl;
+                    }
+                }
+            }
+            __syncwarp();
+            P mel[2];
+#pragma unroll
+            for (int rnd = 0; rnd < 2; ++rnd) {
+                const int b = lane + 32 * rnd;
+                P acc = pdup(0.f);
+                if (b < n_mels) {
+                    const int2 cbn = s_comb[b];
+                    int n = cbn.x >> 16;
+                    if (n) {
+                        const int la = cbn.x & 0xff;
+                        acc = part_r[((cbn.x >> 8) & 0xff) * 32 + la];
+                        for (int j = 1; j < n; ++j) acc = padd(acc, part_r[la + j]);
+                    }
+                    n = cbn.y >> 16;
+                    if (n) {
+                        const int la = cbn.y & 0xff;
+                        acc = padd(acc, part_f[((cbn.y >> 8) & 0xff) * 32 + la]);
+                        for (int j = 1; j < n; ++j) acc = padd(acc, part_f[la + j]);
+                    }
+                }
+                mel[rnd] = acc;
+            }
+            const long long fa = clip * p.frames_per_clip + t;
+            float* dst_a = p.out + (size_t)fa * n_out;
+            const bool has_b = (t + 1 < t1);
+            if constexpr (!DCT) {
+#pragma unroll
+                for (int rnd = 0; rnd < 2; ++rnd) {
+                    const int b = lane + 32 * rnd;
+                    if (b < n_mels) {
+                        const float la = 10.f * log10f(fmaxf(mel[rnd].x, p.log_floor));
+                        const float lb = 10.f * log10f(fmaxf(mel[rnd].y, p.log_floor));
+                        const float mu = smem[p.t.mean + b], is = smem[p.t.inv_scale + b];
+                        dst_a[b] = (la - mu) * is;
+                        if (has_b) dst_a[n_out + b] = (lb - mu) * is;
+                    }
+                }
+                __syncwarp();
+            } else {
+#pragma unroll
+                for (int rnd = 0; rnd < 2; ++rnd) {
+                    const int b = lane + 32 * rnd;
+                    if (b < n_mels)
+                        s_lm[b] = make_float2(10.f * log10f(fmaxf(mel[rnd].x, p.log_floor)),
+                                              10.f * log10f(fmaxf(mel[rnd].y, p.log_floor)));
+                }
+                __syncwarp();
+                // D[c][n-1-b] = (-1)^c D[c][b]: fold the input once, halve the multiply-adds
+                if (lane < half) {
+                    const P a = s_lm[lane], zz = s_lm[n_mels - 1 - lane];
+                    s_sd[lane] = padd(a, zz);
+                    s_sd[half + lane] = psub(a, zz);
+                }
+                __syncwarp();
+                {
+                    const P* sd = s_sd + (lane & 1) * half;
+                    P acc = pdup(0.f);
+#pragma unroll
+                    for (int b = 0; b < half; b += 2) {
+                        const float4 d2 = *reinterpret_cast<const float4*>(sd + b);      // broadcast 16 B
+                        const float c0 = s_dcth[b * n_out + lane], c1 = s_dcth[(b + 1) * n_out + lane];
+                        acc = make_float2(fmaf(c0, d2.x, acc.x), fmaf(c0, d2.y, acc.y));
+                        acc = make_float2(fmaf(c1, d2.z, acc.x), fmaf(c1, d2.w, acc.y));
+                    }
+                    dst_a[lane] = (acc.x - mean0) * inv0;
+                    if (has_b) dst_a[n_out + lane] = (acc.y - mean0) * inv0;
+                }
+                {
+                    // the last 8 coefficients: 4 lanes per coefficient, strided terms, two shuffle rounds
+                    const int c = 32 + (lane >> 2), prt = lane & 3;
+                    const P* sd = s_sd + (c & 1) * half;
+                    P acc = pdup(0.f);
+#pragma unroll
+                    for (int b = 0; b < half / 4; ++b) {
+                        const P d = sd[prt + 4 * b];
+                        const float cf = s_dcth[(prt + 4 * b) * n_out + c];
+                        acc = make_float2(fmaf(cf, d.x, acc.x), fmaf(cf, d.y, acc.y));
+                    }
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 2);
+                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 2);
+                    if (prt == 0) {
+                        dst_a[c] = (acc.x - mean1) * inv1;
+                        if (has_b) dst_a[n_out + c] = (acc.y - mean1) * inv1;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
 // ---- host-side table construction (fp64, mirrors oracle/mfcc_ref.py)
 double hz_to_mel(double f) {
     const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
@@ -498,6 +915,19 @@ int launch_nz(const Params& p, int grid, size_t smem, cudaStream_t st) {
         configured = true;
     }
     mfcc_kernel<NZ, FAST><<<grid, kWarps * 32, smem, st>>>(p);
+    cmoop::count_launch();
+    CMOOP_CUDA_OK(cudaGetLastError());
+    return CMOOP_OK;
+}
+
+template <int DCT>
+int launch_pair(const Params& p, int grid, size_t smem, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        CMOOP_CUDA_OK(cudaFuncSetAttribute(mfcc_pair_kernel<DCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        configured = true;
+    }
+    mfcc_pair_kernel<DCT><<<grid, kPairWarps * 32, smem, st>>>(p);
     cmoop::count_launch();
     CMOOP_CUDA_OK(cudaGetLastError());
     return CMOOP_OK;
@@ -766,6 +1196,26 @@ int cmoop_mfcc_fwd_dev(cmoop_mfcc_handle h, const float* wave, int64_t n_clips, 
     const auto& c = h->cfg;
     const bool fast = c.frame_length == 640 && c.hop == 320 && c.n_mels == 40 && (c.n_mfcc == 0 || c.n_mfcc == 40) &&
                       h->mel_mode == 1 && h->dct_mode == 1 && p.vec2;
+    const bool tma_ok = (((uintptr_t)wave & 15u) == 0) && (n_samples % 4 == 0);
+    static const bool use_v3 = [] {
+        const char* e = getenv("CMOOP_MFCC_KERNEL");       // A/B switch for profiling: "v3" = warp-per-frame kernel
+        return e && strcmp(e, "v3") == 0;
+    }();
+    if (fast && tma_ok && !use_v3) {
+        // frame-pair kernel: runs of consecutive frame pairs, about two runs per resident warp, one CTA per SM
+        const long long warps = (long long)h->sm_count * kPairWarps;
+        long long rpc = (2 * warps + n_clips - 1) / n_clips;
+        rpc = rpc < 1 ? 1 : (rpc > frames ? frames : rpc);
+        int fpr = (int)((frames + rpc - 1) / rpc);
+        fpr += fpr & 1;                                     // pairs never straddle two runs
+        p.frames_per_run = fpr;
+        p.runs_per_clip = (frames + fpr - 1) / fpr;
+        p.total_runs = (long long)n_clips * p.runs_per_clip;
+        const long long blocks_needed = (p.total_runs + kPairWarps - 1) / kPairWarps;
+        const int grid = (int)(blocks_needed < h->sm_count ? blocks_needed : h->sm_count);
+        const size_t smem = ((size_t)((h->t.total + 3) & ~3)) * sizeof(float) + (size_t)kPairWarps * kPairWarpP * sizeof(P) + kPairWarps * sizeof(uint64_t);
+        return c.n_mfcc == 0 ? launch_pair<0>(p, grid, smem, st) : launch_pair<1>(p, grid, smem, st);
+    }
     if (fast) {
         // runs of consecutive frames: about two runs per resident warp, at most one clip per run
         const long long warps = (long long)h->sm_count * 2 * kWarps;
