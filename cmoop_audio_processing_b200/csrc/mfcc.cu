@@ -586,13 +586,13 @@ __host__ __device__ constexpr float sin64(int q) {
     return t[q];
 }
 
-constexpr int kPairWarps = 12;                    // warps per CTA, one CTA per SM
+constexpr int kPairWarps = 16;                    // warps per CTA, one CTA per SM
 constexpr int kPTile = 33;                        // transpose tile stride in P units (odd: conflict-free 64-bit reads)
 constexpr int kPairTileP = 2 * 16 * kPTile;       // re + im planes; the power spectrum (32 * 17 P) aliases them
-constexpr int kPairMiscP = 2 * kMaxFlush * 32 + 2 * 40;   // mel partials (R, F) | log-mel | folded DCT input
+constexpr int kPairMiscP = 2 * 40;                // log-mel | folded DCT input
 constexpr int kPairStageP = 3 * 5 * 32;            // 15 rows of 32 float2: the samples of one frame pair, landed by TMA
 constexpr int kPairWarpP = kPairTileP + kPairMiscP + kPairStageP;
-static_assert(kPairTileP >= kPowFloats, "power spectrum must fit in the transpose tile");
+static_assert(kPairTileP >= kPowFloats + 2 * kMaxFlush * 32, "power spectrum + mel partials must fit in the transpose tile");
 
 template <int DCT>
 __global__ void __launch_bounds__(kPairWarps * 32, 1) mfcc_pair_kernel(Params p) {
@@ -616,9 +616,9 @@ __global__ void __launch_bounds__(kPairWarps * 32, 1) mfcc_pair_kernel(Params p)
     P* t_re = w_base;
     P* t_im = w_base + 16 * kPTile;
     P* s_pow = w_base;                                   // aliases the tile (dead once stage 2 has read it)
-    P* part_r = w_base + kPairTileP;                     // [kMaxFlush][32]
+    P* part_r = w_base + kPowFloats;                     // [kMaxFlush][32], in the tile's upper half (dead during mel)
     P* part_f = part_r + kMaxFlush * 32;
-    P* s_lm = part_f + kMaxFlush * 32;                   // [40]
+    P* s_lm = w_base + kPairTileP;                       // [40]
     P* s_sd = s_lm + 40;                                 // [40]
     const float2* s_stage = s_sd + 40;                   // [15][32] samples of the current pair
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + ((p.t.total + 3) & ~3) + 2 * kPairWarps * kPairWarpP) + warp;
@@ -680,12 +680,12 @@ __global__ void __launch_bounds__(kPairWarps * 32, 1) mfcc_pair_kernel(Params p)
             pc_dft16<NZ>(v);
             {
                 const float2 w1s = s_tw512[32 + lane];
-                P wr[16], wi[16];
-                wr[1] = pdup(w1s.x);
-                wi[1] = pdup(w1s.y);
+                float wr[16], wi[16];                  // scalars: the packed ops broadcast them
+                wr[1] = w1s.x;
+                wi[1] = w1s.y;
                 auto cm = [&](int a, int b, int c) {
-                    wr[c] = pfma(wr[a], wr[b], pneg(pmul(wi[a], wi[b])));
-                    wi[c] = pfma(wr[a], wi[b], pmul(wi[a], wr[b]));
+                    wr[c] = fmaf(wr[a], wr[b], -wi[a] * wi[b]);
+                    wi[c] = fmaf(wr[a], wi[b], wi[a] * wr[b]);
                 };
                 cm(1, 1, 2); cm(2, 1, 3); cm(2, 2, 4); cm(4, 1, 5); cm(4, 2, 6); cm(4, 3, 7); cm(4, 4, 8);
                 cm(8, 1, 9); cm(8, 2, 10); cm(8, 3, 11); cm(8, 4, 12); cm(8, 5, 13); cm(8, 6, 14); cm(8, 7, 15);
@@ -693,7 +693,7 @@ __global__ void __launch_bounds__(kPairWarps * 32, 1) mfcc_pair_kernel(Params p)
                     constexpr int I = decltype(ic)::value;
                     constexpr int K1 = brev4(I);
                     PC y = v[I];
-                    if constexpr (K1 != 0) y = pc_mul(y, wr[K1], wi[K1]);
+                    if constexpr (K1 != 0) y = pc_mul(y, pdup(wr[K1]), pdup(wi[K1]));
                     t_re[K1 * kPTile + lane] = y.re;
                     t_im[K1 * kPTile + lane] = y.im;
                 });
@@ -712,7 +712,11 @@ __global__ void __launch_bounds__(kPairWarps * 32, 1) mfcc_pair_kernel(Params p)
                 constexpr int I = decltype(ic)::value;
                 constexpr int Q = brev4(I);
                 PC s = v[I];
-                if (h) s = pc_mul_w32<Q>(s);
+                if constexpr (Q != 0) {
+                    // lanes with h == 0 multiply by 1: pick the twiddle, not the product (2 selects instead of 4)
+                    const float tc = h ? cos32(Q) : 1.f, ts = h ? sin32(Q) : 0.f;      // w = tc - i ts
+                    s = pc_mul(s, pdup(tc), pdup(-ts));
+                }
                 PC r;
                 r.re.x = __shfl_xor_sync(0xffffffffu, s.re.x, 16);
                 r.re.y = __shfl_xor_sync(0xffffffffu, s.re.y, 16);
@@ -722,7 +726,6 @@ __global__ void __launch_bounds__(kPairWarps * 32, 1) mfcc_pair_kernel(Params p)
                 z[Q].im = pfma(sg, s.im, r.im);
             });
             // ---- real-FFT unpack with shuffles -> power spectrum (aliases the tile)
-            const P cb2 = pdup(cb), sb2 = pdup(sb);
             static_for<0, 16>([&](auto qc) {
                 constexpr int Q = decltype(qc)::value;
                 PC own = z[Q];
@@ -734,15 +737,15 @@ __global__ void __launch_bounds__(kPairWarps * 32, 1) mfcc_pair_kernel(Params p)
                 rcv.im.y = __shfl_sync(0xffffffffu, z[15 - Q].im.y, src_lane);
                 // W1024^(kb + 16 Q) = (cb - i sb)(cq - i sq)
                 constexpr float cq = cos64(Q), sq = sin64(Q);
-                P c2 = pfma(sb2, pdup(-sq), pmul(cb2, pdup(cq)));
-                P s2 = pfma(cb2, pdup(sq), pmul(sb2, pdup(cq)));
+                float c1 = fmaf(sb, -sq, cb * cq), s1 = fmaf(cb, sq, sb * cq);
                 if constexpr (Q == 15) {
                     if (edge) {
                         rcv = own;
-                        c2 = pdup(h ? 0.f : 1.f);
-                        s2 = pdup(h ? 1.f : 0.f);
+                        c1 = h ? 0.f : 1.f;
+                        s1 = h ? 1.f : 0.f;
                     }
                 }
+                const P c2 = pdup(c1), s2 = pdup(s1);
                 const P er = padd(own.re, rcv.re), ei = psub(own.im, rcv.im);
                 const P od = padd(own.im, rcv.im), oi = psub(rcv.re, own.re);
                 const P xr = pfma(c2, od, pfma(s2, oi, er));
@@ -768,8 +771,8 @@ __global__ void __launch_bounds__(kPairWarps * 32, 1) mfcc_pair_kernel(Params p)
                 for (int i = 0; i < kChunk; ++i) {
                     const P pw = s_pow[k0 + i];
                     const float2 w = s_melwt[k0 + i];
-                    accr = make_float2(fmaf(w.x, pw.x, accr.x), fmaf(w.x, pw.y, accr.y));
-                    accf = make_float2(fmaf(w.y, pw.x, accf.x), fmaf(w.y, pw.y, accf.y));
+                    accr = pfma(pdup(w.x), pw, accr);        // FFMA2 with a scalar-broadcast register operand
+                    accf = pfma(pdup(w.y), pw, accf);
                     const bool fl = (flush_mask >> i) & 1u;
                     if (fl) {
                         part_r[nfl * 32 + lane] = accr;
@@ -842,8 +845,8 @@ __global__ void __launch_bounds__(kPairWarps * 32, 1) mfcc_pair_kernel(Params p)
                     for (int b = 0; b < half; b += 2) {
                         const float4 d2 = *reinterpret_cast<const float4*>(sd + b);      // broadcast 16 B
                         const float c0 = s_dcth[b * n_out + lane], c1 = s_dcth[(b + 1) * n_out + lane];
-                        acc = make_float2(fmaf(c0, d2.x, acc.x), fmaf(c0, d2.y, acc.y));
-                        acc = make_float2(fmaf(c1, d2.z, acc.x), fmaf(c1, d2.w, acc.y));
+                        acc = pfma(pdup(c0), make_float2(d2.x, d2.y), acc);
+                        acc = pfma(pdup(c1), make_float2(d2.z, d2.w), acc);
                     }
                     dst_a[lane] = (acc.x - mean0) * inv0;
                     if (has_b) dst_a[n_out + lane] = (acc.y - mean0) * inv0;
@@ -857,7 +860,7 @@ __global__ void __launch_bounds__(kPairWarps * 32, 1) mfcc_pair_kernel(Params p)
                     for (int b = 0; b < half / 4; ++b) {
                         const P d = sd[prt + 4 * b];
                         const float cf = s_dcth[(prt + 4 * b) * n_out + c];
-                        acc = make_float2(fmaf(cf, d.x, acc.x), fmaf(cf, d.y, acc.y));
+                        acc = pfma(pdup(cf), d, acc);
                     }
                     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
                     acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
@@ -924,7 +927,7 @@ template <int DCT>
 int launch_pair(const Params& p, int grid, size_t smem, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        CMOOP_CUDA_OK(cudaFuncSetAttribute(mfcc_pair_kernel<DCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CMOOP_CUDA_OK(cudaFuncSetAttribute(mfcc_pair_kernel<DCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         configured = true;
     }
     mfcc_pair_kernel<DCT><<<grid, kPairWarps * 32, smem, st>>>(p);
