@@ -14,6 +14,7 @@
 namespace cmoop_cnn {
 
 constexpr int kBatch = 64;
+constexpr int kStemRows = 1024;     // output pixels per block of the stem (Cin = 1) kernels = weight-gradient split size
 
 struct ConvTask {
     const float* x;        // input activations (or dataset base)
@@ -203,6 +204,12 @@ struct Launch {
     static int wgrad_tc(const TcWgradTask* tasks, int n_tasks, int total_tiles, int n_b, void* stream);
     static int wt_bf16(const WtBf16Task* tasks, int n_tasks, int total_blocks, void* stream);
     static int bn_stats(const StatTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
+    // stem.cu: dedicated Cin = 1 kernels; every task of a launch has the same M (= n_b*H*W) and W
+    static bool stem_ok(int H, int W, int Cin, int Cout, int k, int stride, int n_b);
+    static int stem_conv(const ConvTask* tasks, int n_tasks, int max_k, int W, int max_cout, long long M, int n_b, int step,
+                         void* stream);
+    static int stem_wgrad(const WgradTask* tasks, int n_tasks, int max_k, int W, int max_cout, int splits, int n_b, int step,
+                          void* stream);
 };
 
 }  // namespace cmoop_cnn

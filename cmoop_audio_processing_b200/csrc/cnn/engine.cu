@@ -56,6 +56,7 @@ struct Unit {
     float* wt = nullptr;
     uint8_t* idx = nullptr;
     bool tc = false;                 // convolution runs on the tcgen05 path (bf16 operands)
+    bool stem = false;               // Cin = 1 first convolution: dedicated kernels (stem.cu)
     int kpad_f = 0, kpad_d = 0;      // padded K of the forward / data-gradient GEMM
     bool need_vh = false;            // a tensor-core unit consumes this unit's output
     __nv_bfloat16* Vh = nullptr;     // bf16 shadow of V
@@ -218,6 +219,12 @@ void build_units(Cand& c, const cmoop_cnn_config& cfg, int H, int W, int batch) 
         const int gran = u.tc ? 64 : 16;
         chunk = (chunk + gran - 1) / gran * gran;
         splits = (int)((M + chunk - 1) / chunk);
+        static const bool no_stem = getenv("CMOOP_CNN_NO_STEM") != nullptr;      // A/B switch: generic SIMT kernels for the stem
+        u.stem = !no_stem && !u.dense && u.input == -1 && Launch::stem_ok(u.H, u.W, u.cin, u.cout, u.k, u.stride, batch);
+        if (u.stem) {
+            chunk = kStemRows;
+            splits = (int)((M + chunk - 1) / chunk);
+        }
         u.wg_splits = splits;
         u.wg_chunk = chunk;
     }
@@ -298,6 +305,9 @@ struct StageLists {
     DevList<TcConvTask> conv_tc, dgrad_tc;
     DevList<TcWgradTask> wgrad_tc;
     DevList<StatTask> stat;
+    // stem.cu path: every task of conv / conv_eval / wgrad is an eligible Cin = 1 convolution
+    bool stem = true;
+    int stem_k = 0, stem_w = 0, stem_cout = 0, stem_splits = 0;
     bool any = false;
     int max_bn_c = 0;                // widest BN unit of the stage (grid.y of the finalize kernels)
     DevList<PostTask> post_fwd, post_bn, post_bwd;
@@ -393,6 +403,12 @@ struct Engine {
                     t.use_bias = 1;
                     t.tiles_n = (u.cout + 63) / 64;
                     t.tile_begin = S.conv.total;
+                    if (u.stem && (S.stem_w == 0 || (S.stem_w == u.W && S.stem_splits == u.wg_splits))) {
+                        S.stem_k = std::max(S.stem_k, u.k); S.stem_w = u.W; S.stem_cout = std::max(S.stem_cout, u.cout);
+                        S.stem_splits = u.wg_splits;
+                    } else {
+                        S.stem = false;
+                    }
                     if (u.input == -1) {
                         t.gather = c.perm;
                         t.gather_step = batch;
@@ -626,7 +642,13 @@ struct Engine {
             if (s == ST_FC0) CNN_LAUNCH(Launch::gap_fwd(wv.head.d, (int)wv.head.h.size(), wv.head.total, n_b, stream));
             if (!S.any) continue;
             DevList<ConvTask>& cl = (s == 0 && !training) ? S.conv_eval : S.conv;
-            if (!cl.h.empty()) CNN_LAUNCH(Launch::conv(cl.d, (int)cl.h.size(), cl.total, n_b, step, stream));
+            if (!cl.h.empty()) {
+                if (S.stem && S.stem_w > 0)
+                    CNN_LAUNCH(Launch::stem_conv(cl.d, (int)cl.h.size(), S.stem_k, S.stem_w, S.stem_cout,
+                                                 (long long)n_b * cl.h[0].H * cl.h[0].W, n_b, step, stream));
+                else
+                    CNN_LAUNCH(Launch::conv(cl.d, (int)cl.h.size(), cl.total, n_b, step, stream));
+            }
             if (!S.conv_tc.h.empty()) {
                 CNN_LAUNCH(Launch::conv_tc(S.conv_tc.d, (int)S.conv_tc.h.size(), S.conv_tc.total, n_b, step, stream));
                 if (!S.stat.h.empty() && training)
@@ -661,8 +683,13 @@ struct Engine {
             }
             if (!S.post_bwd.h.empty())
                 CNN_LAUNCH(Launch::post_bwd_apply(S.post_bwd.d, (int)S.post_bwd.h.size(), S.post_bwd.total, n_b, stream));
-            if (!S.wgrad.h.empty())
-                CNN_LAUNCH(Launch::wgrad(S.wgrad.d, (int)S.wgrad.h.size(), S.wgrad.total, n_b, step, stream));
+            if (!S.wgrad.h.empty()) {
+                if (S.stem && S.stem_w > 0)
+                    CNN_LAUNCH(Launch::stem_wgrad(S.wgrad.d, (int)S.wgrad.h.size(), S.stem_k, S.stem_w, S.stem_cout,
+                                                  S.stem_splits, n_b, step, stream));
+                else
+                    CNN_LAUNCH(Launch::wgrad(S.wgrad.d, (int)S.wgrad.h.size(), S.wgrad.total, n_b, step, stream));
+            }
             if (!S.wgrad_tc.h.empty())
                 CNN_LAUNCH(Launch::wgrad_tc(S.wgrad_tc.d, (int)S.wgrad_tc.h.size(), S.wgrad_tc.total, n_b, stream));
             if (!S.wreduce.h.empty())
@@ -853,6 +880,8 @@ int run_wave(Engine& eng, Wave& wv, double* out, double* history, int debug_step
     const cmoop_cnn_config& cfg = eng.cfg;
     const int batch = eng.batch;
     cudaStream_t st = eng.stream;
+    eng.global_step = 0;       // the dropout stream counts a candidate's own optimiser steps (oracle: drop_ctx=(seed, step)),
+                               // so a candidate's masks must not depend on which wave it lands in
     int rc = eng.init_params(wv.cands);
     if (rc != CMOOP_OK) return rc;
     rc = eng.build_lists(wv);
@@ -1106,7 +1135,9 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
                          int Cin, int Cout, int k, int stride, int relu, float* out) {
     CMOOP_REQUIRE(in && w && out, "debug_conv: null pointer");
     CMOOP_REQUIRE(n >= 1 && n <= kBatch && (stride == 1 || (stride == 2 && k == 1)), "debug_conv: unsupported shape");
-    CMOOP_REQUIRE(!use_tc || (Cin % 16 == 0 && Cout % 16 == 0), "debug_conv: tensor-core path needs Cin, Cout multiples of 16");
+    CMOOP_REQUIRE(use_tc != 1 || (Cin % 16 == 0 && Cout % 16 == 0), "debug_conv: tensor-core path needs Cin, Cout multiples of 16");
+    CMOOP_REQUIRE(use_tc != 2 || (mode == 0 && Launch::stem_ok(H, W, Cin, Cout, k, stride, n)),
+                  "debug_conv: shape not eligible for the stem (Cin = 1) kernel");
     if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
     cudaStream_t st = cmoop::internal_stream();
     const int pad = stride == 1 ? (k - 1) / 2 : 0;
@@ -1138,7 +1169,7 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
     CMOOP_CUDA_OK(cudaMemsetAsync(d_out, 0, n_out * 4, st));
     const int tiles_m64 = (int)(((long long)n * Ho * Wo + 63) / 64), tiles_m128 = (int)(((long long)n * Ho * Wo + 127) / 128);
     int rc = 0;
-    if (!use_tc) {
+    if (use_tc != 1) {
         ConvTask t{};
         t.x = d_in; t.y = d_out;
         t.Ho = Ho; t.Wo = Wo; t.k = k;
@@ -1157,7 +1188,10 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
         }
         t.tiles_n = (t.Cout + 63) / 64;
         CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &t, sizeof(t), cudaMemcpyHostToDevice, st));
-        if (rc == 0) rc = Launch::conv((const ConvTask*)d_task, 1, tiles_m64 * t.tiles_n, n, 0, st);
+        if (rc == 0 && use_tc == 2)
+            rc = Launch::stem_conv((const ConvTask*)d_task, 1, k, W, Cout, (long long)n * H * W, n, 0, st);
+        else if (rc == 0)
+            rc = Launch::conv((const ConvTask*)d_task, 1, tiles_m64 * t.tiles_n, n, 0, st);
     } else {
         WtBf16Task wb{};
         wb.w = d_w; wb.out = d_wb; wb.k = k; wb.Cin = Cin; wb.Cout = Cout; wb.K_pad = K_pad; wb.mode = mode;
@@ -1197,7 +1231,9 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
     CMOOP_REQUIRE(x && dy && out, "debug_wgrad: null pointer");
     CMOOP_REQUIRE(n >= 1 && n <= kBatch && (stride == 1 || (stride == 2 && k == 1)) && splits >= 1 && splits <= 32,
                   "debug_wgrad: unsupported shape");
-    CMOOP_REQUIRE(!use_tc || (Cin % 16 == 0 && Cout % 16 == 0), "debug_wgrad: tensor-core path needs Cin, Cout multiples of 16");
+    CMOOP_REQUIRE(use_tc != 1 || (Cin % 16 == 0 && Cout % 16 == 0), "debug_wgrad: tensor-core path needs Cin, Cout multiples of 16");
+    CMOOP_REQUIRE(use_tc != 2 || Launch::stem_ok(H, W, Cin, Cout, k, stride, n),
+                  "debug_wgrad: shape not eligible for the stem (Cin = 1) kernel");
     if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
     cudaStream_t st = cmoop::internal_stream();
     const int pad = stride == 1 ? (k - 1) / 2 : 0;
@@ -1209,6 +1245,10 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
     const int gran = use_tc ? 64 : 16;
     int chunk = (int)((M + splits - 1) / splits);
     chunk = (chunk + gran - 1) / gran * gran;
+    if (use_tc == 2) {                                   // the stem kernel fixes the split size
+        chunk = kStemRows;
+        splits = (int)((M + chunk - 1) / chunk);
+    }
     float *d_x, *d_y, *d_ws, *d_o;
     __nv_bfloat16 *d_xh, *d_yh;
     void* d_task;
@@ -1228,7 +1268,7 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
     CMOOP_CUDA_OK(cudaMemcpyAsync(d_y, dy, n_y * 4, cudaMemcpyHostToDevice, st));
     CMOOP_CUDA_OK(cudaMemsetAsync(d_ws, 0xff, n_o * 4 * splits, st));       // poison: every partial must be written
     int rc;
-    if (use_tc) {
+    if (use_tc == 1) {
         TcWgradTask g{};
         g.xh = d_xh; g.dyh = d_yh; g.out = d_ws; g.H = H; g.W = W; g.Cin = Cin; g.Ho = Ho; g.Wo = Wo; g.Cout = Cout;
         g.k = k; g.stride = stride; g.pad = pad; g.splits = splits; g.m_chunk = chunk;
@@ -1241,7 +1281,8 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
         g.k = k; g.stride = stride; g.pad = pad; g.splits = splits; g.m_chunk = chunk;
         g.tiles_k = (kext + 63) / 64; g.tiles_n = (Cout + 63) / 64;
         CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &g, sizeof(g), cudaMemcpyHostToDevice, st));
-        rc = Launch::wgrad((const WgradTask*)d_task, 1, g.tiles_k * g.tiles_n * splits, n, 0, st);
+        rc = use_tc == 2 ? Launch::stem_wgrad((const WgradTask*)d_task, 1, k, W, Cout, splits, n, 0, st)
+                         : Launch::wgrad((const WgradTask*)d_task, 1, g.tiles_k * g.tiles_n * splits, n, 0, st);
     }
     cmoop::count_launch();
     CMOOP_CUDA_OK(cudaStreamSynchronize(st));

@@ -1,0 +1,294 @@
+// Stem convolution (Cin = 1) of the candidate CNNs: forward and weight gradient as dedicated HBM-bound kernels.
+//
+// The first Conv2D of both model families (nsga_penalty.py:255, sa_nsga_penalty.py:150) reads the 1-channel
+// feature map and writes the largest activation of the network ([64*H*W][F] fp32); its GEMM has K = k*k (+1 bias)
+// = 10 or 26, so the generic 64x64x16 SIMT GEMM spent its time on im2col bookkeeping (1.0 ms forward / 1.8 ms
+// weight gradient per grouped launch of 32 candidates against ~0.1 ms of HBM traffic).  Here a block owns 1024
+// consecutive output pixels of one candidate: the feature-map rows they touch (<= 2 samples) are staged once in
+// shared memory with their zero padding, a thread owns 4 (or 2) output channels of a pixel, taps are immediate
+// offsets into the staged tile, stores / gradient loads are 16-byte and coalesced.  Contracts are those of
+// conv_gemm_kernel / conv_wgrad_kernel (ConvTask / WgradTask): same BN partial-sum layout (64-row tiles), same
+// [split][K+1][Cout] partial gradients reduced by reduce_kernel, deterministic (no atomics).
+#include <cuda_runtime.h>
+
+#include "cnn.cuh"
+
+namespace cmoop_cnn {
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+struct Segs {
+    int n_first, ha[2];
+};
+
+// Stages the weights-independent part: the rows of the (<= 2) samples touched by output pixels [m0, m1).
+template <int KS>
+__device__ __forceinline__ void stage_rows(float* tile, int seg_floats, const float* xbase, const int* gather, int H, int W,
+                                           int m0, int m1, Segs& sg) {
+    constexpr int P = (KS - 1) / 2;
+    const int HW = H * W, Wp = W + 2 * P;
+    sg.n_first = m0 / HW;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int n = sg.n_first + s;
+        const int lo = max(m0, n * HW), hi = min(m1, (n + 1) * HW);
+        sg.ha[s] = 0;
+        if (lo >= hi) continue;
+        const int ha = (lo - n * HW) / W, hb = (hi - 1 - n * HW) / W;
+        sg.ha[s] = ha;
+        const float* src = xbase + (long long)(gather ? gather[n] : n) * HW;
+        float* dst = tile + s * seg_floats;
+        const int cnt = (hb - ha + 1 + 2 * P) * Wp;
+        for (int i = threadIdx.x; i < cnt; i += kThreads) {
+            const int r = i / Wp, c = i - r * Wp;
+            const int hi_ = ha - P + r, wi_ = c - P;
+            float v = 0.f;
+            if ((unsigned)hi_ < (unsigned)H && (unsigned)wi_ < (unsigned)W) v = __ldg(src + hi_ * W + wi_);
+            dst[i] = v;
+        }
+    }
+}
+
+// y[m][co] = relu?(b[co] + sum_taps x[m + tap] w[tap][co]);  BN partial sums per 64-row tile
+template <int KS>
+__device__ __forceinline__ void stem_conv_body(const ConvTask& T, float* sm, int chunk, int rows_per_block, int seg_floats,
+                                               int n_b, int step) {
+    constexpr int P = (KS - 1) / 2, TAPS = KS * KS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = T.H, W = T.W, HW = H * W, Wp = W + 2 * P, Cout = T.Cout;
+    const int M = n_b * HW, m0 = chunk * rows_per_block, m1 = min(M, m0 + rows_per_block);
+    if (m0 >= M) return;
+    float* ws = sm;                                   // [(TAPS+1)][Cout]
+    float* tile = ws + (TAPS + 1) * Cout;             // [2][seg_floats]
+    float* red = tile + 2 * seg_floats;               // [8 warps][2][Cout]
+    for (int i = tid; i < (TAPS + 1) * Cout; i += kThreads) ws[i] = T.w[i];
+    Segs sg;
+    stage_rows<KS>(tile, seg_floats, T.x + T.x_step * step, T.gather ? T.gather + T.gather_step * step : nullptr, H, W, m0,
+                   m1, sg);
+    __syncthreads();
+
+    const int C4 = Cout >> 2, PP = kThreads / C4;     // threads per pixel, pixels per pass
+    const int cg = tid % C4, pl = tid / C4;
+    const int passes_per_tile = 64 / PP;              // PP in {64, 32, 16, 8, 4}
+    const float4 bias = ld4(ws + TAPS * Cout + cg * 4);
+    const int tiles = (m1 - m0 + 63) >> 6;
+    for (int tl = 0; tl < tiles; ++tl) {
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+        for (int pp = 0; pp < passes_per_tile; ++pp) {
+            const int m = m0 + tl * 64 + pp * PP + pl;
+            if (m < m1) {
+                const int n = m / HW, rem = m - n * HW;
+                const int h = rem / W, w = rem - h * W;
+                const int s = n - sg.n_first;
+                const float* tp = tile + s * seg_floats + (h - sg.ha[s]) * Wp + w;
+                float4 acc = bias;
+#pragma unroll
+                for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < KS; ++kw) {
+                        const float x = tp[kh * Wp + kw];
+                        const float4 wv = ld4(ws + (kh * KS + kw) * Cout + cg * 4);
+                        acc.x = fmaf(x, wv.x, acc.x);
+                        acc.y = fmaf(x, wv.y, acc.y);
+                        acc.z = fmaf(x, wv.z, acc.z);
+                        acc.w = fmaf(x, wv.w, acc.w);
+                    }
+                if (T.relu) {
+                    acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f);
+                    acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+                }
+                const long long o = (long long)m * Cout + cg * 4;
+                *reinterpret_cast<float4*>(T.y + o) = acc;
+                if (T.yh) {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi2 = __floats2bfloat162_rn(acc.z, acc.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<unsigned*>(&lo);
+                    pk.y = *reinterpret_cast<unsigned*>(&hi2);
+                    *reinterpret_cast<uint2*>(T.yh + o) = pk;
+                }
+                s1.x += acc.x; s1.y += acc.y; s1.z += acc.z; s1.w += acc.w;
+                s2.x = fmaf(acc.x, acc.x, s2.x); s2.y = fmaf(acc.y, acc.y, s2.y);
+                s2.z = fmaf(acc.z, acc.z, s2.z); s2.w = fmaf(acc.w, acc.w, s2.w);
+            }
+        }
+        if (T.stat_part) {
+            for (int msk = C4; msk < 32; msk <<= 1) {
+                s1.x += __shfl_xor_sync(0xffffffffu, s1.x, msk); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, msk);
+                s1.z += __shfl_xor_sync(0xffffffffu, s1.z, msk); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, msk);
+                s2.x += __shfl_xor_sync(0xffffffffu, s2.x, msk); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, msk);
+                s2.z += __shfl_xor_sync(0xffffffffu, s2.z, msk); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, msk);
+            }
+            // C4 <= 32: lanes [0, C4) of every warp hold the warp's sums for channel groups cg = lane (+ 32 j, C4 = 64)
+            if (C4 >= 32 || lane < C4) {
+                *reinterpret_cast<float4*>(red + (warp * 2 + 0) * Cout + cg * 4) = s1;
+                *reinterpret_cast<float4*>(red + (warp * 2 + 1) * Cout + cg * 4) = s2;
+            }
+            __syncthreads();
+            for (int i = tid; i < 2 * Cout; i += kThreads) {
+                const int which = i / Cout, c = i - which * Cout;
+                // warps that share a channel group: all of them when C4 <= 32, every second one when C4 == 64
+                float a = 0.f;
+                if (C4 <= 32) {
+#pragma unroll
+                    for (int wq = 0; wq < kThreads / 32; ++wq) a += red[(wq * 2 + which) * Cout + c];
+                } else {
+                    const int par = (c >> 7) & 1;      // cg >= 32 lives in odd warps (tid % 64 >= 32)
+                    for (int wq = par; wq < kThreads / 32; wq += 2) a += red[(wq * 2 + which) * Cout + c];
+                }
+                T.stat_part[((long long)((m0 >> 6) + tl) * 2 + which) * Cout + c] = a;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// the two kernel sizes of the genotype space (nsga_penalty.py:189) share one grouped launch
+__global__ void __launch_bounds__(kThreads) stem_conv_kernel(const ConvTask* __restrict__ tasks, int blocks_per_task,
+                                                             int rows_per_block, int seg_floats, int n_b, int step) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ ConvTask T;
+    const int task = blockIdx.x / blocks_per_task, chunk = blockIdx.x - task * blocks_per_task;
+    if (threadIdx.x == 0) T = tasks[task];
+    __syncthreads();
+    if (T.k == 3)
+        stem_conv_body<3>(T, sm, chunk, rows_per_block, seg_floats, n_b, step);
+    else
+        stem_conv_body<5>(T, sm, chunk, rows_per_block, seg_floats, n_b, step);
+}
+
+// out[split][tap][co] = sum_{m in split} x[m + tap] dy[m][co]  (row TAPS = bias gradient = sum of dy)
+template <int KS, int CPT>
+__device__ __forceinline__ void stem_wgrad_body(const WgradTask& T, float* sm, int split, int seg_floats, int n_b, int step) {
+    constexpr int P = (KS - 1) / 2, TAPS = KS * KS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = T.H, W = T.W, HW = H * W, Wp = W + 2 * P, Cout = T.Cout;
+    const int M = n_b * HW, m0 = split * T.m_chunk, m1 = min(M, m0 + T.m_chunk);
+    float* tile = sm;                                 // [2][seg_floats]
+    float* red = tile + 2 * seg_floats;               // [8 warps][(TAPS+1)][Cout]
+    const int n_out = (TAPS + 1) * Cout;
+    float* out = T.out + (long long)split * n_out;
+    if (m0 >= M) {                                    // empty split: its partial must still be defined
+        for (int i = tid; i < n_out; i += kThreads) out[i] = 0.f;
+        return;
+    }
+    Segs sg;
+    stage_rows<KS>(tile, seg_floats, T.x + T.x_step * step, T.gather ? T.gather + T.gather_step * step : nullptr, H, W, m0,
+                   m1, sg);
+    __syncthreads();
+
+    const int CG = Cout / CPT, PP = kThreads / CG;
+    const int cg = tid % CG, pl = tid / CG;
+    float acc[TAPS + 1][CPT];
+#pragma unroll
+    for (int t = 0; t <= TAPS; ++t)
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) acc[t][j] = 0.f;
+    for (int m = m0 + pl; m < m1; m += PP) {
+        const int n = m / HW, rem = m - n * HW;
+        const int h = rem / W, w = rem - h * W;
+        const int s = n - sg.n_first;
+        const float* tp = tile + s * seg_floats + (h - sg.ha[s]) * Wp + w;
+        float g[CPT];
+        if constexpr (CPT == 4) {
+            const float4 v = ld4(T.dy + (long long)m * Cout + cg * 4);
+            g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
+        } else {
+            const float2 v = *reinterpret_cast<const float2*>(T.dy + (long long)m * Cout + cg * 2);
+            g[0] = v.x; g[1] = v.y;
+        }
+#pragma unroll
+        for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < KS; ++kw) {
+                const float x = tp[kh * Wp + kw];
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) acc[kh * KS + kw][j] = fmaf(x, g[j], acc[kh * KS + kw][j]);
+            }
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) acc[TAPS][j] += g[j];
+    }
+    // lanes with the same channel group, then the 8 warps
+#pragma unroll
+    for (int t = 0; t <= TAPS; ++t)
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            float v = acc[t][j];
+            for (int msk = CG; msk < 32; msk <<= 1) v += __shfl_xor_sync(0xffffffffu, v, msk);
+            if (CG >= 32 || lane < CG) red[(warp * (TAPS + 1) + t) * Cout + cg * CPT + j] = v;
+        }
+    __syncthreads();
+    for (int i = tid; i < n_out; i += kThreads) {
+        const int c = i % Cout;
+        float a = 0.f;
+        if (CG <= 32) {
+#pragma unroll
+            for (int wq = 0; wq < kThreads / 32; ++wq) a += red[wq * n_out + i];
+        } else {
+            // CG in {64, 128}: channel group cg lives in the warps with (warp % (CG / 32)) == cg / 32
+            const int per = CG / 32, mine = (c / CPT) / 32;
+            for (int wq = mine; wq < kThreads / 32; wq += per) a += red[wq * n_out + i];
+        }
+        out[i] = a;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) stem_wgrad_kernel(const WgradTask* __restrict__ tasks, int blocks_per_task,
+                                                              int seg_floats, int n_b, int step) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ WgradTask T;
+    const int task = blockIdx.x / blocks_per_task, split = blockIdx.x - task * blocks_per_task;
+    if (threadIdx.x == 0) T = tasks[task];
+    __syncthreads();
+    if (T.k == 3)
+        stem_wgrad_body<3, 4>(T, sm, split, seg_floats, n_b, step);
+    else
+        stem_wgrad_body<5, 2>(T, sm, split, seg_floats, n_b, step);
+}
+
+int seg_floats_for(int W, int k, int rows) {
+    const int P = (k - 1) / 2;
+    return ((rows / W + 2 + 2 * P) * (W + 2 * P) + 3) & ~3;
+}
+
+template <class K>
+cudaError_t opt_in(K kernel, size_t smem) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem < 48 * 1024 ? 48 * 1024 : smem));
+}
+
+}  // namespace
+
+bool Launch::stem_ok(int H, int W, int Cin, int Cout, int k, int stride, int n_b) {
+    if (Cin != 1 || stride != 1 || (k != 3 && k != 5)) return false;
+    if (Cout < 16 || Cout > 256 || (Cout & (Cout - 1)) != 0) return false;
+    if ((long long)H * W < kStemRows) return false;                 // a block may touch at most two samples
+    (void)n_b;
+    const size_t smem = ((size_t)(k * k + 1) * Cout + 2 * (size_t)seg_floats_for(W, k, kStemRows) +
+                         (size_t)8 * (k * k + 1) * Cout) * sizeof(float);
+    return smem <= 200 * 1024;
+}
+
+int Launch::stem_conv(const ConvTask* tasks, int n_tasks, int max_k, int W, int max_cout, long long M, int n_b, int step,
+                      void* stream) {
+    const int bpt = (int)((M + kStemRows - 1) / kStemRows);
+    const int seg = seg_floats_for(W, max_k, kStemRows);
+    const size_t smem = ((size_t)(max_k * max_k + 1) * max_cout + 2 * (size_t)seg + 8 * 2 * (size_t)max_cout) * sizeof(float);
+    cudaError_t e = opt_in(stem_conv_kernel, smem);
+    if (e != cudaSuccess) return (int)e;
+    stem_conv_kernel<<<n_tasks * bpt, kThreads, smem, (cudaStream_t)stream>>>(tasks, bpt, kStemRows, seg, n_b, step);
+    return (int)cudaGetLastError();
+}
+
+int Launch::stem_wgrad(const WgradTask* tasks, int n_tasks, int max_k, int W, int max_cout, int splits, int n_b, int step,
+                       void* stream) {
+    const int seg = seg_floats_for(W, max_k, kStemRows);
+    const size_t smem = (2 * (size_t)seg + (size_t)8 * (max_k * max_k + 1) * max_cout) * sizeof(float);
+    cudaError_t e = opt_in(stem_wgrad_kernel, smem);
+    if (e != cudaSuccess) return (int)e;
+    stem_wgrad_kernel<<<n_tasks * splits, kThreads, smem, (cudaStream_t)stream>>>(tasks, splits, seg, n_b, step);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace cmoop_cnn

@@ -103,3 +103,40 @@ def test_weight_gradient(n, H, W, Cin, Cout, k, stride, splits):
     want32 = ref(x, dy)
     got32 = run_wgrad(0, x, dy, n, H, W, Cin, Cout, k, stride, splits)
     np.testing.assert_allclose(got32, want32, rtol=1e-3, atol=2e-4 * np.abs(want32).max())
+
+
+STEM_CASES = [  # n, H, W, Cout, k   (Cin = 1; the dedicated kernels of csrc/cnn/stem.cu, use_tc = 2)
+    (64, 49, 40, 16, 3),       # KWS stem, every genotype corner
+    (64, 49, 40, 64, 5),
+    (7, 49, 40, 32, 5),        # ragged last batch: blocks past M, a block straddling two samples
+    (1, 49, 40, 64, 3),
+    (3, 128, 313, 32, 3),      # BirdCLEF-shaped map: a block covers ~3 rows
+    (5, 33, 37, 128, 5),       # odd sizes, 32 channel groups per pixel
+    (2, 40, 40, 256, 3),       # 64 channel groups: one pixel spans two warps
+]
+
+
+@pytest.mark.parametrize("n,H,W,Cout,k", STEM_CASES)
+def test_stem_kernels(n, H, W, Cout, k):
+    """Cin = 1 forward (+bias, ReLU) and weight gradient against torch fp64 and against the generic fp32 SIMT kernels."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(n + H + W + Cout + k)
+    x = rng.standard_normal((n, H, W, 1)).astype(np.float32)
+    w = (rng.standard_normal((k, k, 1, Cout)) / k).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    pad = (k - 1) // 2
+    full = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2).double(), torch.from_numpy(w).permute(3, 2, 0, 1).double(),
+                    torch.from_numpy(b).double(), padding=pad).permute(0, 2, 3, 1).numpy()
+    for relu in (0, 1):
+        got = run_conv(0, 2, x, w, b, n, H, W, 1, Cout, k, 1, relu)
+        np.testing.assert_allclose(got, np.maximum(full, 0) if relu else full, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(run_conv(0, 2, x, w, b, n, H, W, 1, Cout, k, 1, 0), run_conv(0, 0, x, w, b, n, H, W, 1, Cout, k, 1, 0),
+                               rtol=1e-5, atol=1e-5)
+    dy = rng.standard_normal((n, H, W, Cout)).astype(np.float32)
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2).double()
+    yt = torch.from_numpy(dy).permute(0, 3, 1, 2).double()
+    gw = torch.nn.grad.conv2d_weight(xt, (Cout, 1, k, k), yt, padding=pad)
+    want = np.concatenate([gw.permute(2, 3, 1, 0).reshape(k * k, Cout).numpy(), yt.sum(dim=(0, 2, 3)).numpy()[None]])
+    got = run_wgrad(2, x, dy, n, H, W, 1, Cout, k, 1, 1)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-5 * np.abs(want).max())
