@@ -61,7 +61,8 @@ struct TcWgradTask {
 struct WtBf16Task {
     const float* w;              // fp32 HWIO master weights
     __nv_bfloat16* out;
-    int k, Cin, Cout, K_pad, mode;   // mode 0: forward copy, 1: flipped/transposed copy for the data gradient
+    int k, Cin, Cout, K_pad, mode;   // mode 0: forward copy, 1: flipped/transposed copy for the data gradient;
+                                     // 2 / 3: the same two operands in the stage layout of conv_tc2.cu
     int block_begin;
 };
 
@@ -204,6 +205,12 @@ struct Launch {
     static int wgrad_tc(const TcWgradTask* tasks, int n_tasks, int total_tiles, int n_b, void* stream);
     static int wt_bf16(const WtBf16Task* tasks, int n_tasks, int total_blocks, void* stream);
     static int bn_stats(const StatTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
+    // conv_tc2.cu: patch-resident tcgen05 convolution (stride 1); tiles = ceil(n_b*Hp*Wp / tc2_rows()) * tiles_n
+    static bool tc2_ok(int H, int W, int Cin, int Cout, int k, int stride);
+    static int tc2_q(int W, int k);
+    static int tc2_rows();
+    static int conv_tc2(const TcConvTask* tasks, int n_tasks, int total_tiles, int n_b, int step, int q_max, void* stream);
+    static int wt_bf16_v2(const WtBf16Task* tasks, int n_tasks, int total_blocks, void* stream);
     // stem.cu: dedicated Cin = 1 kernels; every task of a launch has the same M (= n_b*H*W) and W
     static bool stem_ok(int H, int W, int Cin, int Cout, int k, int stride, int n_b);
     static int stem_conv(const ConvTask* tasks, int n_tasks, int max_k, int W, int max_cout, long long M, int n_b, int step,

@@ -57,6 +57,7 @@ struct Unit {
     uint8_t* idx = nullptr;
     bool tc = false;                 // convolution runs on the tcgen05 path (bf16 operands)
     bool stem = false;               // Cin = 1 first convolution: dedicated kernels (stem.cu)
+    bool tc2 = false;                // tensor-core unit on the patch-resident kernel (conv_tc2.cu)
     int kpad_f = 0, kpad_d = 0;      // padded K of the forward / data-gradient GEMM
     bool need_vh = false;            // a tensor-core unit consumes this unit's output
     __nv_bfloat16* Vh = nullptr;     // bf16 shadow of V
@@ -205,6 +206,9 @@ void build_units(Cand& c, const cmoop_cnn_config& cfg, int H, int W, int batch) 
     c.n_params = off;
     for (Unit& u : c.units) {
         u.tc = cfg.precision == 1 && !u.dense && u.cin % 16 == 0 && u.cout % 16 == 0;
+        static const bool no_tc2 = getenv("CMOOP_CNN_NO_TC2") != nullptr;       // A/B switch: im2col-staging tcgen05 kernel
+        u.tc2 = u.tc && !no_tc2 && Launch::tc2_ok(u.H, u.W, u.cin, u.cout, u.k, u.stride) &&
+                Launch::tc2_ok(u.H, u.W, u.cout, u.cin, u.k, u.stride);
         u.kpad_f = (u.k * u.k * u.cin + 63) / 64 * 64;
         u.kpad_d = (u.k * u.k * u.cout + 63) / 64 * 64;
         u.u_elems = (long long)batch * u.Ho * u.Wo * u.cout;
@@ -302,7 +306,8 @@ struct DevList {
 
 struct StageLists {
     DevList<ConvTask> conv, conv_eval, dgrad;
-    DevList<TcConvTask> conv_tc, dgrad_tc;
+    DevList<TcConvTask> conv_tc, dgrad_tc, conv_tc2, dgrad_tc2;
+    int q_max = 0;                   // largest patch of the stage's conv_tc2 / dgrad_tc2 tasks
     DevList<TcWgradTask> wgrad_tc;
     DevList<StatTask> stat;
     // stem.cu path: every task of conv / conv_eval / wgrad is an eligible Cin = 1 convolution
@@ -323,7 +328,7 @@ struct Wave {
     DevList<CeTask> ce_train, ce_val, ce_pred;
     DevList<AdamTask> adam;
     DevList<WtTask> wt;
-    DevList<WtBf16Task> wt_bf16;
+    DevList<WtBf16Task> wt_bf16, wt_bf16_v2;
     bool weights_dirty = true;
     char* d_blob = nullptr;
     size_t blob_cap = 0;
@@ -353,6 +358,7 @@ struct Engine {
         wv.adam = DevList<AdamTask>();
         wv.wt = DevList<WtTask>();
         wv.wt_bf16 = DevList<WtBf16Task>();
+        wv.wt_bf16_v2 = DevList<WtBf16Task>();
         wv.weights_dirty = true;
         const long long img = (long long)data->H * data->W;
         for (Cand* cp : wv.cands) {
@@ -374,9 +380,17 @@ struct Engine {
                     t.bn = u.cout < 128 ? u.cout : 128;
                     t.relu = u.relu_epi;
                     t.tiles_n = (u.cout + t.bn - 1) / t.bn;
-                    t.tile_begin = S.conv_tc.total;
-                    S.conv_tc.h.push_back(t);
-                    S.conv_tc.total += (int)(((long long)batch * u.Ho * u.Wo + 127) / 128) * t.tiles_n;
+                    if (u.tc2) {
+                        const long long mq = (long long)batch * (u.H + 2 * u.pad) * (u.W + 2 * u.pad);
+                        t.tile_begin = S.conv_tc2.total;
+                        S.conv_tc2.h.push_back(t);
+                        S.conv_tc2.total += (int)((mq + Launch::tc2_rows() - 1) / Launch::tc2_rows()) * t.tiles_n;
+                        S.q_max = std::max(S.q_max, Launch::tc2_q(u.W, u.k));
+                    } else {
+                        t.tile_begin = S.conv_tc.total;
+                        S.conv_tc.h.push_back(t);
+                        S.conv_tc.total += (int)(((long long)batch * u.Ho * u.Wo + 127) / 128) * t.tiles_n;
+                    }
                     if (u.has_bn) {
                         StatTask sk{};
                         sk.y = u.U; sk.part = u.stat; sk.C = u.cout; sk.rows_per_sample = u.Ho * u.Wo;
@@ -386,10 +400,16 @@ struct Engine {
                     }
                     WtBf16Task wb{};
                     wb.w = c.p + u.w_off; wb.out = u.wtb; wb.k = u.k; wb.Cin = u.cin; wb.Cout = u.cout;
-                    wb.K_pad = u.kpad_f; wb.mode = 0;
-                    wb.block_begin = wv.wt_bf16.total;
-                    wv.wt_bf16.h.push_back(wb);
-                    wv.wt_bf16.total += blocks_for((long long)u.cout * u.kpad_f);
+                    wb.K_pad = u.kpad_f; wb.mode = u.tc2 ? 2 : 0;
+                    if (u.tc2) {
+                        wb.block_begin = wv.wt_bf16_v2.total;
+                        wv.wt_bf16_v2.h.push_back(wb);
+                        wv.wt_bf16_v2.total += blocks_for((long long)u.k * u.k * u.cin * u.cout);
+                    } else {
+                        wb.block_begin = wv.wt_bf16.total;
+                        wv.wt_bf16.h.push_back(wb);
+                        wv.wt_bf16.total += blocks_for((long long)u.cout * u.kpad_f);
+                    }
                 } else {
                     ConvTask t{};
                     t.x = xin;
@@ -521,10 +541,16 @@ struct Engine {
                 if (u.need_dgrad && u.tc) {
                     WtBf16Task wb{};
                     wb.w = c.p + u.w_off; wb.out = u.wtd; wb.k = u.k; wb.Cin = u.cin; wb.Cout = u.cout;
-                    wb.K_pad = u.kpad_d; wb.mode = 1;
-                    wb.block_begin = wv.wt_bf16.total;
-                    wv.wt_bf16.h.push_back(wb);
-                    wv.wt_bf16.total += blocks_for((long long)u.cin * u.kpad_d);
+                    wb.K_pad = u.kpad_d; wb.mode = u.tc2 ? 3 : 1;
+                    if (u.tc2) {
+                        wb.block_begin = wv.wt_bf16_v2.total;
+                        wv.wt_bf16_v2.h.push_back(wb);
+                        wv.wt_bf16_v2.total += blocks_for((long long)u.k * u.k * u.cin * u.cout);
+                    } else {
+                        wb.block_begin = wv.wt_bf16.total;
+                        wv.wt_bf16.h.push_back(wb);
+                        wv.wt_bf16.total += blocks_for((long long)u.cin * u.kpad_d);
+                    }
                     TcConvTask d{};
                     d.xh = u.is_skip ? c.gSh : c.gBh;
                     d.wt = u.wtd;
@@ -539,9 +565,17 @@ struct Engine {
                     }
                     d.bn = u.cin < 128 ? u.cin : 128;
                     d.tiles_n = (u.cin + d.bn - 1) / d.bn;
-                    d.tile_begin = S.dgrad_tc.total;
-                    S.dgrad_tc.h.push_back(d);
-                    S.dgrad_tc.total += (int)(((long long)batch * u.Ho * u.Wo + 127) / 128) * d.tiles_n;
+                    if (u.tc2) {
+                        const long long mq = (long long)batch * (u.H + 2 * u.pad) * (u.W + 2 * u.pad);
+                        d.tile_begin = S.dgrad_tc2.total;
+                        S.dgrad_tc2.h.push_back(d);
+                        S.dgrad_tc2.total += (int)((mq + Launch::tc2_rows() - 1) / Launch::tc2_rows()) * d.tiles_n;
+                        S.q_max = std::max(S.q_max, Launch::tc2_q(u.W, u.k));
+                    } else {
+                        d.tile_begin = S.dgrad_tc.total;
+                        S.dgrad_tc.h.push_back(d);
+                        S.dgrad_tc.total += (int)(((long long)batch * u.Ho * u.Wo + 127) / 128) * d.tiles_n;
+                    }
                 } else if (u.need_dgrad) {
                     WtTask w{};
                     w.w = c.p + u.w_off; w.wt = u.wt; w.k = u.k; w.Cin = u.cin; w.Cout = u.cout;
@@ -594,11 +628,12 @@ struct Engine {
             StageLists& S = wv.st[s];
             blob_add(blob, S.conv); blob_add(blob, S.conv_eval); blob_add(blob, S.dgrad);
             blob_add(blob, S.conv_tc); blob_add(blob, S.dgrad_tc); blob_add(blob, S.stat); blob_add(blob, S.wgrad_tc);
+            blob_add(blob, S.conv_tc2); blob_add(blob, S.dgrad_tc2);
             blob_add(blob, S.post_fwd); blob_add(blob, S.post_bn); blob_add(blob, S.post_bwd);
             blob_add(blob, S.wgrad); blob_add(blob, S.wreduce); blob_add(blob, S.drop_fwd); blob_add(blob, S.drop_bwd);
         }
         blob_add(blob, wv.head); blob_add(blob, wv.ce_train); blob_add(blob, wv.ce_val); blob_add(blob, wv.ce_pred);
-        blob_add(blob, wv.adam); blob_add(blob, wv.wt); blob_add(blob, wv.wt_bf16);
+        blob_add(blob, wv.adam); blob_add(blob, wv.wt); blob_add(blob, wv.wt_bf16); blob_add(blob, wv.wt_bf16_v2);
         if (blob.size() > wv.blob_cap) {
             if (wv.d_blob) {
                 CMOOP_CUDA_OK(cudaStreamSynchronize(stream));
@@ -613,10 +648,10 @@ struct Engine {
         for (int s = 0; s < N_STAGES; ++s) {
             StageLists& S = wv.st[s];
             fix(S.conv); fix(S.conv_eval); fix(S.dgrad); fix(S.post_fwd); fix(S.post_bn); fix(S.post_bwd);
-            fix(S.conv_tc); fix(S.dgrad_tc); fix(S.stat); fix(S.wgrad_tc);
+            fix(S.conv_tc); fix(S.dgrad_tc); fix(S.stat); fix(S.wgrad_tc); fix(S.conv_tc2); fix(S.dgrad_tc2);
             fix(S.wgrad); fix(S.wreduce); fix(S.drop_fwd); fix(S.drop_bwd);
         }
-        fix(wv.head); fix(wv.ce_train); fix(wv.ce_val); fix(wv.ce_pred); fix(wv.adam); fix(wv.wt); fix(wv.wt_bf16);
+        fix(wv.head); fix(wv.ce_train); fix(wv.ce_val); fix(wv.ce_pred); fix(wv.adam); fix(wv.wt); fix(wv.wt_bf16); fix(wv.wt_bf16_v2);
         return CMOOP_OK;
     }
 
@@ -636,6 +671,9 @@ struct Engine {
         if (wv.weights_dirty && !wv.wt_bf16.h.empty()) {
             CNN_LAUNCH(Launch::wt_bf16(wv.wt_bf16.d, (int)wv.wt_bf16.h.size(), wv.wt_bf16.total, stream));
         }
+        if (wv.weights_dirty && !wv.wt_bf16_v2.h.empty()) {
+            CNN_LAUNCH(Launch::wt_bf16_v2(wv.wt_bf16_v2.d, (int)wv.wt_bf16_v2.h.size(), wv.wt_bf16_v2.total, stream));
+        }
         wv.weights_dirty = false;
         for (int s = 0; s < N_STAGES; ++s) {
             StageLists& S = wv.st[s];
@@ -649,11 +687,13 @@ struct Engine {
                 else
                     CNN_LAUNCH(Launch::conv(cl.d, (int)cl.h.size(), cl.total, n_b, step, stream));
             }
-            if (!S.conv_tc.h.empty()) {
+            if (!S.conv_tc.h.empty())
                 CNN_LAUNCH(Launch::conv_tc(S.conv_tc.d, (int)S.conv_tc.h.size(), S.conv_tc.total, n_b, step, stream));
-                if (!S.stat.h.empty() && training)
-                    CNN_LAUNCH(Launch::bn_stats(S.stat.d, (int)S.stat.h.size(), S.stat.total, n_b, stream));
-            }
+            if (!S.conv_tc2.h.empty())
+                CNN_LAUNCH(Launch::conv_tc2(S.conv_tc2.d, (int)S.conv_tc2.h.size(), S.conv_tc2.total, n_b, step, S.q_max,
+                                            stream));
+            if (!S.stat.h.empty() && training)
+                CNN_LAUNCH(Launch::bn_stats(S.stat.d, (int)S.stat.h.size(), S.stat.total, n_b, stream));
             if (!S.post_bn.h.empty())
                 CNN_LAUNCH(Launch::bn_finalize(S.post_bn.d, (int)S.post_bn.h.size(), S.max_bn_c, n_b, training, cfg.bn_momentum,
                                                cfg.bn_eps, stream));
@@ -698,6 +738,9 @@ struct Engine {
                 CNN_LAUNCH(Launch::conv(S.dgrad.d, (int)S.dgrad.h.size(), S.dgrad.total, n_b, 0, stream));
             if (!S.dgrad_tc.h.empty())
                 CNN_LAUNCH(Launch::conv_tc(S.dgrad_tc.d, (int)S.dgrad_tc.h.size(), S.dgrad_tc.total, n_b, 0, stream));
+            if (!S.dgrad_tc2.h.empty())
+                CNN_LAUNCH(Launch::conv_tc2(S.dgrad_tc2.d, (int)S.dgrad_tc2.h.size(), S.dgrad_tc2.total, n_b, 0, S.q_max,
+                                            stream));
         }
         return CMOOP_OK;
     }
@@ -1135,7 +1178,9 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
                          int Cin, int Cout, int k, int stride, int relu, float* out) {
     CMOOP_REQUIRE(in && w && out, "debug_conv: null pointer");
     CMOOP_REQUIRE(n >= 1 && n <= kBatch && (stride == 1 || (stride == 2 && k == 1)), "debug_conv: unsupported shape");
-    CMOOP_REQUIRE(use_tc != 1 || (Cin % 16 == 0 && Cout % 16 == 0), "debug_conv: tensor-core path needs Cin, Cout multiples of 16");
+    CMOOP_REQUIRE((use_tc != 1 && use_tc != 3) || (Cin % 16 == 0 && Cout % 16 == 0), "debug_conv: tensor-core path needs Cin, Cout multiples of 16");
+    CMOOP_REQUIRE(use_tc != 3 || (Launch::tc2_ok(H, W, Cin, Cout, k, stride) && Launch::tc2_ok(H, W, Cout, Cin, k, stride)),
+                  "debug_conv: shape not eligible for the patch-resident tcgen05 kernel");
     CMOOP_REQUIRE(use_tc != 2 || (mode == 0 && Launch::stem_ok(H, W, Cin, Cout, k, stride, n)),
                   "debug_conv: shape not eligible for the stem (Cin = 1) kernel");
     if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
@@ -1169,7 +1214,7 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
     CMOOP_CUDA_OK(cudaMemsetAsync(d_out, 0, n_out * 4, st));
     const int tiles_m64 = (int)(((long long)n * Ho * Wo + 63) / 64), tiles_m128 = (int)(((long long)n * Ho * Wo + 127) / 128);
     int rc = 0;
-    if (use_tc != 1) {
+    if (use_tc != 1 && use_tc != 3) {
         ConvTask t{};
         t.x = d_in; t.y = d_out;
         t.Ho = Ho; t.Wo = Wo; t.k = k;
@@ -1194,9 +1239,10 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
             rc = Launch::conv((const ConvTask*)d_task, 1, tiles_m64 * t.tiles_n, n, 0, st);
     } else {
         WtBf16Task wb{};
-        wb.w = d_w; wb.out = d_wb; wb.k = k; wb.Cin = Cin; wb.Cout = Cout; wb.K_pad = K_pad; wb.mode = mode;
+        wb.w = d_w; wb.out = d_wb; wb.k = k; wb.Cin = Cin; wb.Cout = Cout; wb.K_pad = K_pad; wb.mode = mode + (use_tc == 3 ? 2 : 0);
         CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &wb, sizeof(wb), cudaMemcpyHostToDevice, st));
-        rc = Launch::wt_bf16((const WtBf16Task*)d_task, 1, (int)(((long long)go * K_pad + 255) / 256), st);
+        rc = use_tc == 3 ? Launch::wt_bf16_v2((const WtBf16Task*)d_task, 1, (int)((n_w + 255) / 256), st)
+                         : Launch::wt_bf16((const WtBf16Task*)d_task, 1, (int)(((long long)go * K_pad + 255) / 256), st);
         CMOOP_CUDA_OK(cudaStreamSynchronize(st));
         TcConvTask t{};
         t.xh = d_inh; t.wt = d_wb; t.y = d_out; t.k = k; t.K_pad = K_pad;
@@ -1211,7 +1257,13 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
         t.bn = t.Cout < 128 ? t.Cout : 128;
         t.tiles_n = (t.Cout + t.bn - 1) / t.bn;
         CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &t, sizeof(t), cudaMemcpyHostToDevice, st));
-        if (rc == 0) rc = Launch::conv_tc((const TcConvTask*)d_task, 1, tiles_m128 * t.tiles_n, n, 0, st);
+        if (rc == 0 && use_tc == 3) {
+            const long long mq = (long long)n * (H + 2 * pad) * (W + 2 * pad);
+            rc = Launch::conv_tc2((const TcConvTask*)d_task, 1, (int)((mq + Launch::tc2_rows() - 1) / Launch::tc2_rows()) * t.tiles_n,
+                                  n, 0, Launch::tc2_q(W, k), st);
+        } else if (rc == 0) {
+            rc = Launch::conv_tc((const TcConvTask*)d_task, 1, tiles_m128 * t.tiles_n, n, 0, st);
+        }
     }
     cmoop::count_launch();
     cudaError_t e = cudaStreamSynchronize(st);

@@ -5,7 +5,7 @@
 // = 10 or 26, so the generic 64x64x16 SIMT GEMM spent its time on im2col bookkeeping (1.0 ms forward / 1.8 ms
 // weight gradient per grouped launch of 32 candidates against ~0.1 ms of HBM traffic).  Here a block owns 1024
 // consecutive output pixels of one candidate: the feature-map rows they touch (<= 2 samples) are staged once in
-// shared memory with their zero padding, a thread owns 4 (or 2) output channels of a pixel, taps are immediate
+// shared memory with their zero padding, a thread owns 4 (k = 3) or 2 (k = 5) output channels of a pixel with their weights in registers, taps are immediate
 // offsets into the staged tile, stores / gradient loads are 16-byte and coalesced.  Contracts are those of
 // conv_gemm_kernel / conv_wgrad_kernel (ConvTask / WgradTask): same BN partial-sum layout (64-row tiles), same
 // [split][K+1][Cout] partial gradients reduced by reduce_kernel, deterministic (no atomics).
@@ -52,8 +52,10 @@ __device__ __forceinline__ void stage_rows(float* tile, int seg_floats, const fl
     }
 }
 
-// y[m][co] = relu?(b[co] + sum_taps x[m + tap] w[tap][co]);  BN partial sums per 64-row tile
-template <int KS>
+// y[m][co] = relu?(b[co] + sum_taps x[m + tap] w[tap][co]);  BN partial sums per 64-row tile.
+// A thread keeps the weights of its CPT channels for every tap in registers (its channel group never changes), so a
+// tap costs one shared-memory read of x (broadcast among the threads of a pixel) and CPT FMAs.
+template <int KS, int CPT>
 __device__ __forceinline__ void stem_conv_body(const ConvTask& T, float* sm, int chunk, int rows_per_block, int seg_floats,
                                                int n_b, int step) {
     constexpr int P = (KS - 1) / 2, TAPS = KS * KS;
@@ -61,22 +63,26 @@ __device__ __forceinline__ void stem_conv_body(const ConvTask& T, float* sm, int
     const int H = T.H, W = T.W, HW = H * W, Wp = W + 2 * P, Cout = T.Cout;
     const int M = n_b * HW, m0 = chunk * rows_per_block, m1 = min(M, m0 + rows_per_block);
     if (m0 >= M) return;
-    float* ws = sm;                                   // [(TAPS+1)][Cout]
-    float* tile = ws + (TAPS + 1) * Cout;             // [2][seg_floats]
+    float* tile = sm;                                 // [2][seg_floats]
     float* red = tile + 2 * seg_floats;               // [8 warps][2][Cout]
-    for (int i = tid; i < (TAPS + 1) * Cout; i += kThreads) ws[i] = T.w[i];
     Segs sg;
     stage_rows<KS>(tile, seg_floats, T.x + T.x_step * step, T.gather ? T.gather + T.gather_step * step : nullptr, H, W, m0,
                    m1, sg);
+    const int CG = Cout / CPT, PP = kThreads / CG;    // threads per pixel, pixels per pass (PP <= 64)
+    const int cg = tid % CG, pl = tid / CG;
+    const int passes_per_tile = 64 / PP;
+    float wr[TAPS + 1][CPT];
+#pragma unroll
+    for (int t = 0; t <= TAPS; ++t)
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) wr[t][j] = __ldg(T.w + t * Cout + cg * CPT + j);
     __syncthreads();
 
-    const int C4 = Cout >> 2, PP = kThreads / C4;     // threads per pixel, pixels per pass
-    const int cg = tid % C4, pl = tid / C4;
-    const int passes_per_tile = 64 / PP;              // PP in {64, 32, 16, 8, 4}
-    const float4 bias = ld4(ws + TAPS * Cout + cg * 4);
     const int tiles = (m1 - m0 + 63) >> 6;
     for (int tl = 0; tl < tiles; ++tl) {
-        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+        float s1[CPT], s2[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) s1[j] = s2[j] = 0.f;
         for (int pp = 0; pp < passes_per_tile; ++pp) {
             const int m = m0 + tl * 64 + pp * PP + pl;
             if (m < m1) {
@@ -84,60 +90,58 @@ __device__ __forceinline__ void stem_conv_body(const ConvTask& T, float* sm, int
                 const int h = rem / W, w = rem - h * W;
                 const int s = n - sg.n_first;
                 const float* tp = tile + s * seg_floats + (h - sg.ha[s]) * Wp + w;
-                float4 acc = bias;
+                float acc[CPT];
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) acc[j] = wr[TAPS][j];
 #pragma unroll
                 for (int kh = 0; kh < KS; ++kh)
 #pragma unroll
                     for (int kw = 0; kw < KS; ++kw) {
                         const float x = tp[kh * Wp + kw];
-                        const float4 wv = ld4(ws + (kh * KS + kw) * Cout + cg * 4);
-                        acc.x = fmaf(x, wv.x, acc.x);
-                        acc.y = fmaf(x, wv.y, acc.y);
-                        acc.z = fmaf(x, wv.z, acc.z);
-                        acc.w = fmaf(x, wv.w, acc.w);
+#pragma unroll
+                        for (int j = 0; j < CPT; ++j) acc[j] = fmaf(x, wr[kh * KS + kw][j], acc[j]);
                     }
                 if (T.relu) {
-                    acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f);
-                    acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) acc[j] = fmaxf(acc[j], 0.f);
                 }
-                const long long o = (long long)m * Cout + cg * 4;
-                *reinterpret_cast<float4*>(T.y + o) = acc;
+                const long long o = (long long)m * Cout + cg * CPT;
+                if constexpr (CPT == 4) {
+                    *reinterpret_cast<float4*>(T.y + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                } else {
+                    *reinterpret_cast<float2*>(T.y + o) = make_float2(acc[0], acc[1]);
+                }
                 if (T.yh) {
-                    __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi2 = __floats2bfloat162_rn(acc.z, acc.w);
-                    uint2 pk;
-                    pk.x = *reinterpret_cast<unsigned*>(&lo);
-                    pk.y = *reinterpret_cast<unsigned*>(&hi2);
-                    *reinterpret_cast<uint2*>(T.yh + o) = pk;
+#pragma unroll
+                    for (int j = 0; j < CPT; j += 2)
+                        *reinterpret_cast<__nv_bfloat162*>(T.yh + o + j) = __floats2bfloat162_rn(acc[j], acc[j + 1]);
                 }
-                s1.x += acc.x; s1.y += acc.y; s1.z += acc.z; s1.w += acc.w;
-                s2.x = fmaf(acc.x, acc.x, s2.x); s2.y = fmaf(acc.y, acc.y, s2.y);
-                s2.z = fmaf(acc.z, acc.z, s2.z); s2.w = fmaf(acc.w, acc.w, s2.w);
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    s1[j] += acc[j];
+                    s2[j] = fmaf(acc[j], acc[j], s2[j]);
+                }
             }
         }
         if (T.stat_part) {
-            for (int msk = C4; msk < 32; msk <<= 1) {
-                s1.x += __shfl_xor_sync(0xffffffffu, s1.x, msk); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, msk);
-                s1.z += __shfl_xor_sync(0xffffffffu, s1.z, msk); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, msk);
-                s2.x += __shfl_xor_sync(0xffffffffu, s2.x, msk); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, msk);
-                s2.z += __shfl_xor_sync(0xffffffffu, s2.z, msk); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, msk);
-            }
-            // C4 <= 32: lanes [0, C4) of every warp hold the warp's sums for channel groups cg = lane (+ 32 j, C4 = 64)
-            if (C4 >= 32 || lane < C4) {
-                *reinterpret_cast<float4*>(red + (warp * 2 + 0) * Cout + cg * 4) = s1;
-                *reinterpret_cast<float4*>(red + (warp * 2 + 1) * Cout + cg * 4) = s2;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                for (int msk = CG; msk < 32; msk <<= 1) {
+                    s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], msk);
+                    s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], msk);
+                }
+                if (CG >= 32 || lane < CG) {
+                    red[(warp * 2 + 0) * Cout + cg * CPT + j] = s1[j];
+                    red[(warp * 2 + 1) * Cout + cg * CPT + j] = s2[j];
+                }
             }
             __syncthreads();
             for (int i = tid; i < 2 * Cout; i += kThreads) {
                 const int which = i / Cout, c = i - which * Cout;
-                // warps that share a channel group: all of them when C4 <= 32, every second one when C4 == 64
+                // channel group cg is held by every warp (CG <= 32) or by the warps with warp % (CG / 32) == cg / 32
+                const int per = CG <= 32 ? 1 : CG / 32, mine = CG <= 32 ? 0 : (c / CPT) / 32;
                 float a = 0.f;
-                if (C4 <= 32) {
-#pragma unroll
-                    for (int wq = 0; wq < kThreads / 32; ++wq) a += red[(wq * 2 + which) * Cout + c];
-                } else {
-                    const int par = (c >> 7) & 1;      // cg >= 32 lives in odd warps (tid % 64 >= 32)
-                    for (int wq = par; wq < kThreads / 32; wq += 2) a += red[(wq * 2 + which) * Cout + c];
-                }
+                for (int wq = mine; wq < kThreads / 32; wq += per) a += red[(wq * 2 + which) * Cout + c];
                 T.stat_part[((long long)((m0 >> 6) + tl) * 2 + which) * Cout + c] = a;
             }
             __syncthreads();
@@ -146,7 +150,7 @@ __device__ __forceinline__ void stem_conv_body(const ConvTask& T, float* sm, int
 }
 
 // the two kernel sizes of the genotype space (nsga_penalty.py:189) share one grouped launch
-__global__ void __launch_bounds__(kThreads) stem_conv_kernel(const ConvTask* __restrict__ tasks, int blocks_per_task,
+__global__ void __launch_bounds__(kThreads, 3) stem_conv_kernel(const ConvTask* __restrict__ tasks, int blocks_per_task,
                                                              int rows_per_block, int seg_floats, int n_b, int step) {
     extern __shared__ __align__(16) float sm[];
     __shared__ ConvTask T;
@@ -154,9 +158,9 @@ __global__ void __launch_bounds__(kThreads) stem_conv_kernel(const ConvTask* __r
     if (threadIdx.x == 0) T = tasks[task];
     __syncthreads();
     if (T.k == 3)
-        stem_conv_body<3>(T, sm, chunk, rows_per_block, seg_floats, n_b, step);
+        stem_conv_body<3, 4>(T, sm, chunk, rows_per_block, seg_floats, n_b, step);
     else
-        stem_conv_body<5>(T, sm, chunk, rows_per_block, seg_floats, n_b, step);
+        stem_conv_body<5, 2>(T, sm, chunk, rows_per_block, seg_floats, n_b, step);
 }
 
 // out[split][tap][co] = sum_{m in split} x[m + tap] dy[m][co]  (row TAPS = bias gradient = sum of dy)
@@ -186,29 +190,42 @@ __device__ __forceinline__ void stem_wgrad_body(const WgradTask& T, float* sm, i
     for (int t = 0; t <= TAPS; ++t)
 #pragma unroll
         for (int j = 0; j < CPT; ++j) acc[t][j] = 0.f;
-    for (int m = m0 + pl; m < m1; m += PP) {
-        const int n = m / HW, rem = m - n * HW;
-        const int h = rem / W, w = rem - h * W;
-        const int s = n - sg.n_first;
-        const float* tp = tile + s * seg_floats + (h - sg.ha[s]) * Wp + w;
-        float g[CPT];
-        if constexpr (CPT == 4) {
-            const float4 v = ld4(T.dy + (long long)m * Cout + cg * 4);
-            g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
-        } else {
-            const float2 v = *reinterpret_cast<const float2*>(T.dy + (long long)m * Cout + cg * 2);
-            g[0] = v.x; g[1] = v.y;
+    constexpr int UN = 4;                             // gradient loads in flight per thread (HBM latency)
+    for (int mb = m0 + pl; mb < m1; mb += UN * PP) {
+        float g[UN][CPT];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int m = mb + u * PP;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) g[u][j] = 0.f;
+            if (m < m1) {
+                if constexpr (CPT == 4) {
+                    const float4 v = ld4(T.dy + (long long)m * Cout + cg * 4);
+                    g[u][0] = v.x; g[u][1] = v.y; g[u][2] = v.z; g[u][3] = v.w;
+                } else {
+                    const float2 v = *reinterpret_cast<const float2*>(T.dy + (long long)m * Cout + cg * 2);
+                    g[u][0] = v.x; g[u][1] = v.y;
+                }
+            }
         }
 #pragma unroll
-        for (int kh = 0; kh < KS; ++kh)
+        for (int u = 0; u < UN; ++u) {
+            const int m = min(mb + u * PP, m1 - 1);   // past the end: g == 0, any valid tile position will do
+            const int n = m / HW, rem = m - n * HW;
+            const int h = rem / W, w = rem - h * W;
+            const int s = n - sg.n_first;
+            const float* tp = tile + s * seg_floats + (h - sg.ha[s]) * Wp + w;
 #pragma unroll
-            for (int kw = 0; kw < KS; ++kw) {
-                const float x = tp[kh * Wp + kw];
+            for (int kh = 0; kh < KS; ++kh)
 #pragma unroll
-                for (int j = 0; j < CPT; ++j) acc[kh * KS + kw][j] = fmaf(x, g[j], acc[kh * KS + kw][j]);
-            }
+                for (int kw = 0; kw < KS; ++kw) {
+                    const float x = tp[kh * Wp + kw];
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) acc[TAPS][j] += g[j];
+                    for (int j = 0; j < CPT; ++j) acc[kh * KS + kw][j] = fmaf(x, g[u][j], acc[kh * KS + kw][j]);
+                }
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) acc[TAPS][j] += g[u][j];
+        }
     }
     // lanes with the same channel group, then the 8 warps
 #pragma unroll
@@ -274,7 +291,7 @@ int Launch::stem_conv(const ConvTask* tasks, int n_tasks, int max_k, int W, int 
                       void* stream) {
     const int bpt = (int)((M + kStemRows - 1) / kStemRows);
     const int seg = seg_floats_for(W, max_k, kStemRows);
-    const size_t smem = ((size_t)(max_k * max_k + 1) * max_cout + 2 * (size_t)seg + 8 * 2 * (size_t)max_cout) * sizeof(float);
+    const size_t smem = (2 * (size_t)seg + 8 * 2 * (size_t)max_cout) * sizeof(float);
     cudaError_t e = opt_in(stem_conv_kernel, smem);
     if (e != cudaSuccess) return (int)e;
     stem_conv_kernel<<<n_tasks * bpt, kThreads, smem, (cudaStream_t)stream>>>(tasks, bpt, kStemRows, seg, n_b, step);

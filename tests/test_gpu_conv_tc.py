@@ -140,3 +140,35 @@ def test_stem_kernels(n, H, W, Cout, k):
     want = np.concatenate([gw.permute(2, 3, 1, 0).reshape(k * k, Cout).numpy(), yt.sum(dim=(0, 2, 3)).numpy()[None]])
     got = run_wgrad(2, x, dy, n, H, W, 1, Cout, k, 1, 1)
     np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-5 * np.abs(want).max())
+
+
+PATCH_CASES = [c for c in CASES if c[6] == 1] + [
+    (64, 25, 20, 16, 32, 3, 1),      # first residual conv of the smallest genotype: one sub-slab, nine taps
+    (64, 13, 10, 128, 256, 5, 1),    # deep block: 8 sub-slabs x 25 taps, two N tiles
+    (9, 7, 5, 256, 512, 3, 1),       # last block: 16 sub-slabs, four N tiles, rows mostly padding positions
+    (3, 49, 40, 32, 32, 5, 1),       # variant-A stem2 shape with the widest patch (Wp = 44)
+]
+
+
+@pytest.mark.parametrize("n,H,W,Cin,Cout,k,stride", PATCH_CASES)
+def test_patch_resident_kernel(n, H, W, Cin, Cout, k, stride):
+    """conv_tc2.cu (use_tc = 3): forward (+bias, ReLU) and data gradient vs torch fp64 on bf16-rounded operands."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(n * 1000 + Cin + Cout + k)
+    x = rng.standard_normal((n, H, W, Cin)).astype(np.float32)
+    w = (rng.standard_normal((k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    pad = (k - 1) // 2
+    xt = torch.from_numpy(bf16_round(x)).permute(0, 3, 1, 2).double()
+    wt = torch.from_numpy(bf16_round(w)).permute(3, 2, 0, 1).double()
+    ref = F.conv2d(xt, wt, torch.from_numpy(b).double(), padding=pad).permute(0, 2, 3, 1).numpy()
+    for relu in (0, 1):
+        got = run_conv(0, 3, x, w, b, n, H, W, Cin, Cout, k, 1, relu)
+        np.testing.assert_allclose(got, np.maximum(ref, 0) if relu else ref, rtol=2e-4, atol=2e-4)
+    dy = rng.standard_normal((n, H, W, Cout)).astype(np.float32)
+    dyt = torch.from_numpy(bf16_round(dy)).permute(0, 3, 1, 2).double()
+    xin = torch.zeros((n, Cin, H, W), dtype=torch.float64, requires_grad=True)
+    F.conv2d(xin, wt, None, padding=pad).backward(dyt)
+    got_dx = run_conv(1, 3, dy, w, None, n, H, W, Cin, Cout, k, 1, 0)
+    np.testing.assert_allclose(got_dx, xin.grad.permute(0, 2, 3, 1).numpy(), rtol=2e-4, atol=2e-4)
