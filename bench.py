@@ -355,7 +355,7 @@ def run_ours(args) -> None:
                     "steps": e2e_steps, "api": "cmoop_mfcc_fwd_host via MfccFrontEnd(host array), pinned host buffers",
                     "checksum": checksum},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "mfcc_kernel<10>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "mfcc_pair_kernel<1>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": recorded_traffic(clips),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_CLIP * clips,
                          "kernel_ms_avg": kernel_avg_ms, "kernel_ms_min": min(kernel_ms)},
