@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
     const int local = blockIdx.x - T.tile_begin;
     const int tm = local / T.tiles_n, tn = local - tm * T.tiles_n;
     const int p = T.pad, Hp = T.H + 2 * p, Wp = T.W + 2 * p, HpWp = Hp * Wp;
-    const long long Mq = (long long)n_b * HpWp;
-    const long long q0 = (long long)tm * P2_ROWS;
+    const int Mq = n_b * HpWp;                         // < 2^31 for every supported shape (n_b <= 64)
+    const int q0 = tm * P2_ROWS;
     if (q0 >= Mq) return;
     const int S = p * Wp + p;
     const int Q = P2_ROWS + 2 * S;                     // patch positions of this task (<= q_max)
@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
     uint8_t* patch = smem_raw;                                          // [P2_PB][2][Q][16 B] (stride 32*q_max)
     uint8_t* wsm = patch + (size_t)P2_PB * 32 * q_max;                  // [P2_WS][P2_W_STAGE]
     int* src_off = reinterpret_cast<int*>(wsm + P2_WS * P2_W_STAGE);    // [q_max] element offset of a position's pixel, -1 = zero
-    uint64_t* bars = reinterpret_cast<uint64_t*>(src_off + ((q_max + 3) & ~3));
+    float* bias_s = reinterpret_cast<float*>(src_off + ((q_max + 3) & ~3));   // [128] this N tile's bias (0 without bias)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 128);
     uint64_t* pfull = bars;                     // [P2_PB]  256 producer arrivals
     uint64_t* pempty = bars + P2_PB;            // [P2_PB]  tcgen05.commit
     uint64_t* wfull = bars + 2 * P2_PB;         // [P2_WS]  TMA transaction
@@ -167,12 +168,13 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (tid < bn) bias_s[tid] = T.bias ? __ldg(T.bias + n0 + tid) : 0.f;
     // element offsets of the patch positions (shared by every sub-slab)
     for (int i = tid; i < Q; i += P2_THREADS) {
-        const long long q = q0 - S + i;
+        const int q = q0 - S + i;
         int off = -1;
         if (q >= 0 && q < Mq) {
-            const int n = (int)(q / HpWp), rem = (int)(q - (long long)n * HpWp);
+            const int n = q / HpWp, rem = q - n * HpWp;
             const int hp = rem / Wp, wp = rem - hp * Wp;
             if (hp >= p && hp < T.H + p && wp >= p && wp < T.W + p)
                 off = ((n * T.H + hp - p) * T.W + wp - p) * T.Cin;
@@ -214,10 +216,10 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
         const int c_end = bn >= 32 ? c_begin + bn / 2 : ((warp >> 2) == 0 ? bn : 0);
 #pragma unroll 1
         for (int mt = 0; mt < P2_MT; ++mt) {
-            const long long q = q0 + mt * 128 + lane_grp * 32 + lane;
+            const int q = q0 + mt * 128 + lane_grp * 32 + lane;
             long long obase = -1;
             if (q < Mq) {
-                const int n = (int)(q / HpWp), rem = (int)(q - (long long)n * HpWp);
+                const int n = q / HpWp, rem = q - n * HpWp;
                 const int hp = rem / Wp, wp = rem - hp * Wp;
                 if (hp >= p && hp < T.H + p && wp >= p && wp < T.W + p)
                     obase = ((long long)(n * T.H + hp - p) * T.W + wp - p) * T.Cout;
@@ -236,15 +238,12 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
                     float* dst = T.y + obase + n0 + c0;
 #pragma unroll
                     for (int qd = 0; qd < 16; qd += 4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + qd);
                         float4 o;
-                        o.x = __uint_as_float(v[qd + 0]);
-                        o.y = __uint_as_float(v[qd + 1]);
-                        o.z = __uint_as_float(v[qd + 2]);
-                        o.w = __uint_as_float(v[qd + 3]);
-                        if (T.bias) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4*>(T.bias + n0 + c0 + qd));
-                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                        }
+                        o.x = __uint_as_float(v[qd + 0]) + bb.x;
+                        o.y = __uint_as_float(v[qd + 1]) + bb.y;
+                        o.z = __uint_as_float(v[qd + 2]) + bb.z;
+                        o.w = __uint_as_float(v[qd + 3]) + bb.w;
                         if (T.relu) {
                             o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                         }
@@ -347,7 +346,7 @@ __global__ void __launch_bounds__(256) wt_bf16_v2_kernel(const WtBf16Task* __res
 }
 
 size_t p2_smem_bytes(int q_max) {
-    return (size_t)P2_PB * 32 * q_max + (size_t)P2_WS * P2_W_STAGE + (size_t)((q_max + 3) & ~3) * 4 + 256;
+    return (size_t)P2_PB * 32 * q_max + (size_t)P2_WS * P2_W_STAGE + (size_t)((q_max + 3) & ~3) * 4 + 512 + 256;
 }
 
 }  // namespace
