@@ -29,7 +29,9 @@ namespace {
 constexpr int P2_MT = 2;                    // 128-row tiles per CTA
 constexpr int P2_ROWS = P2_MT * 128;
 constexpr int P2_PB = 4;                    // patch sub-slab buffers
-constexpr int P2_WS = 8;                    // weight stages
+constexpr int P2_WS = 12;                   // weight stages of 4 KB = 128 / bn (sub-slab, tap) entries each: 48 KB in flight per
+                                            // CTA, about the L2 latency at the 32 B/clk the tensor pipe consumes (the first
+                                            // version's 8 single-tap stages left the MMA thread waiting on weights)
 constexpr int P2_LOOK = 2;                  // sub-slabs whose copies are in flight per producer thread
 constexpr int P2_PRODUCERS = 256;
 constexpr int P2_THREADS = P2_PRODUCERS + 64;     // + MMA warp + weight-TMA warp
@@ -266,25 +268,33 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(bn);
             const uint32_t lbo_a = 16u * (uint32_t)Q, lbo_b = 16u * (uint32_t)bn;
-            int st = 0;
+            const int tps = 128 / bn;                  // (sub-slab, tap) entries per 4 KB weight stage
+            const int total = n_cs * taps;
+            int st = 0, e = 0;                         // stage counter; entry = cs * taps + tap in weight-stream order
             for (int cs = 0; cs < n_cs; ++cs) {
                 const int b = cs % P2_PB;
                 mbar_wait(&pfull[b], ((uint32_t)(cs / P2_PB)) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_base = smem_u32(patch + (size_t)b * 32 * q_max);
-                for (int t = 0; t < taps; ++t, ++st) {
-                    const int ws = st % P2_WS;
-                    mbar_wait(&wfull[ws], ((uint32_t)(st / P2_WS)) & 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const int kh = t / T.k, kw = t - kh * T.k;
+                int kh = 0, kw = 0;
+                for (int t = 0; t < taps; ++t, ++e) {
+                    const int sub = e % tps, ws = st % P2_WS;
+                    if (sub == 0) {
+                        mbar_wait(&wfull[ws], ((uint32_t)(st / P2_WS)) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
                     const uint32_t shift = (uint32_t)(kh * Wp + kw) * 16u;
-                    const uint64_t bd = make_desc_k_none(smem_u32(wsm + ws * P2_W_STAGE), lbo_b, 128);
+                    const uint64_t bd = make_desc_k_none(smem_u32(wsm + ws * P2_W_STAGE) + (uint32_t)sub * w_stage_bytes, lbo_b, 128);
 #pragma unroll
                     for (int mt = 0; mt < P2_MT; ++mt) {
                         const uint64_t ad = make_desc_k_none(a_base + shift + (uint32_t)mt * 128u * 16u, lbo_a, 128);
                         umma_bf16(tmem_base + (uint32_t)(mt * 128), ad, bd, idesc, (cs | t) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&wempty[ws]);
+                    if (sub == tps - 1 || e == total - 1) {        // last entry of the stage (or of the tile)
+                        umma_commit(&wempty[ws]);
+                        ++st;
+                    }
+                    if (++kw == T.k) { kw = 0; ++kh; }
                 }
                 umma_commit(&pempty[b]);
             }
@@ -294,12 +304,14 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
     } else {
         // ================= weight stages: one bulk copy per (sub-slab, tap) =================
         if (lane == 0) {
-            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(T.wt) + (size_t)tn * n_cs * taps * w_stage_bytes;
-            const int total = n_cs * taps;
-            for (int st = 0; st < total; ++st) {
+            const uint32_t total_bytes = (uint32_t)(n_cs * taps) * w_stage_bytes;
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(T.wt) + (size_t)tn * total_bytes;
+            int st = 0;
+            for (uint32_t o = 0; o < total_bytes; o += P2_W_STAGE, ++st) {
                 const int ws = st % P2_WS;
+                const uint32_t bytes = total_bytes - o < (uint32_t)P2_W_STAGE ? total_bytes - o : (uint32_t)P2_W_STAGE;
                 mbar_wait(&wempty[ws], (((uint32_t)(st / P2_WS)) & 1u) ^ 1u);
-                tma_load_1d(wsm + ws * P2_W_STAGE, wsrc + (size_t)st * w_stage_bytes, w_stage_bytes, &wfull[ws]);
+                tma_load_1d(wsm + ws * P2_W_STAGE, wsrc + o, bytes, &wfull[ws]);
             }
         }
         __syncwarp();
@@ -346,7 +358,7 @@ __global__ void __launch_bounds__(256) wt_bf16_v2_kernel(const WtBf16Task* __res
 }
 
 size_t p2_smem_bytes(int q_max) {
-    return (size_t)P2_PB * 32 * q_max + (size_t)P2_WS * P2_W_STAGE + (size_t)((q_max + 3) & ~3) * 4 + 512 + 256;
+    return (size_t)P2_PB * 32 * q_max + (size_t)P2_WS * P2_W_STAGE + (size_t)((q_max + 3) & ~3) * 4 + 512 + 512;
 }
 
 }  // namespace
@@ -360,7 +372,7 @@ bool Launch::tc2_ok(int H, int W, int Cin, int Cout, int k, int stride) {
     (void)H;
     if (stride != 1 || (k & 1) == 0 || Cin % 16 != 0 || Cout % 16 != 0) return false;
     if (Cout > 128 && Cout % 128 != 0) return false;
-    return p2_smem_bytes(tc2_q(W, k)) <= 100 * 1024;          // two CTAs per SM
+    return p2_smem_bytes(tc2_q(W, k)) <= 110 * 1024;          // two CTAs per SM
 }
 
 int Launch::conv_tc2(const TcConvTask* tasks, int n, int tiles, int n_b, int step, int q_max, void* st) {
