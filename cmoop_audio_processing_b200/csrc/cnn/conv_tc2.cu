@@ -335,26 +335,33 @@ __global__ void __launch_bounds__(256) wt_bf16_v2_kernel(const WtBf16Task* __res
     const WtBf16Task T = tasks[lo];
     const int gi = T.mode == 2 ? T.Cin : T.Cout, go = T.mode == 2 ? T.Cout : T.Cin;     // GEMM input / output channels
     const int taps = T.k * T.k;
-    const long long total = (long long)taps * gi * go;
-    const long long e = (long long)(blockIdx.x - T.block_begin) * 256 + threadIdx.x;
-    if (e >= total) return;
+    const long long chunks = (long long)taps * gi * go / 8;             // one thread = one 16-byte chunk (8 input channels)
+    const long long c = (long long)(blockIdx.x - T.block_begin) * 256 + threadIdx.x;
+    if (c >= chunks) return;
     const int bn = go < 128 ? go : 128, n_cs = gi >> 4;
-    // e -> (tn, cs, tap, plane, n, c8)
-    long long r = e;
-    const int c8 = (int)(r % 8); r /= 8;
+    // c -> (tn, cs, tap, plane, n): consecutive threads take consecutive output channels, so the forward reads
+    // (stride Cout between a thread's 8 values) coalesce across the warp and the 16-byte stores are contiguous
+    long long r = c;
     const int n = (int)(r % bn); r /= bn;
     const int plane = (int)(r % 2); r /= 2;
     const int tap = (int)(r % taps); r /= taps;
     const int cs = (int)(r % n_cs); r /= n_cs;
     const int tn = (int)r;
-    const int ch_in = cs * 16 + plane * 8 + c8, ch_out = tn * bn + n;
+    const int ch_in0 = cs * 16 + plane * 8, ch_out = tn * bn + n;
     const int kh = tap / T.k, kw = tap - kh * T.k;
-    float v;
-    if (T.mode == 2)
-        v = T.w[((long long)(kh * T.k + kw) * T.Cin + ch_in) * T.Cout + ch_out];
-    else
-        v = T.w[((long long)((T.k - 1 - kh) * T.k + (T.k - 1 - kw)) * T.Cin + ch_out) * T.Cout + ch_in];
-    T.out[e] = __float2bfloat16_rn(v);
+    float v[8];
+    if (T.mode == 2) {
+        const float* src = T.w + ((long long)(kh * T.k + kw) * T.Cin + ch_in0) * T.Cout + ch_out;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (long long)j * T.Cout);
+    } else {
+        const float* src = T.w + ((long long)((T.k - 1 - kh) * T.k + (T.k - 1 - kw)) * T.Cin + ch_out) * T.Cout + ch_in0;
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(src)), a1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+    }
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    reinterpret_cast<uint4*>(T.out)[c] = o;
 }
 
 size_t p2_smem_bytes(int q_max) {

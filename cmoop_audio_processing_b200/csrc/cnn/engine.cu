@@ -404,7 +404,7 @@ struct Engine {
                     if (u.tc2) {
                         wb.block_begin = wv.wt_bf16_v2.total;
                         wv.wt_bf16_v2.h.push_back(wb);
-                        wv.wt_bf16_v2.total += blocks_for((long long)u.k * u.k * u.cin * u.cout);
+                        wv.wt_bf16_v2.total += blocks_for((long long)u.k * u.k * u.cin * u.cout / 8);
                     } else {
                         wb.block_begin = wv.wt_bf16.total;
                         wv.wt_bf16.h.push_back(wb);
@@ -545,7 +545,7 @@ struct Engine {
                     if (u.tc2) {
                         wb.block_begin = wv.wt_bf16_v2.total;
                         wv.wt_bf16_v2.h.push_back(wb);
-                        wv.wt_bf16_v2.total += blocks_for((long long)u.k * u.k * u.cin * u.cout);
+                        wv.wt_bf16_v2.total += blocks_for((long long)u.k * u.k * u.cin * u.cout / 8);
                     } else {
                         wb.block_begin = wv.wt_bf16.total;
                         wv.wt_bf16.h.push_back(wb);
@@ -1241,7 +1241,7 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
         WtBf16Task wb{};
         wb.w = d_w; wb.out = d_wb; wb.k = k; wb.Cin = Cin; wb.Cout = Cout; wb.K_pad = K_pad; wb.mode = mode + (use_tc == 3 ? 2 : 0);
         CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &wb, sizeof(wb), cudaMemcpyHostToDevice, st));
-        rc = use_tc == 3 ? Launch::wt_bf16_v2((const WtBf16Task*)d_task, 1, (int)((n_w + 255) / 256), st)
+        rc = use_tc == 3 ? Launch::wt_bf16_v2((const WtBf16Task*)d_task, 1, (int)((n_w / 8 + 255) / 256), st)
                          : Launch::wt_bf16((const WtBf16Task*)d_task, 1, (int)(((long long)go * K_pad + 255) / 256), st);
         CMOOP_CUDA_OK(cudaStreamSynchronize(st));
         TcConvTask t{};

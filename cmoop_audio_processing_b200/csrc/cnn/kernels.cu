@@ -29,6 +29,16 @@ __device__ __forceinline__ int find_task(const T* tasks, int n, int block, F beg
     return lo;
 }
 
+// One binary search per block instead of one per thread (the elementwise kernels move 16 bytes per thread, so the
+// ~8 dependent loads of a per-thread search were most of their instruction stream).
+template <class T, class F>
+__device__ __forceinline__ int block_find_task(const T* tasks, int n, int block, F begin_of) {
+    __shared__ int s_task;
+    if (threadIdx.x == 0) s_task = find_task(tasks, n, block, begin_of);
+    __syncthreads();
+    return s_task;
+}
+
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ------------------------------------------------------------------------------------------------
@@ -294,7 +304,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradTask* __rest
 }
 
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceTask* __restrict__ tasks, int n_tasks) {
-    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const ReduceTask& r) { return r.block_begin; });
+    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const ReduceTask& r) { return r.block_begin; });
     const ReduceTask T = tasks[t];
     const int i = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
     if (i >= T.n) return;
@@ -304,7 +314,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceTask* __restric
 }
 
 __global__ void __launch_bounds__(256) wt_kernel(const WtTask* __restrict__ tasks, int n_tasks) {
-    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const WtTask& r) { return r.block_begin; });
+    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const WtTask& r) { return r.block_begin; });
     const WtTask T = tasks[t];
     const int e = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
     const int total = T.k * T.k * T.Cin * T.Cout;
@@ -375,7 +385,7 @@ __device__ __forceinline__ uint2 bf16x4(float4 v) {
 
 // [BN] -> [ReLU] -> [2x2/s2 'same' max-pool] -> [+skip, ReLU]; one thread = 4 consecutive channels of one output pixel
 __global__ void __launch_bounds__(256) post_fwd_kernel(const PostTask* __restrict__ tasks, int n_tasks, int n_b) {
-    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin; });
+    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin; });
     const PostTask T = tasks[t];
     const int C4 = T.C >> 2;
     const long long e4 = (long long)(blockIdx.x - T.block_begin) * 256 + threadIdx.x;
@@ -447,7 +457,7 @@ __global__ void __launch_bounds__(256) post_fwd_kernel(const PostTask* __restric
 // A CTA covers 128 output pixels; thread = (pixel lane, 4 channels); one partial row per (CTA, pixel lane).
 __global__ void __launch_bounds__(128) post_bwd_reduce_kernel(const PostTask* __restrict__ tasks, int n_tasks,
                                                               int n_b) {
-    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin_bwd; });
+    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin_bwd; });
     const PostTask T = tasks[t];
     const int blk = blockIdx.x - T.block_begin_bwd;
     const int C4 = T.C >> 2;
@@ -540,7 +550,7 @@ __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const PostTask* __
 
 // backward of the whole post stage, dense over the conv-output grid; one thread = 4 channels of one input pixel
 __global__ void __launch_bounds__(256) post_bwd_apply_kernel(const PostTask* __restrict__ tasks, int n_tasks, int n_b) {
-    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin; });
+    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin; });
     const PostTask T = tasks[t];
     const int C4 = T.C >> 2;
     const long long e4 = (long long)(blockIdx.x - T.block_begin) * 256 + threadIdx.x;
@@ -614,7 +624,7 @@ __global__ void __launch_bounds__(256) post_bwd_apply_kernel(const PostTask* __r
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gap_fwd_kernel(const HeadTask* __restrict__ tasks, int n_tasks, int n_b) {
-    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const HeadTask& r) { return r.block_begin; });
+    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const HeadTask& r) { return r.block_begin; });
     const HeadTask T = tasks[t];
     const int e = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
     if (e >= n_b * T.C) return;
@@ -626,7 +636,7 @@ __global__ void __launch_bounds__(256) gap_fwd_kernel(const HeadTask* __restrict
 }
 
 __global__ void __launch_bounds__(256) gap_bwd_kernel(const HeadTask* __restrict__ tasks, int n_tasks, int n_b) {
-    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const HeadTask& r) { return r.block_begin; });
+    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const HeadTask& r) { return r.block_begin; });
     const HeadTask T = tasks[t];
     const long long e = (long long)(blockIdx.x - T.block_begin) * 256 + threadIdx.x;
     const int hw = T.Hf * T.Wf;
@@ -638,7 +648,7 @@ __global__ void __launch_bounds__(256) gap_bwd_kernel(const HeadTask* __restrict
 
 __global__ void __launch_bounds__(256) drop_fwd_kernel(const DropTask* __restrict__ tasks, int n_tasks, int n_b, int step,
                                                        int training, float rate) {
-    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const DropTask& r) { return r.block_begin; });
+    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const DropTask& r) { return r.block_begin; });
     const DropTask T = tasks[t];
     const int e = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
     if (e >= n_b * T.units) return;
@@ -652,7 +662,7 @@ __global__ void __launch_bounds__(256) drop_fwd_kernel(const DropTask* __restric
 
 __global__ void __launch_bounds__(256) drop_bwd_kernel(const DropTask* __restrict__ tasks, int n_tasks, int n_b, int step,
                                                        float rate) {
-    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const DropTask& r) { return r.block_begin; });
+    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const DropTask& r) { return r.block_begin; });
     const DropTask T = tasks[t];
     const int e = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
     if (e >= n_b * T.units) return;
@@ -748,7 +758,7 @@ __global__ void __launch_bounds__(256) ce_kernel(const CeTask* __restrict__ task
 
 __global__ void __launch_bounds__(256) adam_kernel(const AdamTask* __restrict__ tasks, int n_tasks, float alpha, float b1,
                                                    float b2, float eps) {
-    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const AdamTask& r) { return r.block_begin; });
+    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const AdamTask& r) { return r.block_begin; });
     const AdamTask T = tasks[t];
     const int i = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
     if (i >= T.n) return;
@@ -761,7 +771,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTask* __restrict__ 
 }
 
 __global__ void __launch_bounds__(256) init_kernel(const InitTask* __restrict__ tasks, int n_tasks) {
-    const int t = find_task(tasks, n_tasks, blockIdx.x, [](const InitTask& r) { return r.block_begin; });
+    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const InitTask& r) { return r.block_begin; });
     const InitTask T = tasks[t];
     const int i = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
     if (i >= T.n) return;
