@@ -64,13 +64,13 @@ __device__ __forceinline__ void stem_conv_body(const ConvTask& T, float* sm, int
     const int M = n_b * HW, m0 = chunk * rows_per_block, m1 = min(M, m0 + rows_per_block);
     if (m0 >= M) return;
     float* tile = sm;                                 // [2][seg_floats]
-    float* red = tile + 2 * seg_floats;               // [8 warps][2][Cout]
     Segs sg;
     stage_rows<KS>(tile, seg_floats, T.x + T.x_step * step, T.gather ? T.gather + T.gather_step * step : nullptr, H, W, m0,
                    m1, sg);
-    const int CG = Cout / CPT, PP = kThreads / CG;    // threads per pixel, pixels per pass (PP <= 64)
-    const int cg = tid % CG, pl = tid / CG;
-    const int passes_per_tile = 64 / PP;
+    // A warp owns whole 64-row BN tiles (tiles warp, warp + 8 of the block's 16), so the per-tile statistics are a
+    // warp-shuffle reduction and the main loop has no block barrier.
+    const int CG = Cout / CPT, PW = 32 / CG;          // threads per pixel (<= 32), pixels per warp pass
+    const int cg = lane % CG, pl = lane / CG;
     float wr[TAPS + 1][CPT];
 #pragma unroll
     for (int t = 0; t <= TAPS; ++t)
@@ -79,12 +79,12 @@ __device__ __forceinline__ void stem_conv_body(const ConvTask& T, float* sm, int
     __syncthreads();
 
     const int tiles = (m1 - m0 + 63) >> 6;
-    for (int tl = 0; tl < tiles; ++tl) {
+    for (int tl = warp; tl < tiles; tl += kThreads / 32) {
         float s1[CPT], s2[CPT];
 #pragma unroll
         for (int j = 0; j < CPT; ++j) s1[j] = s2[j] = 0.f;
-        for (int pp = 0; pp < passes_per_tile; ++pp) {
-            const int m = m0 + tl * 64 + pp * PP + pl;
+        for (int r = pl; r < 64; r += PW) {
+            const int m = m0 + tl * 64 + r;
             if (m < m1) {
                 const int n = m / HW, rem = m - n * HW;
                 const int h = rem / W, w = rem - h * W;
@@ -124,27 +124,19 @@ __device__ __forceinline__ void stem_conv_body(const ConvTask& T, float* sm, int
             }
         }
         if (T.stat_part) {
+            __syncwarp();
+            float* dst = T.stat_part + (long long)((m0 >> 6) + tl) * 2 * Cout + cg * CPT;
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 for (int msk = CG; msk < 32; msk <<= 1) {
                     s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], msk);
                     s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], msk);
                 }
-                if (CG >= 32 || lane < CG) {
-                    red[(warp * 2 + 0) * Cout + cg * CPT + j] = s1[j];
-                    red[(warp * 2 + 1) * Cout + cg * CPT + j] = s2[j];
+                if (lane < CG) {
+                    dst[j] = s1[j];
+                    dst[Cout + j] = s2[j];
                 }
             }
-            __syncthreads();
-            for (int i = tid; i < 2 * Cout; i += kThreads) {
-                const int which = i / Cout, c = i - which * Cout;
-                // channel group cg is held by every warp (CG <= 32) or by the warps with warp % (CG / 32) == cg / 32
-                const int per = CG <= 32 ? 1 : CG / 32, mine = CG <= 32 ? 0 : (c / CPT) / 32;
-                float a = 0.f;
-                for (int wq = mine; wq < kThreads / 32; wq += per) a += red[(wq * 2 + which) * Cout + c];
-                T.stat_part[((long long)((m0 >> 6) + tl) * 2 + which) * Cout + c] = a;
-            }
-            __syncthreads();
         }
     }
 }
@@ -279,7 +271,8 @@ cudaError_t opt_in(K kernel, size_t smem) {
 
 bool Launch::stem_ok(int H, int W, int Cin, int Cout, int k, int stride, int n_b) {
     if (Cin != 1 || stride != 1 || (k != 3 && k != 5)) return false;
-    if (Cout < 16 || Cout > 256 || (Cout & (Cout - 1)) != 0) return false;
+    if (Cout < 16 || (Cout & (Cout - 1)) != 0) return false;
+    if (Cout > (k == 3 ? 128 : 64)) return false;                  // a pixel's channel groups must fit one warp
     if ((long long)H * W < kStemRows) return false;                 // a block may touch at most two samples
     (void)n_b;
     const size_t smem = ((size_t)(k * k + 1) * Cout + 2 * (size_t)seg_floats_for(W, k, kStemRows) +

@@ -111,8 +111,8 @@ STEM_CASES = [  # n, H, W, Cout, k   (Cin = 1; the dedicated kernels of csrc/cnn
     (7, 49, 40, 32, 5),        # ragged last batch: blocks past M, a block straddling two samples
     (1, 49, 40, 64, 3),
     (3, 128, 313, 32, 3),      # BirdCLEF-shaped map: a block covers ~3 rows
-    (5, 33, 37, 128, 5),       # odd sizes, 32 channel groups per pixel
-    (2, 40, 40, 256, 3),       # 64 channel groups: one pixel spans two warps
+    (5, 33, 37, 64, 5),        # odd sizes, 32 channel groups per pixel (k = 5: 2 channels per thread)
+    (2, 40, 40, 128, 3),       # 32 channel groups per pixel (k = 3: 4 channels per thread)
 ]
 
 
