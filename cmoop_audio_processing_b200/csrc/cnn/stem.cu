@@ -71,56 +71,64 @@ __device__ __forceinline__ void stem_conv_body(const ConvTask& T, float* sm, int
     // warp-shuffle reduction and the main loop has no block barrier.
     const int CG = Cout / CPT, PW = 32 / CG;          // threads per pixel (<= 32), pixels per warp pass
     const int cg = lane % CG, pl = lane / CG;
-    float wr[TAPS + 1][CPT];
+    // weights as packed pairs: one FFMA2 (x broadcast) updates two channels
+    float2 wr[TAPS + 1][CPT / 2];
 #pragma unroll
     for (int t = 0; t <= TAPS; ++t)
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) wr[t][j] = __ldg(T.w + t * Cout + cg * CPT + j);
+        for (int j = 0; j < CPT / 2; ++j)
+            wr[t][j] = __ldg(reinterpret_cast<const float2*>(T.w + t * Cout + cg * CPT) + j);
     __syncthreads();
 
     const int tiles = (m1 - m0 + 63) >> 6;
     for (int tl = warp; tl < tiles; tl += kThreads / 32) {
-        float s1[CPT], s2[CPT];
+        float2 s1[CPT / 2], s2[CPT / 2];
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) s1[j] = s2[j] = 0.f;
-        for (int r = pl; r < 64; r += PW) {
-            const int m = m0 + tl * 64 + r;
+        for (int j = 0; j < CPT / 2; ++j) s1[j] = s2[j] = make_float2(0.f, 0.f);
+        // (sample, row, column) of this thread's first pixel of the tile, then advanced by PW pixels per pass
+        int m = m0 + tl * 64 + pl;
+        int n = m / HW, rem = m - n * HW;
+        int h = rem / W, w = rem - h * W;
+        for (int r = pl; r < 64; r += PW, m += PW) {
             if (m < m1) {
-                const int n = m / HW, rem = m - n * HW;
-                const int h = rem / W, w = rem - h * W;
                 const int s = n - sg.n_first;
                 const float* tp = tile + s * seg_floats + (h - sg.ha[s]) * Wp + w;
-                float acc[CPT];
+                float2 acc[CPT / 2];
 #pragma unroll
-                for (int j = 0; j < CPT; ++j) acc[j] = wr[TAPS][j];
+                for (int j = 0; j < CPT / 2; ++j) acc[j] = wr[TAPS][j];
 #pragma unroll
                 for (int kh = 0; kh < KS; ++kh)
 #pragma unroll
                     for (int kw = 0; kw < KS; ++kw) {
                         const float x = tp[kh * Wp + kw];
 #pragma unroll
-                        for (int j = 0; j < CPT; ++j) acc[j] = fmaf(x, wr[kh * KS + kw][j], acc[j]);
+                        for (int j = 0; j < CPT / 2; ++j) acc[j] = __ffma2_rn(make_float2(x, x), wr[kh * KS + kw][j], acc[j]);
                     }
                 if (T.relu) {
 #pragma unroll
-                    for (int j = 0; j < CPT; ++j) acc[j] = fmaxf(acc[j], 0.f);
+                    for (int j = 0; j < CPT / 2; ++j) acc[j] = make_float2(fmaxf(acc[j].x, 0.f), fmaxf(acc[j].y, 0.f));
                 }
                 const long long o = (long long)m * Cout + cg * CPT;
                 if constexpr (CPT == 4) {
-                    *reinterpret_cast<float4*>(T.y + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    *reinterpret_cast<float4*>(T.y + o) = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
                 } else {
-                    *reinterpret_cast<float2*>(T.y + o) = make_float2(acc[0], acc[1]);
+                    *reinterpret_cast<float2*>(T.y + o) = acc[0];
                 }
                 if (T.yh) {
 #pragma unroll
-                    for (int j = 0; j < CPT; j += 2)
-                        *reinterpret_cast<__nv_bfloat162*>(T.yh + o + j) = __floats2bfloat162_rn(acc[j], acc[j + 1]);
+                    for (int j = 0; j < CPT / 2; ++j)
+                        *reinterpret_cast<__nv_bfloat162*>(T.yh + o + 2 * j) = __floats2bfloat162_rn(acc[j].x, acc[j].y);
                 }
 #pragma unroll
-                for (int j = 0; j < CPT; ++j) {
-                    s1[j] += acc[j];
-                    s2[j] = fmaf(acc[j], acc[j], s2[j]);
+                for (int j = 0; j < CPT / 2; ++j) {
+                    s1[j] = __fadd2_rn(s1[j], acc[j]);
+                    s2[j] = __ffma2_rn(acc[j], acc[j], s2[j]);
                 }
+            }
+            w += PW;                                      // PW <= 8 < W: at most one row wrap per pass
+            if (w >= W) {
+                w -= W;
+                if (++h == H) { h = 0; ++n; }
             }
         }
         if (T.stat_part) {
@@ -128,13 +136,14 @@ __device__ __forceinline__ void stem_conv_body(const ConvTask& T, float* sm, int
             float* dst = T.stat_part + (long long)((m0 >> 6) + tl) * 2 * Cout + cg * CPT;
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
+                float a1 = (j & 1) ? s1[j >> 1].y : s1[j >> 1].x, a2 = (j & 1) ? s2[j >> 1].y : s2[j >> 1].x;
                 for (int msk = CG; msk < 32; msk <<= 1) {
-                    s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], msk);
-                    s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], msk);
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, msk);
+                    a2 += __shfl_xor_sync(0xffffffffu, a2, msk);
                 }
                 if (lane < CG) {
-                    dst[j] = s1[j];
-                    dst[Cout + j] = s2[j];
+                    dst[j] = a1;
+                    dst[Cout + j] = a2;
                 }
             }
         }
@@ -273,7 +282,7 @@ bool Launch::stem_ok(int H, int W, int Cin, int Cout, int k, int stride, int n_b
     if (Cin != 1 || stride != 1 || (k != 3 && k != 5)) return false;
     if (Cout < 16 || (Cout & (Cout - 1)) != 0) return false;
     if (Cout > (k == 3 ? 128 : 64)) return false;                  // a pixel's channel groups must fit one warp
-    if ((long long)H * W < kStemRows) return false;                 // a block may touch at most two samples
+    if ((long long)H * W < kStemRows || W < 8) return false;        // a block may touch at most two samples
     (void)n_b;
     const size_t smem = ((size_t)(k * k + 1) * Cout + 2 * (size_t)seg_floats_for(W, k, kStemRows) +
                          (size_t)8 * (k * k + 1) * Cout) * sizeof(float);
