@@ -209,7 +209,9 @@ struct Launch {
     static bool tc2_ok(int H, int W, int Cin, int Cout, int k, int stride);
     static int tc2_q(int W, int k);
     static int tc2_rows();
-    static int conv_tc2(const TcConvTask* tasks, int n_tasks, int total_tiles, int n_b, int step, int q_max, void* stream);
+    static long long tc2_weight_elems(int Cin, int Cout, int k);     // bf16 elements of the (slab-padded) weight blocks
+    static int conv_tc2(const TcConvTask* tasks, int n_tasks, int total_tiles, int n_b, int step, int q_max, int max_cin,
+                        void* stream);
     static int wt_bf16_v2(const WtBf16Task* tasks, int n_tasks, int total_blocks, void* stream);
     // stem.cu: dedicated Cin = 1 kernels; every task of a launch has the same M (= n_b*H*W) and W
     static bool stem_ok(int H, int W, int Cin, int Cout, int k, int stride, int n_b);

@@ -5,21 +5,25 @@
 // launch, i.e. the kernel ran at L2 sector throughput with the tensor pipe 10-13 % active).  Here the GEMM rows are
 // *padded-linear* output positions q = (n*Hp + h + p)*Wp + (w + p) (Hp = H + 2p, Wp = W + 2p), so the input of tap
 // (kh, kw) for row q is simply position q + (kh - p)*Wp + (kw - p): one shared-memory patch serves all k*k taps.
-//   * patch: for a 16-channel sub-slab, positions [q0 - S, q0 + 256 + S) (S = p*Wp + p) as two 8-channel planes
-//     [plane][position][16 B] -- the canonical K-major *no-swizzle* UMMA layout (core matrix = 8 positions x 16 B,
-//     contiguous 128 B; SBO = 128 B, LBO = plane stride), whose start address may sit at ANY position, so the A
-//     operand of a tap is the same buffer with the start address advanced by (kh*Wp + kw)*16 bytes.  Loaded once per
-//     sub-slab by 256 producer threads with zero-filling 16-byte cp.async (padding, batch tail), 4-deep ring.
-//   * weights: pre-arranged per (16-channel sub-slab, tap) as [plane][cout][16 B] by wt_bf16_kernel (modes 2 / 3),
-//     one contiguous 32*bn-byte stage -> one 1-D bulk TMA (cp.async.bulk + mbarrier), 8-deep ring, own warp.
-//   * one elected thread issues, per (sub-slab, tap), two UMMAs 128 x bn x 16 (the CTA's two 128-row tiles) into
-//     two TMEM accumulators; tcgen05.commit frees the weight stage / the patch buffer.
+//   * patch: for a 64-channel slab, positions [q0 - S, q0 + 256 + S) (S = p*Wp + p) as rows of 128 B in the K-major
+//     SWIZZLE_128B UMMA layout (16-byte chunk c of row i at i*128 + ((c ^ (i & 7)) << 4), buffer 1 KB aligned).  The A
+//     operand of tap (kh, kw) is the same buffer with the start address advanced by (kh*Wp + kw) rows (the swizzle is
+//     a function of the absolute address, so any row offset is valid), so every tap reads the one resident patch.
+//     (A first version used the no-swizzle layout, whose start address is unconstrained; measured with the in-kernel
+//     phase clocks below it fetched the A operand at ~16 B/clk: 270 clk per UMMA whatever N.)  Loaded once per slab by
+//     256 producer threads with zero-filling 16-byte cp.async (padding, batch tail).
+//   * weights: pre-arranged and pre-swizzled per (slab, tap) as [cout][64 ch] rows of 128 B by wt_bf16_v2_kernel,
+//     16 KB stages of 128 / bn entries -> one 1-D bulk TMA each (cp.async.bulk + mbarrier), 4-deep ring, own warp.
+//   * one elected thread issues, per (slab, tap, 16-channel step), two UMMAs 128 x bn x 16 (the CTA's two 128-row
+//     tiles) into two TMEM accumulators; tcgen05.commit frees the weight stage / the patch buffer.
 //   * epilogue as in conv_tc.cu (tcgen05.ld, bias, ReLU, fp32 store, optional bf16 shadow); rows that are padding
 //     positions or beyond the batch are skipped.
 // Rows on padding positions cost (Hp*Wp)/(H*W) - 1 extra tensor work (16 % at 25x20, k = 3) in exchange for a k*k-fold
 // cut of the staging traffic.  Grouped over candidates like every kernel here (cnn.cuh).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "cnn.cuh"
 
@@ -28,15 +32,13 @@ namespace {
 
 constexpr int P2_MT = 2;                    // 128-row tiles per CTA
 constexpr int P2_ROWS = P2_MT * 128;
-constexpr int P2_PB = 4;                    // patch sub-slab buffers
-constexpr int P2_WS = 12;                   // weight stages of 4 KB = 128 / bn (sub-slab, tap) entries each: 48 KB in flight per
-                                            // CTA, about the L2 latency at the 32 B/clk the tensor pipe consumes (the first
-                                            // version's 8 single-tap stages left the MMA thread waiting on weights)
-constexpr int P2_LOOK = 2;                  // sub-slabs whose copies are in flight per producer thread
+constexpr int P2_SLAB = 64;                 // channels per patch slab (one 128-byte swizzled row per position)
+constexpr int P2_WS = 2;                    // weight stages of 16 KB = 128 / bn (slab, tap) entries each; with two CTAs per SM
+                                            // 64 KB of weights are in flight per SM
 constexpr int P2_PRODUCERS = 256;
 constexpr int P2_THREADS = P2_PRODUCERS + 64;     // + MMA warp + weight-TMA warp
 constexpr uint32_t P2_TMEM_COLS = 256;
-constexpr int P2_W_STAGE = 32 * 128;        // bytes of a weight stage at bn = 128
+constexpr int P2_W_STAGE = 128 * 128;       // bytes of a weight stage: 128 rows x 128 B
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -78,15 +80,18 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// K-major, no swizzle (cute::UMMA::LayoutType::SWIZZLE_NONE): core matrices of 8 rows x 16 B (128 contiguous bytes);
-// LBO = byte distance between the two 8-element K chunks of a UMMA (plane stride), SBO = between 8-row groups.
-__device__ __forceinline__ uint64_t make_desc_k_none(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart (SBO).  The start address may be ANY 128-byte row
+// of a buffer that was written with the absolute-address swizzle (chunk ^ (row & 7)): measured here, the hardware XORs
+// address bits [4:6] with bits [7:9] of the absolute shared-memory address, so a tap shift needs no base-offset field
+// (setting base_offset = (start >> 7) & 7 gave wrong results; 0 is exact for every shift).
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;             // descriptor version (sm_100)
-    return d;                           // layout_type = 0 (no swizzle), base_offset = 0
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;                              // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+    return d;
 }
 __device__ __forceinline__ uint32_t make_idesc_bf16(int bn) {
     uint32_t d = 0;
@@ -114,8 +119,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// prof (CMOOP_TC2_PROF=1): per-launch sums of clock64 spans -- [0] CTAs, [1] prologue, [2] MMA thread: start -> first
+// operands ready, [3] MMA issue loop, [4] producers: start -> accumulator complete, [5] epilogue, [6] whole CTA
 __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTask* __restrict__ tasks, int n_tasks, int n_b,
-                                                                 int step, int q_max) {
+                                                                 int step, int q_max, int pb, unsigned long long* prof) {
+    const long long t_start = clock64();
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ TcConvTask T;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -137,23 +145,25 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
     const int S = p * Wp + p;
     const int Q = P2_ROWS + 2 * S;                     // patch positions of this task (<= q_max)
     const int bn = T.bn, n0 = tn * bn;
-    const int taps = T.k * T.k, n_cs = T.Cin >> 4;     // 16-channel sub-slabs
-    const uint32_t w_stage_bytes = 32u * (uint32_t)bn;
+    const int taps = T.k * T.k, n_slab = (T.Cin + P2_SLAB - 1) / P2_SLAB;
+    const uint32_t entry_bytes = 128u * (uint32_t)bn;  // one (slab, tap) weight block
 
-    uint8_t* patch = smem_raw;                                          // [P2_PB][2][Q][16 B] (stride 32*q_max)
-    uint8_t* wsm = patch + (size_t)P2_PB * 32 * q_max;                  // [P2_WS][P2_W_STAGE]
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const size_t patch_stride = ((size_t)q_max * 128 + 1023) & ~size_t(1023);
+    uint8_t* patch = base;                                              // [pb][Q rows][128 B], swizzled
+    uint8_t* wsm = patch + (size_t)pb * patch_stride;                   // [P2_WS][P2_W_STAGE]
     int* src_off = reinterpret_cast<int*>(wsm + P2_WS * P2_W_STAGE);    // [q_max] element offset of a position's pixel, -1 = zero
     float* bias_s = reinterpret_cast<float*>(src_off + ((q_max + 3) & ~3));   // [128] this N tile's bias (0 without bias)
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 128);
-    uint64_t* pfull = bars;                     // [P2_PB]  256 producer arrivals
-    uint64_t* pempty = bars + P2_PB;            // [P2_PB]  tcgen05.commit
-    uint64_t* wfull = bars + 2 * P2_PB;         // [P2_WS]  TMA transaction
+    uint64_t* pfull = bars;                     // [2]  256 producer arrivals
+    uint64_t* pempty = bars + 2;                // [2]  tcgen05.commit
+    uint64_t* wfull = bars + 4;                 // [P2_WS]  TMA transaction
     uint64_t* wempty = wfull + P2_WS;           // [P2_WS]  tcgen05.commit
     uint64_t* accum_bar = wempty + P2_WS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
     if (tid == 0) {
-        for (int s = 0; s < P2_PB; ++s) {
+        for (int s = 0; s < 2; ++s) {
             mbar_init(&pfull[s], P2_PRODUCERS);
             mbar_init(&pempty[s], 1);
         }
@@ -187,32 +197,38 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    const long long t_pro = clock64();
+    if (prof && tid == 0) {
+        atomicAdd(prof + 0, 1ull);
+        atomicAdd(prof + 1, (unsigned long long)(t_pro - t_start));
+    }
 
     if (warp < P2_PRODUCERS / 32) {
-        // ================= producers: one 16-channel sub-slab of the patch per ring slot =================
+        // ================= producers: one 64-channel slab of the patch per buffer =================
         const __nv_bfloat16* xbase = T.xh + T.x_step * step;
-        const int plane = tid & 1, pix0 = tid >> 1;
-        for (int cs = 0; cs < n_cs + P2_LOOK; ++cs) {
-            if (cs < n_cs) {
-                const int b = cs % P2_PB;
-                mbar_wait(&pempty[b], (((uint32_t)(cs / P2_PB)) & 1u) ^ 1u);
-                uint8_t* dst = patch + (size_t)b * 32 * q_max + (size_t)plane * 16 * Q;
-                const int coff = cs * 16 + plane * 8;
-                for (int i = pix0; i < Q; i += 128) {
+        for (int sl = 0; sl < n_slab; ++sl) {
+            const int b = sl % pb;
+            mbar_wait(&pempty[b], (((uint32_t)(sl / pb)) & 1u) ^ 1u);
+            uint8_t* dst = patch + (size_t)b * patch_stride;
+            const int cs = min(T.Cin - sl * P2_SLAB, P2_SLAB) >> 3;      // 16-byte chunks per position in this slab
+            const int chunk = tid % cs, pix0 = tid / cs, pstep = P2_PRODUCERS / cs;
+            const int coff = sl * P2_SLAB + chunk * 8;
+            if (pix0 < pstep) {
+                for (int i = pix0; i < Q; i += pstep) {
                     const int off = src_off[i];
-                    cp_async16(dst + (size_t)i * 16, off >= 0 ? xbase + off + coff : xbase, off >= 0 ? 16u : 0u);
+                    cp_async16(dst + (size_t)i * 128 + ((chunk ^ (i & 7)) << 4), off >= 0 ? xbase + off + coff : xbase,
+                               off >= 0 ? 16u : 0u);
                 }
             }
             cp_async_commit();
-            if (cs >= P2_LOOK) {
-                cp_async_wait<P2_LOOK>();
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(&pfull[(cs - P2_LOOK) % P2_PB]);
-            }
+            cp_async_wait<0>();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&pfull[b]);
         }
         // ================= epilogue =================
         mbar_wait(accum_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const long long t_acc = clock64();
         const int lane_grp = warp & 3;
         const int c_begin = bn >= 32 ? (warp >> 2) * (bn / 2) : 0;
         const int c_end = bn >= 32 ? c_begin + bn / 2 : ((warp >> 2) == 0 ? bn : 0);
@@ -263,19 +279,28 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (prof && tid == 0) {
+            atomicAdd(prof + 4, (unsigned long long)(t_acc - t_pro));
+            atomicAdd(prof + 5, (unsigned long long)(clock64() - t_acc));
+        }
     } else if (warp == P2_PRODUCERS / 32) {
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(bn);
-            const uint32_t lbo_a = 16u * (uint32_t)Q, lbo_b = 16u * (uint32_t)bn;
-            const int tps = 128 / bn;                  // (sub-slab, tap) entries per 4 KB weight stage
-            const int total = n_cs * taps;
-            int st = 0, e = 0;                         // stage counter; entry = cs * taps + tap in weight-stream order
-            for (int cs = 0; cs < n_cs; ++cs) {
-                const int b = cs % P2_PB;
-                mbar_wait(&pfull[b], ((uint32_t)(cs / P2_PB)) & 1u);
+            const int tps = 128 / bn;                  // (slab, tap) entries per 16 KB weight stage
+            const int total = n_slab * taps;
+            int st = 0, e = 0;                         // stage counter; entry = slab * taps + tap in weight-stream order
+            long long t_first = 0;
+            for (int sl = 0; sl < n_slab; ++sl) {
+                const int b = sl % pb;
+                mbar_wait(&pfull[b], ((uint32_t)(sl / pb)) & 1u);
+                if (sl == 0) {
+                    mbar_wait(&wfull[0], 0);
+                    t_first = clock64();
+                }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_base = smem_u32(patch + (size_t)b * 32 * q_max);
+                const uint32_t a_base = smem_u32(patch + (size_t)b * patch_stride);
+                const int ksteps = min(T.Cin - sl * P2_SLAB, P2_SLAB) >> 4;
                 int kh = 0, kw = 0;
                 for (int t = 0; t < taps; ++t, ++e) {
                     const int sub = e % tps, ws = st % P2_WS;
@@ -283,12 +308,15 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
                         mbar_wait(&wfull[ws], ((uint32_t)(st / P2_WS)) & 1u);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
-                    const uint32_t shift = (uint32_t)(kh * Wp + kw) * 16u;
-                    const uint64_t bd = make_desc_k_none(smem_u32(wsm + ws * P2_W_STAGE) + (uint32_t)sub * w_stage_bytes, lbo_b, 128);
+                    const uint32_t a_tap = a_base + (uint32_t)(kh * Wp + kw) * 128u;
+                    const uint32_t b_ent = smem_u32(wsm + ws * P2_W_STAGE) + (uint32_t)sub * entry_bytes;
+                    for (int k4 = 0; k4 < ksteps; ++k4) {
+                        const uint64_t bd = make_desc_k_sw128(b_ent + (uint32_t)k4 * 32u);
 #pragma unroll
-                    for (int mt = 0; mt < P2_MT; ++mt) {
-                        const uint64_t ad = make_desc_k_none(a_base + shift + (uint32_t)mt * 128u * 16u, lbo_a, 128);
-                        umma_bf16(tmem_base + (uint32_t)(mt * 128), ad, bd, idesc, (cs | t) != 0 ? 1u : 0u);
+                        for (int mt = 0; mt < P2_MT; ++mt) {
+                            const uint64_t ad = make_desc_k_sw128(a_tap + (uint32_t)mt * 128u * 128u + (uint32_t)k4 * 32u);
+                            umma_bf16(tmem_base + (uint32_t)(mt * 128), ad, bd, idesc, (sl | t | k4) != 0 ? 1u : 0u);
+                        }
                     }
                     if (sub == tps - 1 || e == total - 1) {        // last entry of the stage (or of the tile)
                         umma_commit(&wempty[ws]);
@@ -299,12 +327,16 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
                 umma_commit(&pempty[b]);
             }
             umma_commit(accum_bar);
+            if (prof) {
+                atomicAdd(prof + 2, (unsigned long long)(t_first - t_pro));
+                atomicAdd(prof + 3, (unsigned long long)(clock64() - t_first));
+            }
         }
         __syncwarp();
     } else {
         // ================= weight stages: one bulk copy per (sub-slab, tap) =================
         if (lane == 0) {
-            const uint32_t total_bytes = (uint32_t)(n_cs * taps) * w_stage_bytes;
+            const uint32_t total_bytes = (uint32_t)(n_slab * taps) * entry_bytes;
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(T.wt) + (size_t)tn * total_bytes;
             int st = 0;
             for (uint32_t o = 0; o < total_bytes; o += P2_W_STAGE, ++st) {
@@ -321,9 +353,11 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P2_TMEM_COLS) : "memory");
     }
+    if (prof && tid == 0) atomicAdd(prof + 6, (unsigned long long)(clock64() - t_start));
 }
 
-// bf16 weight stages for conv_tc2_kernel: out[tn][cs][tap][plane][n][8] (n < bn = min(Cout_gemm, 128)).
+// bf16 weight blocks for conv_tc2_kernel: out[tn][slab][tap][n (bn rows)][64 ch], every row 128 B, 16-byte chunk c of
+// row n stored at chunk position c ^ (n & 7) (SWIZZLE_128B as the UMMA descriptor reads it; channels past Cin are zero).
 //   mode 2 (forward):       B[n = co][k = (tap, ci)]        = w[(kh, kw), ci, co]
 //   mode 3 (data gradient): B[n = ci][k = (tap, co)]        = w[(k-1-kh, k-1-kw), ci, co]
 __global__ void __launch_bounds__(256) wt_bf16_v2_kernel(const WtBf16Task* __restrict__ tasks, int n_tasks) {
@@ -334,39 +368,44 @@ __global__ void __launch_bounds__(256) wt_bf16_v2_kernel(const WtBf16Task* __res
     }
     const WtBf16Task T = tasks[lo];
     const int gi = T.mode == 2 ? T.Cin : T.Cout, go = T.mode == 2 ? T.Cout : T.Cin;     // GEMM input / output channels
-    const int taps = T.k * T.k;
-    const long long chunks = (long long)taps * gi * go / 8;             // one thread = one 16-byte chunk (8 input channels)
+    const int taps = T.k * T.k, n_slab = (gi + P2_SLAB - 1) / P2_SLAB;
+    const long long chunks = (long long)taps * n_slab * go * 8;         // one thread = one 16-byte chunk
     const long long c = (long long)(blockIdx.x - T.block_begin) * 256 + threadIdx.x;
     if (c >= chunks) return;
-    const int bn = go < 128 ? go : 128, n_cs = gi >> 4;
-    // c -> (tn, cs, tap, plane, n): consecutive threads take consecutive output channels, so the forward reads
-    // (stride Cout between a thread's 8 values) coalesce across the warp and the 16-byte stores are contiguous
+    const int bn = go < 128 ? go : 128;
+    // c -> (tn, slab, tap, chunk, n): consecutive threads take consecutive output channels (coalesced forward reads)
     long long r = c;
     const int n = (int)(r % bn); r /= bn;
-    const int plane = (int)(r % 2); r /= 2;
+    const int ch = (int)(r % 8); r /= 8;
     const int tap = (int)(r % taps); r /= taps;
-    const int cs = (int)(r % n_cs); r /= n_cs;
+    const int sl = (int)(r % n_slab); r /= n_slab;
     const int tn = (int)r;
-    const int ch_in0 = cs * 16 + plane * 8, ch_out = tn * bn + n;
+    const int ch_in0 = sl * P2_SLAB + ch * 8, ch_out = tn * bn + n;
     const int kh = tap / T.k, kw = tap - kh * T.k;
-    float v[8];
-    if (T.mode == 2) {
-        const float* src = T.w + ((long long)(kh * T.k + kw) * T.Cin + ch_in0) * T.Cout + ch_out;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ch_in0 < gi) {
+        if (T.mode == 2) {
+            const float* src = T.w + ((long long)(kh * T.k + kw) * T.Cin + ch_in0) * T.Cout + ch_out;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (long long)j * T.Cout);
-    } else {
-        const float* src = T.w + ((long long)((T.k - 1 - kh) * T.k + (T.k - 1 - kw)) * T.Cin + ch_out) * T.Cout + ch_in0;
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(src)), a1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-        v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (long long)j * T.Cout);
+        } else {
+            const float* src = T.w + ((long long)((T.k - 1 - kh) * T.k + (T.k - 1 - kw)) * T.Cin + ch_out) * T.Cout + ch_in0;
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(src)), a1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+        }
     }
     uint4 o;
     o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-    reinterpret_cast<uint4*>(T.out)[c] = o;
+    const long long entry = ((long long)tn * n_slab + sl) * taps + tap;      // block of bn rows x 128 B
+    reinterpret_cast<uint4*>(T.out)[(entry * bn + n) * 8 + (ch ^ (n & 7))] = o;
 }
 
-size_t p2_smem_bytes(int q_max) {
-    return (size_t)P2_PB * 32 * q_max + (size_t)P2_WS * P2_W_STAGE + (size_t)((q_max + 3) & ~3) * 4 + 512 + 512;
+size_t p2_smem_bytes(int q_max, int pb) {
+    const size_t patch_stride = ((size_t)q_max * 128 + 1023) & ~size_t(1023);
+    return 1024 /*align*/ + (size_t)pb * patch_stride + (size_t)P2_WS * P2_W_STAGE + (size_t)((q_max + 3) & ~3) * 4 + 512 + 512;
 }
+// two patch buffers (the next slab loads while the current one is multiplied) only when two CTAs still fit one SM
+int p2_buffers(int cin, int q_max) { return cin > P2_SLAB && p2_smem_bytes(q_max, 2) <= 113 * 1024 ? 2 : 1; }
 
 }  // namespace
 
@@ -375,23 +414,53 @@ int Launch::tc2_q(int W, int k) {
     return P2_ROWS + 2 * (p * (W + 2 * p) + p);
 }
 int Launch::tc2_rows() { return P2_ROWS; }
+long long Launch::tc2_weight_elems(int Cin, int Cout, int k) {
+    return (long long)k * k * ((Cin + P2_SLAB - 1) / P2_SLAB) * P2_SLAB * Cout;
+}
 bool Launch::tc2_ok(int H, int W, int Cin, int Cout, int k, int stride) {
     (void)H;
     if (stride != 1 || (k & 1) == 0 || Cin % 16 != 0 || Cout % 16 != 0) return false;
     if (Cout > 128 && Cout % 128 != 0) return false;
-    return p2_smem_bytes(tc2_q(W, k)) <= 110 * 1024;          // two CTAs per SM
+    return p2_smem_bytes(tc2_q(W, k), 1) <= 227 * 1024;
 }
 
-int Launch::conv_tc2(const TcConvTask* tasks, int n, int tiles, int n_b, int step, int q_max, void* st) {
+int Launch::conv_tc2(const TcConvTask* tasks, int n, int tiles, int n_b, int step, int q_max, int max_cin, void* st) {
     if (n == 0 || tiles == 0) return 0;
-    const size_t smem = p2_smem_bytes(q_max);
+    const int pb = p2_buffers(max_cin, q_max);
+    const size_t smem = p2_smem_bytes(q_max, pb);
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
+        // all of the SM's unified L1/shared storage as shared memory: two ~100 KB CTAs must be co-resident
+        e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return (int)e;
         configured = smem;
     }
-    conv_tc2_kernel<<<tiles, P2_THREADS, smem, (cudaStream_t)st>>>(tasks, n, n_b, step, q_max);
+    // optional phase profile (development aid): CMOOP_TC2_PROF=1 prints per-launch clock sums at process exit
+    static unsigned long long* prof = nullptr;
+    static bool prof_checked = false;
+    if (!prof_checked) {
+        prof_checked = true;
+        if (getenv("CMOOP_TC2_PROF")) {
+            cudaMalloc((void**)&prof, 64 * 8 * sizeof(unsigned long long));
+            cudaMemset(prof, 0, 64 * 8 * sizeof(unsigned long long));
+            atexit([] {
+                unsigned long long h[64 * 8];
+                cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+                for (int i = 0; i < 64; ++i) {
+                    const unsigned long long* r = h + i * 8;
+                    if (!r[0]) continue;
+                    fprintf(stderr, "tc2 prof slot %2d: ctas %6llu  per-CTA clk: prologue %6llu  first-operands %6llu  mma-loop %6llu  "
+                            "to-accum %6llu  epilogue %6llu  total %6llu\n", i, r[0], r[1] / r[0], r[2] / r[0], r[3] / r[0],
+                            r[4] / r[0], r[5] / r[0], r[6] / r[0]);
+                }
+            });
+        }
+    }
+    static int launch_no = 0;
+    unsigned long long* slot = prof ? prof + (size_t)(launch_no++ % 64) * 8 : nullptr;
+    conv_tc2_kernel<<<tiles, P2_THREADS, smem, (cudaStream_t)st>>>(tasks, n, n_b, step, q_max, pb, slot);
     return (int)cudaGetLastError();
 }
 

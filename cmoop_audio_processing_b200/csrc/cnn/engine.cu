@@ -270,8 +270,10 @@ void place(Cand& c, Arena& a, const cmoop_cnn_config& cfg, int n_train, int n_va
         }
         u.wt = (u.need_dgrad && !u.tc) ? (float*)a.take((size_t)u.k * u.k * u.cin * u.cout * f4) : nullptr;
         if (u.tc) {
-            u.wtb = (__nv_bfloat16*)a.take((size_t)u.cout * u.kpad_f * 2);
-            u.wtd = u.need_dgrad ? (__nv_bfloat16*)a.take((size_t)u.cin * u.kpad_d * 2) : nullptr;
+            const size_t wf = u.tc2 ? (size_t)Launch::tc2_weight_elems(u.cin, u.cout, u.k) : (size_t)u.cout * u.kpad_f;
+            const size_t wd = u.tc2 ? (size_t)Launch::tc2_weight_elems(u.cout, u.cin, u.k) : (size_t)u.cin * u.kpad_d;
+            u.wtb = (__nv_bfloat16*)a.take(wf * 2);
+            u.wtd = u.need_dgrad ? (__nv_bfloat16*)a.take(wd * 2) : nullptr;
         }
         maxV = std::max(maxV, u.v_elems);
         maxV = std::max(maxV, (long long)batch * u.H * u.W * u.cin);
@@ -307,7 +309,7 @@ struct DevList {
 struct StageLists {
     DevList<ConvTask> conv, conv_eval, dgrad;
     DevList<TcConvTask> conv_tc, dgrad_tc, conv_tc2, dgrad_tc2;
-    int q_max = 0;                   // largest patch of the stage's conv_tc2 / dgrad_tc2 tasks
+    int q_max = 0, tc2_cin = 0, tc2_cin_d = 0;   // largest patch; most GEMM input channels of the conv_tc2 / dgrad_tc2 tasks
     DevList<TcWgradTask> wgrad_tc;
     DevList<StatTask> stat;
     // stem.cu path: every task of conv / conv_eval / wgrad is an eligible Cin = 1 convolution
@@ -386,6 +388,7 @@ struct Engine {
                         S.conv_tc2.h.push_back(t);
                         S.conv_tc2.total += (int)((mq + Launch::tc2_rows() - 1) / Launch::tc2_rows()) * t.tiles_n;
                         S.q_max = std::max(S.q_max, Launch::tc2_q(u.W, u.k));
+                        S.tc2_cin = std::max(S.tc2_cin, u.cin);
                     } else {
                         t.tile_begin = S.conv_tc.total;
                         S.conv_tc.h.push_back(t);
@@ -404,7 +407,7 @@ struct Engine {
                     if (u.tc2) {
                         wb.block_begin = wv.wt_bf16_v2.total;
                         wv.wt_bf16_v2.h.push_back(wb);
-                        wv.wt_bf16_v2.total += blocks_for((long long)u.k * u.k * u.cin * u.cout / 8);
+                        wv.wt_bf16_v2.total += blocks_for(Launch::tc2_weight_elems(u.cin, u.cout, u.k) / 8);
                     } else {
                         wb.block_begin = wv.wt_bf16.total;
                         wv.wt_bf16.h.push_back(wb);
@@ -545,7 +548,7 @@ struct Engine {
                     if (u.tc2) {
                         wb.block_begin = wv.wt_bf16_v2.total;
                         wv.wt_bf16_v2.h.push_back(wb);
-                        wv.wt_bf16_v2.total += blocks_for((long long)u.k * u.k * u.cin * u.cout / 8);
+                        wv.wt_bf16_v2.total += blocks_for(Launch::tc2_weight_elems(u.cout, u.cin, u.k) / 8);
                     } else {
                         wb.block_begin = wv.wt_bf16.total;
                         wv.wt_bf16.h.push_back(wb);
@@ -571,6 +574,7 @@ struct Engine {
                         S.dgrad_tc2.h.push_back(d);
                         S.dgrad_tc2.total += (int)((mq + Launch::tc2_rows() - 1) / Launch::tc2_rows()) * d.tiles_n;
                         S.q_max = std::max(S.q_max, Launch::tc2_q(u.W, u.k));
+                        S.tc2_cin_d = std::max(S.tc2_cin_d, u.cout);
                     } else {
                         d.tile_begin = S.dgrad_tc.total;
                         S.dgrad_tc.h.push_back(d);
@@ -691,7 +695,7 @@ struct Engine {
                 CNN_LAUNCH(Launch::conv_tc(S.conv_tc.d, (int)S.conv_tc.h.size(), S.conv_tc.total, n_b, step, stream));
             if (!S.conv_tc2.h.empty())
                 CNN_LAUNCH(Launch::conv_tc2(S.conv_tc2.d, (int)S.conv_tc2.h.size(), S.conv_tc2.total, n_b, step, S.q_max,
-                                            stream));
+                                            S.tc2_cin, stream));
             if (!S.stat.h.empty() && training)
                 CNN_LAUNCH(Launch::bn_stats(S.stat.d, (int)S.stat.h.size(), S.stat.total, n_b, stream));
             if (!S.post_bn.h.empty())
@@ -740,7 +744,7 @@ struct Engine {
                 CNN_LAUNCH(Launch::conv_tc(S.dgrad_tc.d, (int)S.dgrad_tc.h.size(), S.dgrad_tc.total, n_b, 0, stream));
             if (!S.dgrad_tc2.h.empty())
                 CNN_LAUNCH(Launch::conv_tc2(S.dgrad_tc2.d, (int)S.dgrad_tc2.h.size(), S.dgrad_tc2.total, n_b, 0, S.q_max,
-                                            stream));
+                                            S.tc2_cin_d, stream));
         }
         return CMOOP_OK;
     }
@@ -1203,7 +1207,7 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_w, (n_w + Cout) * 4));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_out, n_out * 4));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_wt, n_w * 4));
-    CMOOP_CUDA_OK(cudaMalloc((void**)&d_wb, (size_t)go * K_pad * 2));
+    CMOOP_CUDA_OK(cudaMalloc((void**)&d_wb, std::max((size_t)go * K_pad, (size_t)Launch::tc2_weight_elems(gi, go, k)) * 2));
     CMOOP_CUDA_OK(cudaMalloc(&d_task, 1024));
     CMOOP_CUDA_OK(cudaMemcpyAsync(d_in, in, n_in * 4, cudaMemcpyHostToDevice, st));
     CMOOP_CUDA_OK(cudaMemcpyAsync(d_w, w, n_w * 4, cudaMemcpyHostToDevice, st));
@@ -1241,7 +1245,7 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
         WtBf16Task wb{};
         wb.w = d_w; wb.out = d_wb; wb.k = k; wb.Cin = Cin; wb.Cout = Cout; wb.K_pad = K_pad; wb.mode = mode + (use_tc == 3 ? 2 : 0);
         CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &wb, sizeof(wb), cudaMemcpyHostToDevice, st));
-        rc = use_tc == 3 ? Launch::wt_bf16_v2((const WtBf16Task*)d_task, 1, (int)((n_w / 8 + 255) / 256), st)
+        rc = use_tc == 3 ? Launch::wt_bf16_v2((const WtBf16Task*)d_task, 1, (int)((Launch::tc2_weight_elems(gi, go, k) / 8 + 255) / 256), st)
                          : Launch::wt_bf16((const WtBf16Task*)d_task, 1, (int)(((long long)go * K_pad + 255) / 256), st);
         CMOOP_CUDA_OK(cudaStreamSynchronize(st));
         TcConvTask t{};
@@ -1260,7 +1264,7 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
         if (rc == 0 && use_tc == 3) {
             const long long mq = (long long)n * (H + 2 * pad) * (W + 2 * pad);
             rc = Launch::conv_tc2((const TcConvTask*)d_task, 1, (int)((mq + Launch::tc2_rows() - 1) / Launch::tc2_rows()) * t.tiles_n,
-                                  n, 0, Launch::tc2_q(W, k), st);
+                                  n, 0, Launch::tc2_q(W, k), gi, st);
         } else if (rc == 0) {
             rc = Launch::conv_tc((const TcConvTask*)d_task, 1, tiles_m128 * t.tiles_n, n, 0, st);
         }
