@@ -388,15 +388,17 @@ __global__ void __launch_bounds__(256) post_fwd_kernel(const PostTask* __restric
     const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin; });
     const PostTask T = tasks[t];
     const int C4 = T.C >> 2;
-    const long long e4 = (long long)(blockIdx.x - T.block_begin) * 256 + threadIdx.x;
-    if (e4 >= (long long)n_b * T.Ho * T.Wo * C4) return;
-    const int c = (int)(e4 % C4) * 4;
-    long long pix = e4 / C4;
-    const long long e = pix * T.C + c;
-    const int wo = (int)(pix % T.Wo);
-    pix /= T.Wo;
-    const int ho = (int)(pix % T.Ho);
-    const int n = (int)(pix / T.Ho);
+    // 32-bit index math: a unit's activation has < 2^31 elements, and 64-bit div/mod chains cost more instructions
+    // than the 16 bytes this thread moves
+    const unsigned e4 = (unsigned)(blockIdx.x - T.block_begin) * 256u + threadIdx.x;
+    if (e4 >= (unsigned)n_b * T.Ho * T.Wo * C4) return;
+    unsigned pix = e4 / (unsigned)C4;
+    const int c = (int)(e4 - pix * C4) * 4;
+    const long long e = (long long)pix * T.C + c;
+    const unsigned r1 = pix / (unsigned)T.Wo;
+    const int wo = (int)(pix - r1 * T.Wo);
+    const int n = (int)(r1 / (unsigned)T.Ho);
+    const int ho = (int)(r1 - (unsigned)n * T.Ho);
     float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
     if (T.has_bn) {
         const float4 a = ld4(T.bn + 2 * T.C + c), b = ld4(T.bn + 3 * T.C + c);
@@ -465,8 +467,8 @@ __global__ void __launch_bounds__(128) post_bwd_reduce_kernel(const PostTask* __
     const int lanes = 128 / cb;
     const int p_lane = threadIdx.x / cb, c_lane = threadIdx.x - p_lane * cb;
     if (p_lane >= lanes) return;
-    const long long n_pix = (long long)n_b * T.Ho * T.Wo;
-    const long long pix0 = (long long)blk * 128, pix1 = pix0 + 128 < n_pix ? pix0 + 128 : n_pix;
+    const int n_pix = n_b * T.Ho * T.Wo;
+    const int pix0 = blk * 128, pix1 = pix0 + 128 < n_pix ? pix0 + 128 : n_pix;
     for (int c4 = c_lane; c4 < C4; c4 += cb) {
         const int c = c4 * 4;
         const float4 mean = ld4(T.bn + 0 * T.C + c), invstd = ld4(T.bn + 1 * T.C + c);
@@ -474,8 +476,8 @@ __global__ void __launch_bounds__(128) post_bwd_reduce_kernel(const PostTask* __
         const float mu[4] = {mean.x, mean.y, mean.z, mean.w}, is[4] = {invstd.x, invstd.y, invstd.z, invstd.w};
         const float sc[4] = {scale.x, scale.y, scale.z, scale.w}, sh[4] = {shift.x, shift.y, shift.z, shift.w};
         float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};
-        for (long long pix = pix0 + p_lane; pix < pix1; pix += lanes) {
-            const long long e = pix * T.C + c;
+        for (int pix = pix0 + p_lane; pix < pix1; pix += lanes) {
+            const long long e = (long long)pix * T.C + c;
             const float4 gv = ld4(T.dv + e);
             float g[4] = {gv.x, gv.y, gv.z, gv.w};
             if (T.add_skip) {
@@ -487,10 +489,8 @@ __global__ void __launch_bounds__(128) post_bwd_reduce_kernel(const PostTask* __
             }
             float u[4];
             if (T.pool) {
-                const int wo = (int)(pix % T.Wo);
-                const long long r = pix / T.Wo;
-                const int ho = (int)(r % T.Ho);
-                const int n = (int)(r / T.Ho);
+                const int r = pix / T.Wo, wo = pix - r * T.Wo;
+                const int n = r / T.Ho, ho = r - n * T.Ho;
                 const uchar4 cd = *reinterpret_cast<const uchar4*>(T.idx + e);
                 const unsigned char code[4] = {cd.x, cd.y, cd.z, cd.w};
                 const long long base = (((long long)n * T.H + 2 * ho) * T.W + 2 * wo) * T.C + c;
@@ -553,15 +553,15 @@ __global__ void __launch_bounds__(256) post_bwd_apply_kernel(const PostTask* __r
     const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin; });
     const PostTask T = tasks[t];
     const int C4 = T.C >> 2;
-    const long long e4 = (long long)(blockIdx.x - T.block_begin) * 256 + threadIdx.x;
-    if (e4 >= (long long)n_b * T.H * T.W * C4) return;
-    const int c = (int)(e4 % C4) * 4;
-    long long pix = e4 / C4;
-    const long long e = pix * T.C + c;
-    const int wi = (int)(pix % T.W);
-    pix /= T.W;
-    const int hi = (int)(pix % T.H);
-    const int n = (int)(pix / T.H);
+    const unsigned e4 = (unsigned)(blockIdx.x - T.block_begin) * 256u + threadIdx.x;      // 32-bit index math (see post_fwd)
+    if (e4 >= (unsigned)n_b * T.H * T.W * C4) return;
+    const unsigned pix = e4 / (unsigned)C4;
+    const int c = (int)(e4 - pix * C4) * 4;
+    const long long e = (long long)pix * T.C + c;
+    const unsigned r1 = pix / (unsigned)T.W;
+    const int wi = (int)(pix - r1 * T.W);
+    const int n = (int)(r1 / (unsigned)T.H);
+    const int hi = (int)(r1 - (unsigned)n * T.H);
     long long oe = e;
     bool origin = true;
     bool routed[4] = {true, true, true, true};
