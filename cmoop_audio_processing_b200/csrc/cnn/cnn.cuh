@@ -213,6 +213,14 @@ struct Launch {
     static int conv_tc2(const TcConvTask* tasks, int n_tasks, int total_tiles, int n_b, int step, int q_max, int max_cin,
                         void* stream);
     static int wt_bf16_v2(const WtBf16Task* tasks, int n_tasks, int total_blocks, void* stream);
+    // wgrad_tc2.cu: tcgen05 weight gradient on the patch layout; tiles = splits * wg2_items(), TcWgradTask.m_chunk /
+    // splits from wg2_splits(n_b * Hp * Wp), bn = wg2_bn(Cout), tiles_n = Cout / bn
+    static bool wg2_ok(int H, int W, int Cin, int Cout, int k, int stride);
+    static int wg2_bn(int Cout);
+    static int wg2_q(int W, int k);
+    static int wg2_items(int Cin, int Cout, int k);
+    static void wg2_splits(long long Mq, int* splits, int* m_chunk);
+    static int wgrad_tc2(const TcWgradTask* tasks, int n_tasks, int total_tiles, int n_b, int q_max, void* stream);
     // stem.cu: dedicated Cin = 1 kernels; every task of a launch has the same M (= n_b*H*W) and W
     static bool stem_ok(int H, int W, int Cin, int Cout, int k, int stride, int n_b);
     static int stem_conv(const ConvTask* tasks, int n_tasks, int max_k, int W, int max_cout, long long M, int n_b, int step,

@@ -58,6 +58,7 @@ struct Unit {
     bool tc = false;                 // convolution runs on the tcgen05 path (bf16 operands)
     bool stem = false;               // Cin = 1 first convolution: dedicated kernels (stem.cu)
     bool tc2 = false;                // tensor-core unit on the patch-resident kernel (conv_tc2.cu)
+    bool wg2 = false;                // ... and its weight gradient on wgrad_tc2.cu
     int kpad_f = 0, kpad_d = 0;      // padded K of the forward / data-gradient GEMM
     bool need_vh = false;            // a tensor-core unit consumes this unit's output
     __nv_bfloat16* Vh = nullptr;     // bf16 shadow of V
@@ -229,6 +230,11 @@ void build_units(Cand& c, const cmoop_cnn_config& cfg, int H, int W, int batch) 
             chunk = kStemRows;
             splits = (int)((M + chunk - 1) / chunk);
         }
+        // wgrad_tc2 (patch layout, two taps per UMMA) is opt-in: MN-major operands whose start row is not a multiple of 8
+        // are fetched ~3x slower than aligned ones (tools/diag_wg2.py), which makes it 2.4x slower than wgrad_tc
+        static const bool use_wg2 = getenv("CMOOP_CNN_WG2") != nullptr;
+        u.wg2 = u.tc2 && use_wg2 && Launch::wg2_ok(u.H, u.W, u.cin, u.cout, u.k, u.stride);
+        if (u.wg2) Launch::wg2_splits((long long)batch * (u.H + 2 * u.pad) * (u.W + 2 * u.pad), &splits, &chunk);
         u.wg_splits = splits;
         u.wg_chunk = chunk;
     }
@@ -310,7 +316,8 @@ struct StageLists {
     DevList<ConvTask> conv, conv_eval, dgrad;
     DevList<TcConvTask> conv_tc, dgrad_tc, conv_tc2, dgrad_tc2;
     int q_max = 0, tc2_cin = 0, tc2_cin_d = 0;   // largest patch; most GEMM input channels of the conv_tc2 / dgrad_tc2 tasks
-    DevList<TcWgradTask> wgrad_tc;
+    DevList<TcWgradTask> wgrad_tc, wgrad_tc2;
+    int wg2_q = 0;                   // largest X patch of the stage's wgrad_tc2 tasks
     DevList<StatTask> stat;
     // stem.cu path: every task of conv / conv_eval / wgrad is an eligible Cin = 1 convolution
     bool stem = true;
@@ -515,9 +522,18 @@ struct Engine {
                         g.splits = u.wg_splits; g.m_chunk = u.wg_chunk;
                         g.bn = u.cout < 128 ? u.cout : 128;
                         g.tiles_k = (kext + 127) / 128; g.tiles_n = (u.cout + g.bn - 1) / g.bn;
-                        g.tile_begin = S.wgrad_tc.total;
-                        S.wgrad_tc.h.push_back(g);
-                        S.wgrad_tc.total += g.tiles_k * g.tiles_n * g.splits;
+                        if (u.wg2) {
+                            g.bn = Launch::wg2_bn(u.cout);
+                            g.tiles_n = u.cout / g.bn;
+                            g.tile_begin = S.wgrad_tc2.total;
+                            S.wgrad_tc2.h.push_back(g);
+                            S.wgrad_tc2.total += g.splits * Launch::wg2_items(u.cin, u.cout, u.k);
+                            S.wg2_q = std::max(S.wg2_q, Launch::wg2_q(u.W, u.k));
+                        } else {
+                            g.tile_begin = S.wgrad_tc.total;
+                            S.wgrad_tc.h.push_back(g);
+                            S.wgrad_tc.total += g.tiles_k * g.tiles_n * g.splits;
+                        }
                     } else {
                         WgradTask g{};
                         g.x = xin;
@@ -632,7 +648,7 @@ struct Engine {
             StageLists& S = wv.st[s];
             blob_add(blob, S.conv); blob_add(blob, S.conv_eval); blob_add(blob, S.dgrad);
             blob_add(blob, S.conv_tc); blob_add(blob, S.dgrad_tc); blob_add(blob, S.stat); blob_add(blob, S.wgrad_tc);
-            blob_add(blob, S.conv_tc2); blob_add(blob, S.dgrad_tc2);
+            blob_add(blob, S.conv_tc2); blob_add(blob, S.dgrad_tc2); blob_add(blob, S.wgrad_tc2);
             blob_add(blob, S.post_fwd); blob_add(blob, S.post_bn); blob_add(blob, S.post_bwd);
             blob_add(blob, S.wgrad); blob_add(blob, S.wreduce); blob_add(blob, S.drop_fwd); blob_add(blob, S.drop_bwd);
         }
@@ -652,7 +668,7 @@ struct Engine {
         for (int s = 0; s < N_STAGES; ++s) {
             StageLists& S = wv.st[s];
             fix(S.conv); fix(S.conv_eval); fix(S.dgrad); fix(S.post_fwd); fix(S.post_bn); fix(S.post_bwd);
-            fix(S.conv_tc); fix(S.dgrad_tc); fix(S.stat); fix(S.wgrad_tc); fix(S.conv_tc2); fix(S.dgrad_tc2);
+            fix(S.conv_tc); fix(S.dgrad_tc); fix(S.stat); fix(S.wgrad_tc); fix(S.conv_tc2); fix(S.dgrad_tc2); fix(S.wgrad_tc2);
             fix(S.wgrad); fix(S.wreduce); fix(S.drop_fwd); fix(S.drop_bwd);
         }
         fix(wv.head); fix(wv.ce_train); fix(wv.ce_val); fix(wv.ce_pred); fix(wv.adam); fix(wv.wt); fix(wv.wt_bf16); fix(wv.wt_bf16_v2);
@@ -736,6 +752,8 @@ struct Engine {
             }
             if (!S.wgrad_tc.h.empty())
                 CNN_LAUNCH(Launch::wgrad_tc(S.wgrad_tc.d, (int)S.wgrad_tc.h.size(), S.wgrad_tc.total, n_b, stream));
+            if (!S.wgrad_tc2.h.empty())
+                CNN_LAUNCH(Launch::wgrad_tc2(S.wgrad_tc2.d, (int)S.wgrad_tc2.h.size(), S.wgrad_tc2.total, n_b, S.wg2_q, stream));
             if (!S.wreduce.h.empty())
                 CNN_LAUNCH(Launch::reduce(S.wreduce.d, (int)S.wreduce.h.size(), S.wreduce.total, stream));
             if (!S.dgrad.h.empty())
@@ -1288,6 +1306,7 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
     CMOOP_REQUIRE(n >= 1 && n <= kBatch && (stride == 1 || (stride == 2 && k == 1)) && splits >= 1 && splits <= 32,
                   "debug_wgrad: unsupported shape");
     CMOOP_REQUIRE(use_tc != 1 || (Cin % 16 == 0 && Cout % 16 == 0), "debug_wgrad: tensor-core path needs Cin, Cout multiples of 16");
+    CMOOP_REQUIRE(use_tc != 3 || Launch::wg2_ok(H, W, Cin, Cout, k, stride), "debug_wgrad: shape not eligible for wgrad_tc2");
     CMOOP_REQUIRE(use_tc != 2 || Launch::stem_ok(H, W, Cin, Cout, k, stride, n),
                   "debug_wgrad: shape not eligible for the stem (Cin = 1) kernel");
     if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
@@ -1305,6 +1324,7 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
         chunk = kStemRows;
         splits = (int)((M + chunk - 1) / chunk);
     }
+    if (use_tc == 3) Launch::wg2_splits((long long)n * (H + 2 * pad) * (W + 2 * pad), &splits, &chunk);
     float *d_x, *d_y, *d_ws, *d_o;
     __nv_bfloat16 *d_xh, *d_yh;
     void* d_task;
@@ -1324,7 +1344,14 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
     CMOOP_CUDA_OK(cudaMemcpyAsync(d_y, dy, n_y * 4, cudaMemcpyHostToDevice, st));
     CMOOP_CUDA_OK(cudaMemsetAsync(d_ws, 0xff, n_o * 4 * splits, st));       // poison: every partial must be written
     int rc;
-    if (use_tc == 1) {
+    if (use_tc == 3) {
+        TcWgradTask g{};
+        g.xh = d_xh; g.dyh = d_yh; g.out = d_ws; g.H = H; g.W = W; g.Cin = Cin; g.Ho = Ho; g.Wo = Wo; g.Cout = Cout;
+        g.k = k; g.stride = stride; g.pad = pad; g.splits = splits; g.m_chunk = chunk;
+        g.bn = Launch::wg2_bn(Cout); g.tiles_n = Cout / g.bn;
+        CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &g, sizeof(g), cudaMemcpyHostToDevice, st));
+        rc = Launch::wgrad_tc2((const TcWgradTask*)d_task, 1, splits * Launch::wg2_items(Cin, Cout, k), n, Launch::wg2_q(W, k), st);
+    } else if (use_tc == 1) {
         TcWgradTask g{};
         g.xh = d_xh; g.dyh = d_yh; g.out = d_ws; g.H = H; g.W = W; g.Cin = Cin; g.Ho = Ho; g.Wo = Wo; g.Cout = Cout;
         g.k = k; g.stride = stride; g.pad = pad; g.splits = splits; g.m_chunk = chunk;

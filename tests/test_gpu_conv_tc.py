@@ -172,3 +172,20 @@ def test_patch_resident_kernel(n, H, W, Cin, Cout, k, stride):
     F.conv2d(xin, wt, None, padding=pad).backward(dyt)
     got_dx = run_conv(1, 3, dy, w, None, n, H, W, Cin, Cout, k, 1, 0)
     np.testing.assert_allclose(got_dx, xin.grad.permute(0, 2, 3, 1).numpy(), rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("n,H,W,Cin,Cout,k,stride", [c for c in PATCH_CASES if c[5] in (3, 5)])
+def test_patch_weight_gradient(n, H, W, Cin, Cout, k, stride):
+    """wgrad_tc2.cu (use_tc = 3): dW and db from the resident patch (two taps per UMMA, bias gradient as the tap after
+    the last) vs torch fp64 on bf16-rounded operands."""
+    import torch
+    rng = np.random.default_rng(11 + n + Cin + Cout + k)
+    x = rng.standard_normal((n, H, W, Cin)).astype(np.float32)
+    dy = rng.standard_normal((n, H, W, Cout)).astype(np.float32)
+    pad = (k - 1) // 2
+    xt = torch.from_numpy(bf16_round(x)).permute(0, 3, 1, 2).double()
+    yt = torch.from_numpy(bf16_round(dy)).permute(0, 3, 1, 2).double()
+    gw = torch.nn.grad.conv2d_weight(xt, (Cout, Cin, k, k), yt, padding=pad)
+    want = np.concatenate([gw.permute(2, 3, 1, 0).reshape(k * k * Cin, Cout).numpy(), yt.sum(dim=(0, 2, 3)).numpy()[None]])
+    got = run_wgrad(3, x, dy, n, H, W, Cin, Cout, k, 1, 1)
+    np.testing.assert_allclose(got, want, rtol=1e-3, atol=2e-4 * np.abs(want).max())
