@@ -479,7 +479,7 @@ struct Engine {
                         PostTask q = p;
                         q.block_begin = S.post_fwd.total;
                         S.post_fwd.h.push_back(q);
-                        S.post_fwd.total += blocks_for(u.v_elems / 4);
+                        S.post_fwd.total += blocks_for(u.v_elems / 8);
                     }
                     if (u.has_bn) {
                         S.max_bn_c = std::max(S.max_bn_c, u.cout);

@@ -387,56 +387,74 @@ __device__ __forceinline__ uint2 bf16x4(float4 v) {
 __global__ void __launch_bounds__(256) post_fwd_kernel(const PostTask* __restrict__ tasks, int n_tasks, int n_b) {
     const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin; });
     const PostTask T = tasks[t];
-    const int C4 = T.C >> 2;
-    // 32-bit index math: a unit's activation has < 2^31 elements, and 64-bit div/mod chains cost more instructions
-    // than the 16 bytes this thread moves
-    const unsigned e4 = (unsigned)(blockIdx.x - T.block_begin) * 256u + threadIdx.x;
-    if (e4 >= (unsigned)n_b * T.Ho * T.Wo * C4) return;
-    unsigned pix = e4 / (unsigned)C4;
-    const int c = (int)(e4 - pix * C4) * 4;
+    // one thread = 8 channels of one output pixel (two float4 per source position: index math amortised over 32 B and
+    // twice the loads in flight); 32-bit index math: a unit's activation has < 2^31 elements
+    const int C8 = T.C >> 3;
+    const unsigned e8 = (unsigned)(blockIdx.x - T.block_begin) * 256u + threadIdx.x;
+    if (e8 >= (unsigned)n_b * T.Ho * T.Wo * C8) return;
+    const unsigned pix = e8 / (unsigned)C8;
+    const int c = (int)(e8 - pix * C8) * 8;
     const long long e = (long long)pix * T.C + c;
     const unsigned r1 = pix / (unsigned)T.Wo;
     const int wo = (int)(pix - r1 * T.Wo);
     const int n = (int)(r1 / (unsigned)T.Ho);
     const int ho = (int)(r1 - (unsigned)n * T.Ho);
-    float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+    float sc[8], sh[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { sc[q] = 1.f; sh[q] = 0.f; }
     if (T.has_bn) {
-        const float4 a = ld4(T.bn + 2 * T.C + c), b = ld4(T.bn + 3 * T.C + c);
-        sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w;
-        sh[0] = b.x; sh[1] = b.y; sh[2] = b.z; sh[3] = b.w;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const float4 a = ld4(T.bn + 2 * T.C + c + 4 * h2), b = ld4(T.bn + 3 * T.C + c + 4 * h2);
+            sc[4 * h2 + 0] = a.x; sc[4 * h2 + 1] = a.y; sc[4 * h2 + 2] = a.z; sc[4 * h2 + 3] = a.w;
+            sh[4 * h2 + 0] = b.x; sh[4 * h2 + 1] = b.y; sh[4 * h2 + 2] = b.z; sh[4 * h2 + 3] = b.w;
+        }
     }
-    float z[4];
+    float z[8];
     if (T.pool) {
-        int code[4] = {0, 0, 0, 0};
+        // all (up to) eight loads first, then the max in the reference's scan order (first maximum wins)
+        float v[4][8];
+        bool ok[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int hi = 2 * ho + (d >> 1), wi = 2 * wo + (d & 1);
+            ok[d] = hi < T.H && wi < T.W;
+            if (ok[d]) {
+                const float* src = T.u + (((long long)n * T.H + hi) * T.W + wi) * T.C + c;
+                const float4 u0 = ld4(src), u1 = ld4(src + 4);
+                v[d][0] = u0.x; v[d][1] = u0.y; v[d][2] = u0.z; v[d][3] = u0.w;
+                v[d][4] = u1.x; v[d][5] = u1.y; v[d][6] = u1.z; v[d][7] = u1.w;
+            }
+        }
+        int code[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) code[q] = 0;
         bool first = true;
 #pragma unroll
-        for (int dh = 0; dh < 2; ++dh)
+        for (int d = 0; d < 4; ++d) {
+            if (ok[d]) {
 #pragma unroll
-            for (int dw = 0; dw < 2; ++dw) {
-                const int hi = 2 * ho + dh, wi = 2 * wo + dw;
-                if (hi < T.H && wi < T.W) {
-                    const float4 uv = ld4(T.u + (((long long)n * T.H + hi) * T.W + wi) * T.C + c);
-                    const float v[4] = {uv.x, uv.y, uv.z, uv.w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float x = v[q];
-                        if (T.has_bn) x = fmaf(x, sc[q], sh[q]);
-                        if (T.relu_mid) x = fmaxf(x, 0.f);
-                        if (first || x > z[q]) {
-                            z[q] = x;
-                            code[q] = dh * 2 + dw;
-                        }
+                for (int q = 0; q < 8; ++q) {
+                    float x = v[d][q];
+                    if (T.has_bn) x = fmaf(x, sc[q], sh[q]);
+                    if (T.relu_mid) x = fmaxf(x, 0.f);
+                    if (first || x > z[q]) {
+                        z[q] = x;
+                        code[q] = d;
                     }
-                    first = false;
                 }
+                first = false;
             }
-        *reinterpret_cast<uchar4*>(T.idx + e) = make_uchar4((unsigned char)code[0], (unsigned char)code[1],
-                                                             (unsigned char)code[2], (unsigned char)code[3]);
+        }
+        uint2 pk;
+        pk.x = (unsigned)code[0] | ((unsigned)code[1] << 8) | ((unsigned)code[2] << 16) | ((unsigned)code[3] << 24);
+        pk.y = (unsigned)code[4] | ((unsigned)code[5] << 8) | ((unsigned)code[6] << 16) | ((unsigned)code[7] << 24);
+        *reinterpret_cast<uint2*>(T.idx + e) = pk;
     } else {
-        const float4 uv = ld4(T.u + e);
-        const float v[4] = {uv.x, uv.y, uv.z, uv.w};
+        const float4 u0 = ld4(T.u + e), u1 = ld4(T.u + e + 4);
+        const float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 8; ++q) {
             float x = v[q];
             if (T.has_bn) x = fmaf(x, sc[q], sh[q]);
             if (T.relu_mid) x = fmaxf(x, 0.f);
@@ -444,15 +462,18 @@ __global__ void __launch_bounds__(256) post_fwd_kernel(const PostTask* __restric
         }
     }
     if (T.add_skip) {
-        const float4 sk = ld4(T.skip + e);
-        z[0] = fmaxf(z[0] + sk.x, 0.f);
-        z[1] = fmaxf(z[1] + sk.y, 0.f);
-        z[2] = fmaxf(z[2] + sk.z, 0.f);
-        z[3] = fmaxf(z[3] + sk.w, 0.f);
+        const float4 s0 = ld4(T.skip + e), s1 = ld4(T.skip + e + 4);
+        const float sk[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) z[q] = fmaxf(z[q] + sk[q], 0.f);
     }
-    const float4 out = make_float4(z[0], z[1], z[2], z[3]);
-    *reinterpret_cast<float4*>(T.v + e) = out;
-    if (T.vh) *reinterpret_cast<uint2*>(T.vh + e) = bf16x4(out);
+    const float4 o0 = make_float4(z[0], z[1], z[2], z[3]), o1 = make_float4(z[4], z[5], z[6], z[7]);
+    *reinterpret_cast<float4*>(T.v + e) = o0;
+    *reinterpret_cast<float4*>(T.v + e + 4) = o1;
+    if (T.vh) {
+        const uint2 h0 = bf16x4(o0), h1 = bf16x4(o1);
+        *reinterpret_cast<uint4*>(T.vh + e) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    }
 }
 
 // BN backward, pass 1: per-channel partial sums of g and g*xhat over the unit's output elements.
