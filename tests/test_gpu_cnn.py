@@ -279,3 +279,27 @@ def test_waves_and_bf16_batching_invariance():
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
     np.testing.assert_array_equal(outs[0][1], outs[1][1])
     assert np.isfinite(outs[0][0]).all()
+
+
+def test_birdclef_shaped_problem():
+    """BASELINE configs[3] shape: 128 x 313 feature maps, 397 classes (sa_nsga_penalty.py:61,102,141).  Exercises the stem
+    kernels on wide rows, the patch-resident convolution with its widest patch (one CTA per SM) and the im2col fallback;
+    the tensor-core and the exact path must agree on the validation loss of a one-epoch run."""
+    import random
+    from cmoop_audio_processing_b200.nsga import HPARAM_SPACE
+    from cmoop_audio_processing_b200.problem import FitnessProblem, TrainConfig
+    rng = np.random.default_rng(0)
+    n_tr, n_va, H, W, C = 128, 64, 128, 313, 397
+    xt = rng.standard_normal((n_tr, H, W, 1)).astype(np.float32)
+    yt = rng.integers(0, C, n_tr)
+    xv = rng.standard_normal((n_va, H, W, 1)).astype(np.float32)
+    yv = rng.integers(0, C, n_va)
+    pyr = random.Random(1)
+    hps = [{k: pyr.choice(v) for k, v in HPARAM_SPACE.items()} for _ in range(4)]
+    outs = {}
+    for prec in ("bf16", "fp32"):
+        prob = FitnessProblem(xt, yt, xv, yv, classes=C, config=TrainConfig(variant="B", epochs=1, patience=1, precision=prec))
+        outs[prec], _ = prob.train_eval(hps, list(range(len(hps))))
+        assert np.isfinite(outs[prec]).all()
+    np.testing.assert_array_equal(outs["bf16"][:, 1], outs["fp32"][:, 1])                    # size objective is exact
+    assert np.abs(outs["bf16"][:, 4] - outs["fp32"][:, 4]).max() < 0.05                     # validation loss ~ ln(397)
