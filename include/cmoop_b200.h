@@ -217,13 +217,15 @@ int cmoop_cnn_debug_train_steps(cmoop_cnn_dataset_handle data, const cmoop_genot
                                 const cmoop_cnn_config* cfg, int n_steps, float* losses, float* grads_first,
                                 float* params_out);
 
-/* one convolution through the fp32 SIMT kernel (use_tc = 0) or the tcgen05 kernel (use_tc = 1); host pointers.
+/* one convolution through a chosen kernel; host pointers.  use_tc: 0 = generic fp32 SIMT, 1 = tcgen05 with im2col staging
+ * (conv_tc.cu), 2 = dedicated Cin = 1 stem kernel (stem.cu, mode 0 only), 3 = patch-resident tcgen05 (conv_tc2.cu, stride 1).
  * mode 0: out[n][Ho][Wo][Cout] = conv(in[n][H][W][Cin], w[k][k][Cin][Cout]) + bias (optional ReLU)
  * mode 1: out[n][H][W][Cin] = data gradient of that convolution for in = dy[n][Ho][Wo][Cout] */
 int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, const float* bias, int n, int H,
                          int W, int Cin, int Cout, int k, int stride, int relu, float* out);
 
-/* weight (+ bias, last row) gradient out[k*k*Cin + 1][Cout] of one convolution; `splits` deterministic split-M partials */
+/* weight (+ bias, last row) gradient out[k*k*Cin + 1][Cout] of one convolution; `splits` deterministic split-M partials
+ * (use_tc as above; 2 and 3 choose their own split geometry: stem_wgrad_kernel / wgrad_tc2_kernel) */
 int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, int H, int W, int Cin, int Cout, int k,
                           int stride, int splits, float* out);
 
