@@ -309,7 +309,13 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceTask* __restric
     const int i = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
     if (i >= T.n) return;
     float s = 0.f;
-    for (int k = 0; k < T.splits; ++k) s += T.part[(long long)k * T.n + i];
+    int k = 0;
+    for (; k + 3 < T.splits; k += 4) {          // four independent loads per iteration, same summation order
+        const float a0 = T.part[(long long)k * T.n + i], a1 = T.part[(long long)(k + 1) * T.n + i];
+        const float a2 = T.part[(long long)(k + 2) * T.n + i], a3 = T.part[(long long)(k + 3) * T.n + i];
+        s += a0; s += a1; s += a2; s += a3;
+    }
+    for (; k < T.splits; ++k) s += T.part[(long long)k * T.n + i];
     T.out[i] = s;
 }
 
@@ -548,11 +554,24 @@ __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const PostTask* __
     const long long rows = ((n_pix + 127) / 128) * lanes_w;
     const double count = (double)n_b * T.H * T.W;
     double sg = 0.0, sgx = 0.0;
-    if (c < T.C)
-        for (long long r = r_lane; r < rows; r += 16) {
+    if (c < T.C) {
+        // four rows per iteration: the loads are independent, the summation order stays r_lane, r_lane + 16, ...
+        long long r = r_lane;
+        for (; r + 48 < rows; r += 64) {
+            const float a0 = T.bwd_part[(r * 2 + 0) * T.C + c], b0 = T.bwd_part[(r * 2 + 1) * T.C + c];
+            const float a1 = T.bwd_part[((r + 16) * 2 + 0) * T.C + c], b1 = T.bwd_part[((r + 16) * 2 + 1) * T.C + c];
+            const float a2 = T.bwd_part[((r + 32) * 2 + 0) * T.C + c], b2 = T.bwd_part[((r + 32) * 2 + 1) * T.C + c];
+            const float a3 = T.bwd_part[((r + 48) * 2 + 0) * T.C + c], b3 = T.bwd_part[((r + 48) * 2 + 1) * T.C + c];
+            sg += (double)a0; sgx += (double)b0;
+            sg += (double)a1; sgx += (double)b1;
+            sg += (double)a2; sgx += (double)b2;
+            sg += (double)a3; sgx += (double)b3;
+        }
+        for (; r < rows; r += 16) {
             sg += (double)T.bwd_part[(r * 2 + 0) * T.C + c];
             sgx += (double)T.bwd_part[(r * 2 + 1) * T.C + c];
         }
+    }
     red[0][threadIdx.x] = sg;
     red[1][threadIdx.x] = sgx;
     __syncthreads();
