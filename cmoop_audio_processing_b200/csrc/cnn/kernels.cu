@@ -81,8 +81,10 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvTask* __restri
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < Kext; k0 += BK) {
-        float a[4] = {0.f, 0.f, 0.f, 0.f};
+    // register double-buffering: the global loads of K block k0 + BK are in flight while block k0 is multiplied
+    // (same accumulation order as a plain loop, so results are bit-identical)
+    auto load_a = [&](int k0, float (&a)[4]) {
+        a[0] = a[1] = a[2] = a[3] = 0.f;
         const int kb = k0 + kq * 4;
         if (mvalid) {
             if (vec_a && kb + 3 < K) {
@@ -109,9 +111,9 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvTask* __restri
                 }
             }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) As[kq * 4 + j][row] = a[j];
-        float b[4] = {0.f, 0.f, 0.f, 0.f};
+    };
+    auto load_b = [&](int k0, float (&b)[4]) {
+        b[0] = b[1] = b[2] = b[3] = 0.f;
         const int kB = k0 + bk;
         if (kB < Kext) {
             const float* wr = T.w + (long long)kB * T.Cout + n0 + bn4;
@@ -124,8 +126,19 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvTask* __restri
                     if (n0 + bn4 + j < T.Cout) b[j] = wr[j];
             }
         }
+    };
+    float a[4], b[4];
+    load_a(0, a);
+    load_b(0, b);
+    for (int k0 = 0; k0 < Kext; k0 += BK) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) As[kq * 4 + j][row] = a[j];
         *reinterpret_cast<float4*>(&Bs[bk][bn4]) = make_float4(b[0], b[1], b[2], b[3]);
         __syncthreads();
+        if (k0 + BK < Kext) {
+            load_a(k0 + BK, a);
+            load_b(k0 + BK, b);
+        }
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
             const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
