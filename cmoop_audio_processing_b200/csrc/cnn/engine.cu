@@ -1117,12 +1117,20 @@ int run_population(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotype
             if (arena_base) CMOOP_CUDA_OK(cudaFree(arena_base));
             arena_base = nullptr;
             arena_cap = 0;
-            if (cudaMalloc((void**)&arena_base, need) != cudaSuccess) {
+            // grow with 25 % headroom (never past the budget): successive populations of a search differ a little in
+            // size, and re-allocating tens of GB costs hundreds of milliseconds per call
+            size_t want = need + need / 4;
+            if (want > budget) want = budget > need ? budget : need;
+            if (cudaMalloc((void**)&arena_base, want) != cudaSuccess) {
                 (void)cudaGetLastError();
-                cmoop::set_error("cnn: cannot allocate a %.2f GB arena for candidates [%d,%d)", need / 1e9, next, end);
-                return CMOOP_ERR_CUDA;
+                want = need;
+                if (cudaMalloc((void**)&arena_base, want) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    cmoop::set_error("cnn: cannot allocate a %.2f GB arena for candidates [%d,%d)", need / 1e9, next, end);
+                    return CMOOP_ERR_CUDA;
+                }
             }
-            arena_cap = need;
+            arena_cap = want;
         }
         Arena a;
         a.base = arena_base;
