@@ -9,8 +9,10 @@ Mirrors, name for name:
   ``vector_to_hparams``       mobo_penalty.py:252-338
 
 Hyper-parameter fitting (L-BFGS-B on the log marginal likelihood with random restarts)
-stays in scikit-learn -- it is the reference's third-party dependency behind the same
-API and its restarts are unseeded.  Everything that is *queried* (K*.alpha, the
+stays scikit-learn's arithmetic -- it is the reference's third-party dependency behind the
+same API and its restarts are unseeded -- but the independent optimiser starts of the four
+models run concurrently in worker processes (gp_fit.py; same objective, same RNG order,
+same fitted model).  Everything that is *queried* (K*.alpha, the
 triangular solve and the variance) runs on the GPU through ``cmoop_gp_predict_*``.
 Because the genotype space has only 288 points, ``SurrogateManager`` evaluates the
 whole space in ONE launch after every update and serves ``predict`` (including the
@@ -179,9 +181,9 @@ class SurrogateManager:
         self._categories = {k: sorted(set(bool(r[k]) for r in rows)) for k in self.categorical_features}
         x = self._encode(rows)
         y_affine = []
-        gprs = []
         from sklearn.preprocessing import StandardScaler
 
+        kernels, ys = [], []
         for key in TARGET_KEYS:
             y = self.training_data[f"y_{key}"].to_numpy(dtype=np.float64).reshape(-1, 1)
             scaler = StandardScaler()                       # same statistics as sa_nsga_local.py:207
@@ -189,12 +191,14 @@ class SurrogateManager:
             self.scalers[key] = scaler
             mean, var, scale = float(scaler.mean_[0]), float(scaler.var_[0]), float(scaler.scale_[0])
             self.scaler_mean[key], self.scaler_var[key], self.scaler_scale[key] = mean, var, scale
-            kernel = ConstantKernel(1.0) * Matern(length_scale=1.0, nu=1.5) + WhiteKernel(noise_level=0.1)
-            gpr = GaussianProcessRegressor(kernel=kernel, n_restarts_optimizer=self.n_restarts_optimizer)
-            gpr.fit(x, y_scaled)
-            self.models[key] = gpr
-            gprs.append(gpr)
+            kernels.append(ConstantKernel(1.0) * Matern(length_scale=1.0, nu=1.5) + WhiteKernel(noise_level=0.1))
+            ys.append(y_scaled)
             y_affine.append((scale, mean))
+        # the reference fits the four regressors one after the other (sa_nsga_local.py:180-181,209); the optimiser starts
+        # are independent, so they run concurrently here (fit_gprs_parallel) with unchanged arithmetic and RNG order
+        gprs = fit_gprs_parallel(kernels, x, ys, n_restarts_optimizer=self.n_restarts_optimizer)
+        for key, gpr in zip(TARGET_KEYS, gprs):
+            self.models[key] = gpr
         self._install(gprs, y_affine)
 
     def _install(self, gprs, y_affine):
@@ -325,6 +329,9 @@ class _GroupMember:
         return (mean[self.index], std[self.index]) if return_std else mean[self.index]
 
 
+from .gp_fit import fit_gprs_parallel  # noqa: E402  (re-exported: the concurrent multi-start GP fit)
+
+
 def train_gps(X, Y):
     """One GaussianProcessRegressor(Matern(nu=2.5), normalize_y=True) per column of Y
     (mobo_penalty.py:252-263); fitted by scikit-learn, uploaded as one device group."""
@@ -333,11 +340,8 @@ def train_gps(X, Y):
 
     X = np.asarray(X, np.float64)
     Y = np.asarray(Y, np.float64)
-    fitted = []
-    for dim in range(Y.shape[1]):
-        gp = GaussianProcessRegressor(kernel=Matern(nu=2.5), normalize_y=True)
-        gp.fit(X, Y[:, dim])
-        fitted.append(gp)
+    fitted = fit_gprs_parallel([Matern(nu=2.5) for _ in range(Y.shape[1])], X, [Y[:, dim] for dim in range(Y.shape[1])],
+                               n_restarts_optimizer=0, normalize_y=True)
     group = DeviceGPGroup.from_sklearn(fitted)
     return [_GroupMember(group, i, g) for i, g in enumerate(fitted)]
 

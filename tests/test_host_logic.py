@@ -65,3 +65,43 @@ def test_synthetic_clips_are_deterministic_and_bounded():
     assert np.abs(w1).max() <= 1.0 and sorted(set(l1.tolist())) == list(range(12))
     u = synth.uniform_clips(4)
     assert u.shape == (4, 16000) and u.min() >= -1 and u.max() <= 1
+
+
+def test_parallel_gp_fit_matches_sklearn():
+    """fit_gprs_parallel = scikit-learn's own objective / L-BFGS-B / best-start selection on a different schedule: with the
+    same RandomState the log-marginal likelihood and the predictions of GaussianProcessRegressor.fit are reproduced, both
+    in-process (small n) and through the worker subprocesses (n >= 64)."""
+    import warnings
+
+    import numpy as np
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import ConstantKernel, Matern, WhiteKernel
+
+    from cmoop_audio_processing_b200.gp_fit import fit_gprs_parallel
+
+    warnings.filterwarnings("ignore")
+    rng = np.random.default_rng(3)
+
+    def kernel():
+        return ConstantKernel(1.0) * Matern(length_scale=1.0, nu=1.5) + WhiteKernel(noise_level=0.1)
+
+    for n, workers in ((24, None), (72, 2)):
+        x = np.column_stack([rng.choice([16, 32, 64], n), rng.choice([3, 5], n), rng.choice([1, 2, 3], n),
+                             rng.choice([1, 2, 3, 4], n), rng.integers(0, 2, n), rng.integers(0, 2, n)]).astype(float)
+        ys = [np.sin(x[:, 0] / 20.0 + j) + 0.1 * rng.standard_normal(n) for j in range(2)]
+        state = np.random.RandomState(11)
+        ref = [GaussianProcessRegressor(kernel=kernel(), n_restarts_optimizer=3, random_state=state).fit(x, y) for y in ys]
+        got = fit_gprs_parallel([kernel() for _ in ys], x, ys, n_restarts_optimizer=3, random_state=np.random.RandomState(11),
+                                max_workers=workers)
+        xq = rng.random((40, 6)) * np.array([64, 5, 3, 4, 1, 1])
+        for a, b in zip(ref, got):
+            assert abs(a.log_marginal_likelihood_value_ - b.log_marginal_likelihood_value_) < 1e-8
+            ma, sa = a.predict(xq, return_std=True)
+            mb, sb = b.predict(xq, return_std=True)
+            np.testing.assert_allclose(mb, ma, rtol=1e-6, atol=1e-7)
+            np.testing.assert_allclose(sb, sa, rtol=1e-6, atol=1e-7)
+    # the draws come from the same stream in the same order: the next number of both generators agrees
+    s1, s2 = np.random.RandomState(5), np.random.RandomState(5)
+    GaussianProcessRegressor(kernel=kernel(), n_restarts_optimizer=2, random_state=s1).fit(x[:24], ys[0][:24])
+    fit_gprs_parallel([kernel()], x[:24], [ys[0][:24]], n_restarts_optimizer=2, random_state=s2)
+    assert s1.uniform() == s2.uniform()
