@@ -107,6 +107,13 @@ def test_mfcc_shapes_edges_and_standardise():
     assert np.abs(got - scaled).max() < 2e-4
     fe.set_standardise(None, None)
     _check_features(fe(wave), base)
+    # a device pointer that is 8- but not 16-byte aligned cannot be a bulk-TMA source: the one-frame-per-warp kernel
+    # (float2 loads) serves it and must meet the same tolerance
+    flat = torch.zeros(5 * 16000 + 2, device="cuda")
+    view = flat[2:].view(5, 16000)
+    view.copy_(torch.from_numpy(wave))
+    assert view.data_ptr() % 16 == 8
+    _check_features(fe(view).cpu().numpy(), base)
     with pytest.raises(RuntimeError):
         MfccFrontEnd(MfccConfig(n_fft=1000))                       # not a power of two
     with pytest.raises(RuntimeError):
