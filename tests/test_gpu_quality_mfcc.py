@@ -107,6 +107,12 @@ def test_mfcc_shapes_edges_and_standardise():
     assert np.abs(got - scaled).max() < 2e-4
     fe.set_standardise(None, None)
     _check_features(fe(wave), base)
+    # other clip lengths on the frame-pair kernel: even (24) and odd (37) frame counts, a lone last frame per clip
+    for n_samples in (8000, 12160):
+        short = np.ascontiguousarray(wave[:, :n_samples])
+        got_s = fe(short)
+        assert got_s.shape == (5, 1 + (n_samples - 640) // 320, 40)
+        _check_features(got_s, mfcc_ref.mfcc(short))
     # a device pointer that is 8- but not 16-byte aligned cannot be a bulk-TMA source: the one-frame-per-warp kernel
     # (float2 loads) serves it and must meet the same tolerance
     flat = torch.zeros(5 * 16000 + 2, device="cuda")
