@@ -62,6 +62,8 @@ SIGNATURES = {
     "cmoop_mfcc_n_out": (C.c_int, [C.c_void_p]),
     "cmoop_mfcc_fwd_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "cmoop_mfcc_fwd_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "cmoop_mfcc_fwd_dev_i16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "cmoop_mfcc_fwd_host_i16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "cmoop_mfcc_set_standardise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cmoop_cnn_dataset_create_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                                 C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

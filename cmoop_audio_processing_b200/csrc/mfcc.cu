@@ -923,6 +923,25 @@ int launch_nz(const Params& p, int grid, size_t smem, cudaStream_t st) {
     return CMOOP_OK;
 }
 
+// int16 PCM -> fp32 in [-1, 1) (exact: x / 32768), 8 samples per thread
+__global__ void __launch_bounds__(256) pcm16_to_f32_kernel(const int16_t* __restrict__ src, float* __restrict__ dst, long long n) {
+    const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 8;
+    if (i + 8 <= n && ((reinterpret_cast<uintptr_t>(src + i) & 15u) == 0)) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + i);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            f[2 * j] = (float)(short)(w[j] & 0xffffu) * (1.f / 32768.f);
+            f[2 * j + 1] = (float)(short)(w[j] >> 16) * (1.f / 32768.f);
+        }
+        *reinterpret_cast<float4*>(dst + i) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(dst + i + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    } else {
+        for (long long j = i; j < n && j < i + 8; ++j) dst[j] = (float)src[j] * (1.f / 32768.f);
+    }
+}
+
 template <int DCT>
 int launch_pair(const Params& p, int grid, size_t smem, cudaStream_t st) {
     static bool configured = false;
@@ -1275,6 +1294,68 @@ int cmoop_mfcc_fwd_host(cmoop_mfcc_handle h, const float* wave, int64_t n_clips,
         if (rc != CMOOP_OK) return rc;
         CMOOP_CUDA_OK(cudaMemcpyAsync(out + (size_t)c0 * frames * h->n_out, d_out[slot],
                                       (size_t)nc * frames * h->n_out * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    CMOOP_CUDA_OK(cudaStreamSynchronize(streams[0]));
+    CMOOP_CUDA_OK(cudaStreamSynchronize(streams[1]));
+    return CMOOP_OK;
+}
+
+// 16-bit PCM input (what a wav file holds): x = sample / 32768.  Device form: converted chunk-wise into library scratch on
+// `stream`, then the fp32 kernels run unchanged.  Host form: half the PCIe bytes of the fp32 entry point.
+int cmoop_mfcc_fwd_dev_i16(cmoop_mfcc_handle h, const int16_t* wave, int64_t n_clips, int n_samples, float* out, void* stream) {
+    CMOOP_REQUIRE(h != nullptr, "mfcc_fwd: null handle");
+    CMOOP_REQUIRE(n_clips >= 0 && n_samples >= 0, "mfcc_fwd: negative size");
+    const int frames = cmoop_mfcc_n_frames(h, n_samples);
+    if (n_clips == 0 || frames == 0) return CMOOP_OK;
+    CMOOP_REQUIRE(wave && out, "mfcc_fwd: null pointer");
+    const int64_t chunk = 4096;
+    float* d_f = (float*)cmoop::device_scratch(5, (size_t)chunk * n_samples * sizeof(float));
+    if (!d_f) return CMOOP_ERR_CUDA;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int64_t c0 = 0; c0 < n_clips; c0 += chunk) {
+        const int64_t nc = (n_clips - c0) < chunk ? (n_clips - c0) : chunk;
+        const long long n = (long long)nc * n_samples;
+        pcm16_to_f32_kernel<<<(unsigned)((n + 2047) / 2048), 256, 0, st>>>(wave + (size_t)c0 * n_samples, d_f, n);
+        cmoop::count_launch();
+        CMOOP_CUDA_OK(cudaGetLastError());
+        int rc = cmoop_mfcc_fwd_dev(h, d_f, nc, n_samples, out + (size_t)c0 * frames * h->n_out, stream);
+        if (rc != CMOOP_OK) return rc;
+    }
+    return CMOOP_OK;
+}
+
+int cmoop_mfcc_fwd_host_i16(cmoop_mfcc_handle h, const int16_t* wave, int64_t n_clips, int n_samples, float* out) {
+    CMOOP_REQUIRE(h != nullptr, "mfcc_fwd: null handle");
+    CMOOP_REQUIRE(n_clips >= 0 && n_samples >= 0, "mfcc_fwd: negative size");
+    const int frames = cmoop_mfcc_n_frames(h, n_samples);
+    if (n_clips == 0 || frames == 0) return CMOOP_OK;
+    CMOOP_REQUIRE(wave && out, "mfcc_fwd: null pointer");
+    // same double-buffered pipeline as the fp32 form; the staged bytes are int16 and widened on the device
+    const int64_t chunk = 2048;
+    const size_t pcm_bytes = cmoop::align_up((size_t)chunk * n_samples * sizeof(int16_t), 256);
+    const size_t in_bytes = cmoop::align_up((size_t)chunk * n_samples * sizeof(float), 256);
+    const size_t out_bytes = cmoop::align_up((size_t)chunk * frames * h->n_out * sizeof(float), 256);
+    char* d = (char*)cmoop::device_scratch(6, 2 * (pcm_bytes + in_bytes + out_bytes));
+    if (!d) return CMOOP_ERR_CUDA;
+    static cudaStream_t streams[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; ++i)
+        if (!streams[i]) CMOOP_CUDA_OK(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
+    int slot = 0;
+    for (int64_t c0 = 0; c0 < n_clips; c0 += chunk, slot ^= 1) {
+        const int64_t nc = (n_clips - c0) < chunk ? (n_clips - c0) : chunk;
+        cudaStream_t st = streams[slot];
+        int16_t* d_pcm = (int16_t*)(d + slot * (pcm_bytes + in_bytes + out_bytes));
+        float* d_in = (float*)((char*)d_pcm + pcm_bytes);
+        float* d_out = (float*)((char*)d_in + in_bytes);
+        const long long n = (long long)nc * n_samples;
+        CMOOP_CUDA_OK(cudaMemcpyAsync(d_pcm, wave + (size_t)c0 * n_samples, (size_t)n * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        pcm16_to_f32_kernel<<<(unsigned)((n + 2047) / 2048), 256, 0, st>>>(d_pcm, d_in, n);
+        cmoop::count_launch();
+        CMOOP_CUDA_OK(cudaGetLastError());
+        int rc = cmoop_mfcc_fwd_dev(h, d_in, nc, n_samples, d_out, st);
+        if (rc != CMOOP_OK) return rc;
+        CMOOP_CUDA_OK(cudaMemcpyAsync(out + (size_t)c0 * frames * h->n_out, d_out, (size_t)nc * frames * h->n_out * sizeof(float),
+                                      cudaMemcpyDeviceToHost, st));
     }
     CMOOP_CUDA_OK(cudaStreamSynchronize(streams[0]));
     CMOOP_CUDA_OK(cudaStreamSynchronize(streams[1]));

@@ -58,7 +58,7 @@ class MfccFrontEnd:
                    "cmoop_mfcc_set_standardise")
 
     def __call__(self, wave, out=None):
-        """wave: (n_clips, n_samples) float32 -- a CUDA torch tensor (stream-ordered, no sync,
+        """wave: (n_clips, n_samples) float32, or int16 PCM (x = sample / 32768) -- a CUDA torch tensor (stream-ordered, no sync,
         returns a CUDA tensor) or a host numpy array / CPU tensor (chunked overlapped copies,
         returns numpy)."""
         try:
@@ -66,30 +66,31 @@ class MfccFrontEnd:
         except ImportError:  # pragma: no cover
             torch = None
         if torch is not None and isinstance(wave, torch.Tensor) and wave.is_cuda:
-            if wave.dtype != torch.float32 or wave.dim() != 2:
-                raise ValueError("wave must be a 2-D float32 tensor")
+            if wave.dtype not in (torch.float32, torch.int16) or wave.dim() != 2:
+                raise ValueError("wave must be a 2-D float32 (or int16 PCM) tensor")
             wave = wave.contiguous()
             n_clips, n_samples = wave.shape
             frames = self.n_frames(n_samples)
             if out is None:
                 out = torch.empty((n_clips, frames, self.n_out), dtype=torch.float32, device=wave.device)
             stream = torch.cuda.current_stream(wave.device).cuda_stream
+            fwd = self._lib.cmoop_mfcc_fwd_dev if wave.dtype == torch.float32 else self._lib.cmoop_mfcc_fwd_dev_i16
             with torch.cuda.device(wave.device):
-                _lib.check(self._lib.cmoop_mfcc_fwd_dev(self._handle, C.c_void_p(wave.data_ptr()), n_clips, n_samples,
-                                                        C.c_void_p(out.data_ptr()), C.c_void_p(stream)),
-                           "cmoop_mfcc_fwd_dev")
+                _lib.check(fwd(self._handle, C.c_void_p(wave.data_ptr()), n_clips, n_samples,
+                               C.c_void_p(out.data_ptr()), C.c_void_p(stream)), "cmoop_mfcc_fwd_dev")
             return out
         if torch is not None and isinstance(wave, torch.Tensor):
             wave = wave.numpy()
-        wave = np.ascontiguousarray(wave, np.float32)
+        pcm = np.asarray(wave).dtype == np.int16                   # 16-bit PCM: x = sample / 32768, half the PCIe bytes
+        wave = np.ascontiguousarray(wave, np.int16 if pcm else np.float32)
         if wave.ndim != 2:
             raise ValueError("wave must be 2-D (n_clips, n_samples)")
         n_clips, n_samples = wave.shape
         frames = self.n_frames(n_samples)
         if out is None:
             out = np.empty((n_clips, frames, self.n_out), np.float32)
-        _lib.check(self._lib.cmoop_mfcc_fwd_host(self._handle, _lib.ptr(wave), n_clips, n_samples, _lib.ptr(out)),
-                   "cmoop_mfcc_fwd_host")
+        fwd = self._lib.cmoop_mfcc_fwd_host_i16 if pcm else self._lib.cmoop_mfcc_fwd_host
+        _lib.check(fwd(self._handle, _lib.ptr(wave), n_clips, n_samples, _lib.ptr(out)), "cmoop_mfcc_fwd_host")
         return out
 
     def close(self):

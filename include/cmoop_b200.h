@@ -159,6 +159,11 @@ int cmoop_mfcc_fwd_dev(cmoop_mfcc_handle h, const float* wave, int64_t n_clips, 
                        void* stream);
 /* host buffers (pinned or pageable); copies are chunked and overlapped with compute */
 int cmoop_mfcc_fwd_host(cmoop_mfcc_handle h, const float* wave, int64_t n_clips, int n_samples, float* out);
+/* 16-bit PCM waveforms (x = sample / 32768, the content of a wav file; SURVEY.md section 8a-1 "fp32 (or int16)"): same
+ * features as the fp32 entry points on the widened samples, half the host->device bytes */
+int cmoop_mfcc_fwd_dev_i16(cmoop_mfcc_handle h, const int16_t* wave, int64_t n_clips, int n_samples, float* out,
+                           void* stream);
+int cmoop_mfcc_fwd_host_i16(cmoop_mfcc_handle h, const int16_t* wave, int64_t n_clips, int n_samples, float* out);
 /* optional fused per-feature standardisation (prepare_dataset, nsga_penalty.py:102-114):
  * out = (out - mean[f]) / scale[f]; pass NULL/NULL to disable. mean/scale are host fp32 [n_out]. */
 int cmoop_mfcc_set_standardise(cmoop_mfcc_handle h, const float* mean, const float* scale);

@@ -171,3 +171,23 @@ def test_generic_front_end_birdclef_shape_and_other_fft_sizes():
         got = fe(small)
         assert got.shape == want.shape
         _check_features(got, want)
+
+
+def test_mfcc_int16_pcm_input():
+    """16-bit PCM entry points (cmoop_mfcc_fwd_{host,dev}_i16): features of sample / 32768, the widening is exact, so
+    the result must equal the fp32 path on the widened waveform bit for bit and meet the oracle tolerance."""
+    import torch
+    from cmoop_audio_processing_b200 import synth
+    from cmoop_audio_processing_b200.features import MfccFrontEnd
+    wave, _ = synth.make_clips(37, 12, seed=5)
+    pcm = np.clip(np.round(wave * 32767.0), -32768, 32767).astype(np.int16)
+    widened = pcm.astype(np.float32) / 32768.0
+    fe = MfccFrontEnd()
+    got_host = fe(pcm)
+    np.testing.assert_array_equal(got_host, fe(widened))
+    _check_features(got_host, mfcc_ref.mfcc(widened))
+    got_dev = fe(torch.from_numpy(pcm).cuda())
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(got_dev.cpu().numpy(), got_host)
+    odd = np.ascontiguousarray(pcm[:3, :15999])                    # unaligned rows exercise the scalar tail of the widening
+    np.testing.assert_array_equal(fe(odd), fe(odd.astype(np.float32) / 32768.0))
