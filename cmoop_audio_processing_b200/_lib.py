@@ -67,7 +67,10 @@ SIGNATURES = {
     "cmoop_mfcc_set_standardise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cmoop_cnn_dataset_create_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                                 C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "cmoop_cnn_dataset_create_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                               C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "cmoop_cnn_dataset_destroy": (C.c_int, [C.c_void_p]),
+    "cmoop_feature_stats_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cmoop_cnn_param_count": (C.c_longlong, [C.c_void_p, C.c_void_p]),
     "cmoop_cnn_pop_train_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                            C.c_void_p]),

@@ -920,6 +920,32 @@ int cmoop_cnn_dataset_create_host(const float* x_train, const int* y_train, int 
     return CMOOP_OK;
 }
 
+int cmoop_cnn_dataset_create_dev(const float* x_train_dev, const int* y_train, int n_train, const float* x_val_dev,
+                                 const int* y_val, int n_val, int height, int width, void* stream,
+                                 cmoop_cnn_dataset_handle* out) {
+    CMOOP_REQUIRE(out && x_train_dev && y_train && x_val_dev && y_val, "cnn_dataset: null pointer");
+    CMOOP_REQUIRE(n_train > 0 && n_val > 0 && height > 0 && width > 0, "cnn_dataset: empty split or bad shape");
+    *out = nullptr;
+    if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
+    cmoop_cnn_dataset* d = new cmoop_cnn_dataset();
+    d->n_train = n_train; d->n_val = n_val; d->H = height; d->W = width;
+    const size_t img = (size_t)height * width * sizeof(float);
+    if (cudaMalloc((void**)&d->x_train, img * n_train) != cudaSuccess || cudaMalloc((void**)&d->y_train, sizeof(int) * n_train) != cudaSuccess ||
+        cudaMalloc((void**)&d->x_val, img * n_val) != cudaSuccess || cudaMalloc((void**)&d->y_val, sizeof(int) * n_val) != cudaSuccess) {
+        cmoop::set_error("cnn_dataset: cudaMalloc failed");
+        cmoop_cnn_dataset_destroy(d);
+        return CMOOP_ERR_CUDA;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CMOOP_CUDA_OK(cudaMemcpyAsync(d->x_train, x_train_dev, img * n_train, cudaMemcpyDeviceToDevice, st));
+    CMOOP_CUDA_OK(cudaMemcpyAsync(d->x_val, x_val_dev, img * n_val, cudaMemcpyDeviceToDevice, st));
+    CMOOP_CUDA_OK(cudaMemcpyAsync(d->y_train, y_train, sizeof(int) * n_train, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cudaMemcpyAsync(d->y_val, y_val, sizeof(int) * n_val, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+    *out = d;
+    return CMOOP_OK;
+}
+
 long long cmoop_cnn_param_count(const cmoop_genotype* g, const cmoop_cnn_config* cfg) {
     if (!g || check_config(g, 1, cfg) != CMOOP_OK) return -1;
     Cand c;

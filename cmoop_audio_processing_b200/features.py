@@ -105,6 +105,52 @@ class MfccFrontEnd:
             pass
 
 
+def feature_stats(feats):
+    """StandardScaler statistics of a CUDA feature tensor (..., F): per-feature mean and population variance over all
+    leading axes (prepare_dataset, nsga_penalty.py:102-114), computed on the device in fp64.  Returns numpy float64."""
+    import torch
+    lib = _lib.load()
+    if not (isinstance(feats, torch.Tensor) and feats.is_cuda and feats.dtype == torch.float32):
+        raise ValueError("feats must be a float32 CUDA tensor")
+    flat = feats.contiguous().reshape(-1, feats.shape[-1])
+    mean, var = np.empty(flat.shape[1], np.float64), np.empty(flat.shape[1], np.float64)
+    with torch.cuda.device(flat.device):
+        _lib.check(lib.cmoop_feature_stats_dev(C.c_void_p(flat.data_ptr()), flat.shape[0], flat.shape[1], _lib.ptr(mean),
+                                               _lib.ptr(var), C.c_void_p(torch.cuda.current_stream(flat.device).cuda_stream)),
+                   "cmoop_feature_stats_dev")
+    return mean, var
+
+
+def prepare_dataset_device(front_end: "MfccFrontEnd", splits, policy: str = "fit_train"):
+    """Waveforms -> standardised features without leaving the GPU.
+
+    ``splits``: CUDA waveform tensors (float32 or int16 PCM), training split first.  ``policy`` is the reference's scaler
+    handling: ``"fit_train"`` -- fit on the training split, transform the others
+    (mobo_penalty.py:69-79, sa_nsga_local.py:52-60); ``"fit_each"`` -- fit_transform every split separately
+    (nsga_penalty.py:111,124,137); ``"none"`` (sa_nsga_penalty.py).  The statistics come from one un-scaled pass
+    (cmoop_feature_stats_dev), the scaled features from a second pass with the scaler fused into the kernel epilogue.
+    Returns the list of (N, T, F) CUDA tensors, ready for ``FitnessProblem`` / ``CnnDataset``.
+    """
+    if policy not in ("fit_train", "fit_each", "none"):
+        raise ValueError("policy must be 'fit_train', 'fit_each' or 'none'")
+    front_end.set_standardise(None, None)
+    if policy == "none":
+        return [front_end(w) for w in splits]
+    out, stats = [], None
+    for i, w in enumerate(splits):
+        if policy == "fit_each" or i == 0:
+            raw = front_end(w)
+            mean, var = feature_stats(raw)
+            del raw
+            scale = np.sqrt(var)
+            scale[scale == 0.0] = 1.0                                   # sklearn _handle_zeros_in_scale
+            stats = (mean.astype(np.float32), scale.astype(np.float32))
+        front_end.set_standardise(*stats)
+        out.append(front_end(w))
+        front_end.set_standardise(None, None)
+    return out
+
+
 def mfcc(wave, config: MfccConfig = MfccConfig()):
     """One-shot convenience wrapper."""
     fe = MfccFrontEnd(config)

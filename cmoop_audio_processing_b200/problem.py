@@ -122,6 +122,9 @@ class DeviceDataset:
     def __init__(self, x_train, y_train, x_val, y_val):
         self._lib = _lib.load()
         _lib.bind_device()
+        if hasattr(x_train, "is_cuda") and x_train.is_cuda:
+            self._init_from_device(x_train, y_train, x_val, y_val)
+            return
         xt = np.ascontiguousarray(np.asarray(x_train, np.float32).reshape(len(x_train), *np.shape(x_train)[1:3]))
         xv = np.ascontiguousarray(np.asarray(x_val, np.float32).reshape(len(x_val), *np.shape(x_val)[1:3]))
         yt = np.ascontiguousarray(np.asarray(y_train).reshape(-1), np.int32)
@@ -134,6 +137,29 @@ class DeviceDataset:
         _lib.check(self._lib.cmoop_cnn_dataset_create_host(_lib.ptr(xt), _lib.ptr(yt), self.n_train, _lib.ptr(xv),
                                                            _lib.ptr(yv), self.n_val, self.height, self.width,
                                                            C.byref(handle)), "cmoop_cnn_dataset_create_host")
+        self._handle = handle
+
+    def _init_from_device(self, x_train, y_train, x_val, y_val):
+        """Features that already live on the GPU (CUDA torch tensors (N, H, W[, 1]) float32, e.g. straight out of
+        MfccFrontEnd): device-to-device copies, the feature tensors never touch the host."""
+        import torch
+        if not (x_val.is_cuda and x_train.dtype == torch.float32 and x_val.dtype == torch.float32):
+            raise ValueError("device features must be float32 CUDA tensors")
+        xt = x_train.reshape(x_train.shape[0], x_train.shape[1], x_train.shape[2]).contiguous()
+        xv = x_val.reshape(x_val.shape[0], x_val.shape[1], x_val.shape[2]).contiguous()
+        if xt.shape[1:] != xv.shape[1:]:
+            raise ValueError("train and validation features differ in shape")
+        to_np = lambda y: np.ascontiguousarray((y.cpu().numpy() if hasattr(y, "cpu") else np.asarray(y)).reshape(-1), np.int32)
+        yt, yv = to_np(y_train), to_np(y_val)
+        self.n_train, self.height, self.width = (int(v) for v in xt.shape)
+        self.n_val = int(xv.shape[0])
+        stream = torch.cuda.current_stream(xt.device).cuda_stream
+        handle = C.c_void_p()
+        with torch.cuda.device(xt.device):
+            _lib.check(self._lib.cmoop_cnn_dataset_create_dev(C.c_void_p(xt.data_ptr()), _lib.ptr(yt), self.n_train,
+                                                              C.c_void_p(xv.data_ptr()), _lib.ptr(yv), self.n_val, self.height,
+                                                              self.width, C.c_void_p(stream), C.byref(handle)),
+                       "cmoop_cnn_dataset_create_dev")
         self._handle = handle
 
     def close(self):

@@ -167,6 +167,10 @@ int cmoop_mfcc_fwd_host_i16(cmoop_mfcc_handle h, const int16_t* wave, int64_t n_
 /* optional fused per-feature standardisation (prepare_dataset, nsga_penalty.py:102-114):
  * out = (out - mean[f]) / scale[f]; pass NULL/NULL to disable. mean/scale are host fp32 [n_out]. */
 int cmoop_mfcc_set_standardise(cmoop_mfcc_handle h, const float* mean, const float* scale);
+/* StandardScaler statistics (prepare_dataset, nsga_penalty.py:102-114: per feature over feats.reshape(-1, F), population
+ * variance) of a DEVICE-resident feature tensor [rows][n_features] fp32; fp64 two-pass, deterministic.  mean/var: host. */
+int cmoop_feature_stats_dev(const float* feats, int64_t rows, int n_features, double* mean_host, double* var_host,
+                            void* stream);
 
 /* ------------------------------------------------------------------ (2) candidate-CNN train + score
  * Replaces build_model / evaluate_individual / the serial loop of compute_objectives_and_constraints
@@ -210,6 +214,11 @@ typedef struct cmoop_cnn_dataset* cmoop_cnn_dataset_handle;
 int cmoop_cnn_dataset_create_host(const float* x_train, const int* y_train, int n_train, const float* x_val,
                                   const int* y_val, int n_val, int height, int width,
                                   cmoop_cnn_dataset_handle* out);
+/* the same with DEVICE-resident features (e.g. straight out of cmoop_mfcc_fwd_dev): device-to-device copies on `stream`;
+ * labels stay host pointers */
+int cmoop_cnn_dataset_create_dev(const float* x_train_dev, const int* y_train, int n_train, const float* x_val_dev,
+                                 const int* y_val, int n_val, int height, int width, void* stream,
+                                 cmoop_cnn_dataset_handle* out);
 int cmoop_cnn_dataset_destroy(cmoop_cnn_dataset_handle h);
 long long cmoop_cnn_param_count(const cmoop_genotype* g, const cmoop_cnn_config* cfg);
 int cmoop_cnn_pop_train_eval(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotypes, const uint64_t* seeds,

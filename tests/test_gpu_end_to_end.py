@@ -89,3 +89,40 @@ def test_run_mobo_loop(kws_features):
     assert np.all((x_vec >= 0) & (x_vec <= 1))
     for hp, objs, cv in pareto:
         assert cv <= 1e-8
+
+
+def test_device_resident_dataset_staging():
+    """waveforms -> MFCC -> StandardScaler statistics -> standardised features -> CNN dataset without a
+    host round trip.  Statistics vs NumPy float64, scaled features vs the oracle for the three scaler policies of the
+    reference scripts, and a population evaluated from the device-resident dataset equals the host-staged one bit for bit."""
+    import torch
+    from cmoop_audio_processing_b200 import synth
+    from cmoop_audio_processing_b200.features import MfccFrontEnd, feature_stats, prepare_dataset_device
+    from cmoop_audio_processing_b200.problem import FitnessProblem, TrainConfig
+    from oracle import mfcc_ref
+
+    wave, labels = synth.make_clips(96 + 48, 12, seed=21)
+    w_tr, w_va = torch.from_numpy(wave[:96]).cuda(), torch.from_numpy(wave[96:]).cuda()
+    fe = MfccFrontEnd()
+    raw = fe(w_tr)
+    mean, var = feature_stats(raw)
+    flat = raw.cpu().numpy().astype(np.float64).reshape(-1, 40)
+    np.testing.assert_allclose(mean, flat.mean(axis=0), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(var, flat.var(axis=0), rtol=1e-11)
+    base_tr, base_va = mfcc_ref.mfcc(wave[:96]), mfcc_ref.mfcc(wave[96:])
+    want_tr, m, s = mfcc_ref.standardise(base_tr)
+    for policy, want_va in (("fit_train", mfcc_ref.standardise(base_va, m, s)[0]), ("fit_each", mfcc_ref.standardise(base_va)[0]),
+                            ("none", base_va)):
+        x_tr, x_va = prepare_dataset_device(fe, [w_tr, w_va], policy)
+        assert x_tr.is_cuda and x_tr.shape == (96, 49, 40)
+        assert np.abs(x_va.cpu().numpy() - want_va).max() < (2e-4 if policy != "none" else 2e-3)
+        if policy != "none":
+            assert np.abs(x_tr.cpu().numpy() - want_tr).max() < 2e-4
+    x_tr, x_va = prepare_dataset_device(fe, [w_tr, w_va], "fit_train")
+    hps = [dict(filters=16, kernel_size=3, use_bn=True, residual_blocks=1, fc_layers=1, use_dropout=False),
+           dict(filters=32, kernel_size=5, use_bn=False, residual_blocks=2, fc_layers=2, use_dropout=True)]
+    cfg = TrainConfig(variant="B", epochs=2, patience=2, precision="bf16")
+    dev = FitnessProblem(x_tr, labels[:96], x_va, labels[96:], classes=12, config=cfg).train_eval(hps, [3, 4])[0]
+    host = FitnessProblem(x_tr.cpu().numpy()[..., None], labels[:96], x_va.cpu().numpy()[..., None], labels[96:], classes=12,
+                          config=cfg).train_eval(hps, [3, 4])[0]
+    np.testing.assert_array_equal(dev, host)
