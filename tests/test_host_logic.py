@@ -105,3 +105,37 @@ def test_parallel_gp_fit_matches_sklearn():
     GaussianProcessRegressor(kernel=kernel(), n_restarts_optimizer=2, random_state=s1).fit(x[:24], ys[0][:24])
     fit_gprs_parallel([kernel()], x[:24], [ys[0][:24]], n_restarts_optimizer=2, random_state=s2)
     assert s1.uniform() == s2.uniform()
+
+
+def test_run_log_formats_round_trip(tmp_path):
+    """persistence.py: the reference's per-generation / Pareto table columns (nsga_penalty.py:700-763,785-820) and the
+    seeded initial population of psi_sa_nsga_local.py:255-269 (CV recomputed from the thresholds)."""
+    import random
+
+    from cmoop_audio_processing_b200 import persistence
+    from cmoop_audio_processing_b200.nsga import HPARAM_SPACE
+
+    rnd = random.Random(4)
+    pops = []
+    for gen in range(3):
+        pop = []
+        for _ in range(5):
+            hp = {k: rnd.choice(v) for k, v in HPARAM_SPACE.items()}
+            acc, size, fpr = rnd.uniform(0.7, 0.99), rnd.uniform(0.05, 4.0), rnd.uniform(0.0, 0.2)
+            cv = max(0, 0.9 - acc) + max(0, size - 2.5) + max(0, fpr - 0.09)
+            pop.append({"hparams": hp, "objs": [-acc, size, fpr], "CV": cv})
+        pops.append(pop)
+    frames = [persistence.generation_frame(g, p) for g, p in enumerate(pops)]
+    assert list(frames[0].columns) == ["Generation", "Accuracy", "Size_MB", "FPR", "CV"] + list(HPARAM_SPACE)
+    written = persistence.save_generations(frames, str(tmp_path / "all_generations.xlsx"))
+    back = persistence.load_generations(written)
+    assert len(back) == 3
+    for a, b in zip(frames, back):
+        assert (a["Accuracy"].to_numpy() - b["Accuracy"].to_numpy()).__abs__().max() < 1e-12
+        assert a["filters"].tolist() == b["filters"].tolist() and a["use_bn"].tolist() == [bool(v) for v in b["use_bn"]]
+    path = persistence.save_pareto_csv(pops[2], str(tmp_path / "final_pareto.csv"))
+    seeded = persistence.load_seed_population(path, 0.9, 2.5, 0.09)
+    for got, want in zip(seeded, pops[2]):
+        assert got["hparams"] == want["hparams"]
+        assert all(abs(x - y) < 1e-12 for x, y in zip(got["objs"], want["objs"]))
+        assert abs(got["CV"] - want["CV"]) < 1e-12
