@@ -183,7 +183,7 @@ class FitnessProblem:
 
     def __init__(self, x_train, y_train, x_val, y_val, *, classes: int, config: TrainConfig = TrainConfig(),
                  min_accuracy: float = 0.9, max_model_size: float = 2.5, max_fpr: float = 0.1,
-                 objectives=("neg_acc", "size", "fpr"), seed: int = 0):
+                 objectives=("neg_acc", "size", "fpr"), seed: int = 0, memoise: bool = False):
         self.data = x_train if isinstance(x_train, DeviceDataset) else DeviceDataset(x_train, y_train, x_val, y_val)
         self.classes = int(classes)
         self.config = config
@@ -191,6 +191,11 @@ class FitnessProblem:
         self.objectives = tuple(objectives)
         self.seed = int(seed)
         self.evaluations = 0            # true evaluations so far (also the seed counter)
+        # Opt-in: the genotype space has 288 points and the reference re-trains duplicates
+        # (keeping the last result, sa_nsga_penalty.py:325-327); with memoise=True a genotype is trained once per problem
+        # and repeated requests return the stored row.  It changes the evaluation count, hence off by default.
+        self.memoise = bool(memoise)
+        self._memo = {}
         self.last_details = None
         self._lib = _lib.load()
 
@@ -284,8 +289,18 @@ class FitnessProblem:
 
     def compute_objectives_and_constraints(self, population):
         """list[{'hparams','objs','CV'}] in input order -- nsga_penalty.py:418-442."""
-        out = self._sharded_train_eval(population)
-        self.evaluations += len(population)
+        if self.memoise:
+            keys = [tuple(sorted(hp.items())) for hp in population]
+            todo = [i for i, k in enumerate(keys) if k not in self._memo and k not in keys[:i]]
+            if todo:
+                rows = self._sharded_train_eval([population[i] for i in todo])
+                self.evaluations += len(todo)
+                for i, row in zip(todo, rows):
+                    self._memo[keys[i]] = np.array(row, np.float64)
+            out = np.stack([self._memo[k] for k in keys]) if keys else np.zeros((0, 6))
+        else:
+            out = self._sharded_train_eval(population)
+            self.evaluations += len(population)
         self.last_details = out
         results = []
         for ind, row in zip(population, out):

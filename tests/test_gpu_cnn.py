@@ -303,3 +303,20 @@ def test_birdclef_shaped_problem():
         assert np.isfinite(outs[prec]).all()
     np.testing.assert_array_equal(outs["bf16"][:, 1], outs["fp32"][:, 1])                    # size objective is exact
     assert np.abs(outs["bf16"][:, 4] - outs["fp32"][:, 4]).max() < 0.05                     # validation loss ~ ln(397)
+
+
+def test_memoised_evaluations_are_opt_in():
+    """with memoise=True a genotype is trained once; duplicates (within a call and across calls)
+    return the stored row and do not advance the evaluation counter.  The default keeps the reference's behaviour."""
+    from cmoop_audio_processing_b200.problem import FitnessProblem, TrainConfig
+    xt, yt, xv, yv = make_data(128, 64)
+    a, b = GENOTYPES[0][1], GENOTYPES[3][1]
+    cfg = TrainConfig(variant="B", epochs=1)
+    memo = FitnessProblem(xt, yt, xv, yv, classes=N_CLASSES, config=cfg, memoise=True)
+    r1 = memo.compute_objectives_and_constraints([a, b, dict(a)])
+    assert memo.evaluations == 2 and r1[0]["objs"] == r1[2]["objs"] and r1[0]["CV"] == r1[2]["CV"]
+    r2 = memo.compute_objectives_and_constraints([dict(b), a])
+    assert memo.evaluations == 2 and r2[0]["objs"] == r1[1]["objs"] and r2[1]["objs"] == r1[0]["objs"]
+    plain = FitnessProblem(xt, yt, xv, yv, classes=N_CLASSES, config=cfg)
+    plain.compute_objectives_and_constraints([a, b, dict(a)])
+    assert plain.evaluations == 3
