@@ -148,12 +148,24 @@ def _map_on_workers(payloads, n_workers):
     return results
 
 
-def default_workers() -> int:
+def _initialised_dist():
+    try:
+        import torch.distributed as dist
+    except ImportError:                                 # pragma: no cover
+        return None
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def default_workers(shared: bool = True) -> int:
+    """Worker processes for the optimiser starts: all host cores when this process is the only one fitting (rank 0 of a
+    distributed job broadcasts its optima), otherwise the cores divided by the local world size."""
     env = os.environ.get("CMOOP_GP_FIT_WORKERS")
     if env:
         return max(1, int(env))
-    world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
-    return max(1, min(32, (os.cpu_count() or 1) // world))      # every rank fits the (replicated) surrogate
+    world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))) if shared else 1
+    return max(1, min(32, (os.cpu_count() or 1) // world))
 
 
 def fit_gprs_parallel(kernels, x, ys, n_restarts_optimizer=0, normalize_y=False, random_state=None, max_workers=None,
@@ -177,16 +189,26 @@ def fit_gprs_parallel(kernels, x, ys, n_restarts_optimizer=0, normalize_y=False,
         jobs += [(len(probes) - 1, theta0) for theta0 in starts]
     payloads = [(kernels[m], x, ys[m], normalize_y, theta0) for m, theta0 in jobs]
 
-    workers = max_workers if max_workers is not None else default_workers()
-    workers = min(workers, len(jobs))
+    # Under torch.distributed the surrogate is replicated on every rank.  Every rank has drawn the
+    # same starts above (identically seeded streams stay in step), but only rank 0 optimises -- with all host cores -- and
+    # broadcasts the optima, instead of world_size ranks fitting the same models on a slice of the cores each.
+    dist = _initialised_dist()
+    rank0 = dist is None or dist.get_rank() == 0
     results = None
-    if workers > 1 and len(x) >= min_rows_for_pool:
-        try:
-            results = _map_on_workers(payloads, workers)
-        except Exception:                               # no subprocesses here (sandbox, frozen app): same maths in-process
-            results = None
-    if results is None:
-        results = [_optimise_start(pl) for pl in payloads]
+    if rank0:
+        workers = max_workers if max_workers is not None else default_workers(shared=dist is None)
+        workers = min(workers, len(jobs))
+        if workers > 1 and len(x) >= min_rows_for_pool:
+            try:
+                results = _map_on_workers(payloads, workers)
+            except Exception:                           # no subprocesses here (sandbox, frozen app): same maths in-process
+                results = None
+        if results is None:
+            results = [_optimise_start(pl) for pl in payloads]
+    if dist is not None:
+        box = [results]
+        dist.broadcast_object_list(box, src=0)
+        results = box[0]
 
     fitted = []
     for m, probe in enumerate(probes):

@@ -289,7 +289,7 @@ class FitnessProblem:
 
     def compute_objectives_and_constraints(self, population):
         """list[{'hparams','objs','CV'}] in input order -- nsga_penalty.py:418-442."""
-        if self.memoise:
+        if getattr(self, "memoise", False):
             keys = [tuple(sorted(hp.items())) for hp in population]
             todo = [i for i, k in enumerate(keys) if k not in self._memo and k not in keys[:i]]
             if todo:

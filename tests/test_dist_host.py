@@ -59,3 +59,33 @@ def test_sharded_evaluation_all_gathers_rows_gloo(tmp_path):
     # seeds follow the global candidate index, so results do not depend on the world size
     expect = [0.5 + 0.001 * (16 if i < 8 else 64) + 1e-4 * (5 + i) for i in range(13)]
     np.testing.assert_allclose(-a[:, 0], expect, rtol=0, atol=1e-12)
+
+
+def _gp_worker(rank, world, port, tmp):
+    import warnings
+
+    import torch.distributed as dist
+    warnings.filterwarnings("ignore")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), CMOOP_GP_FIT_WORKERS="1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sklearn.gaussian_process.kernels import ConstantKernel, Matern, WhiteKernel
+    from cmoop_audio_processing_b200.gp_fit import fit_gprs_parallel
+    rng = np.random.default_rng(0)
+    x = rng.random((30, 4)) * 4
+    ys = [np.sin(x[:, 0]) + 0.05 * rng.standard_normal(30), np.cos(x[:, 1])]
+    state = np.random.RandomState(9)
+    kernel = lambda: ConstantKernel(1.0) * Matern(length_scale=1.0, nu=1.5) + WhiteKernel(noise_level=0.1)   # noqa: E731
+    gprs = fit_gprs_parallel([kernel(), kernel()], x, ys, n_restarts_optimizer=2, random_state=state)
+    np.save(os.path.join(tmp, f"theta{rank}.npy"), np.array([g.kernel_.theta for g in gprs]))
+    np.save(os.path.join(tmp, f"next{rank}.npy"), np.array([state.uniform()]))
+    dist.destroy_process_group()
+
+
+def test_gp_fit_rank0_broadcast_gloo(tmp_path):
+    """The surrogate is replicated: every rank draws the same optimiser starts (streams stay in step) but rank 0 alone
+    optimises and broadcasts, so all ranks end with identical hyper-parameters."""
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_gp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    np.testing.assert_array_equal(np.load(tmp_path / "theta0.npy"), np.load(tmp_path / "theta1.npy"))
+    np.testing.assert_array_equal(np.load(tmp_path / "next0.npy"), np.load(tmp_path / "next1.npy"))
