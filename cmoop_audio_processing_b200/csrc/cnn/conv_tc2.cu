@@ -13,7 +13,7 @@
 //     phase clocks below it fetched the A operand at ~16 B/clk: 270 clk per UMMA whatever N.)  Loaded once per slab by
 //     256 producer threads with zero-filling 16-byte cp.async (padding, batch tail).
 //   * weights: pre-arranged and pre-swizzled per (slab, tap) as [cout][64 ch] rows of 128 B by wt_bf16_v2_kernel,
-//     16 KB stages of 128 / bn entries -> one 1-D bulk TMA each (cp.async.bulk + mbarrier), 4-deep ring, own warp.
+//     16 KB stages of 128 / bn entries -> one 1-D bulk TMA each (cp.async.bulk + mbarrier), P2_WS-deep ring, own warp.
 //   * one elected thread issues, per (slab, tap, 16-channel step), two UMMAs 128 x bn x 16 (the CTA's two 128-row
 //     tiles) into two TMEM accumulators; tcgen05.commit frees the weight stage / the patch buffer.
 //   * epilogue as in conv_tc.cu (tcgen05.ld, bias, ReLU, fp32 store, optional bf16 shadow); rows that are padding

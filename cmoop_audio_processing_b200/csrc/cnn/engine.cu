@@ -466,11 +466,13 @@ struct Engine {
                         p.dgamma = c.grad + u.bn_off; p.dbeta = c.grad + u.bn_off + u.cout;
                         p.stat_part = u.stat; p.bn = u.bn; p.bwd_part = u.bwd_part;
                     }
-                    p.dv = c.gA; p.du = c.gB;
-                    p.dskip = u.add_skip ? c.gS : nullptr;
+                    // a tensor-core unit's weight and data gradients read the bf16 gradient only
+                    const bool skip_tc = u.add_skip && c.units[u.skip_unit].tc;
+                    p.dv = c.gA; p.du = u.tc ? nullptr : c.gB;
+                    p.dskip = (u.add_skip && !skip_tc) ? c.gS : nullptr;
                     p.vh = u.post_fwd ? u.Vh : nullptr;
                     p.duh = u.tc ? c.gBh : nullptr;
-                    p.dskiph = (u.add_skip && c.units[u.skip_unit].tc) ? c.gSh : nullptr;
+                    p.dskiph = skip_tc ? c.gSh : nullptr;
                     p.H = u.Ho; p.W = u.Wo; p.C = u.cout; p.Ho = u.Po; p.Wo = u.Qo;
                     p.pool = u.pool; p.relu_mid = u.relu_mid; p.add_skip = u.add_skip; p.relu_in = u.relu_epi;
                     p.has_bn = u.has_bn;
@@ -491,7 +493,7 @@ struct Engine {
                     PostTask q = p;
                     q.block_begin = S.post_bwd.total;
                     S.post_bwd.h.push_back(q);
-                    S.post_bwd.total += blocks_for(u.u_elems / 4);
+                    S.post_bwd.total += blocks_for(u.u_elems / 8);
                 }
                 // ---- dense ReLU / dropout
                 if (u.dense && u.fc_index >= 0) {

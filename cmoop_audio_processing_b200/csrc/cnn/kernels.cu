@@ -601,15 +601,16 @@ __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const PostTask* __
     }
 }
 
-// backward of the whole post stage, dense over the conv-output grid; one thread = 4 channels of one input pixel
+// backward of the whole post stage, dense over the conv-output grid; one thread = 8 channels of one input pixel
+// (as post_fwd: index math amortised over 32 B, twice the loads in flight)
 __global__ void __launch_bounds__(256) post_bwd_apply_kernel(const PostTask* __restrict__ tasks, int n_tasks, int n_b) {
     const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin; });
     const PostTask T = tasks[t];
-    const int C4 = T.C >> 2;
-    const unsigned e4 = (unsigned)(blockIdx.x - T.block_begin) * 256u + threadIdx.x;      // 32-bit index math (see post_fwd)
-    if (e4 >= (unsigned)n_b * T.H * T.W * C4) return;
-    const unsigned pix = e4 / (unsigned)C4;
-    const int c = (int)(e4 - pix * C4) * 4;
+    const int C8 = T.C >> 3;
+    const unsigned e8 = (unsigned)(blockIdx.x - T.block_begin) * 256u + threadIdx.x;      // 32-bit index math (see post_fwd)
+    if (e8 >= (unsigned)n_b * T.H * T.W * C8) return;
+    const unsigned pix = e8 / (unsigned)C8;
+    const int c = (int)(e8 - pix * C8) * 8;
     const long long e = (long long)pix * T.C + c;
     const unsigned r1 = pix / (unsigned)T.W;
     const int wi = (int)(pix - r1 * T.W);
@@ -617,49 +618,66 @@ __global__ void __launch_bounds__(256) post_bwd_apply_kernel(const PostTask* __r
     const int hi = (int)(r1 - (unsigned)n * T.H);
     long long oe = e;
     bool origin = true;
-    bool routed[4] = {true, true, true, true};
+    bool routed[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) routed[q] = true;
     if (T.pool) {
         const int ho = hi >> 1, wo = wi >> 1;
         oe = (((long long)n * T.Ho + ho) * T.Wo + wo) * T.C + c;
         origin = ((hi & 1) == 0) && ((wi & 1) == 0);
-        const uchar4 cd = *reinterpret_cast<const uchar4*>(T.idx + oe);
-        const unsigned char me = (unsigned char)((hi & 1) * 2 + (wi & 1));
-        routed[0] = cd.x == me; routed[1] = cd.y == me; routed[2] = cd.z == me; routed[3] = cd.w == me;
-    }
-    const float4 gv = ld4(T.dv + oe);
-    float g[4] = {gv.x, gv.y, gv.z, gv.w};
-    if (T.add_skip) {
-        const float4 vv = ld4(T.v + oe);
-        if (!(vv.x > 0.f)) g[0] = 0.f;
-        if (!(vv.y > 0.f)) g[1] = 0.f;
-        if (!(vv.z > 0.f)) g[2] = 0.f;
-        if (!(vv.w > 0.f)) g[3] = 0.f;
-        if (origin && T.dskip) {
-            const float4 gs = make_float4(g[0], g[1], g[2], g[3]);
-            *reinterpret_cast<float4*>(T.dskip + oe) = gs;
-            if (T.dskiph) *reinterpret_cast<uint2*>(T.dskiph + oe) = bf16x4(gs);
-        }
-    }
-    const float4 uv = ld4(T.u + e);
-    const float u[4] = {uv.x, uv.y, uv.z, uv.w};
-    float du[4];
-    if (T.has_bn) {
-        const float4 mean = ld4(T.bn + 0 * T.C + c), invstd = ld4(T.bn + 1 * T.C + c);
-        const float4 scale = ld4(T.bn + 2 * T.C + c), shift = ld4(T.bn + 3 * T.C + c);
-        const float4 mg = ld4(T.bn + 4 * T.C + c), mgx = ld4(T.bn + 5 * T.C + c);
-        const float mu[4] = {mean.x, mean.y, mean.z, mean.w}, is[4] = {invstd.x, invstd.y, invstd.z, invstd.w};
-        const float sc[4] = {scale.x, scale.y, scale.z, scale.w}, sh[4] = {shift.x, shift.y, shift.z, shift.w};
-        const float a4[4] = {mg.x, mg.y, mg.z, mg.w}, b4[4] = {mgx.x, mgx.y, mgx.z, mgx.w};
+        const uint2 cd = *reinterpret_cast<const uint2*>(T.idx + oe);
+        const unsigned me = (unsigned)((hi & 1) * 2 + (wi & 1));
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            float gq = routed[q] ? g[q] : 0.f;
-            if (T.relu_mid && !(fmaf(u[q], sc[q], sh[q]) > 0.f)) gq = 0.f;
-            const float xhat = (u[q] - mu[q]) * is[q];
-            du[q] = sc[q] * (gq - a4[q] - xhat * b4[q]);
+            routed[q] = ((cd.x >> (8 * q)) & 0xffu) == me;
+            routed[4 + q] = ((cd.y >> (8 * q)) & 0xffu) == me;
+        }
+    }
+    const float4 g0 = ld4(T.dv + oe), g1 = ld4(T.dv + oe + 4);
+    float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    if (T.add_skip) {
+        const float4 v0 = ld4(T.v + oe), v1 = ld4(T.v + oe + 4);
+        const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (!(vv[q] > 0.f)) g[q] = 0.f;
+        if (origin) {       // the tensor-core consumers read only the bf16 copy: the fp32 one is then not written at all
+            const float4 s0 = make_float4(g[0], g[1], g[2], g[3]), s1 = make_float4(g[4], g[5], g[6], g[7]);
+            if (T.dskip) {
+                *reinterpret_cast<float4*>(T.dskip + oe) = s0;
+                *reinterpret_cast<float4*>(T.dskip + oe + 4) = s1;
+            }
+            if (T.dskiph) {
+                const uint2 h0 = bf16x4(s0), h1 = bf16x4(s1);
+                *reinterpret_cast<uint4*>(T.dskiph + oe) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+            }
+        }
+    }
+    const float4 u0 = ld4(T.u + e), u1 = ld4(T.u + e + 4);
+    const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    float du[8];
+    if (T.has_bn) {
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int ch = c + 4 * h2;
+            const float4 mean = ld4(T.bn + 0 * T.C + ch), invstd = ld4(T.bn + 1 * T.C + ch);
+            const float4 scale = ld4(T.bn + 2 * T.C + ch), shift = ld4(T.bn + 3 * T.C + ch);
+            const float4 mg = ld4(T.bn + 4 * T.C + ch), mgx = ld4(T.bn + 5 * T.C + ch);
+            const float mu[4] = {mean.x, mean.y, mean.z, mean.w}, is[4] = {invstd.x, invstd.y, invstd.z, invstd.w};
+            const float sc[4] = {scale.x, scale.y, scale.z, scale.w}, sh[4] = {shift.x, shift.y, shift.z, shift.w};
+            const float a4[4] = {mg.x, mg.y, mg.z, mg.w}, b4[4] = {mgx.x, mgx.y, mgx.z, mgx.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = 4 * h2 + q;
+                float gq = routed[j] ? g[j] : 0.f;
+                if (T.relu_mid && !(fmaf(u[j], sc[q], sh[q]) > 0.f)) gq = 0.f;
+                const float xhat = (u[j] - mu[q]) * is[q];
+                du[j] = sc[q] * (gq - a4[q] - xhat * b4[q]);
+            }
         }
     } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 8; ++q) {
             float gq = routed[q] ? g[q] : 0.f;
             if (T.relu_mid && !(u[q] > 0.f)) gq = 0.f;
             du[q] = gq;
@@ -667,12 +685,18 @@ __global__ void __launch_bounds__(256) post_bwd_apply_kernel(const PostTask* __r
     }
     if (T.relu_in) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < 8; ++q)
             if (!(u[q] > 0.f)) du[q] = 0.f;
     }
-    const float4 out = make_float4(du[0], du[1], du[2], du[3]);
-    *reinterpret_cast<float4*>(T.du + e) = out;
-    if (T.duh) *reinterpret_cast<uint2*>(T.duh + e) = bf16x4(out);
+    const float4 o0 = make_float4(du[0], du[1], du[2], du[3]), o1 = make_float4(du[4], du[5], du[6], du[7]);
+    if (T.du) {
+        *reinterpret_cast<float4*>(T.du + e) = o0;
+        *reinterpret_cast<float4*>(T.du + e + 4) = o1;
+    }
+    if (T.duh) {
+        const uint2 h0 = bf16x4(o0), h1 = bf16x4(o1);
+        *reinterpret_cast<uint4*>(T.duh + e) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
