@@ -49,6 +49,11 @@ SIGNATURES = {
     "cmoop_gp_destroy": (C.c_int, [C.c_void_p]),
     "cmoop_gp_predict_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "cmoop_gp_predict_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cmoop_gp_lml_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                      C.c_int, C.POINTER(C.c_void_p)]),
+    "cmoop_gp_lml_destroy": (C.c_int, [C.c_void_p]),
+    "cmoop_gp_lml_n_theta": (C.c_int, [C.c_void_p]),
+    "cmoop_gp_lml_eval": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cmoop_hypervolume_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cmoop_hypervolume_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                         C.c_void_p]),

@@ -14,6 +14,13 @@ subprocesses fed pickles over pipes -- not ``multiprocessing`` children -- so no
 re-imported (the reference's drivers run at import time, and the parent owns a CUDA context).  With a fixed
 ``random_state`` the fitted models equal those of ``GaussianProcessRegressor.fit`` (same log-marginal likelihood and
 predictions; tests/test_host_logic.py).  Small problems stay in-process.
+
+``backend="device"`` (or ``CMOOP_GP_FIT_BACKEND=device``) keeps SciPy's L-BFGS-B and the start order but evaluates the
+objective -- log-marginal likelihood and gradient -- with ``cmoop_gp_lml_eval`` (csrc/gp_lml.cu): one optimiser thread per
+start, the chains advancing in lock step so that each round of objective requests (44 for a surrogate update) is one
+kernel launch with one CTA per request.  The
+device objective agrees with scikit-learn's to ~1e-10 relative, not bit for bit, so the optima can differ in the last
+digits: it is opt-in, and kernels other than the reference's two forms stay on the host.
 """
 from __future__ import annotations
 
@@ -46,6 +53,123 @@ def _optimise_start(payload):
 
     theta_opt, fval = w._constrained_optimization(obj_func, theta0, w.kernel_.bounds)
     return np.asarray(theta_opt, np.float64), float(fval)
+
+
+def device_kernel_spec(kernel):
+    """(kind, nu) when gp_lml.cu evaluates this kernel -- ``C * Matern + WhiteKernel`` (kind 0, theta = log c, log l, log
+    noise) or a bare ``Matern`` (kind 1), isotropic, nothing fixed -- else None."""
+    from sklearn.gaussian_process.kernels import ConstantKernel, Matern, Product, Sum, WhiteKernel
+
+    def matern_ok(k):
+        return (isinstance(k, Matern) and np.ndim(k.length_scale) == 0 and k.nu in (0.5, 1.5, 2.5)
+                and not isinstance(k.length_scale_bounds, str))
+
+    if matern_ok(kernel):
+        return 1, float(kernel.nu)
+    if (isinstance(kernel, Sum) and isinstance(kernel.k1, Product) and isinstance(kernel.k2, WhiteKernel)
+            and isinstance(kernel.k1.k1, ConstantKernel) and matern_ok(kernel.k1.k2)
+            and not isinstance(kernel.k1.k1.constant_value_bounds, str)
+            and not isinstance(kernel.k2.noise_level_bounds, str)):
+        return 0, float(kernel.k1.k2.nu)
+    return None
+
+
+class _LockStepObjective:
+    """One objective request per live optimiser chain, evaluated together: the chains (threads running SciPy's L-BFGS-B)
+    block in ``evaluate`` until every live chain has asked, then ONE ``cmoop_gp_lml_eval`` launch serves them all (one CTA
+    per request).  A chain that has converged retires and no longer counts."""
+
+    def __init__(self, lib, handle, targets, n_theta):
+        self.lib, self.handle, self.targets, self.n_theta = lib, handle, targets, n_theta
+        self.cv = threading.Condition()
+        self.live = len(targets)
+        self.pending, self.results = {}, {}
+        self.error = None
+        self.rounds = self.requests = 0
+
+    def _flush(self):
+        from . import _lib
+
+        slots = sorted(self.pending)
+        self.rounds += 1
+        self.requests += len(slots)
+        thetas = np.ascontiguousarray([self.pending[s] for s in slots], np.float64)
+        target = np.ascontiguousarray([self.targets[s] for s in slots], np.int32)
+        lml, grad = np.empty(len(slots)), np.empty((len(slots), self.n_theta))
+        try:        # scratch slots are interchangeable: request k of this round uses slot k
+            _lib.check(self.lib.cmoop_gp_lml_eval(self.handle, 0, len(slots), _lib.ptr(thetas), _lib.ptr(target),
+                                                  _lib.ptr(lml), _lib.ptr(grad)), "cmoop_gp_lml_eval")
+        except Exception as exc:
+            self.error = exc
+        for k, s in enumerate(slots):
+            self.results[s] = (float(lml[k]), grad[k].copy())
+        self.pending.clear()
+        self.cv.notify_all()
+
+    def evaluate(self, slot, theta):
+        with self.cv:
+            self.pending[slot] = np.array(theta, np.float64)
+            if len(self.pending) == self.live:
+                self._flush()
+            while slot not in self.results:
+                self.cv.wait()
+            if self.error is not None:
+                raise self.error
+            return self.results.pop(slot)
+
+    def retire(self):
+        with self.cv:
+            self.live -= 1
+            if self.pending and len(self.pending) == self.live:
+                self._flush()
+
+
+def _optimise_on_device(probes, jobs):
+    """Every (model, start) job optimised by SciPy L-BFGS-B (scikit-learn's ``_constrained_optimization``) on the device
+    objective; returns [(theta_opt, -lml)] in job order, or None when a kernel has no device form."""
+    import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+
+    from sklearn.gaussian_process import GaussianProcessRegressor
+
+    from . import _lib
+
+    specs = {device_kernel_spec(p.kernel_) for p in probes}
+    if len(specs) != 1 or None in specs or any(np.ndim(p.y_train_) != 1 for p in probes):
+        return None
+    kind, nu = next(iter(specs))
+    lib = _lib.load()
+    _lib.bind_device()
+    x = np.ascontiguousarray(probes[0].X_train_, np.float64)
+    ys = np.ascontiguousarray(np.stack([p.y_train_ for p in probes]), np.float64)
+    handle = C.c_void_p()
+    _lib.check(lib.cmoop_gp_lml_create(_lib.ptr(x), x.shape[0], x.shape[1], _lib.ptr(ys), ys.shape[0], kind, nu,
+                                       float(probes[0].alpha), len(jobs), C.byref(handle)), "cmoop_gp_lml_create")
+    objective = _LockStepObjective(lib, handle, [m for m, _ in jobs], lib.cmoop_gp_lml_n_theta(handle))
+    driver = GaussianProcessRegressor(optimizer="fmin_l_bfgs_b")      # only its _constrained_optimization is used
+
+    def run(slot):
+        m, theta0 = jobs[slot]
+
+        def obj_func(theta, eval_gradient=True):
+            lml, grad = objective.evaluate(slot, theta)
+            return (-lml, -grad) if eval_gradient else -lml
+
+        try:
+            theta_opt, fval = driver._constrained_optimization(obj_func, theta0, probes[m].kernel_.bounds)
+        finally:
+            objective.retire()
+        return np.asarray(theta_opt, np.float64), float(fval)
+
+    try:
+        with ThreadPoolExecutor(max_workers=len(jobs)) as pool:      # every chain needs its own thread: they meet in evaluate
+            return list(pool.map(run, range(len(jobs))))
+    finally:
+        lib.cmoop_gp_lml_destroy(handle)
+        LAST_DEVICE_FIT.update(rounds=objective.rounds, requests=objective.requests, chains=len(jobs))
+
+
+LAST_DEVICE_FIT: dict = {}       # launches / objective requests of the most recent device-backed fit (diagnostics)
 
 
 # ---- worker side: length-prefixed pickles on stdin / stdout -------------------------------------------------------
@@ -169,7 +293,7 @@ def default_workers(shared: bool = True) -> int:
 
 
 def fit_gprs_parallel(kernels, x, ys, n_restarts_optimizer=0, normalize_y=False, random_state=None, max_workers=None,
-                      min_rows_for_pool=64):
+                      min_rows_for_pool=64, backend=None):
     """Fitted ``GaussianProcessRegressor`` per (kernel, y) pair; see the module docstring."""
     from sklearn.gaussian_process import GaussianProcessRegressor
     from sklearn.utils import check_random_state
@@ -195,7 +319,12 @@ def fit_gprs_parallel(kernels, x, ys, n_restarts_optimizer=0, normalize_y=False,
     dist = _initialised_dist()
     rank0 = dist is None or dist.get_rank() == 0
     results = None
-    if rank0:
+    backend = backend or os.environ.get("CMOOP_GP_FIT_BACKEND", "host")
+    if backend not in ("host", "device"):
+        raise ValueError(f"unknown GP fit backend {backend!r} (host | device)")
+    if rank0 and backend == "device":
+        results = _optimise_on_device(probes, jobs)      # None: a kernel without a device form -> host schedule below
+    if rank0 and results is None:
         workers = max_workers if max_workers is not None else default_workers(shared=dist is None)
         workers = min(workers, len(jobs))
         if workers > 1 and len(x) >= min_rows_for_pool:

@@ -138,9 +138,12 @@ class SurrogateManager:
     onehot(use_bn), onehot(use_dropout)]; targets z-scored per model; training rows
     de-duplicated on the genotype keeping the last evaluation."""
 
-    def __init__(self, n_restarts_optimizer: int = 10, use_table: bool = True):
+    def __init__(self, n_restarts_optimizer: int = 10, use_table: bool = True, fit_backend: str | None = None):
+        """fit_backend: None (CMOOP_GP_FIT_BACKEND, default "host": scikit-learn's objective on the host cores) or
+        "device" (same optimiser and starts, objective evaluated by csrc/gp_lml.cu); see gp_fit.py."""
         import pandas as pd
 
+        self.fit_backend = fit_backend
         self.is_fitted = False
         self.categorical_features = list(CATEGORICAL)
         self.numerical_features = list(NUMERICAL)
@@ -196,7 +199,8 @@ class SurrogateManager:
             y_affine.append((scale, mean))
         # the reference fits the four regressors one after the other (sa_nsga_local.py:180-181,209); the optimiser starts
         # are independent, so they run concurrently here (fit_gprs_parallel) with unchanged arithmetic and RNG order
-        gprs = fit_gprs_parallel(kernels, x, ys, n_restarts_optimizer=self.n_restarts_optimizer)
+        gprs = fit_gprs_parallel(kernels, x, ys, n_restarts_optimizer=self.n_restarts_optimizer,
+                                 backend=getattr(self, "fit_backend", None))
         for key, gpr in zip(TARGET_KEYS, gprs):
             self.models[key] = gpr
         self._install(gprs, y_affine)
@@ -332,16 +336,16 @@ class _GroupMember:
 from .gp_fit import fit_gprs_parallel  # noqa: E402  (re-exported: the concurrent multi-start GP fit)
 
 
-def train_gps(X, Y):
+def train_gps(X, Y, backend=None):
     """One GaussianProcessRegressor(Matern(nu=2.5), normalize_y=True) per column of Y
-    (mobo_penalty.py:252-263); fitted by scikit-learn, uploaded as one device group."""
+    (mobo_penalty.py:252-263); fitted by scikit-learn (backend: see gp_fit.py), uploaded as one device group."""
     from sklearn.gaussian_process import GaussianProcessRegressor
     from sklearn.gaussian_process.kernels import Matern
 
     X = np.asarray(X, np.float64)
     Y = np.asarray(Y, np.float64)
     fitted = fit_gprs_parallel([Matern(nu=2.5) for _ in range(Y.shape[1])], X, [Y[:, dim] for dim in range(Y.shape[1])],
-                               n_restarts_optimizer=0, normalize_y=True)
+                               n_restarts_optimizer=0, normalize_y=True, backend=backend)
     group = DeviceGPGroup.from_sklearn(fitted)
     return [_GroupMember(group, i, g) for i, g in enumerate(fitted)]
 

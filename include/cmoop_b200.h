@@ -109,6 +109,26 @@ int cmoop_gp_destroy(cmoop_gp_handle h);
 int cmoop_gp_predict_host(cmoop_gp_handle h, const double* xq, int q, double* mean, double* std);
 int cmoop_gp_predict_dev(cmoop_gp_handle h, const double* xq, int q, double* mean, double* std, void* stream);
 
+/* ------------------------------------------------------------------ (3b) GP hyper-parameter objective
+ * Replaces GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient=True)
+ * (sklearn/gaussian_process/_gpr.py, the objective fit() hands to L-BFGS-B) for the fits in
+ *   SurrogateManager.update   ablation_study/sa_nsga_local.py:195-210 (4 models x 11 starts per generation)
+ *   train_gps                 mobo_penalty.py:252-263
+ * kind 0: C * Matern(l, nu) + WhiteKernel, theta = (log c, log l, log noise); kind 1: Matern(l, nu), theta = (log l).
+ * x [n][dim] and y [n_targets][n] (already normalised as scikit-learn's y_train_) are host arrays, copied once;
+ * jitter is GaussianProcessRegressor.alpha (1e-10).  A handle has `slots` independent evaluation slots, each with
+ * its own stream and scratch: calls on disjoint slot ranges may be issued concurrently from different host threads.
+ * lml = -inf and grad = 0 when K is not positive definite (scikit-learn's convention). */
+typedef struct cmoop_gp_lml* cmoop_gp_lml_handle;
+int cmoop_gp_lml_create(const double* x, int n, int dim, const double* y, int n_targets, int kind, double nu,
+                        double jitter, int slots, cmoop_gp_lml_handle* out);
+int cmoop_gp_lml_destroy(cmoop_gp_lml_handle h);
+int cmoop_gp_lml_n_theta(cmoop_gp_lml_handle h);
+/* evaluates `count` problems in slots [slot, slot + count): theta [count][n_theta], target [count] (row of y),
+ * lml [count], grad [count][n_theta]; blocks the calling thread until the results are on the host */
+int cmoop_gp_lml_eval(cmoop_gp_lml_handle h, int slot, int count, const double* theta, const int* target, double* lml,
+                      double* grad);
+
 /* ------------------------------------------------------------------ (4) front quality
  * Exact hypervolume for minimisation, m in {2,3}; replaces pg.hypervolume(points).compute(ref)
  * (compare.ipynb cell 0, section 5).  Points not strictly better than ref in every
