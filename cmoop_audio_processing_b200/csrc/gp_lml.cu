@@ -107,6 +107,8 @@ __host__ __device__ inline size_t lml_panel_doubles(int n) {
     return panels > partial ? panels : partial;
 }
 
+// MR = ceil(n / 32): panel rows a thread keeps in registers during a block's sweep steps
+template <int MR>
 __global__ void __launch_bounds__(kLmlThreads) gp_lml_kernel(LmlParams P, int slot0) {
     extern __shared__ __align__(16) double sm[];
     const int n = P.n, dim = P.dim;
@@ -118,7 +120,8 @@ __global__ void __launch_bounds__(kLmlThreads) gp_lml_kernel(LmlParams P, int sl
     double* al = ys + n;                             // [n]
     double* mm = al + n;                             // [kPB]  1 / pivot (kPB * kPB reserved)
     double* red = mm + kPB * kPB;                    // [kLmlWarps * 3]
-    __shared__ int s_fail;
+    __shared__ int s_fail, s_items;
+    __shared__ unsigned short items[(kLmlMaxN / 32) * (kLmlMaxN / kPB + 2) / 2 + 16];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* A = P.a + (size_t)slot * n * n;
     double* io = P.io + (size_t)slot * 8;
@@ -135,8 +138,19 @@ __global__ void __launch_bounds__(kLmlThreads) gp_lml_kernel(LmlParams P, int sl
     const int nu2 = (int)(2.0 * P.nu + 0.5);
     for (int e = tid; e < n * dim; e += kLmlThreads) xs[e] = P.x[e];
     for (int i = tid; i < n; i += kLmlThreads) ys[i] = y[i];
-    if (tid == 0) s_fail = 0;
+    // work items of the rank-16 update: (32-row chunk, 16-column group) pairs that touch the lower triangle
+    const int row_chunks = (n + 31) / 32, col_groups = (n + kPB - 1) / kPB;
+    if (tid == 0) {
+        s_fail = 0;
+        int cnt = 0;
+        for (int rc = 0; rc < row_chunks; ++rc) {
+            const int groups = 2 * rc + 2 < col_groups ? 2 * rc + 2 : col_groups;
+            for (int cg = 0; cg < groups; ++cg) items[cnt++] = (unsigned short)(rc << 8 | cg);
+        }
+        s_items = cnt;
+    }
     __syncthreads();
+    const int n_items = s_items;
 
     // ---- K (lower triangle, column-major): warps over columns, lanes over rows
     for (int j = warp; j < n; j += kLmlWarps) {
@@ -154,8 +168,6 @@ __global__ void __launch_bounds__(kLmlThreads) gp_lml_kernel(LmlParams P, int sl
     __syncthreads();
 
     // ---- blocked sweep
-    double logdet = 0.0;
-    const int row_chunks = (n + 31) / 32, col_groups = (n + kPB - 1) / kPB;
     for (int k0 = 0; k0 < n; k0 += kPB) {
         const int bk = n - k0 < kPB ? n - k0 : kPB;
         // (1) panel S[i][c] = A(i, k0 + c) by symmetry (zero beyond bk); U[:, 0] = S[:, 0], other U columns cleared
@@ -177,6 +189,15 @@ __global__ void __launch_bounds__(kLmlThreads) gp_lml_kernel(LmlParams P, int sl
         __syncthreads();
         // (2) the block's 16 sweep steps on the panel alone, one after the other (an explicit D^-1 would lose
         // cond(D) digits); U[:, k] keeps column k as it was when it became the pivot column, mm[k] = 1 / d_k
+        // A thread keeps its panel elements -- column pc, rows pi0 + 32 m -- in registers across the block's steps
+        // and reads only the pivot column from shared memory; the owners of column k + 1 publish it for the next step.
+        const int pc = tid & (kPB - 1), pi0 = tid >> 4;
+        double sv[MR];
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+            const int i = pi0 + 32 * m;
+            sv[m] = i < n ? pp[i * kPS + pc] : 0.0;
+        }
         bool bad = false;
         for (int k = 0; k < bk; ++k) {
             const int r = k0 + k;
@@ -187,19 +208,32 @@ __global__ void __launch_bounds__(kLmlThreads) gp_lml_kernel(LmlParams P, int sl
             }
             const double inv = 1.0 / d;
             if (tid == 0) {
-                logdet += log(d);
+                al[r] = d;                                                // pivots; their logs are summed after the sweep
                 mm[k] = inv;
             }
-            for (int e = tid; e < n * kPB; e += kLmlThreads) {
-                const int i = e / kPB, c = e - i * kPB;
-                if (c >= bk) continue;
-                const double col_i = qq[i * kPS + k], piv_c = qq[(k0 + c) * kPS + k];
-                double v;
-                if (c == k) v = i == r ? -inv : col_i * inv;
-                else if (i == r) v = piv_c * inv;
-                else v = pp[i * kPS + c] - col_i * (piv_c * inv);
-                pp[i * kPS + c] = v;
-                if (c == k + 1) qq[i * kPS + c] = v;
+            if (pc < bk) {
+                // column pc == k: v = u_i / d (pivot row: -1 / d); other columns: v = s - u_i t with t = u_(k0+pc) / d
+                // (pivot row: t).  Written as one fused form v = a * u_i + b with per-thread a and the row-r exception.
+                const double t = qq[(k0 + pc) * kPS + k] * inv;
+                const bool own = pc == k;
+                const double mul = own ? inv : -t;
+                const double piv_val = own ? -inv : t;
+#pragma unroll
+                for (int m = 0; m < MR; ++m) {
+                    const int i = pi0 + 32 * m;
+                    const double col_i = qq[(i < n ? i : 0) * kPS + k];
+                    double v = fma(mul, col_i, own ? 0.0 : sv[m]);
+                    if (i == r) v = piv_val;
+                    sv[m] = v;
+                }
+                if (pc == k + 1 || k == bk - 1) {                         // publish the next pivot column / the final panel
+                    double* dst = (k == bk - 1 ? pp : qq) + pc;
+#pragma unroll
+                    for (int m = 0; m < MR; ++m) {
+                        const int i = pi0 + 32 * m;
+                        if (i < n) dst[i * kPS] = sv[m];
+                    }
+                }
             }
             __syncthreads();
         }
@@ -209,10 +243,10 @@ __global__ void __launch_bounds__(kLmlThreads) gp_lml_kernel(LmlParams P, int sl
         }
         // (4) rank-16 update of the lower triangle outside the block; a lane owns a row, a warp item = 32 rows x 16 columns
         const int kb = k0 / kPB;
-        for (int rc = 0, item = 0; rc < row_chunks; ++rc) {
-            const int groups = 2 * rc + 2 < col_groups ? 2 * rc + 2 : col_groups;
-            for (int cg = 0; cg < groups; ++cg, ++item) {
-                if ((item % kLmlWarps) != warp || cg == kb) continue;
+        for (int item = warp; item < n_items; item += kLmlWarps) {
+            {
+                const int rc = items[item] >> 8, cg = items[item] & 0xff;
+                if (cg == kb) continue;
                 const int i = rc * 32 + lane;
                 const bool row_ok = i < n && (i < k0 || i >= k0 + kPB);
                 double q[kPB];
@@ -270,6 +304,13 @@ __global__ void __launch_bounds__(kLmlThreads) gp_lml_kernel(LmlParams P, int sl
         }
         return;
     }
+
+    // log det K = sum of the logs of the pivots (kept in al[] by the sweep), all threads in parallel
+    double ld[3] = {0.0, 0.0, 0.0};
+    for (int i = tid; i < n; i += kLmlThreads) ld[0] += log(al[i]);
+    block_sum3(ld, red);
+    const double logdet = ld[0];
+    __syncthreads();
 
     // ---- a = K^-1 y with A = -K^-1 (lower triangle): one coalesced pass, warp per column j.  Element (i, j), i > j,
     // adds A_ij y_j to row i (per-warp partial rows in shared memory) and A_ij y_i to row j (warp reduction).
@@ -370,7 +411,10 @@ int cmoop_gp_lml_create(const double* x, int n, int dim, const double* y, int n_
     if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
     static std::once_flag once;
     std::call_once(once, [] {
-        cudaFuncSetAttribute(gp_lml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(gp_lml_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(gp_lml_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(gp_lml_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(gp_lml_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     });
     auto* h = new cmoop_gp_lml();
     cudaGetDevice(&h->device);
@@ -418,7 +462,11 @@ int cmoop_gp_lml_eval(cmoop_gp_lml_handle h, int slot, int count, const double* 
     CMOOP_CUDA_OK(cudaMemcpyAsync(h->d_io + (size_t)slot * 8, io.data(), io.size() * 8, cudaMemcpyHostToDevice, st));
     CMOOP_CUDA_OK(cudaMemcpyAsync(h->d_target + slot, target, (size_t)count * 4, cudaMemcpyHostToDevice, st));
     LmlParams P{h->n, h->dim, h->kind, nt, h->nu, h->jitter, h->d_x, h->d_y, h->d_a, h->d_io, h->d_target};
-    gp_lml_kernel<<<count, kLmlThreads, lml_smem(h->n, h->dim), st>>>(P, slot);
+    const size_t smem = lml_smem(h->n, h->dim);
+    if (h->n <= 64) gp_lml_kernel<2><<<count, kLmlThreads, smem, st>>>(P, slot);
+    else if (h->n <= 160) gp_lml_kernel<5><<<count, kLmlThreads, smem, st>>>(P, slot);
+    else if (h->n <= 288) gp_lml_kernel<9><<<count, kLmlThreads, smem, st>>>(P, slot);
+    else gp_lml_kernel<16><<<count, kLmlThreads, smem, st>>>(P, slot);
     cmoop::count_launch();
     CMOOP_CUDA_OK(cudaGetLastError());
     CMOOP_CUDA_OK(cudaMemcpyAsync(io.data(), h->d_io + (size_t)slot * 8, io.size() * 8, cudaMemcpyDeviceToHost, st));

@@ -14,7 +14,7 @@ from cmoop_audio_processing_b200 import _lib  # noqa: E402
 def main():
     lib = _lib.load()
     rng = np.random.default_rng(0)
-    for n in (64, 144, 288):
+    for n in ([int(a) for a in sys.argv[1:]] or [64, 144, 288]):
         x = np.ascontiguousarray(rng.integers(0, 4, (n, 8)).astype(np.float64) + 0.01 * rng.standard_normal((n, 8)))
         y = np.ascontiguousarray(rng.standard_normal((4, n)))
         slots = 44

@@ -9,9 +9,14 @@ ix = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 data = []
 total = 0
-for n, r in enumerate(rows[2:]):
+n = -1
+for r in rows[2:]:
     if len(r) < len(hdr):
         continue
+    if r[ix["# Samples"]] == "# Samples":        # next kernel of a multi-kernel report: keep only the last one
+        data, total, n = [], 0, -1
+        continue
+    n += 1
     s = int(r[ix["# Samples"]] or 0)
     total += s
     reasons = sorted(((int(r[ix[h]] or 0), h) for h in stalls), reverse=True)[:2]
