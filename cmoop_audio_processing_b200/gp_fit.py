@@ -135,13 +135,15 @@ def _optimise_on_device(probes, jobs):
     from . import _lib
 
     specs = {device_kernel_spec(p.kernel_) for p in probes}
-    if len(specs) != 1 or None in specs or any(np.ndim(p.y_train_) != 1 for p in probes):
+    targets = [np.asarray(p.y_train_, np.float64) for p in probes]
+    if len(specs) != 1 or None in specs or any(t.size != t.shape[0] for t in targets):      # one output column per model
         return None
     kind, nu = next(iter(specs))
+    LAST_DEVICE_FIT.clear()
     lib = _lib.load()
     _lib.bind_device()
     x = np.ascontiguousarray(probes[0].X_train_, np.float64)
-    ys = np.ascontiguousarray(np.stack([p.y_train_ for p in probes]), np.float64)
+    ys = np.ascontiguousarray(np.stack([t.reshape(-1) for t in targets]), np.float64)
     handle = C.c_void_p()
     _lib.check(lib.cmoop_gp_lml_create(_lib.ptr(x), x.shape[0], x.shape[1], _lib.ptr(ys), ys.shape[0], kind, nu,
                                        float(probes[0].alpha), len(jobs), C.byref(handle)), "cmoop_gp_lml_create")

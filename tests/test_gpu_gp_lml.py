@@ -112,6 +112,7 @@ def test_device_backed_fit_agrees_with_host_fit():
     """Same starts, same optimiser, device objective: fitted hyper-parameters and predictions agree with the host fit."""
     from sklearn.gaussian_process.kernels import ConstantKernel, Matern, WhiteKernel
 
+    from cmoop_audio_processing_b200 import gp_fit
     from cmoop_audio_processing_b200.gp_fit import fit_gprs_parallel
 
     rng = np.random.default_rng(3)
@@ -121,6 +122,7 @@ def test_device_backed_fit_agrees_with_host_fit():
     kernels = [ConstantKernel(1.0) * Matern(length_scale=1.0, nu=1.5) + WhiteKernel(noise_level=0.1) for _ in ys]
     host = fit_gprs_parallel(kernels, x, ys, n_restarts_optimizer=4, random_state=11, max_workers=1, backend="host")
     dev = fit_gprs_parallel(kernels, x, ys, n_restarts_optimizer=4, random_state=11, backend="device")
+    assert gp_fit.LAST_DEVICE_FIT["chains"] == 10 and gp_fit.LAST_DEVICE_FIT["rounds"] > 0
     xq = _genotype_rows(60, np.random.default_rng(5))
     for a, b in zip(host, dev):
         assert b.log_marginal_likelihood_value_ == pytest.approx(a.log_marginal_likelihood_value_, rel=1e-6, abs=1e-6)
@@ -145,6 +147,7 @@ def test_device_fitted_surrogate_reproduces_reference_predictions(golden):
 
     import sklearn
 
+    from cmoop_audio_processing_b200 import gp_fit
     from cmoop_audio_processing_b200.surrogate import SurrogateManager
 
     g = golden("surrogate")
@@ -156,7 +159,9 @@ def test_device_fitted_surrogate_reproduces_reference_predictions(golden):
         recs = [{"hparams": hp, "objs": o, "CV": c}
                 for hp, o, c in zip(case["train_hparams"], case["train_objs"], case["train_cv"])]
         sm = SurrogateManager(fit_backend="device")
+        gp_fit.LAST_DEVICE_FIT.clear()
         sm.update(case["train_hparams"], recs)
+        assert gp_fit.LAST_DEVICE_FIT.get("rounds", 0) > 0 and gp_fit.LAST_DEVICE_FIT["chains"] == 44      # no host fallback
         preds, stds = sm.predict(case["queries"], return_std=True)
         for k in preds:
             np.testing.assert_allclose(preds[k], case["pred"][k], rtol=0, atol=1e-4)
