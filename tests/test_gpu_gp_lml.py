@@ -166,3 +166,23 @@ def test_device_fitted_surrogate_reproduces_reference_predictions(golden):
         for k in preds:
             np.testing.assert_allclose(preds[k], case["pred"][k], rtol=0, atol=1e-4)
             np.testing.assert_allclose(stds[k], case["std"][k], rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("n", [64, 65, 160, 161, 300, 512])
+def test_lml_kernel_instantiation_boundaries(n):
+    """Sizes either side of the rows-per-thread buckets of gp_lml_kernel<MR> (64 / 160 / 288) and the largest n."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import ConstantKernel, Matern, WhiteKernel
+
+    rng = np.random.default_rng(1000 + n)
+    x = rng.uniform(0.0, 4.0, size=(n, 5))
+    y = np.sin(x[:, 0]) + 0.3 * x[:, 1] + 0.05 * rng.standard_normal(n)
+    y = (y - y.mean()) / y.std()
+    kernel = ConstantKernel(1.0) * Matern(length_scale=1.0, nu=2.5) + WhiteKernel(noise_level=0.1)
+    gpr = GaussianProcessRegressor(kernel=kernel, optimizer=None).fit(x, y)
+    thetas = np.array([[0.0, 0.0, np.log(0.1)], [1.5, 0.7, -4.0], [-1.0, -0.5, -1.0]])
+    lml, grad = _device_lml(x, y[None], 0, 2.5, thetas, np.zeros(3))
+    for i, t in enumerate(thetas):
+        wl, wg = gpr.log_marginal_likelihood(t, eval_gradient=True)
+        assert lml[i] == pytest.approx(wl, rel=1e-8, abs=1e-8)
+        np.testing.assert_allclose(grad[i], wg, rtol=1e-6, atol=1e-7 * max(1.0, np.abs(wg).max()))
