@@ -139,3 +139,71 @@ def test_run_log_formats_round_trip(tmp_path):
         assert got["hparams"] == want["hparams"]
         assert all(abs(x - y) < 1e-12 for x, y in zip(got["objs"], want["objs"]))
         assert abs(got["CV"] - want["CV"]) < 1e-12
+
+
+def test_device_kernel_spec_recognises_the_reference_kernels_only():
+    """gp_fit.device_kernel_spec: the two kernel forms the reference fits (sa_nsga_local.py:180, mobo_penalty.py:259) have
+    a device objective; anything else keeps scikit-learn's objective on the host."""
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern, WhiteKernel
+
+    from cmoop_audio_processing_b200.gp_fit import device_kernel_spec
+
+    assert device_kernel_spec(ConstantKernel(1.0) * Matern(length_scale=1.0, nu=1.5) + WhiteKernel(0.1)) == (0, 1.5)
+    assert device_kernel_spec(Matern(nu=2.5)) == (1, 2.5)
+    assert device_kernel_spec(Matern(nu=0.5)) == (1, 0.5)
+    assert device_kernel_spec(RBF()) is None
+    assert device_kernel_spec(Matern(nu=3.5)) is None
+    assert device_kernel_spec(Matern(length_scale=[1.0, 2.0], nu=1.5)) is None                      # anisotropic
+    assert device_kernel_spec(Matern(nu=1.5, length_scale_bounds="fixed")) is None
+    assert device_kernel_spec(WhiteKernel(0.1) + ConstantKernel(1.0) * Matern(nu=1.5)) is None     # other theta order
+    assert device_kernel_spec(ConstantKernel(1.0) * Matern(nu=1.5)) is None
+
+
+def test_lock_step_objective_batches_live_chains():
+    """gp_fit._LockStepObjective with a stand-in library: every round is one call carrying one request per live chain,
+    chains that finish early retire without stalling the others, and each chain sees its own values."""
+    import ctypes as C
+    import threading
+
+    from scipy.optimize import minimize
+
+    from cmoop_audio_processing_b200.gp_fit import _LockStepObjective
+
+    calls = []
+
+    class FakeLib:
+        def cmoop_gp_lml_eval(self, handle, slot, count, theta, target, lml, grad):
+            th = np.ctypeslib.as_array(C.cast(theta, C.POINTER(C.c_double)), (count, 2))
+            tg = np.ctypeslib.as_array(C.cast(target, C.POINTER(C.c_int32)), (count,))
+            out = np.ctypeslib.as_array(C.cast(lml, C.POINTER(C.c_double)), (count,))
+            g = np.ctypeslib.as_array(C.cast(grad, C.POINTER(C.c_double)), (count, 2))
+            centre = tg[:, None].astype(np.float64)                  # chain with target t minimises |theta - t|^2
+            out[:] = -((th - centre) ** 2).sum(axis=1)
+            g[:] = -2.0 * (th - centre)
+            calls.append((slot, count))
+            return 0
+
+    n_chains = 5
+    obj = _LockStepObjective(FakeLib(), None, list(range(n_chains)), 2)
+    found = {}
+
+    def run(s):
+        try:
+            def f(th):
+                lml, grad = obj.evaluate(s, th)
+                return -lml, -grad
+            found[s] = minimize(f, np.array([3.0, -2.0]), jac=True, method="L-BFGS-B", options={"maxiter": 2 + 3 * s}).x
+        finally:
+            obj.retire()
+
+    threads = [threading.Thread(target=run, args=(s,)) for s in range(n_chains)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(30)
+    assert not any(t.is_alive() for t in threads)
+    assert calls[0] == (0, n_chains) and all(slot == 0 for slot, _ in calls)
+    assert [c for _, c in calls] == sorted((c for _, c in calls), reverse=True)      # chains only ever retire
+    assert obj.rounds == len(calls) and obj.requests == sum(c for _, c in calls)
+    for s in range(1, n_chains):                                     # chain 0 is capped at two iterations
+        np.testing.assert_allclose(found[s], [s, s], atol=1e-6)
