@@ -191,8 +191,34 @@ def cnn_generation_extra(args, rank: int, world: int) -> dict:
         out[prec] = {"evals_per_sec": pop / dt, "seconds": dt, "analytic_tflops": flops / dt / 1e12,
                      "records": len(recs)}
         prob.data.close()
+    # the population size of BASELINE configs[4] (256, sharded over the ranks), tensor-core path only
+    big = 256
+    hps_big = [{k: pyr.choice(v) for k, v in HPARAM_SPACE.items()} for _ in range(big)]
+    cfg = TrainConfig(variant="B", epochs=epochs, patience=epochs, restore_best_weights=True, acc_from="evaluate",
+                      precision="bf16")
+    prob = FitnessProblem(xt, yt, xv, yv, classes=12, config=cfg)
+    warm = FitnessProblem(xt[:128], yt[:128], xv[:64], yv[:64], classes=12,
+                          config=TrainConfig(variant="B", epochs=1, patience=1, precision="bf16"))
+    warm.compute_objectives_and_constraints(hps_big)
+    warm.data.close()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    recs = prob.compute_objectives_and_constraints(hps_big)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt[0])
+    macs_big = [forward_macs(hp, 49, 40, 12, "B") for hp in hps_big]
+    flops = sum(epochs * (6 * m * n_train + 2 * m * n_val) + 2 * m * n_val for m in macs_big)
+    out["bf16_pop256"] = {"evals_per_sec": big / dt, "seconds": dt, "analytic_tflops": flops / dt / 1e12,
+                          "records": len(recs)}
+    prob.data.close()
     res = {"workload": f"{pop} random genotypes (variant B), {n_train} train / {n_val} val 49x40 features, {epochs} epochs "
-                       "fixed, batch 64, Adam; one compute_objectives_and_constraints call",
+                       "fixed, batch 64, Adam; one compute_objectives_and_constraints call (bf16_pop256: the same with "
+                       "256 genotypes)",
            "gpu": out}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cnn_ref
