@@ -80,3 +80,79 @@ def unpack_sklearn(gpr) -> dict:
                 alpha=np.asarray(gpr.alpha_, np.float64).ravel(), chol_lower=np.asarray(gpr.L_, np.float64),
                 y_scale=float(np.ravel(getattr(gpr, "_y_train_std", 1.0))[0]),
                 y_shift=float(np.ravel(getattr(gpr, "_y_train_mean", 0.0))[0]))
+
+
+# ---- hyper-parameter objective (the device form is csrc/gp_lml.cu) ---------------------------------------------------
+def matern_dlogl(xa: np.ndarray, length_scale: float, nu: float):
+    """(k, dk/dlog l) of Matern(nu) on xa x xa (kernels.py Matern.__call__ with eval_gradient=True)."""
+    a = np.asarray(xa, np.float64) / length_scale
+    diff = a[:, None, :] - a[None, :, :]
+    r = np.sqrt((diff * diff).sum(axis=2))
+    if nu == 0.5:
+        e = np.exp(-r)
+        return e, r * e
+    if nu == 1.5:
+        s = np.sqrt(3.0) * r
+        e = np.exp(-s)
+        return (1.0 + s) * e, s * s * e
+    if nu == 2.5:
+        s = np.sqrt(5.0) * r
+        e = np.exp(-s)
+        return (1.0 + s + s * s / 3.0) * e, s * s / 3.0 * (1.0 + s) * e
+    raise ValueError("nu must be 0.5, 1.5 or 2.5")
+
+
+def blocked_sweep(k_matrix: np.ndarray, block: int = 16):
+    """(K^-1, log det K) by the symmetric sweep operator in the blocked order gp_lml.cu uses: the block's columns are
+    swept one pivot after the other (each pivot column kept as it was when used), the rest of the matrix then takes the
+    block's rank-`block` update at once.  Returns (None, -inf) on a non-positive pivot (scikit-learn: failed Cholesky)."""
+    a = np.array(k_matrix, np.float64)
+    n = len(a)
+    logdet = 0.0
+    for k0 in range(0, n, block):
+        cols = np.arange(k0, min(n, k0 + block))
+        s = a[:, cols].copy()
+        u = np.zeros_like(s)
+        dinv = np.zeros(len(cols))
+        for k, r in enumerate(cols):
+            col = s[:, k].copy()
+            d = col[r]
+            if not d > 0.0 or not np.isfinite(d):
+                return None, -np.inf
+            logdet += np.log(d)
+            u[:, k], dinv[k] = col, 1.0 / d
+            piv = col[cols].copy()
+            s -= np.outer(col, piv) / d
+            s[r, :] = piv / d
+            s[:, k] = col / d
+            s[r, k] = -1.0 / d
+        outside = np.ones(n, bool)
+        outside[cols] = False
+        upd = (u * dinv) @ u.T
+        a[np.ix_(outside, outside)] -= upd[np.ix_(outside, outside)]
+        a[:, cols] = s
+        a[cols, :] = s.T
+    return -a, logdet
+
+
+def log_marginal_likelihood(theta, x, y, kind: int, nu: float, jitter: float = 1e-10, block: int = 16):
+    """(lml, d lml / d theta) as GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient=True)
+    (sklearn/gaussian_process/_gpr.py) for kind 0 = C * Matern + WhiteKernel, theta = (log c, log l, log noise), and
+    kind 1 = Matern, theta = (log l), computed the way the device kernel does (blocked sweep instead of Cholesky)."""
+    theta = np.asarray(theta, np.float64)
+    x = np.asarray(x, np.float64)
+    y = np.asarray(y, np.float64).reshape(-1)
+    n = len(x)
+    amp, ell, noise = (np.exp(theta[0]), np.exp(theta[1]), np.exp(theta[2])) if kind == 0 else (1.0, np.exp(theta[0]), 0.0)
+    k, dk = matern_dlogl(x, ell, nu)
+    kinv, logdet = blocked_sweep(amp * k + (noise + jitter) * np.eye(n), block)
+    if kinv is None:
+        return -np.inf, np.zeros_like(theta)
+    alpha = kinv @ y
+    inner = np.outer(alpha, alpha) - kinv
+    lml = -0.5 * y @ alpha - 0.5 * logdet - 0.5 * n * np.log(2.0 * np.pi)
+    if kind == 0:
+        grad = 0.5 * np.array([(inner * amp * k).sum(), (inner * amp * dk).sum(), noise * np.trace(inner)])
+    else:
+        grad = 0.5 * np.array([(inner * dk).sum()])
+    return float(lml), grad

@@ -151,3 +151,37 @@ def test_live_reference_matches_golden_when_available(golden):
     for case in golden("nsga")["cases"][:24]:
         recs = records(case["objs"], case["cv"])
         assert sa["fast_non_dominated_sort"](recs, case["lam"]) == case["fronts"]
+
+
+def test_gp_objective_restatement_matches_sklearn():
+    """oracle/gp_ref.log_marginal_likelihood (the blocked-sweep algorithm of csrc/gp_lml.cu in NumPy) against
+    GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient=True), up to cond(K) ~ 1e9."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import ConstantKernel, Matern, WhiteKernel
+
+    from oracle import gp_ref
+
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 4, size=(70, 8)).astype(np.float64)
+    x = np.unique(x, axis=0)
+    y = np.sin(x[:, 0]) + 0.2 * x[:, 1] + 0.05 * rng.standard_normal(len(x))
+    y = (y - y.mean()) / y.std()
+    kernel = ConstantKernel(1.0) * Matern(length_scale=1.0, nu=1.5) + WhiteKernel(noise_level=0.1)
+    gpr = GaussianProcessRegressor(kernel=kernel, optimizer=None).fit(x, y)
+    for theta in ([0.0, 0.0, np.log(0.1)], [2.0, 1.0, -6.0], [-2.0, -1.0, 0.5], [5.0, 3.0, -11.0]):
+        want, want_grad = gpr.log_marginal_likelihood(np.array(theta), eval_gradient=True)
+        for block in (1, 16):
+            got, grad = gp_ref.log_marginal_likelihood(theta, x, y, 0, 1.5, block=block)
+            assert got == pytest.approx(want, rel=1e-8, abs=1e-8)
+            np.testing.assert_allclose(grad, want_grad, rtol=1e-6, atol=1e-7 * max(1.0, np.abs(want_grad).max()))
+    # the MOBO form, smooth kernel with only the 1e-10 jitter: cond(K) grows to ~3e9 at log l = 3
+    xm = np.random.default_rng(7).uniform(size=(45, 6))
+    ym = np.sin(3 * xm[:, 0]) + xm[:, 1] * xm[:, 2]
+    g2 = GaussianProcessRegressor(kernel=Matern(nu=2.5), optimizer=None, normalize_y=True).fit(xm, ym)
+    for t in np.linspace(-3.0, 3.0, 7):
+        want, want_grad = g2.log_marginal_likelihood(np.array([t]), eval_gradient=True)
+        got, grad = gp_ref.log_marginal_likelihood([t], xm, g2.y_train_, 1, 2.5)
+        assert got == pytest.approx(want, rel=1e-8, abs=1e-8)
+        np.testing.assert_allclose(grad, want_grad, rtol=1e-5, atol=1e-8)
+    # not positive definite: duplicate rows without noise
+    assert gp_ref.log_marginal_likelihood([0.0], np.zeros((5, 2)), np.arange(5.0), 1, 1.5, jitter=0.0)[0] == -np.inf
