@@ -16,9 +16,11 @@ re-imported (the reference's drivers run at import time, and the parent owns a C
 predictions; tests/test_host_logic.py).  Small problems stay in-process.
 
 ``backend="device"`` (or ``CMOOP_GP_FIT_BACKEND=device``) keeps SciPy's L-BFGS-B and the start order but evaluates the
-objective -- log-marginal likelihood and gradient -- with ``cmoop_gp_lml_eval`` (csrc/gp_lml.cu): one optimiser thread per
-start, the chains advancing in lock step so that each round of objective requests (44 for a surrogate update) is one
-kernel launch with one CTA per request.  The
+objective -- log-marginal likelihood and gradient -- with ``cmoop_gp_lml_eval`` (csrc/gp_lml.cu): the chains advance in
+lock step so that each round of objective requests (44 for a surrogate update) is one kernel launch with one CTA per
+request.  One host thread steps all chains through SciPy's reverse-communication ``setulb``
+(``minimize_lbfgsb_multiplexed``, per chain bit-identical to ``scipy.optimize.minimize``); SciPy builds without that entry
+point fall back to one optimiser thread per chain meeting in ``_LockStepObjective``.  The
 device objective agrees with scikit-learn's to ~1e-10 relative, not bit for bit, so the optima can differ in the last
 digits: it is opt-in, and kernels other than the reference's two forms stay on the host.
 """
@@ -72,6 +74,104 @@ def device_kernel_spec(kernel):
             and not isinstance(kernel.k2.noise_level_bounds, str)):
         return 0, float(kernel.k1.k2.nu)
     return None
+
+
+def _multiplexed_lbfgsb_available() -> bool:
+    """True when SciPy exposes the reverse-communication L-BFGS-B step this module can drive for many problems at once
+    (scipy.optimize._lbfgsb_py._lbfgsb.setulb with the 17-argument form of SciPy >= 1.15)."""
+    try:
+        from scipy.optimize import _lbfgsb_py as lb
+
+        doc = lb._lbfgsb.setulb.__doc__ or ""
+        return doc.lstrip().startswith("setulb(m, x, l, u, nbd, f, g, factr, pgtol, wa, iwa, task, lsave, isave, dsave, "
+                                       "maxls, ln_task)") and hasattr(lb, "HAS_ILP64")
+    except Exception:
+        return False
+
+
+def minimize_lbfgsb_multiplexed(evaluate_batch, starts, bounds_list):
+    """``scipy.optimize.minimize(fun, x0, method="L-BFGS-B", jac=True, bounds=bounds)`` with default options -- what
+    scikit-learn's ``_constrained_optimization`` runs (sklearn:_gpr.py) -- for several independent problems at once, in
+    one thread: SciPy's own driver loop (scipy/optimize/_lbfgsb_py.py ``_minimize_lbfgsb``) around the same compiled
+    ``setulb`` step, with the objective requests of all live problems collected and handed to
+    ``evaluate_batch([(problem, x), ...]) -> [(f, g), ...]`` together.  Every problem sees exactly the sequence of points,
+    values and decisions it would see alone, so the optima are bit-identical to SciPy's for the same objective.
+    Returns [OptimizeResult] in problem order."""
+    import inspect
+
+    from scipy.optimize import OptimizeResult
+    from scipy.optimize import _lbfgsb_py as lb
+
+    defaults = {k: v.default for k, v in inspect.signature(lb._minimize_lbfgsb).parameters.items()}
+    m, maxls = defaults["maxcor"], defaults["maxls"]
+    maxiter, maxfun = defaults["maxiter"], defaults["maxfun"]
+    factr, pgtol = defaults["ftol"] / np.finfo(float).eps, defaults["gtol"]
+    int_dtype = np.int64 if lb.HAS_ILP64 else np.int32
+    bounds_map = {(-np.inf, np.inf): 0, (1, np.inf): 1, (1, 1): 2, (-np.inf, 1): 3}
+    setulb = lb._lbfgsb.setulb
+
+    class Chain:
+        pass
+
+    chains = []
+    for x0, bounds in zip(starts, bounds_list):
+        c = Chain()
+        b = np.array(lb.old_bound_to_new([tuple(r) for r in np.asarray(bounds, np.float64)]))
+        x0 = np.clip(np.asarray(x0, np.float64).ravel(), b[0], b[1])
+        n = x0.shape[0]
+        c.nbd, c.low, c.up = np.zeros(n, int_dtype), np.zeros(n), np.zeros(n)
+        for i in range(n):
+            lo, hi = b[0, i], b[1, i]
+            if not np.isinf(lo):
+                c.low[i], lo = lo, 1
+            if not np.isinf(hi):
+                c.up[i], hi = hi, 1
+            c.nbd[i] = bounds_map[lo, hi]
+        c.x, c.f, c.g = np.array(x0, np.float64), 0.0, np.zeros(n)
+        c.wa, c.iwa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m), np.zeros(3 * n, int_dtype)
+        c.task, c.ln_task, c.lsave = np.zeros(2, int_dtype), np.zeros(2, int_dtype), np.zeros(4, int_dtype)
+        c.isave, c.dsave = np.zeros(44, int_dtype), np.zeros(29)
+        c.nit = c.nfev = 0
+        c.last_x = None
+        chains.append(c)
+
+    live = list(range(len(chains)))
+    while live:
+        asking = []
+        for ci in live:
+            c = chains[ci]
+            while True:
+                setulb(m, c.x, c.low, c.up, c.nbd, c.f, c.g, factr, pgtol, c.wa, c.iwa, c.task, c.lsave, c.isave, c.dsave,
+                       maxls, c.ln_task)
+                if c.task[0] == 3:                       # wants f and g at the current x
+                    if c.last_x is not None and np.array_equal(c.x, c.last_x):
+                        c.f, c.g = c.last_f, c.last_g.copy()      # SciPy's ScalarFunction does not re-evaluate an unchanged x
+                        continue
+                    asking.append(ci)
+                    break
+                if c.task[0] == 1:                       # new iteration
+                    c.nit += 1
+                    if c.nit >= maxiter:
+                        c.task[0], c.task[1] = 5, 504
+                    elif c.nfev > maxfun:
+                        c.task[0], c.task[1] = 5, 502
+                    continue
+                break                                    # converged / stopped / error
+        live = asking
+        if asking:
+            values = evaluate_batch([(ci, chains[ci].x.copy()) for ci in asking])
+            for ci, (f, g) in zip(asking, values):
+                c = chains[ci]
+                c.f, c.g = float(f), np.asarray(g, np.float64).copy()
+                c.last_x, c.last_f, c.last_g = c.x.copy(), c.f, c.g.copy()
+                c.nfev += 1
+    results = []
+    for c in chains:
+        warnflag = 0 if c.task[0] == 4 else (1 if c.nfev > maxfun or c.nit >= maxiter else 2)
+        results.append(OptimizeResult(fun=c.f, jac=c.g, nfev=c.nfev, njev=c.nfev, nit=c.nit, status=warnflag,
+                                      message=lb.status_messages[c.task[0]] + ": " + lb.task_messages[c.task[1]],
+                                      x=c.x, success=warnflag == 0))
+    return results
 
 
 class _LockStepObjective:
@@ -147,7 +247,34 @@ def _optimise_on_device(probes, jobs):
     handle = C.c_void_p()
     _lib.check(lib.cmoop_gp_lml_create(_lib.ptr(x), x.shape[0], x.shape[1], _lib.ptr(ys), ys.shape[0], kind, nu,
                                        float(probes[0].alpha), len(jobs), C.byref(handle)), "cmoop_gp_lml_create")
-    objective = _LockStepObjective(lib, handle, [m for m, _ in jobs], lib.cmoop_gp_lml_n_theta(handle))
+    n_theta = lib.cmoop_gp_lml_n_theta(handle)
+    if _multiplexed_lbfgsb_available() and not os.environ.get("CMOOP_GP_FIT_THREADS"):
+        # one thread drives every chain through SciPy's own L-BFGS-B step; each round of requests is one launch
+        from sklearn.utils.optimize import _check_optimize_result
+
+        stats = {"rounds": 0, "requests": 0}
+
+        def evaluate_batch(requests):
+            thetas = np.ascontiguousarray([th for _, th in requests], np.float64)
+            target = np.ascontiguousarray([jobs[ci][0] for ci, _ in requests], np.int32)
+            lml, grad = np.empty(len(requests)), np.empty((len(requests), n_theta))
+            _lib.check(lib.cmoop_gp_lml_eval(handle, 0, len(requests), _lib.ptr(thetas), _lib.ptr(target), _lib.ptr(lml),
+                                             _lib.ptr(grad)), "cmoop_gp_lml_eval")
+            stats["rounds"] += 1
+            stats["requests"] += len(requests)
+            return [(-lml[k], -grad[k]) for k in range(len(requests))]
+
+        try:
+            optima = minimize_lbfgsb_multiplexed(evaluate_batch, [theta0 for _, theta0 in jobs],
+                                                 [probes[m].kernel_.bounds for m, _ in jobs])
+        finally:
+            lib.cmoop_gp_lml_destroy(handle)
+        for res in optima:
+            _check_optimize_result("lbfgs", res)                      # scikit-learn's convergence warnings
+        LAST_DEVICE_FIT.update(rounds=stats["rounds"], requests=stats["requests"], chains=len(jobs), driver="multiplexed")
+        return [(np.asarray(res.x, np.float64), float(res.fun)) for res in optima]
+
+    objective = _LockStepObjective(lib, handle, [m for m, _ in jobs], n_theta)
     driver = GaussianProcessRegressor(optimizer="fmin_l_bfgs_b")      # only its _constrained_optimization is used
 
     def run(slot):
@@ -168,7 +295,7 @@ def _optimise_on_device(probes, jobs):
             return list(pool.map(run, range(len(jobs))))
     finally:
         lib.cmoop_gp_lml_destroy(handle)
-        LAST_DEVICE_FIT.update(rounds=objective.rounds, requests=objective.requests, chains=len(jobs))
+        LAST_DEVICE_FIT.update(rounds=objective.rounds, requests=objective.requests, chains=len(jobs), driver="threads")
 
 
 LAST_DEVICE_FIT: dict = {}       # launches / objective requests of the most recent device-backed fit (diagnostics)

@@ -207,3 +207,48 @@ def test_lock_step_objective_batches_live_chains():
     assert obj.rounds == len(calls) and obj.requests == sum(c for _, c in calls)
     for s in range(1, n_chains):                                     # chain 0 is capped at two iterations
         np.testing.assert_allclose(found[s], [s, s], atol=1e-6)
+
+
+def test_multiplexed_lbfgsb_is_bit_identical_to_scipy():
+    """gp_fit.minimize_lbfgsb_multiplexed drives SciPy's own L-BFGS-B step for many problems in one thread (batching their
+    objective requests); for every problem the optimum, value, iteration / evaluation counts and termination message must
+    equal scipy.optimize.minimize(method="L-BFGS-B", jac=True, bounds=...) -- scikit-learn's _constrained_optimization."""
+    import warnings
+
+    from scipy.optimize import minimize
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import ConstantKernel, Matern, WhiteKernel
+
+    from cmoop_audio_processing_b200 import gp_fit
+
+    if not gp_fit._multiplexed_lbfgsb_available():
+        pytest.skip("this SciPy does not expose the reverse-communication L-BFGS-B step")
+    rng = np.random.default_rng(0)
+    x = np.unique(rng.integers(0, 4, (60, 8)).astype(np.float64), axis=0)
+    y = np.sin(x[:, 0]) + 0.1 * rng.standard_normal(len(x))
+    y = (y - y.mean()) / y.std()
+    kernel = ConstantKernel(1.0) * Matern(length_scale=1.0, nu=1.5) + WhiteKernel(0.1)
+    gpr = GaussianProcessRegressor(kernel=kernel, optimizer=None).fit(x, y)
+    bounds = gpr.kernel_.bounds
+    starts = [gpr.kernel_.theta] + [rng.uniform(bounds[:, 0], bounds[:, 1]) for _ in range(10)]
+    starts.append(bounds[:, 1] + 1.0)                                  # outside the box: clipped like SciPy does
+
+    def objective(theta):
+        lml, grad = gpr.log_marginal_likelihood(theta, eval_gradient=True, clone_kernel=False)
+        return -lml, -grad
+
+    batches = []
+
+    def evaluate_batch(requests):
+        batches.append(len(requests))
+        return [objective(theta) for _, theta in requests]
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = [minimize(objective, s0, method="L-BFGS-B", jac=True, bounds=bounds) for s0 in starts]
+        got = gp_fit.minimize_lbfgsb_multiplexed(evaluate_batch, starts, [bounds] * len(starts))
+    assert batches[0] == len(starts) and batches == sorted(batches, reverse=True)
+    for w, g in zip(want, got):
+        assert np.array_equal(w.x, g.x) and w.fun == g.fun and np.array_equal(w.jac, g.jac)
+        assert (w.nit, w.nfev, w.status, w.message, w.success) == (g.nit, g.nfev, g.status, g.message, g.success)
+    assert sum(batches) == sum(w.nfev for w in want)
