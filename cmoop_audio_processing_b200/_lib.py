@@ -77,6 +77,8 @@ SIGNATURES = {
     "cmoop_cnn_dataset_destroy": (C.c_int, [C.c_void_p]),
     "cmoop_feature_stats_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cmoop_cnn_param_count": (C.c_longlong, [C.c_void_p, C.c_void_p]),
+    "cmoop_fpr_from_predictions_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                  C.c_void_p]),
     "cmoop_cnn_pop_train_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                            C.c_void_p]),
     "cmoop_cnn_debug_init_params": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),

@@ -199,6 +199,7 @@ struct Launch {
     static int drop_fwd(const DropTask* tasks, int n_tasks, int total_blocks, int n_b, int step, int training, float rate, void* stream);
     static int drop_bwd(const DropTask* tasks, int n_tasks, int total_blocks, int n_b, int step, float rate, void* stream);
     static int ce(const CeTask* tasks, int n_tasks, int n_b, int step, int training, void* stream);
+    static int confusion(const int* y_true, const int* y_pred, int n, int C, int* cm, void* stream);
     static int adam(const AdamTask* tasks, int n_tasks, int total_blocks, float alpha, float b1, float b2, float eps, void* stream);
     static int init(const InitTask* tasks, int n_tasks, int total_blocks, void* stream);
     static int conv_tc(const TcConvTask* tasks, int n_tasks, int total_tiles, int n_b, int step, void* stream);

@@ -860,6 +860,33 @@ int check_config(const cmoop_genotype* g, int n, const cmoop_cnn_config* cfg) {
     return CMOOP_OK;
 }
 
+// numpy.mean of a short Python list, bit for bit: np.add.reduce's pairwise summation (8 interleaved accumulators on blocks
+// of at most 128 elements, halves split on multiples of 8 above that) followed by one division -- what
+// `return np.mean(fpr_vals)` (nsga_penalty.py:364) does to the per-class rates.
+double np_pairwise_sum(const double* a, size_t n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (size_t i = 0; i < n; ++i) r += a[i];
+        return r;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        size_t i = 8;
+        for (; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    }
+    size_t n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+}
+
+// calculate_fpr from the C x C confusion matrix.  Per class FP / (FP + TN) with FP + TN = total - row_i; classes with an
+// empty denominator count as 0.0 (nsga_penalty.py:357-363, init_sa_nsga_local.py:139-143) or are left out of the mean
+// (filtered form, sa_nsga_local.py:140-141; 0.0 when no class qualifies).
 double fpr_from_confusion(const std::vector<int>& cm, int C, bool filtered) {
     long long total = 0;
     std::vector<long long> row(C, 0), col(C, 0);
@@ -870,19 +897,18 @@ double fpr_from_confusion(const std::vector<int>& cm, int C, bool filtered) {
             row[i] += v;
             col[j] += v;
         }
-    double sum = 0.0;
-    int cnt = 0;
+    std::vector<double> vals;
+    vals.reserve(C);
     for (int i = 0; i < C; ++i) {
         const long long fp = col[i] - cm[(size_t)i * C + i];
         const long long denom = total - row[i];
-        if (denom > 0) {
-            sum += (double)fp / (double)denom;
-            ++cnt;
-        } else if (!filtered) {
-            ++cnt;
-        }
+        if (denom > 0)
+            vals.push_back((double)fp / (double)denom);
+        else if (!filtered)
+            vals.push_back(0.0);
     }
-    return cnt ? sum / cnt : 0.0;
+    if (vals.empty()) return 0.0;
+    return np_pairwise_sum(vals.data(), vals.size()) / (double)vals.size();
 }
 
 }  // namespace
@@ -945,6 +971,41 @@ int cmoop_cnn_dataset_create_dev(const float* x_train_dev, const int* y_train, i
     CMOOP_CUDA_OK(cudaMemcpyAsync(d->y_val, y_val, sizeof(int) * n_val, cudaMemcpyHostToDevice, st));
     CMOOP_CUDA_OK(cudaStreamSynchronize(st));
     *out = d;
+    return CMOOP_OK;
+}
+
+int cmoop_fpr_from_predictions_host(const int* y_true, const int* y_pred, int n, int n_classes, int mode, double* fpr_out,
+                                    int* confusion_out) {
+    CMOOP_REQUIRE(fpr_out && (n == 0 || (y_true && y_pred)), "fpr_from_predictions: null pointer");
+    CMOOP_REQUIRE(n >= 0 && n_classes >= 1 && n_classes <= 4096, "fpr_from_predictions: n=%d n_classes=%d", n, n_classes);
+    CMOOP_REQUIRE(mode >= 0 && mode <= 2, "fpr_from_predictions: mode=%d (0 all classes, 1 filtered, 2 vectorised)", mode);
+    if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
+    cudaStream_t st = cmoop::internal_stream();
+    const size_t b_lab = cmoop::align_up((size_t)std::max(1, n) * sizeof(int), 256);
+    const size_t b_cm = (size_t)n_classes * n_classes * sizeof(int);
+    char* d = (char*)cmoop::device_scratch(8, 2 * b_lab + b_cm);
+    if (!d) return CMOOP_ERR_CUDA;
+    int* d_true = (int*)d;
+    int* d_pred = (int*)(d + b_lab);
+    int* d_cm = (int*)(d + 2 * b_lab);
+    if (n > 0) {
+        CMOOP_CUDA_OK(cudaMemcpyAsync(d_true, y_true, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+        CMOOP_CUDA_OK(cudaMemcpyAsync(d_pred, y_pred, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    CMOOP_CUDA_OK(cudaMemsetAsync(d_cm, 0, b_cm, st));
+    if (n > 0) {
+        const int rc = Launch::confusion(d_true, d_pred, n, n_classes, d_cm, st);
+        cmoop::count_launch();
+        if (rc != 0) {
+            cmoop::set_error("confusion kernel: %s", cudaGetErrorString((cudaError_t)rc));
+            return CMOOP_ERR_CUDA;
+        }
+    }
+    std::vector<int> cm((size_t)n_classes * n_classes);
+    CMOOP_CUDA_OK(cudaMemcpyAsync(cm.data(), d_cm, b_cm, cudaMemcpyDeviceToHost, st));
+    CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+    *fpr_out = fpr_from_confusion(cm, n_classes, mode == 1);
+    if (confusion_out) memcpy(confusion_out, cm.data(), b_cm);
     return CMOOP_OK;
 }
 

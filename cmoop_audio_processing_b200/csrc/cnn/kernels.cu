@@ -833,6 +833,16 @@ __global__ void __launch_bounds__(256) ce_kernel(const CeTask* __restrict__ task
     }
 }
 
+// confusion_matrix(y_true, y_pred, labels=range(C)) of calculate_fpr (nsga_penalty.py:355): integer atomics, samples with a
+// label outside [0, C) are dropped exactly as scikit-learn drops labels that are not in `labels`.
+__global__ void __launch_bounds__(256) confusion_kernel(const int* __restrict__ y_true, const int* __restrict__ y_pred, int n,
+                                                        int C, int* __restrict__ cm) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int t = y_true[i], p = y_pred[i];
+        if (t >= 0 && t < C && p >= 0 && p < C) atomicAdd(&cm[(long long)t * C + p], 1);
+    }
+}
+
 __global__ void __launch_bounds__(256) adam_kernel(const AdamTask* __restrict__ tasks, int n_tasks, float alpha, float b1,
                                                    float b2, float eps) {
     const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const AdamTask& r) { return r.block_begin; });
@@ -929,6 +939,12 @@ int Launch::ce(const CeTask* tasks, int n, int n_b, int step, int training, void
     ce_kernel<<<n, 256, 0, (cudaStream_t)st>>>(tasks, n_b, step, training);
     return check();
 }
+int Launch::confusion(const int* y_true, const int* y_pred, int n, int C, int* cm, void* st) {
+    const int blocks = n < 256 * 592 ? (n + 255) / 256 : 592;
+    confusion_kernel<<<blocks > 0 ? blocks : 1, 256, 0, (cudaStream_t)st>>>(y_true, y_pred, n, C, cm);
+    return (int)cudaGetLastError();
+}
+
 int Launch::adam(const AdamTask* tasks, int n, int blocks, float alpha, float b1, float b2, float eps, void* st) {
     if (n == 0 || blocks == 0) return 0;
     adam_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, alpha, b1, b2, eps);

@@ -1308,20 +1308,29 @@ int cmoop_mfcc_fwd_dev_i16(cmoop_mfcc_handle h, const int16_t* wave, int64_t n_c
     const int frames = cmoop_mfcc_n_frames(h, n_samples);
     if (n_clips == 0 || frames == 0) return CMOOP_OK;
     CMOOP_REQUIRE(wave && out, "mfcc_fwd: null pointer");
-    const int64_t chunk = 4096;
-    float* d_f = (float*)cmoop::device_scratch(5, (size_t)chunk * n_samples * sizeof(float));
-    if (!d_f) return CMOOP_ERR_CUDA;
+    // The widened chunk lives in a STREAM-ORDERED allocation of the caller's stream (cudaMallocAsync: served from the
+    // device's memory pool, no synchronisation), not in process-global scratch: two calls on different streams -- or from
+    // two front-end handles, e.g. the train and validation splits on separate torch streams -- never share a buffer.
+    const int64_t chunk = n_clips < 4096 ? n_clips : 4096;
     cudaStream_t st = (cudaStream_t)stream;
-    for (int64_t c0 = 0; c0 < n_clips; c0 += chunk) {
+    float* d_f = nullptr;
+    CMOOP_CUDA_OK(cudaMallocAsync((void**)&d_f, (size_t)chunk * n_samples * sizeof(float), st));
+    int rc = CMOOP_OK;
+    for (int64_t c0 = 0; c0 < n_clips && rc == CMOOP_OK; c0 += chunk) {
         const int64_t nc = (n_clips - c0) < chunk ? (n_clips - c0) : chunk;
         const long long n = (long long)nc * n_samples;
         pcm16_to_f32_kernel<<<(unsigned)((n + 2047) / 2048), 256, 0, st>>>(wave + (size_t)c0 * n_samples, d_f, n);
         cmoop::count_launch();
-        CMOOP_CUDA_OK(cudaGetLastError());
-        int rc = cmoop_mfcc_fwd_dev(h, d_f, nc, n_samples, out + (size_t)c0 * frames * h->n_out, stream);
-        if (rc != CMOOP_OK) return rc;
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            cmoop::set_error("pcm16_to_f32_kernel: %s", cudaGetErrorString(e));
+            rc = CMOOP_ERR_CUDA;
+            break;
+        }
+        rc = cmoop_mfcc_fwd_dev(h, d_f, nc, n_samples, out + (size_t)c0 * frames * h->n_out, stream);
     }
-    return CMOOP_OK;
+    (void)cudaFreeAsync(d_f, st);
+    return rc;
 }
 
 int cmoop_mfcc_fwd_host_i16(cmoop_mfcc_handle h, const int16_t* wave, int64_t n_clips, int n_samples, float* out) {

@@ -30,13 +30,22 @@ CROSSOVER_PROB = 0.9          # nsga_penalty.py:201
 LAMBDA_INITIAL, LAMBDA_FINAL = 1.0, 50.0
 
 
-def default_ops(problem, *, surrogate=True):
-    """Bundle of the drop-in functions a driver needs; override any of them for testing."""
+def default_ops(problem, *, surrogate=True, script="sa_nsga_local"):
+    """Bundle of the drop-in functions a driver needs; override any of them for testing.
+
+    ``script`` names the reference file whose copies are mirrored where the copies differ:
+    * crowding_distance: nsga_penalty.py:518 skips an objective when ``f_max - f_min < EPSILON`` (CROWD_RANGE_LT);
+      every other script (sa_nsga_penalty.py:437, sa_nsga_local.py:270) skips unless ``> EPSILON`` (CROWD_RANGE_GT).
+      They differ only when the range equals EPSILON exactly.
+    * SurrogateManager: sa_nsga_penalty.py:342-363 ``predict`` returns records (SurrogateManagerPenalty); the
+      ablation_study/*local* scripts return dicts of arrays (+ stds)."""
+    from functools import partial
+    crowd_mode = _nsga.CROWD_RANGE_LT if script == "nsga_penalty" else _nsga.CROWD_RANGE_GT
     ops = SimpleNamespace(
         compute_objectives_and_constraints=problem.compute_objectives_and_constraints,
         evaluate_individual=problem.evaluate_individual,
         fast_non_dominated_sort=_nsga.fast_non_dominated_sort,
-        crowding_distance=_nsga.crowding_distance,
+        crowding_distance=partial(_nsga.crowding_distance, crowd_mode=crowd_mode),
         dominates=_nsga.dominates,
         tournament_selection=_nsga.tournament_selection,
         crossover=_nsga.crossover,
@@ -45,7 +54,7 @@ def default_ops(problem, *, surrogate=True):
     )
     if surrogate:
         from . import surrogate as s
-        ops.SurrogateManager = s.SurrogateManager
+        ops.SurrogateManager = s.SurrogateManagerPenalty if script == "sa_nsga_penalty" else s.SurrogateManager
         ops.perform_local_search = s.perform_local_search
         ops.select_infill_points = s.select_infill_points
     return ops
@@ -119,6 +128,8 @@ def sa_nsga2(pop_size, max_gen, infill_percent, ops, *, local_search=True, on_ge
     for gen in range(max_gen):
         t0 = time.perf_counter()
         lam = get_lambda(gen)
+        if not local_search:
+            ops.fast_non_dominated_sort(pop_data, lam)     # computed and unused in the reference too (sa_nsga_penalty.py:547)
         parents = [ops.tournament_selection(pop_data, lam) for _ in range(pop_size)]
         parent_hparams = [pop_data[i]["hparams"] for i in parents]
         offspring = []
@@ -133,7 +144,11 @@ def sa_nsga2(pop_size, max_gen, infill_percent, ops, *, local_search=True, on_ge
                           "stds": [stds["neg_acc"][i], stds["size"][i], stds["fpr"][i]], "CV": max(0, preds["cv"][i])}
                          for i, hp in enumerate(offspring)]
             offspring = ops.perform_local_search(predicted, sm)
-        final_pred = sm.predict_and_structure(offspring)
+            final_pred = sm.predict_and_structure(offspring)
+        else:
+            final_pred = sm.predict(offspring)             # sa_nsga_penalty.py:563: predict() returns the records
+            if isinstance(final_pred, dict):               # a dict-returning (sa_nsga_local-form) manager was bound
+                final_pred = sm.predict_and_structure(offspring)
         num_infill = max(1, int(pop_size * infill_percent))
         infill_idx, infill_hp = ops.select_infill_points(final_pred, num_infill)
         t_eval = time.perf_counter()

@@ -427,43 +427,56 @@ def fit_gprs_parallel(kernels, x, ys, n_restarts_optimizer=0, normalize_y=False,
     from sklearn.gaussian_process import GaussianProcessRegressor
     from sklearn.utils import check_random_state
 
+    backend = backend or os.environ.get("CMOOP_GP_FIT_BACKEND", "host")
+    if backend not in ("host", "device"):                # validated on EVERY rank, before any rank-dependent branch
+        raise ValueError(f"unknown GP fit backend {backend!r} (host | device)")
     rng = check_random_state(random_state)
     x = np.asarray(x, np.float64)
-    jobs, probes = [], []
-    for kernel, y in zip(kernels, ys):
-        probe = GaussianProcessRegressor(kernel=kernel, optimizer=None, normalize_y=normalize_y).fit(x, y)
-        probes.append(probe)
-        bounds = probe.kernel_.bounds
-        starts = [probe.kernel_.theta.copy()]
-        if n_restarts_optimizer > 0:
-            if not np.isfinite(bounds).all():
-                raise ValueError("Multiple optimizer restarts (n_restarts_optimizer>0) requires that all bounds are finite.")
-            starts += [rng.uniform(bounds[:, 0], bounds[:, 1]) for _ in range(n_restarts_optimizer)]
-        jobs += [(len(probes) - 1, theta0) for theta0 in starts]
-    payloads = [(kernels[m], x, ys[m], normalize_y, theta0) for m, theta0 in jobs]
-
-    # Under torch.distributed the surrogate is replicated on every rank.  Every rank has drawn the
-    # same starts above (identically seeded streams stay in step), but only rank 0 optimises -- with all host cores -- and
+    # Under torch.distributed the surrogate is replicated on every rank.  Every rank draws the
+    # same starts (identically seeded streams stay in step), but only rank 0 optimises -- with all host cores -- and
     # broadcasts the optima, instead of world_size ranks fitting the same models on a slice of the cores each.
+    # Anything that can raise (non-finite bounds, a CUDA error in the device objective, a dead worker) is caught per
+    # rank and exchanged, so that an error on one rank is re-raised on ALL of them instead of leaving the others
+    # blocked in the broadcast until the collective times out.
     dist = _initialised_dist()
     rank0 = dist is None or dist.get_rank() == 0
-    results = None
-    backend = backend or os.environ.get("CMOOP_GP_FIT_BACKEND", "host")
-    if backend not in ("host", "device"):
-        raise ValueError(f"unknown GP fit backend {backend!r} (host | device)")
-    if rank0 and backend == "device":
-        results = _optimise_on_device(probes, jobs)      # None: a kernel without a device form -> host schedule below
-    if rank0 and results is None:
-        workers = max_workers if max_workers is not None else default_workers(shared=dist is None)
-        workers = min(workers, len(jobs))
-        if workers > 1 and len(x) >= min_rows_for_pool:
-            try:
-                results = _map_on_workers(payloads, workers)
-            except Exception:                           # no subprocesses here (sandbox, frozen app): same maths in-process
-                results = None
-        if results is None:
-            results = [_optimise_start(pl) for pl in payloads]
+    jobs, probes, results, error = [], [], None, None
+    try:
+        for kernel, y in zip(kernels, ys):
+            probe = GaussianProcessRegressor(kernel=kernel, optimizer=None, normalize_y=normalize_y).fit(x, y)
+            probes.append(probe)
+            bounds = probe.kernel_.bounds
+            starts = [probe.kernel_.theta.copy()]
+            if n_restarts_optimizer > 0:
+                if not np.isfinite(bounds).all():
+                    raise ValueError("Multiple optimizer restarts (n_restarts_optimizer>0) requires that all bounds are finite.")
+                starts += [rng.uniform(bounds[:, 0], bounds[:, 1]) for _ in range(n_restarts_optimizer)]
+            jobs += [(len(probes) - 1, theta0) for theta0 in starts]
+        payloads = [(kernels[m], x, ys[m], normalize_y, theta0) for m, theta0 in jobs]
+        if rank0 and backend == "device":
+            results = _optimise_on_device(probes, jobs)      # None: a kernel without a device form -> host schedule below
+        if rank0 and results is None:
+            workers = max_workers if max_workers is not None else default_workers(shared=dist is None)
+            workers = min(workers, len(jobs))
+            if workers > 1 and len(x) >= min_rows_for_pool:
+                try:
+                    results = _map_on_workers(payloads, workers)
+                except Exception:                           # no subprocesses here (sandbox, frozen app): same maths in-process
+                    results = None
+            if results is None:
+                results = [_optimise_start(pl) for pl in payloads]
+    except Exception as exc:                                # noqa: BLE001 -- exchanged below, then re-raised
+        if dist is None:
+            raise
+        error = exc
     if dist is not None:
+        states = [None] * dist.get_world_size()
+        dist.all_gather_object(states, None if error is None else f"rank {dist.get_rank()}: {error!r}")
+        failed = [s for s in states if s is not None]
+        if failed:
+            if error is not None:
+                raise error
+            raise RuntimeError("GP hyper-parameter fit failed on another rank -- " + "; ".join(failed))
         box = [results]
         dist.broadcast_object_list(box, src=0)
         results = box[0]

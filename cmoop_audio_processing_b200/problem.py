@@ -94,6 +94,27 @@ def forward_macs(hp: dict, height: int, width: int, n_classes: int, variant: str
     return macs + width_ * n_classes
 
 
+FPR_MODES = {"all": 0, "filtered": 1, "vectorised": 2}
+
+
+def calculate_fpr(y_true, y_pred, num_classes, mode: str = "all", return_confusion: bool = False):
+    """Macro-averaged false-positive rate of fixed label / prediction vectors -- the reference's ``calculate_fpr``:
+    mode "all" nsga_penalty.py:351-364, "filtered" ablation_study/sa_nsga_local.py:138-141, "vectorised"
+    ablation_study/init_sa_nsga_local.py:137-143.  Confusion matrix by integer atomics on the device, per-class rates and
+    numpy-ordered mean in the library (``cmoop_fpr_from_predictions_host``): bit-identical to the reference's float."""
+    lib = _lib.load()
+    yt = np.ascontiguousarray(np.asarray(y_true).reshape(-1), np.int32)
+    yp = np.ascontiguousarray(np.asarray(y_pred).reshape(-1), np.int32)
+    if yt.shape != yp.shape:
+        raise ValueError("y_true and y_pred differ in length")
+    out = np.zeros(1, np.float64)
+    cm = np.zeros((int(num_classes), int(num_classes)), np.int32) if return_confusion else None
+    _lib.check(lib.cmoop_fpr_from_predictions_host(_lib.ptr(yt), _lib.ptr(yp), len(yt), int(num_classes),
+                                                   FPR_MODES[mode], _lib.ptr(out), _lib.ptr(cm)),
+               "cmoop_fpr_from_predictions_host")
+    return (float(out[0]), cm) if return_confusion else float(out[0])
+
+
 class _Genotype(C.Structure):
     _fields_ = [("filters", C.c_int), ("kernel_size", C.c_int), ("use_bn", C.c_int), ("residual_blocks", C.c_int),
                 ("fc_layers", C.c_int), ("use_dropout", C.c_int)]

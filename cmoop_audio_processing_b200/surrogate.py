@@ -260,6 +260,27 @@ class SurrogateManager:
         return self.predict_and_structure(hparams_list)
 
 
+class SurrogateManagerPenalty(SurrogateManager):
+    """The mean-only manager of the top-level script, sa_nsga_penalty.py:258-363: same four GPs, same encoding, same
+    de-duplicated training table, but ``predict(hparams_list)`` takes no ``return_std`` and returns the structured
+    records ``[{'hparams','objs','CV'}]`` that script hands straight to ``select_infill_points`` (call site :563).
+    Bind THIS class as ``SurrogateManager`` when rebinding sa_nsga_penalty.py (INTEGRATION.md section 3);
+    ``predict_and_structure`` / the dict-returning form stay reachable as ``predict_arrays``."""
+
+    def predict_arrays(self, hparams_list, return_std=False):
+        return SurrogateManager.predict(self, hparams_list, return_std=return_std)
+
+    def predict(self, hparams_list):
+        if not self.is_fitted:
+            raise RuntimeError("Surrogate models must be fitted before prediction.")
+        preds = SurrogateManager.predict(self, hparams_list, return_std=False)
+        return [{"hparams": hp, "objs": [preds["neg_acc"][i], preds["size"][i], preds["fpr"][i]],
+                 "CV": max(0, preds["cv"][i])} for i, hp in enumerate(hparams_list)]
+
+    def predict_and_structure(self, hparams_list):
+        return self.predict(hparams_list)
+
+
 # --------------------------------------------------------------------- infill + local search
 def select_infill_points(predicted_offspring_data, num_to_select):
     """Feasible (CV < EPSILON) first by summed min-max-normalised objectives, then infeasible by CV."""

@@ -241,6 +241,16 @@ int cmoop_cnn_dataset_create_dev(const float* x_train_dev, const int* y_train, i
                                  cmoop_cnn_dataset_handle* out);
 int cmoop_cnn_dataset_destroy(cmoop_cnn_dataset_handle h);
 long long cmoop_cnn_param_count(const cmoop_genotype* g, const cmoop_cnn_config* cfg);
+/* calculate_fpr(y_true, y_pred, num_classes) on fixed label / prediction vectors (host int32 [n]); the scoring tail of
+ * cmoop_cnn_pop_train_eval uses the same confusion-matrix accumulation (integer atomics on the device) and the same
+ * host reduction, so this entry point pins it bit-exactly against the reference's three textual forms:
+ *   mode 0  nsga_penalty.py:351-364              mean over all classes, 0.0 where FP + TN == 0
+ *   mode 1  ablation_study/sa_nsga_local.py:138-141   mean over classes with FP + TN > 0 (0.0 if none)
+ *   mode 2  ablation_study/init_sa_nsga_local.py:137-143  vectorised statement of mode 0 (same value)
+ * The per-class rates are averaged with numpy's pairwise summation order, so the result == np.mean(fpr_vals).
+ * Labels outside [0, n_classes) are dropped (sklearn confusion_matrix(labels=range(C))).  confusion_out [C][C] may be NULL. */
+int cmoop_fpr_from_predictions_host(const int* y_true, const int* y_pred, int n, int n_classes, int mode, double* fpr_out,
+                                    int* confusion_out);
 int cmoop_cnn_pop_train_eval(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotypes, const uint64_t* seeds,
                              int n_candidates, const cmoop_cnn_config* cfg, double* out, double* history);
 /* test hooks: the harness-imposed random streams, so the CPU oracle can train on identical inputs */

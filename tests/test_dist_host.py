@@ -89,3 +89,57 @@ def test_gp_fit_rank0_broadcast_gloo(tmp_path):
     mp.spawn(_gp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     np.testing.assert_array_equal(np.load(tmp_path / "theta0.npy"), np.load(tmp_path / "theta1.npy"))
     np.testing.assert_array_equal(np.load(tmp_path / "next0.npy"), np.load(tmp_path / "next1.npy"))
+
+
+def _gp_error_worker(rank, world, port, tmp):
+    import warnings
+
+    import torch.distributed as dist
+    warnings.filterwarnings("ignore")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), CMOOP_GP_FIT_WORKERS="1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sklearn.gaussian_process.kernels import Matern
+    from cmoop_audio_processing_b200 import gp_fit
+    rng = np.random.default_rng(0)
+    x, y = rng.random((12, 3)), rng.random(12)
+    outcome = []
+    # (a) an error that only rank 0 can hit (the optimiser itself runs there alone)
+    real = gp_fit._optimise_start
+
+    def broken(payload):
+        raise FloatingPointError("objective blew up on the optimising rank")
+    gp_fit._optimise_start = broken
+    try:
+        gp_fit.fit_gprs_parallel([Matern(nu=2.5)], x, [y], n_restarts_optimizer=0)
+        outcome.append("no error")
+    except FloatingPointError as exc:
+        outcome.append(f"FloatingPointError:{exc}")
+    except RuntimeError as exc:
+        outcome.append(f"RuntimeError:{exc}")
+    gp_fit._optimise_start = real
+    # (b) backend validation happens on every rank before the rank branch
+    try:
+        gp_fit.fit_gprs_parallel([Matern(nu=2.5)], x, [y], backend="tpu")
+        outcome.append("no error")
+    except ValueError:
+        outcome.append("ValueError")
+    # (c) the group is still usable afterwards
+    g = gp_fit.fit_gprs_parallel([Matern(nu=2.5)], x, [y], n_restarts_optimizer=0)
+    outcome.append(repr(g[0].kernel_.theta.tolist()))
+    with open(os.path.join(tmp, f"out{rank}.txt"), "w") as fh:
+        fh.write("\n".join(outcome))
+    dist.destroy_process_group()
+
+
+def test_gp_fit_error_reaches_every_rank_gloo(tmp_path):
+    """if rank 0 raises while optimising, the other ranks must not sit in the broadcast until the
+    collective times out -- the failure is exchanged and re-raised everywhere."""
+    import torch.multiprocessing as mp
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_gp_error_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = (tmp_path / "out0.txt").read_text().split("\n")
+    r1 = (tmp_path / "out1.txt").read_text().split("\n")
+    assert r0[0].startswith("FloatingPointError:")
+    assert r1[0].startswith("RuntimeError:") and "rank 0" in r1[0] and "FloatingPointError" in r1[0]
+    assert r0[1] == r1[1] == "ValueError"
+    assert r0[2] == r1[2]

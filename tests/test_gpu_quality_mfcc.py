@@ -191,3 +191,26 @@ def test_mfcc_int16_pcm_input():
     np.testing.assert_array_equal(got_dev.cpu().numpy(), got_host)
     odd = np.ascontiguousarray(pcm[:3, :15999])                    # unaligned rows exercise the scalar tail of the widening
     np.testing.assert_array_equal(fe(odd), fe(odd.astype(np.float32) / 32768.0))
+
+
+def test_mfcc_int16_two_streams_do_not_share_scratch():
+    """the device int16 entry point widened PCM into process-global scratch; two calls on different streams
+    (or two handles) raced on it.  The widened chunk is now a stream-ordered allocation of the caller's stream."""
+    import torch
+    from cmoop_audio_processing_b200 import synth
+    from cmoop_audio_processing_b200.features import MfccFrontEnd
+    wave_a, _ = synth.make_clips(600, 12, seed=11)
+    wave_b, _ = synth.make_clips(600, 12, seed=12)
+    to_pcm = lambda w: torch.from_numpy(np.clip(np.round(w * 32767.0), -32768, 32767).astype(np.int16)).cuda()   # noqa: E731
+    pcm_a, pcm_b = to_pcm(wave_a), to_pcm(wave_b)
+    fe_a, fe_b = MfccFrontEnd(), MfccFrontEnd()
+    want_a, want_b = fe_a(pcm_a).clone(), fe_b(pcm_b).clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(5):
+        with torch.cuda.stream(s1):
+            got_a = fe_a(pcm_a)
+        with torch.cuda.stream(s2):
+            got_b = fe_b(pcm_b)
+        torch.cuda.synchronize()
+        assert torch.equal(got_a, want_a) and torch.equal(got_b, want_b)

@@ -44,9 +44,9 @@ def test_lambda_schedule(golden):
 def test_fpr_variants(golden):
     for case in golden("fpr")["cases"]:
         cm = nsga_ref.confusion(case["y_true"], case["y_pred"], case["classes"])
-        assert nsga_ref.fpr_macro(cm, "all") == pytest.approx(case["fpr_all"], rel=1e-14, abs=0)
-        assert nsga_ref.fpr_macro(cm, "filtered") == pytest.approx(case["fpr_filtered"], rel=1e-14, abs=0)
-        assert nsga_ref.fpr_macro(cm, "all") == pytest.approx(case["fpr_vectorised"], rel=1e-12, abs=1e-15)
+        assert nsga_ref.fpr_macro(cm, "all") == case["fpr_all"]                  # bit-exact: same np.mean of the same floats
+        assert nsga_ref.fpr_macro(cm, "filtered") == case["fpr_filtered"]
+        assert nsga_ref.fpr_macro(cm, "all") == case["fpr_vectorised"]
 
 
 def test_fpr_all_zero_labels_quirk():
