@@ -1,26 +1,46 @@
 #!/usr/bin/env python
-"""bench.py -- MFCC/log-mel front-end throughput (BASELINE.json configs[1]) on N B200s.
+"""bench.py -- candidate true-evaluations per second within a SA-NSGA-II generation (BASELINE.json metric, first clause)
+on N B200s, with the MFCC front-end throughput (second clause) and the latency kernels as extra objects.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step = one pass of the front-end over one batch of 65 536 synthetic 1 s / 16 kHz clips per GPU
-(clips shard by clip: no data-path collective, weak scaling).  One JSON line is printed by rank 0:
+Workload (BASELINE configs[4], one generation of it): population 256, CNN variant B, 12 classes, synthetic GSC-shaped 1 s /
+16 kHz clips (synth.make_clips, seed 1234) -> 49x40 MFCC features -> StandardScaler fitted on the 12x256 training clips;
+12x64 validation clips; batch 64, Adam, EarlyStopping(val_loss, patience 5, restore_best_weights) with the epoch count
+CAPPED at --epoch-cap (default 4; the reference's 300 is a ceiling it never reaches either, the cap is stated in `config`).
 
-  value      clips/s, whole job, inputs already resident in HBM, CUDA events on the launching stream
-  e2e        the same metric through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside)
-  roofline   HBM: 71 840 algorithmic bytes/clip (16 000*4 read + 49*40*4 written) / kernel time,
-             against MEASURED_PEAKS.json hbm_gbs (else the 6 650 GB/s fallback)
-  cpu_baseline  the plain-C/OpenMP oracle port on this host's cores, bounded sample (N=1 only)
+A step = ONE `compute_objectives_and_constraints(population)` call (nsga_penalty.py:418-442, the serial loop at :426) over
+the whole population: the 256 candidates are partitioned over the N ranks (longest-processing-time first on a per-genotype
+cost table), trained and scored on the bf16 tcgen05 path, and the objective rows are all-gathered INSIDE the timed region.
+STRONG scaling: the population is fixed as N grows.  One JSON line is printed by rank 0:
 
---impl reference times the CPU path alone (the reference has no feature code, so this is the oracle
-port of the declared spec) on a bounded sample per step, all host threads.
+  value      candidate evaluations / s over K steps: dataset resident in HBM, genotypes in, host records out
+  e2e        the same metric inside a FULL SA-NSGA-II generation (drivers.sa_nsga2 = ablation_study/sa_nsga_local.py:436-554:
+             tournament, variation, GP predict(return_std) + Lamarckian local search, infill selection, the true evaluations
+             of the max(1, int(256*0.334)) = 85 infill points from HOST feature arrays (re-staged host->device every
+             generation), surrogate update, NDS + crowding truncation of the 512 merged records, HV / IGD / Spread of the
+             generation), host records to host records: true evaluations / generation wall time
+  roofline   tensor: analytic FLOPs of the step (E_i*(6*MACs_i*N_train + 2*MACs_i*N_val) + 2*MACs_i*N_val per candidate)
+             / device time of the step, against MEASURED_PEAKS.json bf16_tflops_sustained; `dominant_kernel` gives the same
+             for the kernel family with the largest share of the step, from CUDA-event pairs around every launch
+  cpu_baseline  the torch-CPU oracle (oracle/cnn_ref.py, all host threads) on a stratified sample of whole candidates
+  mfcc       clips/s of the front-end kernel on 65 536 clips per GPU with its own HBM roofline and host-buffer e2e
+  latency    NDS+crowding / hypervolume / GP predict: us per call device-resident and through the host ABI, next to the
+             CPU port timed in the same run
+
+--impl reference times the CPU path alone: the same candidates evaluated serially (exactly the loop of
+nsga_penalty.py:426) by the torch-CPU restatement of evaluate_individual on ALL host threads (the launcher's
+OMP_NUM_THREADS=1 is overridden), one or more WHOLE candidates per step drawn from cost strata of the same population.
+TensorFlow / Keras are not installable here, so `kind` is "port" (DESIGN.md section 2).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
+import random
 import statistics
 import sys
 import threading
@@ -30,42 +50,88 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+METRIC = "candidate_evals_per_sec"
+UNIT = "evals/s"
+POP = 256
+N_CLASSES = 12
+N_TRAIN = 12 * 256
+N_VAL = 12 * 64
+INFILL = 0.334
+VARIANT = "B"
+H, W = 49, 40
+
+# MFCC extra (BASELINE configs[1])
 N_SAMPLES = 16000
 N_FRAMES = 49
 N_OUT = 40
 BYTES_PER_CLIP = N_SAMPLES * 4 + N_FRAMES * N_OUT * 4      # 71 840
-METRIC = "mfcc_clips_per_sec"
-UNIT = "clips/s"
 
 
-def workload_config(clips: int, n_gpus: int) -> dict:
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:                                  # pragma: no cover
+        return os.cpu_count() or 1
+
+
+def use_all_host_threads() -> int:
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the CPU legs must use every host thread at every N."""
+    n = host_threads()
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[var] = str(n)
+    return n
+
+
+def workload_config(args, n_gpus: int) -> dict:
     return {
-        "workload": "BASELINE configs[1]: MFCC front-end, 40 mel x 49 frames (+DCT-II), "
-                    f"{clips} synthetic 1 s 16 kHz fp32 clips per GPU",
-        "clips_per_gpu": clips, "n_samples": N_SAMPLES, "frames": N_FRAMES, "features": N_OUT,
-        "sharding": f"clips partitioned across {n_gpus} GPU(s), no collective",
-        "cache": f"inputs ({clips * N_SAMPLES * 4 / 1e9:.2f} GB/GPU) larger than L2 (126 MB); no flush needed",
+        "workload": f"BASELINE configs[4] (one generation of it): SA-NSGA-II population {args.pop}, CNN variant B, "
+                    f"{N_CLASSES} classes, synthetic GSC-shaped 1 s 16 kHz clips -> 49x40 MFCC, {N_TRAIN} train / {N_VAL} val "
+                    f"clips, batch 64, Adam, EarlyStopping(patience 5, restore best) with the epoch count capped at "
+                    f"{args.epoch_cap}; step = one compute_objectives_and_constraints(population) call",
+        "population": args.pop, "classes": N_CLASSES, "n_train": N_TRAIN, "n_val": N_VAL, "epoch_cap": args.epoch_cap,
+        "patience": 5, "batch_size": 64, "variant": VARIANT, "infill_percent": INFILL,
+        "sharding": f"{args.pop} candidates partitioned over {n_gpus} GPU(s) (LPT on the genotype cost table), one "
+                    "all-gather of the objective rows per call inside the timed region",
+        "cache": "per-step working set (activations of >= 32 candidates per GPU, tens of GB) is far larger than L2 (126 MB); "
+                 "no flush needed",
     }
 
 
-def measured_peak() -> tuple[float, str]:
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+def measured_peaks() -> dict:
     try:
-        with open(path) as fh:
-            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_sustained": float(d["bf16_tflops_sustained"]),
+                "bf16_burst": float(d["bf16_tflops"]), "source": "measured (MEASURED_PEAKS.json)"}
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return {"hbm_gbs": 6650.0, "bf16_sustained": 1400.0, "bf16_burst": 1650.0,
+                "source": "fallback (B200_PROFILING.md)"}
 
 
-def recorded_traffic(clips: int):
-    """dram bytes per launch from the committed ncu --set full capture (profiles/roofline.json), scaled
-    linearly in clips; None when no capture has been recorded."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "roofline.json")) as fh:
-            rec = json.load(fh)["mfcc_kernel"]
-        return rec["dram_bytes_per_clip"] * clips
-    except Exception:
-        return None
+def make_population(pop: int, seed: int = 0):
+    from cmoop_audio_processing_b200.nsga import HPARAM_SPACE
+    rng = random.Random(seed)
+    return [{k: rng.choice(v) for k, v in HPARAM_SPACE.items()} for _ in range(pop)]
+
+
+def analytic_flops(hps, epochs_run, n_final: int = 1) -> float:
+    """E*(6*M*N_train + 2*M*N_val) + 2*M*N_val*n_final per candidate (n_final = the scoring passes
+    actually executed: this engine takes accuracy and the confusion matrix from ONE pass)."""
+    from cmoop_audio_processing_b200.problem import forward_macs
+    total = 0.0
+    for hp, e in zip(hps, epochs_run):
+        m = forward_macs(hp, H, W, N_CLASSES, VARIANT)
+        total += float(e) * (6.0 * m * N_TRAIN + 2.0 * m * N_VAL) + 2.0 * m * N_VAL * n_final
+    return total
+
+
+def stratified_sample(hps, m: int):
+    """m candidates at the mid-quantiles of the population's analytic cost: sample i is the median of the i-th of m
+    equal-count cost strata, so m / sum(t_i) is the plain stratified estimate of the population's evaluations / s."""
+    from cmoop_audio_processing_b200.problem import forward_macs
+    order = sorted(range(len(hps)), key=lambda i: (forward_macs(hps[i], H, W, N_CLASSES, VARIANT), i))
+    picks = [order[min(len(order) - 1, int((i + 0.5) * len(order) / m))] for i in range(m)]
+    return picks
 
 
 class ClockSampler:
@@ -73,7 +139,7 @@ class ClockSampler:
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index: int, period_s: float = 0.02):
+    def __init__(self, index: int, period_s: float = 0.05):
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
@@ -103,7 +169,7 @@ class ClockSampler:
             self._stop.wait(self.period)
 
     def start(self):
-        if self.ok:
+        if self.ok and self._thread is None:
             self._stop.clear()
             self._thread = threading.Thread(target=self._run, daemon=True)
             self._thread.start()
@@ -121,360 +187,535 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def time_cpu_port(target_seconds: float, threads_note: bool = True) -> dict:
-    """Time the C/OpenMP oracle port on a bounded sample of the same workload."""
+# ------------------------------------------------------------------------------------------------ CPU side (oracle port)
+def cpu_features():
+    """The same synthetic clips through the plain-C MFCC oracle + StandardScaler fitted on the training split."""
     import numpy as np
-    from oracle import build_c
     from cmoop_audio_processing_b200 import synth
-
-    lib = build_c.load()
-    cores = int(lib.cmoop_oracle_num_threads())
-    probe = synth.uniform_clips(max(64, 8 * cores), seed=2)
-    build_c.mfcc(probe[:cores])                                   # warm up threads
-    t0 = time.perf_counter()
-    build_c.mfcc(probe)
-    rate = len(probe) / (time.perf_counter() - t0)
-    n = int(min(65536, max(len(probe), rate * target_seconds)))
-    sample = synth.uniform_clips(n, seed=2)
-    t0 = time.perf_counter()
-    build_c.mfcc(sample)
-    dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} clips of the same U(-1,1) 16 000-sample workload, {dt:.1f} s, C/OpenMP fp64 oracle "
-                      "(oracle/c/mfcc_oracle.c; the reference has no feature-extraction code to time)"}
+    from oracle import build_c
+    wave, labels = synth.make_clips(N_TRAIN + N_VAL, N_CLASSES, seed=1234)
+    feats = build_c.mfcc(wave)
+    mean = feats[:N_TRAIN].reshape(-1, N_OUT).mean(axis=0)
+    scale = feats[:N_TRAIN].reshape(-1, N_OUT).std(axis=0)
+    scale[scale == 0.0] = 1.0
+    feats = ((feats - mean) / scale).astype(np.float32)[..., None]
+    return (feats[:N_TRAIN], labels[:N_TRAIN].astype(np.int64), feats[N_TRAIN:], labels[N_TRAIN:].astype(np.int64))
 
 
-def cnn_generation_extra(args, rank: int, world: int) -> dict:
-    """Secondary measurement (BASELINE metric part 1): true candidate evaluations per second for one
-    compute_objectives_and_constraints call on synthetic GSC-shaped features (SA-NSGA-II infill batch, CNN variant B,
-    12 classes), next to the torch-CPU oracle timed on a bounded sample.  Not the headline `value`."""
-    import random
-
+def cpu_evaluate_candidate(hp, data, seed: int, epoch_cap: int) -> tuple[float, dict]:
+    """One WHOLE candidate through the torch-CPU restatement of evaluate_individual (sa_nsga_local policy): Glorot-uniform
+    initialisation, per-epoch shuffles, Adam, per-epoch validation, early stopping, restore, evaluate + FPR.  Seconds."""
     import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    from cmoop_audio_processing_b200.nsga import HPARAM_SPACE
-    from cmoop_audio_processing_b200.problem import FitnessProblem, TrainConfig, forward_macs
-
-    n_train, n_val, epochs, pop = args.cnn_train, 768, args.cnn_epochs, args.cnn_pop * world
-    rng = np.random.default_rng(1234)
-    xt = rng.standard_normal((n_train, 49, 40, 1)).astype(np.float32)
-    yt = rng.integers(0, 12, n_train)
-    xv = rng.standard_normal((n_val, 49, 40, 1)).astype(np.float32)
-    yv = rng.integers(0, 12, n_val)
-    pyr = random.Random(0)
-    hps = [{k: pyr.choice(v) for k, v in HPARAM_SPACE.items()} for _ in range(pop)]
-    out = {}
-    for prec in ("bf16", "fp32"):
-        cfg = TrainConfig(variant="B", epochs=epochs, patience=epochs, restore_best_weights=True, acc_from="evaluate",
-                          precision=prec)
-        prob = FitnessProblem(xt, yt, xv, yv, classes=12, config=cfg)
-        # warm-up: the whole population for one epoch on a 128-sample slice, so the persistent activation arena
-        # is allocated (tens of GB of cudaMalloc) and every kernel is loaded before the timed call
-        warm = FitnessProblem(xt[:128], yt[:128], xv[:64], yv[:64], classes=12,
-                              config=TrainConfig(variant="B", epochs=1, patience=1, precision=prec))
-        warm.compute_objectives_and_constraints(hps)
-        warm.data.close()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        recs = prob.compute_objectives_and_constraints(hps)          # sharded over ranks + all-gather when world > 1
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        dt = float(dt[0])
-        macs = [forward_macs(hp, 49, 40, 12, "B") for hp in hps]
-        flops = sum(epochs * (6 * m * n_train + 2 * m * n_val) + 2 * m * n_val for m in macs)
-        out[prec] = {"evals_per_sec": pop / dt, "seconds": dt, "analytic_tflops": flops / dt / 1e12,
-                     "records": len(recs)}
-        prob.data.close()
-    # the population size of BASELINE configs[4] (256, sharded over the ranks), tensor-core path only
-    big = 256
-    hps_big = [{k: pyr.choice(v) for k, v in HPARAM_SPACE.items()} for _ in range(big)]
-    cfg = TrainConfig(variant="B", epochs=epochs, patience=epochs, restore_best_weights=True, acc_from="evaluate",
-                      precision="bf16")
-    prob = FitnessProblem(xt, yt, xv, yv, classes=12, config=cfg)
-    warm = FitnessProblem(xt[:128], yt[:128], xv[:64], yv[:64], classes=12,
-                          config=TrainConfig(variant="B", epochs=1, patience=1, precision="bf16"))
-    warm.compute_objectives_and_constraints(hps_big)
-    warm.data.close()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    recs = prob.compute_objectives_and_constraints(hps_big)
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    dt = float(dt[0])
-    macs_big = [forward_macs(hp, 49, 40, 12, "B") for hp in hps_big]
-    flops = sum(epochs * (6 * m * n_train + 2 * m * n_val) + 2 * m * n_val for m in macs_big)
-    out["bf16_pop256"] = {"evals_per_sec": big / dt, "seconds": dt, "analytic_tflops": flops / dt / 1e12,
-                          "records": len(recs)}
-    prob.data.close()
-    res = {"workload": f"{pop} random genotypes (variant B), {n_train} train / {n_val} val 49x40 features, {epochs} epochs "
-                       "fixed, batch 64, Adam; one compute_objectives_and_constraints call (bf16_pop256: the same with "
-                       "256 genotypes)",
-           "gpu": out}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import cnn_ref
-        hp = sorted(zip(macs, range(pop)))[pop // 2][1]
-        hp = hps[hp]
-        m = forward_macs(hp, 49, 40, 12, "B")
-        torch.set_num_threads(os.cpu_count() or 1)
-        shapes = cnn_ref.param_shapes(hp, 12, "B")
-        prng = np.random.default_rng(0)
-        params = {}
-        for name, shape in shapes:
-            if name.endswith(".w"):
-                params[name] = (prng.standard_normal(shape) * 0.05).astype(np.float32)
-            elif name.endswith((".gamma", ".var")):
-                params[name] = np.ones(shape, np.float32)
-            else:
-                params[name] = np.zeros(shape, np.float32)
-        model = cnn_ref.RefModel(hp, 12, "B", params)
-        steps = 6
-        cnn_ref.train_steps(model, xt, yt, np.arange(n_train), 1)
-        t0 = time.perf_counter()
-        cnn_ref.train_steps(model, xt, yt, np.arange(n_train), steps, start_step=1)
-        dt = time.perf_counter() - t0
-        cpu_flops = 6 * m * 64 * steps / dt
-        total_flops = sum(epochs * (6 * mm * n_train + 2 * mm * n_val) + 2 * mm * n_val for mm in macs)
-        res["cpu_baseline"] = {"kind": "port", "cores": os.cpu_count(),
-                               "sample": f"{steps} Adam steps (batch 64) of the median-cost genotype with the torch-CPU fp32 "
-                                         "oracle (TensorFlow is not installable here), extrapolated by analytic FLOPs",
-                               "cpu_tflops": cpu_flops / 1e12,
-                               "evals_per_sec": pop / (total_flops / cpu_flops)}
-    return res
-
-
-def surrogate_fit_extra() -> dict:
-    """Extra object of the JSON line: one SurrogateManager.update-sized hyper-parameter fit (4 targets x 11 starts,
-    n = 288 de-duplicated genotypes, sa_nsga_local.py:180-181,195-210) with the objective on the GPU (csrc/gp_lml.cu)
-    and on the host worker pool (scikit-learn's own objective)."""
-    import warnings
-
-    import numpy as np
-    from sklearn.gaussian_process.kernels import ConstantKernel, Matern, WhiteKernel
-
-    from cmoop_audio_processing_b200 import gp_fit
-
-    warnings.filterwarnings("ignore")
-    space = [(f, k, r, fc, bn, 1 - bn, dr, 1 - dr) for f in (16, 32, 64, 128) for k in (3, 5) for r in (1, 2, 3)
-             for fc in (1, 2, 3) for bn in (0, 1) for dr in (0, 1)]
-    rng = np.random.default_rng(288)
-    x = np.asarray(space, np.float64)[rng.permutation(len(space))]
-    f = x[:, 0] / 128.0
-    ys = [-0.9 + 0.2 * np.exp(-f) + 0.02 * rng.standard_normal(len(x)), 0.1 * x[:, 0] * x[:, 1] / 50.0 + 0.3 * x[:, 2],
-          0.05 + 0.02 * rng.standard_normal(len(x)) + 0.01 * x[:, 3],
-          np.maximum(0.0, 0.3 - f + 0.05 * rng.standard_normal(len(x)))]
-    ys = [(y - y.mean()) / y.std() for y in ys]
-    kernels = [ConstantKernel(1.0) * Matern(length_scale=1.0, nu=1.5) + WhiteKernel(noise_level=0.1) for _ in ys]
-    out = {"workload": "4 targets x 11 L-BFGS-B starts, C*Matern(1.5)+White, n = 288 x 8 features"}
-    for backend in ("device", "host"):
-        best = None
-        for _ in range(2):                                          # the second call excludes worker start-up / module load
-            t0 = time.perf_counter()
-            fitted = gp_fit.fit_gprs_parallel(kernels, x, ys, n_restarts_optimizer=10, random_state=1, backend=backend)
-            best = time.perf_counter() - t0
-        out[backend] = {"seconds": best, "lml": [float(g.log_marginal_likelihood_value_) for g in fitted]}
-        if backend == "device":
-            out[backend].update(gp_fit.LAST_DEVICE_FIT)
+    from oracle import cnn_ref
+    rng = np.random.default_rng(seed)
+    params = {}
+    for name, shape in cnn_ref.param_shapes(hp, N_CLASSES, VARIANT):
+        if name.endswith(".w"):
+            fan_in = int(np.prod(shape[:-1]))
+            fan_out = int(np.prod(shape[:-2])) * shape[-1] if len(shape) == 4 else shape[-1]
+            limit = math.sqrt(6.0 / (fan_in + fan_out))
+            params[name] = rng.uniform(-limit, limit, size=shape).astype(np.float32)
+        elif name.endswith((".gamma", ".var")):
+            params[name] = np.ones(shape, np.float32)
         else:
-            out[backend]["cores"] = os.cpu_count()
-    return out
+            params[name] = np.zeros(shape, np.float32)
+    perms = [rng.permutation(N_TRAIN) for _ in range(epoch_cap)]
+    t0 = time.perf_counter()
+    res = cnn_ref.evaluate_individual(hp, data, params, perms, n_classes=N_CLASSES, variant=VARIANT, seed=seed,
+                                      epochs=epoch_cap, patience=5, restore_best_weights=True, acc_from="evaluate",
+                                      fpr_mode="filtered")
+    return time.perf_counter() - t0, res
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
-    from oracle import build_c
-    from cmoop_audio_processing_b200 import synth
-
-    lib = build_c.load()
-    cores = int(lib.cmoop_oracle_num_threads())
-    probe = synth.uniform_clips(max(64, 8 * cores), seed=2)
-    build_c.mfcc(probe[:cores])
-    t0 = time.perf_counter()
-    build_c.mfcc(probe)
-    rate = len(probe) / (time.perf_counter() - t0)
-    budget = 150.0 / max(1, args.steps + args.warmup)              # whole run within a few minutes
-    n = int(min(65536, max(len(probe), rate * min(budget, 4.0))))
-    sample = synth.uniform_clips(n, seed=2)
-    for _ in range(args.warmup):
-        build_c.mfcc(sample)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        build_c.mfcc(sample)
-    dt = time.perf_counter() - t0
-    value = n * args.steps / dt
+    cores = use_all_host_threads()                           # before torch / the OpenMP oracle are loaded
+    import torch
+    torch.set_num_threads(cores)
+    if torch.get_num_threads() < cores:
+        raise SystemExit(f"reference arm: torch uses {torch.get_num_threads()} threads, host has {cores}")
+    from cmoop_audio_processing_b200.problem import forward_macs
+    data = cpu_features()
+    hps = make_population(args.pop)
+    per_step = max(1, -(-args.ref_min_candidates // max(1, args.steps)))   # >= 8 whole candidates in the timed region
+    strata = stratified_sample(hps, args.steps * per_step)
+    cheap = stratified_sample(hps, 8)[:2]                    # warm-up candidates: the two cheapest strata
+    for w in range(args.warmup):
+        cpu_evaluate_candidate(hps[cheap[w % len(cheap)]], data, 1000 + w, args.epoch_cap)
+    times, macs, epochs = [], [], []
+    t_all = time.perf_counter()
+    for s in range(args.steps):
+        for j in range(per_step):
+            i = strata[s * per_step + j]
+            dt, res = cpu_evaluate_candidate(hps[i], data, i, args.epoch_cap)
+            times.append(dt)
+            macs.append(forward_macs(hps[i], H, W, N_CLASSES, VARIANT))
+            epochs.append(res["epochs_run"])
+    total = time.perf_counter() - t_all
+    n = len(times)
+    value = n / total
+    flops = analytic_flops([hps[i] for i in strata], epochs, n_final=2)
+    sample = (f"{n} WHOLE candidates ({per_step} per step) at the mid-quantiles of {n} equal-count cost strata of the same "
+              f"{args.pop}-genotype population (fwd MACs/sample {min(macs) / 1e6:.1f}-{max(macs) / 1e6:.1f} M), each trained "
+              f"{min(epochs)}-{max(epochs)} epochs (cap {args.epoch_cap}) and scored, evaluated serially as "
+              f"nsga_penalty.py:426 does, {total:.1f} s; torch-CPU fp32 restatement of evaluate_individual "
+              f"(oracle/cnn_ref.py; TensorFlow/Keras not installable), {cores} threads; warm-up steps use the two "
+              "cheapest strata")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.clips, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"each step = {n} clips of the workload (bounded sample), C/OpenMP fp64 oracle "
-                                   "port of the declared front-end spec; the reference repo has no feature code and "
-                                   "its librosa dependency is not installed"},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "seconds_per_candidate": [round(t, 3) for t in times],
+                         "cpu_tflops_analytic": flops / total / 1e12},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args) -> None:
+def cpu_baseline_leg(args, hps) -> dict:
+    """Our arm, N = 1, rank 0: the same port on a bounded stratified sample of whole candidates (about 10-30 s)."""
+    cores = host_threads()
+    import torch
+    torch.set_num_threads(cores)
+    data = cpu_features()
+    picks = stratified_sample(hps, args.cpu_candidates)
+    cpu_evaluate_candidate(hps[stratified_sample(hps, 8)[0]], data, 999, 1)          # thread pool / oneDNN warm-up
+    times = []
+    t0 = time.perf_counter()
+    for i in picks:
+        dt, _ = cpu_evaluate_candidate(hps[i], data, i, args.epoch_cap)
+        times.append(dt)
+    total = time.perf_counter() - t0
+    return {"value": len(picks) / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(picks)} whole candidates at the mid-quantiles of {len(picks)} cost strata of the population, epoch "
+                      f"cap {args.epoch_cap}, serial, {total:.1f} s; torch-CPU fp32 restatement (oracle/cnn_ref.py)",
+            "seconds_per_candidate": [round(t, 3) for t in times]}
+
+
+# ------------------------------------------------------------------------------------------------ GPU side
+def device_features(dev):
+    """Synthetic clips -> MFCC -> StandardScaler(fit on train) entirely on the device; returns CUDA tensors + labels."""
     import numpy as np
     import torch
+    from cmoop_audio_processing_b200 import synth
+    from cmoop_audio_processing_b200.features import MfccFrontEnd, prepare_dataset_device
+    wave, labels = synth.make_clips(N_TRAIN + N_VAL, N_CLASSES, seed=1234)
+    w = torch.from_numpy(wave).to(dev)
+    fe = MfccFrontEnd()
+    x_train, x_val = prepare_dataset_device(fe, [w[:N_TRAIN], w[N_TRAIN:]], policy="fit_train")
+    torch.cuda.synchronize()
+    fe.close()
+    return x_train, labels[:N_TRAIN].astype(np.int32), x_val, labels[N_TRAIN:].astype(np.int32)
+
+
+def train_config(args):
+    from cmoop_audio_processing_b200.problem import TrainConfig
+    return TrainConfig(variant=VARIANT, epochs=args.epoch_cap, patience=5, restore_best_weights=True, acc_from="evaluate",
+                       fpr_mode="filtered", precision="bf16")
+
+
+def mfcc_extra(args, rank, world, dev, barrier) -> dict:
+    """BASELINE metric, second clause: MFCC clips/s vs the HBM roofline (configs[1], 65 536 clips per GPU, weak)."""
+    import torch
     import torch.distributed as dist
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
     from cmoop_audio_processing_b200 import _lib
     from cmoop_audio_processing_b200.features import MfccFrontEnd
-
     lib = _lib.load()
-    _lib.check(lib.cmoop_set_device(local_rank), "cmoop_set_device")
-    clips = args.clips
-    dev = torch.device("cuda", local_rank)
+    clips, steps = args.mfcc_clips, args.mfcc_steps
     gen = torch.Generator(device=dev).manual_seed(2 + rank)
     wave = torch.rand((clips, N_SAMPLES), generator=gen, device=dev, dtype=torch.float32).mul_(2).sub_(1)
     out = torch.empty((clips, N_FRAMES, N_OUT), device=dev, dtype=torch.float32)
     fe = MfccFrontEnd()
-    assert fe.n_frames(N_SAMPLES) == N_FRAMES and fe.n_out == N_OUT
+    for _ in range(3):
+        fe(wave, out=out)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for s, e in ev:
+        s.record()
+        fe(wave, out=out)                                   # launched on torch's current stream (passed to the C ABI)
+        e.record()
+    t1.record()
+    barrier()
+    total_ms = t0.elapsed_time(t1)
+    kernel_ms = [s.elapsed_time(e) for s, e in ev]
+    # host-buffer C-ABI call on 16-bit PCM (what a wav file holds) and on fp32, pinned host memory, H2D + D2H inside
+    e2e_steps = 3
+    h_out = torch.empty((clips, N_FRAMES, N_OUT), dtype=torch.float32, pin_memory=True)
+    h_pcm = torch.empty((clips, N_SAMPLES), dtype=torch.int16, pin_memory=True)
+    h_pcm.copy_((wave * 32767.0).round().to(torch.int16))
+    h_wave = torch.empty((clips, N_SAMPLES), dtype=torch.float32, pin_memory=True)
+    h_wave.copy_(wave)
+    torch.cuda.synchronize()
+    res = {}
+    for key, src in (("e2e_fp32", h_wave.numpy()), ("e2e_int16", h_pcm.numpy())):
+        fe(src, out=h_out.numpy())
+        barrier()
+        t = time.perf_counter()
+        for _ in range(e2e_steps):
+            fe(src, out=h_out.numpy())
+        torch.cuda.synchronize()
+        res[key] = time.perf_counter() - t
+    stats = torch.tensor([total_ms, res["e2e_fp32"], res["e2e_int16"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    total_ms, e32, e16 = (float(v) for v in stats)
+    fe.close()
+    del wave, out, h_out, h_pcm, h_wave
+    torch.cuda.empty_cache()
+    peaks = measured_peaks()
+    kavg = sum(kernel_ms) / len(kernel_ms)
+    achieved = BYTES_PER_CLIP * clips / (kavg * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline.json")) as fh:
+            traffic = json.load(fh)["mfcc_kernel"]["dram_bytes_per_clip"] * clips
+    except Exception:
+        pass
+    return {
+        "metric": "mfcc_clips_per_sec", "unit": "clips/s", "scaling": "weak", "clips_per_gpu": clips, "steps": steps,
+        "value": world * clips * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps, "dtype": "f32",
+        "roofline": {"bound": "hbm", "kernel": "mfcc_pair_kernel<1>", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                     "algorithmic_bytes_per_launch": BYTES_PER_CLIP * clips, "kernel_ms_avg": kavg},
+        "e2e": {"value": world * clips * e2e_steps / e32, "unit": "clips/s", "h2d_bytes_per_step": clips * N_SAMPLES * 4,
+                "d2h_bytes_per_step": clips * N_FRAMES * N_OUT * 4, "api": "cmoop_mfcc_fwd_host, pinned fp32 host buffers"},
+        "e2e_int16": {"value": world * clips * e2e_steps / e16, "unit": "clips/s", "h2d_bytes_per_step": clips * N_SAMPLES * 2,
+                      "d2h_bytes_per_step": clips * N_FRAMES * N_OUT * 4,
+                      "api": "cmoop_mfcc_fwd_host_i16 (16-bit PCM host buffers, widened on the device)"},
+    }
+
+
+def latency_extra(dev) -> dict:
+    """us per call of the latency-bound kernels (device-resident, CUDA events on the launching stream; and through the
+    host ABI), next to the CPU port of the reference function (oracle/) timed in the same run."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    from cmoop_audio_processing_b200 import _lib, nsga, quality
+    from cmoop_audio_processing_b200.surrogate import DeviceGPGroup
+    from oracle import gp_ref, hv_ref, nsga_ref
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    out = {}
+
+    def dev_us(fn, reps=50):
+        for _ in range(5):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e3 / reps
+
+    def host_us(fn, reps=20):
+        fn()
+        t = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t) * 1e6 / reps
+
+    for n in (128, 512):                                   # parents / merged population of pop 64 and 256, M = 3
+        objs = rng.random((n, 3))
+        cv = rng.random(n) * (rng.random(n) < 0.5)
+        recs = [{"hparams": {}, "objs": objs[i].tolist(), "CV": float(cv[i])} for i in range(n)]
+        d_objs, d_cv = torch.from_numpy(objs).to(dev), torch.from_numpy(cv).to(dev)
+        d_rank = torch.empty(n, dtype=torch.int32, device=dev)
+        d_order = torch.empty(n, dtype=torch.int32, device=dev)
+        d_foff = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        d_nf = torch.empty(1, dtype=torch.int32, device=dev)
+        d_crowd = torch.empty(n, dtype=torch.float64, device=dev)
+
+        def launch():
+            _lib.check(lib.cmoop_nds_crowding_dev(C.c_void_p(d_objs.data_ptr()), C.c_void_p(d_cv.data_ptr()), n, 3, 1, 7.5,
+                                                  1e-6, 0, C.c_void_p(d_rank.data_ptr()), C.c_void_p(d_order.data_ptr()),
+                                                  C.c_void_p(d_foff.data_ptr()), C.c_void_p(d_nf.data_ptr()),
+                                                  C.c_void_p(d_crowd.data_ptr()), None, 0, C.c_void_p(stream)),
+                       "cmoop_nds_crowding_dev")
+        t = time.perf_counter()
+        fronts = nsga_ref.fast_non_dominated_sort(recs, 7.5)
+        for f in fronts:
+            nsga_ref.crowding_distance(f, recs)
+        cpu = (time.perf_counter() - t) * 1e6
+        assert nsga.fast_non_dominated_sort(recs, 7.5) == fronts
+        out[f"nds_crowding_n{n}_m3"] = {"device_us": dev_us(launch), "host_abi_us": host_us(
+            lambda: nsga.nds_crowding_arrays(objs, cv, 7.5)), "cpu_port_us": cpu,
+            "cpu_port": "oracle/nsga_ref.py fast_non_dominated_sort + crowding_distance (sa_nsga_local.py:247-277)"}
+    pts = rng.random((256, 3))
+    ref = np.array([1.1, 1.1, 1.1])
+    d_pts, d_ref = torch.from_numpy(pts).to(dev), torch.from_numpy(ref).to(dev)
+    d_hv = torch.empty(1, dtype=torch.float64, device=dev)
+    ws_bytes = int(lib.cmoop_hypervolume_workspace_bytes(256))
+    d_ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
+    t = time.perf_counter()
+    hv_cpu = hv_ref.hypervolume(pts, ref)
+    cpu = (time.perf_counter() - t) * 1e6
+    assert quality.hypervolume(pts, ref) == hv_cpu
+    out["hypervolume_n256_m3"] = {
+        "device_us": dev_us(lambda: _lib.check(lib.cmoop_hypervolume_dev(
+            C.c_void_p(d_pts.data_ptr()), 256, 3, C.c_void_p(d_ref.data_ptr()), C.c_void_p(d_hv.data_ptr()),
+            C.c_void_p(d_ws.data_ptr()), ws_bytes, C.c_void_p(stream)), "cmoop_hypervolume_dev")),
+        "host_abi_us": host_us(lambda: quality.hypervolume(pts, ref)), "cpu_port_us": cpu,
+        "cpu_port": "oracle/hv_ref.py (pygmo hv3d restated; compare.ipynb l.230-231)"}
+    n = 288                                                # the whole genotype space as training set and as queries
+    x = rng.random((n, 8)) * 4
+    specs = []
+    for j in range(4):
+        k = 1.3 * gp_ref.matern(x, x, 1.7, 1.5) + 0.1 * np.eye(n)
+        low = np.linalg.cholesky(k)
+        y = rng.standard_normal(n)
+        specs.append(dict(x_train=x, alpha=np.linalg.solve(k, y), chol_lower=low, amplitude=1.3, length_scale=1.7, nu=1.5,
+                          noise=0.1, y_scale=1.0 + j, y_shift=0.1 * j))
+    grp = DeviceGPGroup(specs)
+    d_x = torch.from_numpy(x).to(dev)
+    d_mu = torch.empty((4, n), dtype=torch.float64, device=dev)
+    d_sd = torch.empty((4, n), dtype=torch.float64, device=dev)
+    t = time.perf_counter()
+    for s in specs:
+        gp_ref.posterior(x, s["x_train"], s["alpha"], s["chol_lower"], amplitude=1.3, length_scale=1.7, nu=1.5, noise=0.1,
+                         y_scale=s["y_scale"], y_shift=s["y_shift"])
+    cpu = (time.perf_counter() - t) * 1e6
+    out["gp_predict_q288_n288_x4"] = {
+        "device_us": dev_us(lambda: _lib.check(lib.cmoop_gp_predict_dev(
+            grp._handle, C.c_void_p(d_x.data_ptr()), n, C.c_void_p(d_mu.data_ptr()), C.c_void_p(d_sd.data_ptr()),
+            C.c_void_p(stream)), "cmoop_gp_predict_dev")),
+        "host_abi_us": host_us(lambda: grp.predict(x)), "cpu_port_us": cpu,
+        "cpu_port": "oracle/gp_ref.py posterior (NumPy/LAPACK restatement of sklearn _gpr.py:446-499), 4 models"}
+    grp.close()
+    return out
+
+
+def run_ours(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1:
+        use_all_host_threads()                              # the cpu_baseline leg and the host GP fit use every thread
+    import warnings
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    warnings.filterwarnings("ignore")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from cmoop_audio_processing_b200 import _lib, drivers, quality
+    from cmoop_audio_processing_b200.problem import DeviceDataset, FitnessProblem
+    lib = _lib.load()
+    _lib.check(lib.cmoop_set_device(local_rank), "cmoop_set_device")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    for _ in range(args.warmup):
-        fe(wave, out=out)
-    barrier()
+    def reduce_max(vals):
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
 
-    # ---- device-resident timing (value + roofline): one kernel launch per step
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    hps = make_population(args.pop)
+    x_train, y_train, x_val, y_val = device_features(dev)
+    cfg = train_config(args)
+    prob = FitnessProblem.sa_nsga_local(x_train, y_train, x_val, y_val, classes=N_CLASSES, config=cfg)
+
+    # ---- value: K calls of compute_objectives_and_constraints over the whole population (sharded + all-gather inside)
+    for _ in range(args.warmup):
+        prob.compute_objectives_and_constraints(hps)
+    barrier()
     launches0 = lib.cmoop_launch_count()
     sampler.start()
-    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_all0.record()
-    for s, e in ev:
-        s.record()
-        fe(wave, out=out)
-        e.record()
-    t_all1.record()
-    barrier()
-    launches = int(lib.cmoop_launch_count() - launches0)
-    total_ms = t_all0.elapsed_time(t_all1)
-    kernel_ms = [s.elapsed_time(e) for s, e in ev]
-
-    # ---- end-to-end through the host-buffer C-ABI call (pinned host memory; H2D + D2H inside)
-    e2e_steps = max(1, min(args.steps, 8))
-    h_wave = torch.empty((clips, N_SAMPLES), dtype=torch.float32, pin_memory=True)
-    h_out = torch.empty((clips, N_FRAMES, N_OUT), dtype=torch.float32, pin_memory=True)
-    h_wave.copy_(wave)
-    torch.cuda.synchronize()
-    np_wave, np_out = h_wave.numpy(), h_out.numpy()
-    fe(np_wave, out=np_out)                                       # warm-up (allocates library scratch)
-    barrier()
+    dev_ms, epochs_run, busy = 0.0, None, 0.0
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        fe(np_wave, out=np_out)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    checksum = float(np_out[:: max(1, clips // 64)].sum())        # the host really has the result
-    # the same call on 16-bit PCM host buffers (what a wav file holds): half the host->device bytes; reported beside e2e
-    h_pcm = torch.empty((clips, N_SAMPLES), dtype=torch.int16, pin_memory=True)
-    h_pcm.copy_((wave * 32767.0).round().to(torch.int16))
-    torch.cuda.synchronize()
-    np_pcm = h_pcm.numpy()
-    fe(np_pcm, out=np_out)
+    for _ in range(args.steps):
+        recs = prob.compute_objectives_and_constraints(hps)
+        dev_ms += float(lib.cmoop_cnn_last_device_ms())
+        epochs_run = prob.last_details[:, 3].copy()
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        fe(np_pcm, out=np_out)
-    torch.cuda.synchronize()
-    e2e16_s = time.perf_counter() - t0
+    total_s = time.perf_counter() - t0
     sampler.stop()
-
-    stats = torch.tensor([total_ms, e2e_s, e2e16_s], device=dev, dtype=torch.float64)
+    launches = int(lib.cmoop_launch_count() - launches0)
+    assert len(recs) == args.pop and all(np.isfinite(r["objs"]).all() for r in recs)
+    flops_step = analytic_flops(hps, epochs_run)
+    local_busy_s = dev_ms * 1e-3
+    total_s, dev_s_max = reduce_max([total_s, local_busy_s])
+    busy_all = [local_busy_s]
     if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s, e2e16_s = float(stats[0]), float(stats[1]), float(stats[2])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local_busy_s)
+        busy_all = [float(b) for b in gathered]
+
+    # ---- kernel-family breakdown of one more (untimed) step: CUDA-event pairs around every launch of the engine
+    lib.cmoop_profile_enable(1)
+    prob.compute_objectives_and_constraints(hps)
+    lib.cmoop_profile_enable(0)
+    table = _lib.profile_table()
+    prof_ms = sum(v["ms"] for v in table.values())
+    breakdown = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "share": round(v["ms"] / prof_ms, 4),
+                     **({"tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2)} if v["flops"] > 0 else {})}
+                 for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])}
+
+    # ---- e2e: full SA-NSGA-II generations from host records / host feature arrays to host records
+    h_xt = torch.empty(x_train.shape, dtype=torch.float32, pin_memory=True).copy_(x_train)
+    h_xv = torch.empty(x_val.shape, dtype=torch.float32, pin_memory=True).copy_(x_val)
+    torch.cuda.synchronize()
+    np_xt, np_xv = h_xt.numpy(), h_xv.numpy()
+    gens_w, gens_k = min(args.warmup, 2), max(1, min(args.steps, args.e2e_generations))
+    e2e_prob = FitnessProblem.sa_nsga_local(prob.data, None, None, None, classes=N_CLASSES, config=cfg, seed=10_000)
+    ops = drivers.default_ops(e2e_prob)
+    ops.SurrogateManager = lambda: __import__("cmoop_audio_processing_b200.surrogate", fromlist=["x"]).SurrogateManager(
+        fit_backend=args.gp_fit_backend)
+    staged = {"data": None}
+
+    def evaluate_from_host(population):
+        # the generation's inputs are HOST arrays: features are re-staged host->device for every evaluation batch
+        if staged["data"] is not None:
+            staged["data"].close()
+        staged["data"] = DeviceDataset(np_xt, y_train, np_xv, y_val)
+        e2e_prob.data = staged["data"]
+        return e2e_prob.compute_objectives_and_constraints(population)
+    ops.compute_objectives_and_constraints = evaluate_from_host
+    archive = {"front": None}
+
+    def on_generation(gen, pop_data):
+        # HV (ref = max + 1e-3, compare.ipynb l.215-220) / IGD / Spread of the generation against the running union front
+        feas = np.array([r["objs"] for r in pop_data if r["CV"] == 0], dtype=np.float64).reshape(-1, 3)
+        if len(feas) == 0:
+            return {"hv": 0.0, "n": 0}
+        front = feas[quality.nondominated_mask(feas)]
+        union = front if archive["front"] is None else np.vstack([archive["front"], front])
+        archive["front"] = union[quality.nondominated_mask(union)]
+        out = {"hv": quality.hypervolume(front, quality.reference_point(feas)), "n": int(len(front))}
+        out.update(quality.front_metrics(front, archive["front"]))
+        return out
+
+    random.seed(0)
+    np.random.seed(0)
+    copies = []
+
+    def mark_copies(gen, pop_data):
+        out = on_generation(gen, pop_data)
+        copies.append(_lib.copy_bytes())
+        return out
+    barrier()
+    sampler.start()
+    _front, _history, timings = drivers.sa_nsga2(args.pop, gens_w + gens_k, INFILL, ops, local_search=True,
+                                                 on_generation=mark_copies)
+    barrier()
+    sampler.stop()
+    timed = timings[gens_w:]
+    gen_s = sum(t["seconds"] for t in timed)
+    gen_evals = sum(t["true_evals"] for t in timed)
+    (gen_s,) = reduce_max([gen_s])
+    c_prev = copies[gens_w - 1] if gens_w > 0 else None
+    c_last = copies[-1]
+    if c_prev is None:                                      # no warm-up generation: count from the first timed one on
+        c_prev, n_counted = copies[0], max(1, gens_k - 1)
+    else:
+        n_counted = gens_k
+    h2d_step = (c_last[0] - c_prev[0]) / n_counted
+    d2h_step = (c_last[1] - c_prev[1]) / n_counted
+
+    peaks = measured_peaks()
+    line = None
     if rank == 0:
-        peak, peak_src = measured_peak()
-        kernel_avg_ms = sum(kernel_ms) / len(kernel_ms)
-        achieved = BYTES_PER_CLIP * clips / (kernel_avg_ms * 1e-3) / 1e9
+        achieved = flops_step * args.steps / dev_s_max / 1e12
+        contraction = {k: v for k, v in table.items() if v["flops"] > 0}
+        dom = max(contraction, key=lambda k: contraction[k]["ms"]) if contraction else None
         line = {
-            "metric": METRIC, "value": world * clips * args.steps / (total_ms * 1e-3), "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(clips, world),
-            "e2e": {"value": world * clips * e2e_steps / e2e_s, "unit": UNIT,
-                    "h2d_bytes_per_step": clips * N_SAMPLES * 4, "d2h_bytes_per_step": clips * N_FRAMES * N_OUT * 4,
-                    "steps": e2e_steps, "api": "cmoop_mfcc_fwd_host via MfccFrontEnd(host array), pinned host buffers",
-                    "checksum": checksum},
-            "e2e_int16": {"value": world * clips * e2e_steps / e2e16_s, "unit": UNIT,
-                          "h2d_bytes_per_step": clips * N_SAMPLES * 2, "d2h_bytes_per_step": clips * N_FRAMES * N_OUT * 4,
-                          "api": "cmoop_mfcc_fwd_host_i16 (16-bit PCM host buffers, widened on the device); not the headline"},
+            "metric": METRIC, "value": args.pop * args.steps / total_s, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, world),
+            "e2e": {"value": gen_evals / gen_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step),
+                    "d2h_bytes_per_step": int(d2h_step), "steps": gens_k, "true_evals_per_generation": gen_evals // gens_k,
+                    "generations_per_sec": gens_k / gen_s, "seconds_per_generation": [round(t["seconds"], 3) for t in timed],
+                    "eval_seconds": [round(t["eval_seconds"], 3) for t in timed],
+                    "surrogate_update_seconds": [round(t["update_seconds"], 3) for t in timed],
+                    "indicators_last": timed[-1]["indicators"], "gp_fit_backend": args.gp_fit_backend,
+                    "api": "drivers.sa_nsga2 (ablation_study/sa_nsga_local.py:436-554) over FitnessProblem / SurrogateManager / "
+                           "perform_local_search / select_infill_points / fast_non_dominated_sort / crowding_distance / quality.*; "
+                           "host feature arrays re-staged host->device every generation (cmoop_cnn_dataset_create_host)"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "mfcc_pair_kernel<1>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": recorded_traffic(clips),
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_CLIP * clips,
-                         "kernel_ms_avg": kernel_avg_ms, "kernel_ms_min": min(kernel_ms)},
+            "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["bf16_sustained"],
+                         "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                         "peak_source": peaks["source"] + " bf16_tflops_sustained (the step is seconds long)",
+                         "algorithmic_flops_per_step": flops_step, "device_seconds_per_step": dev_s_max / args.steps,
+                         "note": "achieved = analytic training+scoring FLOPs of the whole step / device time of the step "
+                                 "(max over ranks) summed over ranks' shards; dominant_kernel = the contraction kernel family "
+                                 "with the largest share, its own 2*M*K*N flops / its own event-timed duration",
+                         "dominant_kernel": None if dom is None else {
+                             "name": dom, "launches": table[dom]["launches"], "ms": table[dom]["ms"],
+                             "achieved": table[dom]["flops"] / (table[dom]["ms"] * 1e-3) / 1e12,
+                             "frac": table[dom]["flops"] / (table[dom]["ms"] * 1e-3) / 1e12 / peaks["bf16_sustained"],
+                             "share_of_step": table[dom]["ms"] / prof_ms}},
+            "kernel_breakdown": breakdown,
+            "rank_busy_seconds_per_step": [round(b / args.steps, 4) for b in busy_all],
+            "epochs_run": {"min": int(epochs_run.min()), "max": int(epochs_run.max()), "mean": float(epochs_run.mean())},
             "clocks": sampler.summary(),
         }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = time_cpu_port(args.cpu_seconds)
-    extra = None
-    if not args.no_cnn:
-        del wave, out, h_wave, h_out, np_wave, np_out, h_pcm, np_pcm
-        torch.cuda.empty_cache()
+    if staged["data"] is not None:
+        staged["data"].close()
+    del h_xt, h_xv
+    # ---- extras
+    mf = None
+    if not args.no_mfcc:
         try:
-            extra = cnn_generation_extra(args, rank, world)
-        except Exception as exc:                                   # the headline line must still be printed
-            extra = {"error": repr(exc)}
+            mf = mfcc_extra(args, rank, world, dev, barrier)
+        except Exception as exc:                            # the headline line must still be printed
+            mf = {"error": repr(exc)}
     if rank == 0:
-        if extra is not None:
-            line["candidate_evaluation"] = extra
-        if world == 1 and not args.no_cnn:
+        if mf is not None:
+            line["mfcc"] = mf
+        if world == 1 and not args.no_latency:
             try:
-                line["surrogate_fit"] = surrogate_fit_extra()
+                line["latency"] = latency_extra(dev)
             except Exception as exc:
-                line["surrogate_fit"] = {"error": repr(exc)}
+                line["latency"] = {"error": repr(exc)}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg(args, hps)
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--clips", type=int, default=65536, help="clips per GPU (BASELINE configs[1]: 65 536)")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size in seconds of work")
+    ap.add_argument("--pop", type=int, default=POP, help="population (BASELINE configs[4]: 256)")
+    ap.add_argument("--epoch-cap", type=int, default=4, help="epoch ceiling of every candidate (reference: 300, ES patience 5)")
+    ap.add_argument("--e2e-generations", type=int, default=6, help="timed SA-NSGA-II generations of the e2e leg (<= steps)")
+    ap.add_argument("--gp-fit-backend", choices=["device", "host"], default="device")
+    ap.add_argument("--cpu-candidates", type=int, default=4, help="whole candidates of the N=1 cpu_baseline sample")
+    ap.add_argument("--mfcc-clips", type=int, default=65536, help="clips per GPU of the MFCC extra (BASELINE configs[1])")
+    ap.add_argument("--mfcc-steps", type=int, default=20)
+    ap.add_argument("--ref-min-candidates", type=int, default=8, help="--impl reference: whole candidates timed at least")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-cnn", action="store_true", help="skip the secondary candidate-evaluation measurement")
-    ap.add_argument("--cnn-pop", type=int, default=32, help="candidates per GPU for the secondary measurement")
-    ap.add_argument("--cnn-train", type=int, default=3072)
-    ap.add_argument("--cnn-epochs", type=int, default=2)
+    ap.add_argument("--no-mfcc", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                            # timing rule: W >= 3

@@ -37,6 +37,10 @@ SIGNATURES = {
     "cmoop_device_count": (C.c_int, []),
     "cmoop_set_device": (C.c_int, [C.c_int]),
     "cmoop_launch_count": (C.c_uint64, []),
+    "cmoop_copy_bytes": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "cmoop_profile_enable": (C.c_int, [C.c_int]),
+    "cmoop_profile_read": (C.c_size_t, [C.c_char_p, C.c_size_t]),
+    "cmoop_cnn_last_device_ms": (C.c_double, []),
     "cmoop_nds_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "cmoop_nds_crowding_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                          C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -128,6 +132,26 @@ def check(status: int, what: str) -> None:
     if status != 0:
         msg = load().cmoop_last_error().decode("utf-8", "replace")
         raise CmoopError(f"{what} failed (status {status}): {msg}")
+
+
+def copy_bytes() -> tuple[int, int]:
+    """(host->device, device->host) bytes copied by the library since load."""
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    load().cmoop_copy_bytes(C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
+
+
+def profile_table() -> dict:
+    """{family: {"launches", "ms", "flops"}} accumulated since cmoop_profile_enable(1)."""
+    lib = load()
+    need = lib.cmoop_profile_read(None, 0)
+    buf = C.create_string_buffer(int(need) + 16)
+    lib.cmoop_profile_read(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms, fl = line.rsplit(" ", 3)
+        out[name] = {"launches": int(n), "ms": float(ms), "flops": float(fl)}
+    return out
 
 
 def ptr(arr) -> C.c_void_p:

@@ -159,6 +159,11 @@ struct AdamTask {
     int n, block_begin;
 };
 
+struct PermTask {          // per-epoch shuffle of one candidate (engine.cu make_permutation, same hash stream)
+    int* perm;
+    unsigned seed_lo, seed_hi;
+};
+
 struct InitTask {          // Glorot-uniform / constant initialisation of one tensor
     float* p;
     int n, tensor, kind;   // kind 0: uniform(-limit, limit), 1: constant value
@@ -202,6 +207,8 @@ struct Launch {
     static int confusion(const int* y_true, const int* y_pred, int n, int C, int* cm, void* stream);
     static int adam(const AdamTask* tasks, int n_tasks, int total_blocks, float alpha, float b1, float b2, float eps, void* stream);
     static int init(const InitTask* tasks, int n_tasks, int total_blocks, void* stream);
+    static bool perm_ok(int n);      // the permutation fits the kernel's shared memory
+    static int perm(const PermTask* tasks, int n_tasks, int epoch, int n, void* stream);
     static int conv_tc(const TcConvTask* tasks, int n_tasks, int total_tiles, int n_b, int step, void* stream);
     static int wgrad_tc(const TcWgradTask* tasks, int n_tasks, int total_tiles, int n_b, void* stream);
     static int wt_bf16(const WtBf16Task* tasks, int n_tasks, int total_blocks, void* stream);

@@ -24,6 +24,63 @@
 
 using namespace cmoop_cnn;
 
+// ---- optional per-kernel-family device timing (cmoop_profile_enable): one cudaEvent pair around every grouped launch of
+// the engine's stream, resolved after the call.  Launches are serialised on one stream, so the pairs partition the device
+// time of a call; bench.py uses the table for the `roofline.dominant_kernel` object and the step breakdown.  Off by default
+// (two event records per launch perturb small launches by a few microseconds).
+#include <map>
+#include <string>
+namespace {
+struct ProfAgg { long long launches = 0; double ms = 0.0, flops = 0.0; };
+struct ProfRec { const char* name; cudaEvent_t a, b; double flops; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+std::map<std::string, ProfAgg> g_prof_table;
+double g_last_device_ms = 0.0;
+
+inline cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) {
+        cudaEvent_t e = g_prof_pool.back();
+        g_prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+inline void prof_begin(const char* name, double flops, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfRec r{name, prof_event(), prof_event(), flops};
+    cudaEventRecord(r.a, st);
+    g_prof_recs.push_back(r);
+}
+inline void prof_end(cudaStream_t st) {
+    if (!g_prof_on) return;
+    cudaEventRecord(g_prof_recs.back().b, st);
+}
+// call after the stream has been synchronised
+void prof_resolve() {
+    for (ProfRec& r : g_prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            std::string key(r.name);
+            const size_t cut = key.find('(');
+            if (cut != std::string::npos) key.resize(cut);
+            if (key.rfind("Launch::", 0) == 0) key = key.substr(8);
+            ProfAgg& a = g_prof_table[key];
+            a.launches += 1;
+            a.ms += ms;
+            a.flops += r.flops;
+        }
+        g_prof_pool.push_back(r.a);
+        g_prof_pool.push_back(r.b);
+    }
+    (void)cudaGetLastError();
+    g_prof_recs.clear();
+}
+}  // namespace
+
 struct cmoop_cnn_dataset {
     float* x_train = nullptr;
     int* y_train = nullptr;
@@ -316,6 +373,8 @@ struct StageLists {
     DevList<ConvTask> conv, conv_eval, dgrad;
     DevList<TcConvTask> conv_tc, dgrad_tc, conv_tc2, dgrad_tc2;
     int q_max = 0, tc2_cin = 0, tc2_cin_d = 0;   // largest patch; most GEMM input channels of the conv_tc2 / dgrad_tc2 tasks
+    // algorithmic flop per SAMPLE of the stage's tensor-core launches (2*Ho*Wo*K*Cout summed over tasks; profiler only)
+    double f_fwd2 = 0, f_fwd1 = 0, f_dg2 = 0, f_dg1 = 0, f_wg = 0, f_simt = 0, f_simt_dg = 0, f_simt_wg = 0;
     DevList<TcWgradTask> wgrad_tc, wgrad_tc2;
     int wg2_q = 0;                   // largest X patch of the stage's wgrad_tc2 tasks
     DevList<StatTask> stat;
@@ -338,6 +397,10 @@ struct Wave {
     DevList<AdamTask> adam;
     DevList<WtTask> wt;
     DevList<WtBf16Task> wt_bf16, wt_bf16_v2;
+    DevList<PermTask> perm;          // per-epoch shuffles of the active candidates, generated on the device
+    // one contiguous block per wave, so an epoch's results reach the host with ONE copy and ONE synchronisation:
+    double* d_acc = nullptr;         // [cands][12]: train / validation / predict accumulators (Cand::acc points into it)
+    int* d_cm = nullptr;             // [cands][C][C] confusion matrices (Cand::confusion points into it)
     bool weights_dirty = true;
     char* d_blob = nullptr;
     size_t blob_cap = 0;
@@ -368,6 +431,7 @@ struct Engine {
         wv.wt = DevList<WtTask>();
         wv.wt_bf16 = DevList<WtBf16Task>();
         wv.wt_bf16_v2 = DevList<WtBf16Task>();
+        wv.perm = DevList<PermTask>();
         wv.weights_dirty = true;
         const long long img = (long long)data->H * data->W;
         for (Cand* cp : wv.cands) {
@@ -394,12 +458,14 @@ struct Engine {
                         t.tile_begin = S.conv_tc2.total;
                         S.conv_tc2.h.push_back(t);
                         S.conv_tc2.total += (int)((mq + Launch::tc2_rows() - 1) / Launch::tc2_rows()) * t.tiles_n;
+                        S.f_fwd2 += 2.0 * u.Ho * u.Wo * u.k * u.k * u.cin * u.cout;
                         S.q_max = std::max(S.q_max, Launch::tc2_q(u.W, u.k));
                         S.tc2_cin = std::max(S.tc2_cin, u.cin);
                     } else {
                         t.tile_begin = S.conv_tc.total;
                         S.conv_tc.h.push_back(t);
                         S.conv_tc.total += (int)(((long long)batch * u.Ho * u.Wo + 127) / 128) * t.tiles_n;
+                        S.f_fwd1 += 2.0 * u.Ho * u.Wo * u.k * u.k * u.cin * u.cout;
                     }
                     if (u.has_bn) {
                         StatTask sk{};
@@ -453,6 +519,7 @@ struct Engine {
                     }
                     S.conv.h.push_back(t);
                     S.conv.total += u.stat_tiles * t.tiles_n;
+                    S.f_simt += 2.0 * u.Ho * u.Wo * (u.k * u.k * u.cin + 1) * u.cout;
                 }
                 // ---- post stage (forward / BN / backward lists)
                 if (!u.dense && !u.is_skip) {
@@ -530,11 +597,13 @@ struct Engine {
                             g.tile_begin = S.wgrad_tc2.total;
                             S.wgrad_tc2.h.push_back(g);
                             S.wgrad_tc2.total += g.splits * Launch::wg2_items(u.cin, u.cout, u.k);
+                            S.f_wg += 2.0 * u.Ho * u.Wo * kext * u.cout;
                             S.wg2_q = std::max(S.wg2_q, Launch::wg2_q(u.W, u.k));
                         } else {
                             g.tile_begin = S.wgrad_tc.total;
                             S.wgrad_tc.h.push_back(g);
                             S.wgrad_tc.total += g.tiles_k * g.tiles_n * g.splits;
+                            S.f_wg += 2.0 * u.Ho * u.Wo * kext * u.cout;
                         }
                     } else {
                         WgradTask g{};
@@ -549,6 +618,7 @@ struct Engine {
                         g.tile_begin = S.wgrad.total;
                         S.wgrad.h.push_back(g);
                         S.wgrad.total += g.tiles_k * g.tiles_n * g.splits;
+                        S.f_simt_wg += 2.0 * u.Ho * u.Wo * kext * u.cout;
                     }
                     if (to_ws) {
                         ReduceTask r{};
@@ -591,12 +661,14 @@ struct Engine {
                         d.tile_begin = S.dgrad_tc2.total;
                         S.dgrad_tc2.h.push_back(d);
                         S.dgrad_tc2.total += (int)((mq + Launch::tc2_rows() - 1) / Launch::tc2_rows()) * d.tiles_n;
+                        S.f_dg2 += 2.0 * u.Ho * u.Wo * u.k * u.k * u.cin * u.cout;
                         S.q_max = std::max(S.q_max, Launch::tc2_q(u.W, u.k));
                         S.tc2_cin_d = std::max(S.tc2_cin_d, u.cout);
                     } else {
                         d.tile_begin = S.dgrad_tc.total;
                         S.dgrad_tc.h.push_back(d);
                         S.dgrad_tc.total += (int)(((long long)batch * u.Ho * u.Wo + 127) / 128) * d.tiles_n;
+                        S.f_dg1 += 2.0 * u.Ho * u.Wo * u.k * u.k * u.cin * u.cout;
                     }
                 } else if (u.need_dgrad) {
                     WtTask w{};
@@ -620,6 +692,7 @@ struct Engine {
                     d.tile_begin = S.dgrad.total;
                     S.dgrad.h.push_back(d);
                     S.dgrad.total += u.stat_tiles * d.tiles_n;
+                    S.f_simt_dg += 2.0 * u.Ho * u.Wo * u.k * u.k * u.cin * u.cout;
                 }
             }
             const Unit& lc = c.units[c.last_conv];
@@ -638,6 +711,9 @@ struct Engine {
             wv.ce_val.h.push_back(ce);
             ce.acc = c.acc + 8; ce.pred = c.pred; ce.confusion = c.confusion; ce.y_true_zero = cfg.y_true_zero;
             wv.ce_pred.h.push_back(ce);
+            PermTask pt{};
+            pt.perm = c.perm; pt.seed_lo = (unsigned)(c.seed & 0xffffffffu); pt.seed_hi = (unsigned)(c.seed >> 32);
+            wv.perm.h.push_back(pt);
             AdamTask ad{};
             ad.p = c.p; ad.g = c.grad; ad.m = c.m; ad.v = c.v; ad.n = (int)c.n_params;
             ad.block_begin = wv.adam.total;
@@ -656,6 +732,7 @@ struct Engine {
         }
         blob_add(blob, wv.head); blob_add(blob, wv.ce_train); blob_add(blob, wv.ce_val); blob_add(blob, wv.ce_pred);
         blob_add(blob, wv.adam); blob_add(blob, wv.wt); blob_add(blob, wv.wt_bf16); blob_add(blob, wv.wt_bf16_v2);
+        blob_add(blob, wv.perm);
         if (blob.size() > wv.blob_cap) {
             if (wv.d_blob) {
                 CMOOP_CUDA_OK(cudaStreamSynchronize(stream));
@@ -665,7 +742,7 @@ struct Engine {
             CMOOP_CUDA_OK(cudaMalloc((void**)&wv.d_blob, wv.blob_cap));
         }
         CMOOP_CUDA_OK(cudaStreamSynchronize(stream));   // previous launches may still read the old lists
-        CMOOP_CUDA_OK(cudaMemcpy(wv.d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+        CMOOP_CUDA_OK(cmoop::copy_sync(wv.d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
         auto fix = [&](auto& l) { l.d = reinterpret_cast<decltype(l.d)>(wv.d_blob + l.blob_off); };
         for (int s = 0; s < N_STAGES; ++s) {
             StageLists& S = wv.st[s];
@@ -674,18 +751,22 @@ struct Engine {
             fix(S.wgrad); fix(S.wreduce); fix(S.drop_fwd); fix(S.drop_bwd);
         }
         fix(wv.head); fix(wv.ce_train); fix(wv.ce_val); fix(wv.ce_pred); fix(wv.adam); fix(wv.wt); fix(wv.wt_bf16); fix(wv.wt_bf16_v2);
+        fix(wv.perm);
         return CMOOP_OK;
     }
 
-#define CNN_LAUNCH(expr)                                                                           \
+#define CNN_LAUNCH_N(label, flops, expr)                                                            \
     do {                                                                                           \
+        prof_begin(label, (double)(flops), stream);                                                \
         int _e = (expr);                                                                           \
+        prof_end(stream);                                                                          \
         cmoop::count_launch();                                                                     \
         if (_e != 0) {                                                                             \
             cmoop::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString((cudaError_t)_e)); \
             return CMOOP_ERR_CUDA;                                                                 \
         }                                                                                          \
     } while (0)
+#define CNN_LAUNCH(expr) CNN_LAUNCH_N(#expr, 0.0, expr)
 
     // mode 0: training batch from the permutation; 1: validation loss/accuracy; 2: final predict (+confusion)
     int run_forward(Wave& wv, int mode, int step, int n_b) {
@@ -704,16 +785,20 @@ struct Engine {
             DevList<ConvTask>& cl = (s == 0 && !training) ? S.conv_eval : S.conv;
             if (!cl.h.empty()) {
                 if (S.stem && S.stem_w > 0)
-                    CNN_LAUNCH(Launch::stem_conv(cl.d, (int)cl.h.size(), S.stem_k, S.stem_w, S.stem_cout,
-                                                 (long long)n_b * cl.h[0].H * cl.h[0].W, n_b, step, stream));
+                    CNN_LAUNCH_N("stem_conv", S.f_simt * n_b,
+                                 Launch::stem_conv(cl.d, (int)cl.h.size(), S.stem_k, S.stem_w, S.stem_cout,
+                                                   (long long)n_b * cl.h[0].H * cl.h[0].W, n_b, step, stream));
                 else
-                    CNN_LAUNCH(Launch::conv(cl.d, (int)cl.h.size(), cl.total, n_b, step, stream));
+                    CNN_LAUNCH_N(s >= ST_FC0 ? "dense_fwd(simt)" : "conv_fwd(simt)", S.f_simt * n_b,
+                                 Launch::conv(cl.d, (int)cl.h.size(), cl.total, n_b, step, stream));
             }
             if (!S.conv_tc.h.empty())
-                CNN_LAUNCH(Launch::conv_tc(S.conv_tc.d, (int)S.conv_tc.h.size(), S.conv_tc.total, n_b, step, stream));
+                CNN_LAUNCH_N("conv_tc.fwd", S.f_fwd1 * n_b,
+                             Launch::conv_tc(S.conv_tc.d, (int)S.conv_tc.h.size(), S.conv_tc.total, n_b, step, stream));
             if (!S.conv_tc2.h.empty())
-                CNN_LAUNCH(Launch::conv_tc2(S.conv_tc2.d, (int)S.conv_tc2.h.size(), S.conv_tc2.total, n_b, step, S.q_max,
-                                            S.tc2_cin, stream));
+                CNN_LAUNCH_N("conv_tc2.fwd", S.f_fwd2 * n_b,
+                             Launch::conv_tc2(S.conv_tc2.d, (int)S.conv_tc2.h.size(), S.conv_tc2.total, n_b, step, S.q_max,
+                                              S.tc2_cin, stream));
             if (!S.stat.h.empty() && training)
                 CNN_LAUNCH(Launch::bn_stats(S.stat.d, (int)S.stat.h.size(), S.stat.total, n_b, stream));
             if (!S.post_bn.h.empty())
@@ -747,24 +832,31 @@ struct Engine {
                 CNN_LAUNCH(Launch::post_bwd_apply(S.post_bwd.d, (int)S.post_bwd.h.size(), S.post_bwd.total, n_b, stream));
             if (!S.wgrad.h.empty()) {
                 if (S.stem && S.stem_w > 0)
-                    CNN_LAUNCH(Launch::stem_wgrad(S.wgrad.d, (int)S.wgrad.h.size(), S.stem_k, S.stem_w, S.stem_cout,
-                                                  S.stem_splits, n_b, step, stream));
+                    CNN_LAUNCH_N("stem_wgrad", S.f_simt_wg * n_b,
+                                 Launch::stem_wgrad(S.wgrad.d, (int)S.wgrad.h.size(), S.stem_k, S.stem_w, S.stem_cout,
+                                                    S.stem_splits, n_b, step, stream));
                 else
-                    CNN_LAUNCH(Launch::wgrad(S.wgrad.d, (int)S.wgrad.h.size(), S.wgrad.total, n_b, step, stream));
+                    CNN_LAUNCH_N(s >= ST_FC0 ? "dense_wgrad(simt)" : "conv_wgrad(simt)", S.f_simt_wg * n_b,
+                                 Launch::wgrad(S.wgrad.d, (int)S.wgrad.h.size(), S.wgrad.total, n_b, step, stream));
             }
             if (!S.wgrad_tc.h.empty())
-                CNN_LAUNCH(Launch::wgrad_tc(S.wgrad_tc.d, (int)S.wgrad_tc.h.size(), S.wgrad_tc.total, n_b, stream));
+                CNN_LAUNCH_N("wgrad_tc", S.f_wg * n_b,
+                             Launch::wgrad_tc(S.wgrad_tc.d, (int)S.wgrad_tc.h.size(), S.wgrad_tc.total, n_b, stream));
             if (!S.wgrad_tc2.h.empty())
-                CNN_LAUNCH(Launch::wgrad_tc2(S.wgrad_tc2.d, (int)S.wgrad_tc2.h.size(), S.wgrad_tc2.total, n_b, S.wg2_q, stream));
+                CNN_LAUNCH_N("wgrad_tc2", S.f_wg * n_b,
+                             Launch::wgrad_tc2(S.wgrad_tc2.d, (int)S.wgrad_tc2.h.size(), S.wgrad_tc2.total, n_b, S.wg2_q, stream));
             if (!S.wreduce.h.empty())
                 CNN_LAUNCH(Launch::reduce(S.wreduce.d, (int)S.wreduce.h.size(), S.wreduce.total, stream));
             if (!S.dgrad.h.empty())
-                CNN_LAUNCH(Launch::conv(S.dgrad.d, (int)S.dgrad.h.size(), S.dgrad.total, n_b, 0, stream));
+                CNN_LAUNCH_N(s >= ST_FC0 ? "dense_dgrad(simt)" : "conv_dgrad(simt)", S.f_simt_dg * n_b,
+                             Launch::conv(S.dgrad.d, (int)S.dgrad.h.size(), S.dgrad.total, n_b, 0, stream));
             if (!S.dgrad_tc.h.empty())
-                CNN_LAUNCH(Launch::conv_tc(S.dgrad_tc.d, (int)S.dgrad_tc.h.size(), S.dgrad_tc.total, n_b, 0, stream));
+                CNN_LAUNCH_N("conv_tc.dgrad", S.f_dg1 * n_b,
+                             Launch::conv_tc(S.dgrad_tc.d, (int)S.dgrad_tc.h.size(), S.dgrad_tc.total, n_b, 0, stream));
             if (!S.dgrad_tc2.h.empty())
-                CNN_LAUNCH(Launch::conv_tc2(S.dgrad_tc2.d, (int)S.dgrad_tc2.h.size(), S.dgrad_tc2.total, n_b, 0, S.q_max,
-                                            S.tc2_cin_d, stream));
+                CNN_LAUNCH_N("conv_tc2.dgrad", S.f_dg2 * n_b,
+                             Launch::conv_tc2(S.dgrad_tc2.d, (int)S.dgrad_tc2.h.size(), S.dgrad_tc2.total, n_b, 0, S.q_max,
+                                              S.tc2_cin_d, stream));
         }
         return CMOOP_OK;
     }
@@ -810,7 +902,7 @@ struct Engine {
         }
         InitTask* d = nullptr;
         CMOOP_CUDA_OK(cudaMalloc((void**)&d, tasks.size() * sizeof(InitTask)));
-        CMOOP_CUDA_OK(cudaMemcpyAsync(d, tasks.data(), tasks.size() * sizeof(InitTask), cudaMemcpyHostToDevice, stream));
+        CMOOP_CUDA_OK(cmoop::copy_async(d, tasks.data(), tasks.size() * sizeof(InitTask), cudaMemcpyHostToDevice, stream));
         int rc = Launch::init(d, (int)tasks.size(), total, stream);
         cmoop::count_launch();
         CMOOP_CUDA_OK(cudaStreamSynchronize(stream));
@@ -940,10 +1032,10 @@ int cmoop_cnn_dataset_create_host(const float* x_train, const int* y_train, int 
         cmoop_cnn_dataset_destroy(d);
         return CMOOP_ERR_CUDA;
     }
-    CMOOP_CUDA_OK(cudaMemcpy(d->x_train, x_train, img * n_train, cudaMemcpyHostToDevice));
-    CMOOP_CUDA_OK(cudaMemcpy(d->y_train, y_train, sizeof(int) * n_train, cudaMemcpyHostToDevice));
-    CMOOP_CUDA_OK(cudaMemcpy(d->x_val, x_val, img * n_val, cudaMemcpyHostToDevice));
-    CMOOP_CUDA_OK(cudaMemcpy(d->y_val, y_val, sizeof(int) * n_val, cudaMemcpyHostToDevice));
+    CMOOP_CUDA_OK(cmoop::copy_sync(d->x_train, x_train, img * n_train, cudaMemcpyHostToDevice));
+    CMOOP_CUDA_OK(cmoop::copy_sync(d->y_train, y_train, sizeof(int) * n_train, cudaMemcpyHostToDevice));
+    CMOOP_CUDA_OK(cmoop::copy_sync(d->x_val, x_val, img * n_val, cudaMemcpyHostToDevice));
+    CMOOP_CUDA_OK(cmoop::copy_sync(d->y_val, y_val, sizeof(int) * n_val, cudaMemcpyHostToDevice));
     *out = d;
     return CMOOP_OK;
 }
@@ -965,14 +1057,37 @@ int cmoop_cnn_dataset_create_dev(const float* x_train_dev, const int* y_train, i
         return CMOOP_ERR_CUDA;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d->x_train, x_train_dev, img * n_train, cudaMemcpyDeviceToDevice, st));
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d->x_val, x_val_dev, img * n_val, cudaMemcpyDeviceToDevice, st));
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d->y_train, y_train, sizeof(int) * n_train, cudaMemcpyHostToDevice, st));
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d->y_val, y_val, sizeof(int) * n_val, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d->x_train, x_train_dev, img * n_train, cudaMemcpyDeviceToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d->x_val, x_val_dev, img * n_val, cudaMemcpyDeviceToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d->y_train, y_train, sizeof(int) * n_train, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d->y_val, y_val, sizeof(int) * n_val, cudaMemcpyHostToDevice, st));
     CMOOP_CUDA_OK(cudaStreamSynchronize(st));
     *out = d;
     return CMOOP_OK;
 }
+
+int cmoop_profile_enable(int on) {
+    if (on && !g_prof_on) g_prof_table.clear();
+    g_prof_on = on != 0;
+    return CMOOP_OK;
+}
+
+size_t cmoop_profile_read(char* buf, size_t cap) {
+    std::string out;
+    char line[256];
+    for (const auto& kv : g_prof_table) {
+        snprintf(line, sizeof(line), "%s %lld %.6f %.6e\n", kv.first.c_str(), kv.second.launches, kv.second.ms, kv.second.flops);
+        out += line;
+    }
+    if (buf && cap > 0) {
+        const size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return out.size() + 1;
+}
+
+double cmoop_cnn_last_device_ms(void) { return g_last_device_ms; }
 
 int cmoop_fpr_from_predictions_host(const int* y_true, const int* y_pred, int n, int n_classes, int mode, double* fpr_out,
                                     int* confusion_out) {
@@ -989,8 +1104,8 @@ int cmoop_fpr_from_predictions_host(const int* y_true, const int* y_pred, int n,
     int* d_pred = (int*)(d + b_lab);
     int* d_cm = (int*)(d + 2 * b_lab);
     if (n > 0) {
-        CMOOP_CUDA_OK(cudaMemcpyAsync(d_true, y_true, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
-        CMOOP_CUDA_OK(cudaMemcpyAsync(d_pred, y_pred, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+        CMOOP_CUDA_OK(cmoop::copy_async(d_true, y_true, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+        CMOOP_CUDA_OK(cmoop::copy_async(d_pred, y_pred, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
     }
     CMOOP_CUDA_OK(cudaMemsetAsync(d_cm, 0, b_cm, st));
     if (n > 0) {
@@ -1002,7 +1117,7 @@ int cmoop_fpr_from_predictions_host(const int* y_true, const int* y_pred, int n,
         }
     }
     std::vector<int> cm((size_t)n_classes * n_classes);
-    CMOOP_CUDA_OK(cudaMemcpyAsync(cm.data(), d_cm, b_cm, cudaMemcpyDeviceToHost, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(cm.data(), d_cm, b_cm, cudaMemcpyDeviceToHost, st));
     CMOOP_CUDA_OK(cudaStreamSynchronize(st));
     *fpr_out = fpr_from_confusion(cm, n_classes, mode == 1);
     if (confusion_out) memcpy(confusion_out, cm.data(), b_cm);
@@ -1042,25 +1157,32 @@ int run_wave(Engine& eng, Wave& wv, double* out, double* history, int debug_step
     if (rc != CMOOP_OK) return rc;
     const int steps_per_epoch = (data->n_train + batch - 1) / batch;
     const int val_steps = (data->n_val + batch - 1) / batch;
-    std::vector<double> acc(12);
     int t_adam = 0;
     const int max_epochs = debug_steps > 0 ? 1 : cfg.max_epochs;
     for (int epoch = 0; epoch < max_epochs; ++epoch) {
         bool any = false;
-        {
-            int n_active = 0;
-            for (Cand* c : wv.cands) n_active += c->active ? 1 : 0;
-            int* stage = (int*)cmoop::pinned_scratch(5, (size_t)std::max(1, n_active) * data->n_train * sizeof(int));
-            if (!stage) return CMOOP_ERR_CUDA;
-            int slot = 0;
-            for (Cand* c : wv.cands) {
-                if (!c->active) continue;
-                any = true;
-                int* dst = stage + (size_t)slot++ * data->n_train;
-                make_permutation(c->seed, epoch, data->n_train, dst);
-                CMOOP_CUDA_OK(cudaMemcpyAsync(c->perm, dst, sizeof(int) * data->n_train, cudaMemcpyHostToDevice, st));
-                CMOOP_CUDA_OK(cudaMemsetAsync(c->acc, 0, 8 * sizeof(double), st));
+        for (Cand* c : wv.cands) any = any || c->active;
+        if (any) {
+            // per-epoch shuffles: generated on the device for every active candidate in one launch (same fmix32 stream as
+            // make_permutation / cmoop_cnn_debug_permutation); a training split too large for the kernel's shared memory
+            // falls back to host-generated index arrays
+            cudaStream_t stream = st;
+            if (Launch::perm_ok(data->n_train)) {
+                CNN_LAUNCH(Launch::perm(wv.perm.d, (int)wv.perm.h.size(), epoch, data->n_train, st));
+            } else {
+                int n_active = 0;
+                for (Cand* c : wv.cands) n_active += c->active ? 1 : 0;
+                int* stage = (int*)cmoop::pinned_scratch(5, (size_t)n_active * data->n_train * sizeof(int));
+                if (!stage) return CMOOP_ERR_CUDA;
+                int slot = 0;
+                for (Cand* c : wv.cands) {
+                    if (!c->active) continue;
+                    int* dst = stage + (size_t)slot++ * data->n_train;
+                    make_permutation(c->seed, epoch, data->n_train, dst);
+                    CMOOP_CUDA_OK(cmoop::copy_async(c->perm, dst, sizeof(int) * data->n_train, cudaMemcpyHostToDevice, st));
+                }
             }
+            CMOOP_CUDA_OK(cudaMemsetAsync(wv.d_acc, 0, wv.cands.size() * 12 * sizeof(double), st));
         }
         if (!any) break;
         const int n_steps = debug_steps > 0 ? std::min(debug_steps, steps_per_epoch) : steps_per_epoch;
@@ -1071,10 +1193,10 @@ int run_wave(Engine& eng, Wave& wv, double* out, double* history, int debug_step
             if (debug_steps > 0) {
                 Cand* c = wv.cands[0];
                 if (s == 0 && dbg_grads)
-                    CMOOP_CUDA_OK(cudaMemcpyAsync(dbg_grads, c->grad, c->n_params * sizeof(float), cudaMemcpyDeviceToHost, st));
+                    CMOOP_CUDA_OK(cmoop::copy_async(dbg_grads, c->grad, c->n_params * sizeof(float), cudaMemcpyDeviceToHost, st));
                 if (dbg_losses) {
                     double a[4];
-                    CMOOP_CUDA_OK(cudaMemcpyAsync(a, c->acc, sizeof(a), cudaMemcpyDeviceToHost, st));
+                    CMOOP_CUDA_OK(cmoop::copy_async(a, c->acc, sizeof(a), cudaMemcpyDeviceToHost, st));
                     CMOOP_CUDA_OK(cudaStreamSynchronize(st));
                     dbg_losses[s] = (float)(a[0] / a[1]);
                     CMOOP_CUDA_OK(cudaMemsetAsync(c->acc, 0, 4 * sizeof(double), st));
@@ -1087,7 +1209,7 @@ int run_wave(Engine& eng, Wave& wv, double* out, double* history, int debug_step
         if (debug_steps > 0) {
             Cand* c = wv.cands[0];
             if (dbg_params)
-                CMOOP_CUDA_OK(cudaMemcpyAsync(dbg_params, c->p, c->n_params * sizeof(float), cudaMemcpyDeviceToHost, st));
+                CMOOP_CUDA_OK(cmoop::copy_async(dbg_params, c->p, c->n_params * sizeof(float), cudaMemcpyDeviceToHost, st));
             CMOOP_CUDA_OK(cudaStreamSynchronize(st));
             return CMOOP_OK;
         }
@@ -1096,10 +1218,15 @@ int run_wave(Engine& eng, Wave& wv, double* out, double* history, int debug_step
             if ((rc = eng.run_forward(wv, 1, s, n_b)) != CMOOP_OK) return rc;
         }
         bool changed = false;
-        for (Cand* c : wv.cands) {
+        // ONE device->host copy and ONE synchronisation per epoch for the whole wave (accumulators are contiguous)
+        double* h_acc = (double*)cmoop::pinned_scratch(6, wv.cands.size() * 12 * sizeof(double));
+        if (!h_acc) return CMOOP_ERR_CUDA;
+        CMOOP_CUDA_OK(cmoop::copy_async(h_acc, wv.d_acc, wv.cands.size() * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+        for (size_t ci = 0; ci < wv.cands.size(); ++ci) {
+            Cand* c = wv.cands[ci];
             if (!c->active) continue;
-            CMOOP_CUDA_OK(cudaMemcpyAsync(acc.data(), c->acc, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+            const double* acc = h_acc + ci * 12;
             const double train_loss = acc[0] / acc[1], val_loss = acc[4] / acc[5], val_acc = acc[6] / acc[5];
             c->epochs_run = epoch + 1;
             c->last_val_loss = val_loss;
@@ -1110,7 +1237,7 @@ int run_wave(Engine& eng, Wave& wv, double* out, double* history, int debug_step
             }
             // keras.callbacks.EarlyStopping(monitor='val_loss', patience, restore_best_weights)
             if (cfg.restore_best_weights && !c->has_best) {
-                CMOOP_CUDA_OK(cudaMemcpyAsync(c->best, c->p, c->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                CMOOP_CUDA_OK(cmoop::copy_async(c->best, c->p, c->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
                 c->has_best = true;
             }
             c->wait += 1;
@@ -1118,7 +1245,7 @@ int run_wave(Engine& eng, Wave& wv, double* out, double* history, int debug_step
                 c->best_loss = val_loss;
                 c->wait = 0;
                 if (cfg.restore_best_weights)
-                    CMOOP_CUDA_OK(cudaMemcpyAsync(c->best, c->p, c->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                    CMOOP_CUDA_OK(cmoop::copy_async(c->best, c->p, c->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
             } else if (c->wait >= cfg.patience && epoch > 0) {
                 c->active = false;
                 changed = true;
@@ -1135,20 +1262,27 @@ int run_wave(Engine& eng, Wave& wv, double* out, double* history, int debug_step
     for (Cand* c : wv.cands) {
         c->active = true;
         if (cfg.restore_best_weights && c->has_best)
-            CMOOP_CUDA_OK(cudaMemcpyAsync(c->p, c->best, c->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        CMOOP_CUDA_OK(cudaMemsetAsync(c->acc + 8, 0, 4 * sizeof(double), st));
-        CMOOP_CUDA_OK(cudaMemsetAsync(c->confusion, 0, sizeof(int) * cfg.n_classes * cfg.n_classes, st));
+            CMOOP_CUDA_OK(cmoop::copy_async(c->p, c->best, c->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
+    const size_t cm_elems = (size_t)cfg.n_classes * cfg.n_classes;
+    CMOOP_CUDA_OK(cudaMemsetAsync(wv.d_acc, 0, wv.cands.size() * 12 * sizeof(double), st));
+    CMOOP_CUDA_OK(cudaMemsetAsync(wv.d_cm, 0, wv.cands.size() * cm_elems * sizeof(int), st));
     if ((rc = eng.build_lists(wv)) != CMOOP_OK) return rc;
     for (int s = 0; s < val_steps; ++s) {
         const int n_b = std::min(batch, data->n_val - s * batch);
         if ((rc = eng.run_forward(wv, 2, s, n_b)) != CMOOP_OK) return rc;
     }
-    std::vector<int> cm((size_t)cfg.n_classes * cfg.n_classes);
-    for (Cand* c : wv.cands) {
-        CMOOP_CUDA_OK(cudaMemcpyAsync(acc.data(), c->acc + 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        CMOOP_CUDA_OK(cudaMemcpyAsync(cm.data(), c->confusion, cm.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+    double* h_acc = (double*)cmoop::pinned_scratch(6, wv.cands.size() * 12 * sizeof(double));
+    int* h_cm = (int*)cmoop::pinned_scratch(7, wv.cands.size() * cm_elems * sizeof(int));
+    if (!h_acc || !h_cm) return CMOOP_ERR_CUDA;
+    CMOOP_CUDA_OK(cmoop::copy_async(h_acc, wv.d_acc, wv.cands.size() * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(h_cm, wv.d_cm, wv.cands.size() * cm_elems * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<int> cm(cm_elems);
+    for (size_t ci = 0; ci < wv.cands.size(); ++ci) {
+        Cand* c = wv.cands[ci];
+        const double* acc = h_acc + ci * 12 + 8;
+        memcpy(cm.data(), h_cm + ci * cm_elems, cm_elems * sizeof(int));
         const double acc_eval = acc[2] / acc[1];
         c->final_acc = cfg.acc_from_history ? c->last_val_acc : acc_eval;
         c->fpr = fpr_from_confusion(cm, cfg.n_classes, cfg.fpr_filtered != 0);
@@ -1176,6 +1310,12 @@ int run_population(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotype
     eng.cfg = *cfg;
     eng.batch = cfg->batch_size;
     eng.stream = cmoop::internal_stream();
+    static cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    if (!ev_begin) {
+        CMOOP_CUDA_OK(cudaEventCreate(&ev_begin));
+        CMOOP_CUDA_OK(cudaEventCreate(&ev_end));
+    }
+    CMOOP_CUDA_OK(cudaEventRecord(ev_begin, eng.stream));
     std::vector<Cand> cands(P);
     for (int i = 0; i < P; ++i) {
         cands[i].g = genotypes[i];
@@ -1225,15 +1365,28 @@ int run_population(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotype
         a.base = arena_base;
         a.cap = arena_cap;
         wv.cands.clear();
+        const size_t n_wave = (size_t)(end - next), cm_elems = (size_t)cfg->n_classes * cfg->n_classes;
+        wv.d_acc = (double*)cmoop::device_scratch(9, n_wave * 12 * sizeof(double));
+        wv.d_cm = (int*)cmoop::device_scratch(10, n_wave * cm_elems * sizeof(int));
+        if (!wv.d_acc || !wv.d_cm) return CMOOP_ERR_CUDA;
         for (int i = next; i < end; ++i) {
             place(cands[i], a, *cfg, data->n_train, data->n_val, eng.batch);
+            cands[i].acc = wv.d_acc + (size_t)(i - next) * 12;
+            cands[i].confusion = wv.d_cm + (size_t)(i - next) * cm_elems;
             wv.cands.push_back(&cands[i]);
         }
         rc = run_wave(eng, wv, out, history, debug_steps, dbg_losses, dbg_grads, dbg_params);
         if (rc != CMOOP_OK) break;
         next = end;
     }
+    cudaEventRecord(ev_end, eng.stream);
     cudaStreamSynchronize(eng.stream);
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev_begin, ev_end) == cudaSuccess) g_last_device_ms = ms;
+        (void)cudaGetLastError();
+    }
+    prof_resolve();
     if (wv.d_blob) cudaFree(wv.d_blob);
     return rc;
 }
@@ -1280,7 +1433,7 @@ int cmoop_cnn_debug_init_params(const cmoop_genotype* g, uint64_t seed, const cm
     std::vector<Cand*> one{&c};
     rc = eng.init_params(one);
     if (rc == CMOOP_OK) {
-        cudaError_t e = cudaMemcpy(out, c.p, c.n_params * sizeof(float), cudaMemcpyDeviceToHost);
+        cudaError_t e = cmoop::copy_sync(out, c.p, c.n_params * sizeof(float), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) {
             cmoop::set_error("debug_init_params: %s", cudaGetErrorString(e));
             rc = CMOOP_ERR_CUDA;
@@ -1317,17 +1470,17 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
     std::vector<__nv_bfloat16> in_h((size_t)n_in);
     for (long long i = 0; i < n_in; ++i) in_h[i] = __float2bfloat16_rn(in[i]);
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_inh, n_in * 2));
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d_inh, in_h.data(), n_in * 2, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d_inh, in_h.data(), n_in * 2, cudaMemcpyHostToDevice, st));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_in, n_in * 4));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_w, (n_w + Cout) * 4));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_out, n_out * 4));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_wt, n_w * 4));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_wb, std::max((size_t)go * K_pad, (size_t)Launch::tc2_weight_elems(gi, go, k)) * 2));
     CMOOP_CUDA_OK(cudaMalloc(&d_task, 1024));
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d_in, in, n_in * 4, cudaMemcpyHostToDevice, st));
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d_w, w, n_w * 4, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d_in, in, n_in * 4, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d_w, w, n_w * 4, cudaMemcpyHostToDevice, st));
     if (bias)
-        CMOOP_CUDA_OK(cudaMemcpyAsync(d_w + n_w, bias, Cout * 4, cudaMemcpyHostToDevice, st));
+        CMOOP_CUDA_OK(cmoop::copy_async(d_w + n_w, bias, Cout * 4, cudaMemcpyHostToDevice, st));
     else
         CMOOP_CUDA_OK(cudaMemsetAsync(d_w + n_w, 0, Cout * 4, st));
     CMOOP_CUDA_OK(cudaMemsetAsync(d_out, 0, n_out * 4, st));
@@ -1343,7 +1496,7 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
         } else {
             WtTask wt{};
             wt.w = d_w; wt.wt = d_wt; wt.k = k; wt.Cin = Cin; wt.Cout = Cout;
-            CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &wt, sizeof(wt), cudaMemcpyHostToDevice, st));
+            CMOOP_CUDA_OK(cmoop::copy_async(d_task, &wt, sizeof(wt), cudaMemcpyHostToDevice, st));
             rc = Launch::wt((const WtTask*)d_task, 1, (int)((n_w + 255) / 256), st);
             CMOOP_CUDA_OK(cudaStreamSynchronize(st));
             t.w = d_wt; t.use_bias = 0;
@@ -1351,7 +1504,7 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
             if (stride == 2) { t.out_h = H; t.out_w = W; t.out_s = 2; t.accumulate = 1; }
         }
         t.tiles_n = (t.Cout + 63) / 64;
-        CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &t, sizeof(t), cudaMemcpyHostToDevice, st));
+        CMOOP_CUDA_OK(cmoop::copy_async(d_task, &t, sizeof(t), cudaMemcpyHostToDevice, st));
         if (rc == 0 && use_tc == 2)
             rc = Launch::stem_conv((const ConvTask*)d_task, 1, k, W, Cout, (long long)n * H * W, n, 0, st);
         else if (rc == 0)
@@ -1359,7 +1512,7 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
     } else {
         WtBf16Task wb{};
         wb.w = d_w; wb.out = d_wb; wb.k = k; wb.Cin = Cin; wb.Cout = Cout; wb.K_pad = K_pad; wb.mode = mode + (use_tc == 3 ? 2 : 0);
-        CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &wb, sizeof(wb), cudaMemcpyHostToDevice, st));
+        CMOOP_CUDA_OK(cmoop::copy_async(d_task, &wb, sizeof(wb), cudaMemcpyHostToDevice, st));
         rc = use_tc == 3 ? Launch::wt_bf16_v2((const WtBf16Task*)d_task, 1, (int)((Launch::tc2_weight_elems(gi, go, k) / 8 + 255) / 256), st)
                          : Launch::wt_bf16((const WtBf16Task*)d_task, 1, (int)(((long long)go * K_pad + 255) / 256), st);
         CMOOP_CUDA_OK(cudaStreamSynchronize(st));
@@ -1375,7 +1528,7 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
         }
         t.bn = t.Cout < 128 ? t.Cout : 128;
         t.tiles_n = (t.Cout + t.bn - 1) / t.bn;
-        CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &t, sizeof(t), cudaMemcpyHostToDevice, st));
+        CMOOP_CUDA_OK(cmoop::copy_async(d_task, &t, sizeof(t), cudaMemcpyHostToDevice, st));
         if (rc == 0 && use_tc == 3) {
             const long long mq = (long long)n * (H + 2 * pad) * (W + 2 * pad);
             rc = Launch::conv_tc2((const TcConvTask*)d_task, 1, (int)((mq + Launch::tc2_rows() - 1) / Launch::tc2_rows()) * t.tiles_n,
@@ -1386,7 +1539,7 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
     }
     cmoop::count_launch();
     cudaError_t e = cudaStreamSynchronize(st);
-    if (rc == 0 && e == cudaSuccess) e = cudaMemcpy(out, d_out, n_out * 4, cudaMemcpyDeviceToHost);
+    if (rc == 0 && e == cudaSuccess) e = cmoop::copy_sync(out, d_out, n_out * 4, cudaMemcpyDeviceToHost);
     cudaFree(d_in); cudaFree(d_w); cudaFree(d_out); cudaFree(d_wt); cudaFree(d_wb); cudaFree(d_task); cudaFree(d_inh);
     if (rc != 0 || e != cudaSuccess) {
         cmoop::set_error("debug_conv: %s", cudaGetErrorString(rc != 0 ? (cudaError_t)rc : e));
@@ -1430,15 +1583,15 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
     for (long long i = 0; i < n_y; ++i) yh[i] = __float2bfloat16_rn(dy[i]);
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_xh, n_x * 2));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_yh, n_y * 2));
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d_xh, xh.data(), n_x * 2, cudaMemcpyHostToDevice, st));
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d_yh, yh.data(), n_y * 2, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d_xh, xh.data(), n_x * 2, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d_yh, yh.data(), n_y * 2, cudaMemcpyHostToDevice, st));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_x, n_x * 4));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_y, n_y * 4));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_ws, n_o * 4 * splits));
     CMOOP_CUDA_OK(cudaMalloc((void**)&d_o, n_o * 4));
     CMOOP_CUDA_OK(cudaMalloc(&d_task, 1024));
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d_x, x, n_x * 4, cudaMemcpyHostToDevice, st));
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d_y, dy, n_y * 4, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d_x, x, n_x * 4, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d_y, dy, n_y * 4, cudaMemcpyHostToDevice, st));
     CMOOP_CUDA_OK(cudaMemsetAsync(d_ws, 0xff, n_o * 4 * splits, st));       // poison: every partial must be written
     int rc;
     if (use_tc == 3) {
@@ -1446,21 +1599,21 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
         g.xh = d_xh; g.dyh = d_yh; g.out = d_ws; g.H = H; g.W = W; g.Cin = Cin; g.Ho = Ho; g.Wo = Wo; g.Cout = Cout;
         g.k = k; g.stride = stride; g.pad = pad; g.splits = splits; g.m_chunk = chunk;
         g.bn = Launch::wg2_bn(Cout); g.tiles_n = Cout / g.bn;
-        CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &g, sizeof(g), cudaMemcpyHostToDevice, st));
+        CMOOP_CUDA_OK(cmoop::copy_async(d_task, &g, sizeof(g), cudaMemcpyHostToDevice, st));
         rc = Launch::wgrad_tc2((const TcWgradTask*)d_task, 1, splits * Launch::wg2_items(Cin, Cout, k), n, Launch::wg2_q(W, k), st);
     } else if (use_tc == 1) {
         TcWgradTask g{};
         g.xh = d_xh; g.dyh = d_yh; g.out = d_ws; g.H = H; g.W = W; g.Cin = Cin; g.Ho = Ho; g.Wo = Wo; g.Cout = Cout;
         g.k = k; g.stride = stride; g.pad = pad; g.splits = splits; g.m_chunk = chunk;
         g.bn = Cout < 128 ? Cout : 128; g.tiles_k = (kext + 127) / 128; g.tiles_n = (Cout + g.bn - 1) / g.bn;
-        CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &g, sizeof(g), cudaMemcpyHostToDevice, st));
+        CMOOP_CUDA_OK(cmoop::copy_async(d_task, &g, sizeof(g), cudaMemcpyHostToDevice, st));
         rc = Launch::wgrad_tc((const TcWgradTask*)d_task, 1, g.tiles_k * g.tiles_n * splits, n, st);
     } else {
         WgradTask g{};
         g.x = d_x; g.dy = d_y; g.out = d_ws; g.H = H; g.W = W; g.Cin = Cin; g.Ho = Ho; g.Wo = Wo; g.Cout = Cout;
         g.k = k; g.stride = stride; g.pad = pad; g.splits = splits; g.m_chunk = chunk;
         g.tiles_k = (kext + 63) / 64; g.tiles_n = (Cout + 63) / 64;
-        CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &g, sizeof(g), cudaMemcpyHostToDevice, st));
+        CMOOP_CUDA_OK(cmoop::copy_async(d_task, &g, sizeof(g), cudaMemcpyHostToDevice, st));
         rc = use_tc == 2 ? Launch::stem_wgrad((const WgradTask*)d_task, 1, k, W, Cout, splits, n, 0, st)
                          : Launch::wgrad((const WgradTask*)d_task, 1, g.tiles_k * g.tiles_n * splits, n, 0, st);
     }
@@ -1469,11 +1622,11 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
     if (rc == 0) {
         ReduceTask r{};
         r.part = d_ws; r.out = d_o; r.n = (int)n_o; r.splits = splits;
-        CMOOP_CUDA_OK(cudaMemcpyAsync(d_task, &r, sizeof(r), cudaMemcpyHostToDevice, st));
+        CMOOP_CUDA_OK(cmoop::copy_async(d_task, &r, sizeof(r), cudaMemcpyHostToDevice, st));
         rc = Launch::reduce((const ReduceTask*)d_task, 1, (int)((n_o + 255) / 256), st);
     }
     cudaError_t e = cudaStreamSynchronize(st);
-    if (rc == 0 && e == cudaSuccess) e = cudaMemcpy(out, d_o, n_o * 4, cudaMemcpyDeviceToHost);
+    if (rc == 0 && e == cudaSuccess) e = cmoop::copy_sync(out, d_o, n_o * 4, cudaMemcpyDeviceToHost);
     cudaFree(d_x); cudaFree(d_y); cudaFree(d_ws); cudaFree(d_o); cudaFree(d_task); cudaFree(d_xh); cudaFree(d_yh);
     if (rc != 0 || e != cudaSuccess) {
         cmoop::set_error("debug_wgrad: %s", cudaGetErrorString(rc != 0 ? (cudaError_t)rc : e));

@@ -857,6 +857,31 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTask* __restrict__ 
     T.p[i] -= alpha * m / (sqrtf(v) + eps);
 }
 
+// Per-epoch shuffle on the device: the harness-imposed "Keras shuffle" is a Fisher-Yates walk driven by the fmix32 counter
+// hash (engine.cu make_permutation; cmoop_cnn_debug_permutation exports the same stream to the oracle).  The walk is
+// sequential by construction (swap i with hash(i) % (i + 1), i = n-1 .. 1), so one thread per candidate runs it in shared
+// memory (n = 3 072: ~0.2 ms, all candidates of the wave in parallel) and the warp writes the result out coalesced --
+// no host-generated index arrays, no per-candidate upload.
+__global__ void __launch_bounds__(32) perm_kernel(const PermTask* __restrict__ tasks, int epoch, int n) {
+    extern __shared__ int s_perm[];
+    const PermTask T = tasks[blockIdx.x];
+    for (int i = threadIdx.x; i < n; i += 32) s_perm[i] = i;
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        const unsigned s = fmix32(T.seed_lo ^ 0x5bd1e995u * (unsigned)(epoch + 1)) ^ T.seed_hi;
+        const unsigned s2 = fmix32(s ^ 0x27d4eb2fu);
+        for (int i = n - 1; i > 0; --i) {
+            const unsigned r = fmix32(s2 ^ (unsigned)i);
+            const int j = (int)(r % (unsigned)(i + 1));
+            const int t = s_perm[i];
+            s_perm[i] = s_perm[j];
+            s_perm[j] = t;
+        }
+    }
+    __syncwarp();
+    for (int i = threadIdx.x; i < n; i += 32) T.perm[i] = s_perm[i];
+}
+
 __global__ void __launch_bounds__(256) init_kernel(const InitTask* __restrict__ tasks, int n_tasks) {
     const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const InitTask& r) { return r.block_begin; });
     const InitTask T = tasks[t];
@@ -950,6 +975,20 @@ int Launch::adam(const AdamTask* tasks, int n, int blocks, float alpha, float b1
     adam_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, alpha, b1, b2, eps);
     return check();
 }
+bool Launch::perm_ok(int n) { return n >= 1 && (size_t)n * sizeof(int) <= 200 * 1024; }
+int Launch::perm(const PermTask* tasks, int n_tasks, int epoch, int n, void* st) {
+    if (n_tasks == 0) return 0;
+    const size_t smem = (size_t)n * sizeof(int);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(perm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    perm_kernel<<<n_tasks, 32, smem, (cudaStream_t)st>>>(tasks, epoch, n);
+    return (int)cudaGetLastError();
+}
+
 int Launch::init(const InitTask* tasks, int n, int blocks, void* st) {
     if (n == 0 || blocks == 0) return 0;
     init_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n);

@@ -18,6 +18,12 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+static std::atomic<uint64_t> g_h2d{0}, g_d2h{0};
+void count_copy(size_t bytes, cudaMemcpyKind kind) {
+    if (kind == cudaMemcpyHostToDevice) g_h2d.fetch_add((uint64_t)bytes, std::memory_order_relaxed);
+    else if (kind == cudaMemcpyDeviceToHost) g_d2h.fetch_add((uint64_t)bytes, std::memory_order_relaxed);
+}
+
 static const int kSlots = 16;
 static void* g_dev[kSlots];
 static size_t g_dev_bytes[kSlots];
@@ -105,5 +111,10 @@ int cmoop_set_device(int device) {
 }
 
 uint64_t cmoop_launch_count(void) { return cmoop::g_launches.load(); }
+
+void cmoop_copy_bytes(uint64_t* h2d, uint64_t* d2h) {
+    if (h2d) *h2d = cmoop::g_h2d.load();
+    if (d2h) *d2h = cmoop::g_d2h.load();
+}
 
 }  // extern "C"

@@ -12,6 +12,17 @@ namespace cmoop {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// host<->device traffic of every entry point (bench.py e2e "h2d_bytes_per_step" / "d2h_bytes_per_step"): all copies of the
+// library go through these two wrappers
+void count_copy(size_t bytes, cudaMemcpyKind kind);
+inline cudaError_t copy_async(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+    count_copy(bytes, kind);
+    return cudaMemcpyAsync(dst, src, bytes, kind, st);
+}
+inline cudaError_t copy_sync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    count_copy(bytes, kind);
+    return cudaMemcpy(dst, src, bytes, kind);
+}
 
 // Grow-only device/pinned scratch owned by the library (one per slot).
 void* device_scratch(int slot, size_t bytes);

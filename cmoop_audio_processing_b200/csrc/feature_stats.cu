@@ -66,8 +66,8 @@ int cmoop_feature_stats_dev(const float* feats, int64_t rows, int n_features, do
     feature_finalize_kernel<<<1, kMaxF, 0, st>>>(d, blocks, n_features, (double)rows, d_var);
     cmoop::count_launch(4);
     CMOOP_CUDA_OK(cudaGetLastError());
-    CMOOP_CUDA_OK(cudaMemcpyAsync(mean_host, d_mean, n_features * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CMOOP_CUDA_OK(cudaMemcpyAsync(var_host, d_var, n_features * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(mean_host, d_mean, n_features * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(var_host, d_var, n_features * sizeof(double), cudaMemcpyDeviceToHost, st));
     CMOOP_CUDA_OK(cudaStreamSynchronize(st));
     return CMOOP_OK;
 }

@@ -147,7 +147,7 @@ int cmoop_gp_create(const cmoop_gp_model* models, int n_models, cmoop_gp_handle*
         void* d = nullptr;
         CMOOP_CUDA_OK(cudaMalloc(&d, count * sizeof(double)));
         h->owned.push_back(d);
-        CMOOP_CUDA_OK(cudaMemcpy(d, src, count * sizeof(double), cudaMemcpyHostToDevice));
+        CMOOP_CUDA_OK(cmoop::copy_sync(d, src, count * sizeof(double), cudaMemcpyHostToDevice));
         *dst = (const double*)d;
         return CMOOP_OK;
     };
@@ -180,7 +180,7 @@ int cmoop_gp_create(const cmoop_gp_model* models, int n_models, cmoop_gp_handle*
         }
     }
     if (cudaMalloc((void**)&h->d_models, sizeof(DevModel) * n_models) != cudaSuccess ||
-        cudaMemcpy(h->d_models, host.data(), sizeof(DevModel) * n_models, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cmoop::copy_sync(h->d_models, host.data(), sizeof(DevModel) * n_models, cudaMemcpyHostToDevice) != cudaSuccess) {
         cmoop::set_error("gp_create: device allocation failed");
         cmoop_gp_destroy(h);
         return CMOOP_ERR_CUDA;
@@ -222,11 +222,11 @@ int cmoop_gp_predict_host(cmoop_gp_handle h, const double* xq, int q, double* me
     double* d_x = (double*)d;
     double* d_mean = (double*)(d + b_x);
     double* d_std = std ? (double*)(d + b_x + b_o) : nullptr;
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d_x, xq, (size_t)q * h->dim * 8, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d_x, xq, (size_t)q * h->dim * 8, cudaMemcpyHostToDevice, st));
     int rc = cmoop_gp_predict_dev(h, d_x, q, d_mean, d_std, st);
     if (rc != CMOOP_OK) return rc;
-    CMOOP_CUDA_OK(cudaMemcpyAsync(mean, d_mean, (size_t)q * h->n_models * 8, cudaMemcpyDeviceToHost, st));
-    if (std) CMOOP_CUDA_OK(cudaMemcpyAsync(std, d_std, (size_t)q * h->n_models * 8, cudaMemcpyDeviceToHost, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(mean, d_mean, (size_t)q * h->n_models * 8, cudaMemcpyDeviceToHost, st));
+    if (std) CMOOP_CUDA_OK(cmoop::copy_async(std, d_std, (size_t)q * h->n_models * 8, cudaMemcpyDeviceToHost, st));
     CMOOP_CUDA_OK(cudaStreamSynchronize(st));
     return CMOOP_OK;
 }

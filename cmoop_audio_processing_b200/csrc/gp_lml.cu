@@ -425,8 +425,8 @@ int cmoop_gp_lml_create(const double* x, int n, int dim, const double* y, int n_
               cudaMalloc((void**)&h->d_a, (size_t)slots * n * n * 8) == cudaSuccess &&
               cudaMalloc((void**)&h->d_io, (size_t)slots * 8 * 8) == cudaSuccess &&
               cudaMalloc((void**)&h->d_target, (size_t)slots * 4) == cudaSuccess &&
-              cudaMemcpy(h->d_x, x, (size_t)n * dim * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaMemcpy(h->d_y, y, (size_t)n_targets * n * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+              cmoop::copy_sync(h->d_x, x, (size_t)n * dim * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cmoop::copy_sync(h->d_y, y, (size_t)n_targets * n * 8, cudaMemcpyHostToDevice) == cudaSuccess;
     for (int s = 0; ok && s < slots; ++s) {
         cudaStream_t st;
         ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
@@ -459,8 +459,8 @@ int cmoop_gp_lml_eval(cmoop_gp_lml_handle h, int slot, int count, const double* 
                       h->n_targets);
         for (int q = 0; q < nt; ++q) io[(size_t)b * 8 + q] = theta[(size_t)b * nt + q];
     }
-    CMOOP_CUDA_OK(cudaMemcpyAsync(h->d_io + (size_t)slot * 8, io.data(), io.size() * 8, cudaMemcpyHostToDevice, st));
-    CMOOP_CUDA_OK(cudaMemcpyAsync(h->d_target + slot, target, (size_t)count * 4, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(h->d_io + (size_t)slot * 8, io.data(), io.size() * 8, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(h->d_target + slot, target, (size_t)count * 4, cudaMemcpyHostToDevice, st));
     LmlParams P{h->n, h->dim, h->kind, nt, h->nu, h->jitter, h->d_x, h->d_y, h->d_a, h->d_io, h->d_target};
     const size_t smem = lml_smem(h->n, h->dim);
     if (h->n <= 64) gp_lml_kernel<2><<<count, kLmlThreads, smem, st>>>(P, slot);
@@ -469,7 +469,7 @@ int cmoop_gp_lml_eval(cmoop_gp_lml_handle h, int slot, int count, const double* 
     else gp_lml_kernel<16><<<count, kLmlThreads, smem, st>>>(P, slot);
     cmoop::count_launch();
     CMOOP_CUDA_OK(cudaGetLastError());
-    CMOOP_CUDA_OK(cudaMemcpyAsync(io.data(), h->d_io + (size_t)slot * 8, io.size() * 8, cudaMemcpyDeviceToHost, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(io.data(), h->d_io + (size_t)slot * 8, io.size() * 8, cudaMemcpyDeviceToHost, st));
     CMOOP_CUDA_OK(cudaStreamSynchronize(st));
     for (int b = 0; b < count; ++b) {
         lml[b] = io[(size_t)b * 8 + 3];

@@ -905,7 +905,7 @@ struct cmoop_mfcc {
 namespace {
 
 int upload_tables(cmoop_mfcc* h) {
-    CMOOP_CUDA_OK(cudaMemcpy(h->d_tables, h->host_tables.data(), h->host_tables.size() * sizeof(float),
+    CMOOP_CUDA_OK(cmoop::copy_sync(h->d_tables, h->host_tables.data(), h->host_tables.size() * sizeof(float),
                              cudaMemcpyHostToDevice));
     return CMOOP_OK;
 }
@@ -1288,11 +1288,11 @@ int cmoop_mfcc_fwd_host(cmoop_mfcc_handle h, const float* wave, int64_t n_clips,
     for (int64_t c0 = 0; c0 < n_clips; c0 += chunk, slot ^= 1) {
         const int64_t nc = (n_clips - c0) < chunk ? (n_clips - c0) : chunk;
         cudaStream_t st = streams[slot];
-        CMOOP_CUDA_OK(cudaMemcpyAsync(d_in[slot], wave + (size_t)c0 * n_samples, (size_t)nc * n_samples * sizeof(float),
+        CMOOP_CUDA_OK(cmoop::copy_async(d_in[slot], wave + (size_t)c0 * n_samples, (size_t)nc * n_samples * sizeof(float),
                                       cudaMemcpyHostToDevice, st));
         int rc = cmoop_mfcc_fwd_dev(h, d_in[slot], nc, n_samples, d_out[slot], st);
         if (rc != CMOOP_OK) return rc;
-        CMOOP_CUDA_OK(cudaMemcpyAsync(out + (size_t)c0 * frames * h->n_out, d_out[slot],
+        CMOOP_CUDA_OK(cmoop::copy_async(out + (size_t)c0 * frames * h->n_out, d_out[slot],
                                       (size_t)nc * frames * h->n_out * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     CMOOP_CUDA_OK(cudaStreamSynchronize(streams[0]));
@@ -1357,13 +1357,13 @@ int cmoop_mfcc_fwd_host_i16(cmoop_mfcc_handle h, const int16_t* wave, int64_t n_
         float* d_in = (float*)((char*)d_pcm + pcm_bytes);
         float* d_out = (float*)((char*)d_in + in_bytes);
         const long long n = (long long)nc * n_samples;
-        CMOOP_CUDA_OK(cudaMemcpyAsync(d_pcm, wave + (size_t)c0 * n_samples, (size_t)n * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        CMOOP_CUDA_OK(cmoop::copy_async(d_pcm, wave + (size_t)c0 * n_samples, (size_t)n * sizeof(int16_t), cudaMemcpyHostToDevice, st));
         pcm16_to_f32_kernel<<<(unsigned)((n + 2047) / 2048), 256, 0, st>>>(d_pcm, d_in, n);
         cmoop::count_launch();
         CMOOP_CUDA_OK(cudaGetLastError());
         int rc = cmoop_mfcc_fwd_dev(h, d_in, nc, n_samples, d_out, st);
         if (rc != CMOOP_OK) return rc;
-        CMOOP_CUDA_OK(cudaMemcpyAsync(out + (size_t)c0 * frames * h->n_out, d_out, (size_t)nc * frames * h->n_out * sizeof(float),
+        CMOOP_CUDA_OK(cmoop::copy_async(out + (size_t)c0 * frames * h->n_out, d_out, (size_t)nc * frames * h->n_out * sizeof(float),
                                       cudaMemcpyDeviceToHost, st));
     }
     CMOOP_CUDA_OK(cudaStreamSynchronize(streams[0]));

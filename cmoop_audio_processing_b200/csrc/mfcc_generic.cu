@@ -198,8 +198,8 @@ int generic_mfcc_create(const cmoop_mfcc_config* cfg, GenericMfcc** out) {
     F.insert(F.end(), g->n_out, 1.f);
     if (cudaMalloc((void**)&g->d_float, F.size() * sizeof(float)) != cudaSuccess ||
         cudaMalloc((void**)&g->d_int, ints.size() * sizeof(int)) != cudaSuccess ||
-        cudaMemcpy(g->d_float, F.data(), F.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(g->d_int, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cmoop::copy_sync(g->d_float, F.data(), F.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cmoop::copy_sync(g->d_int, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
         set_error("mfcc_create: device allocation failed");
         generic_mfcc_destroy(g);
         return CMOOP_ERR_CUDA;
@@ -231,7 +231,7 @@ int generic_mfcc_set_standardise(GenericMfcc* g, const float* mean, const float*
         g->h_float[g->o_inv + c] = scale ? 1.f / scale[c] : 1.f;
     }
     CMOOP_CUDA_OK(cudaDeviceSynchronize());
-    CMOOP_CUDA_OK(cudaMemcpy(g->d_float + g->o_mean, g->h_float.data() + g->o_mean, 2 * g->n_out * sizeof(float),
+    CMOOP_CUDA_OK(cmoop::copy_sync(g->d_float + g->o_mean, g->h_float.data() + g->o_mean, 2 * g->n_out * sizeof(float),
                              cudaMemcpyHostToDevice));
     return CMOOP_OK;
 }

@@ -416,17 +416,17 @@ int cmoop_nds_crowding_host(const double* objs, const double* cv, int n, int m, 
         ws = cmoop::device_scratch(1, ws_bytes);
         if (!ws) return CMOOP_ERR_CUDA;
     }
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d_objs, objs, nb * m * 8, cudaMemcpyHostToDevice, st));
-    if (cv) CMOOP_CUDA_OK(cudaMemcpyAsync(d_cv, cv, nb * 8, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d_objs, objs, nb * m * 8, cudaMemcpyHostToDevice, st));
+    if (cv) CMOOP_CUDA_OK(cmoop::copy_async(d_cv, cv, nb * 8, cudaMemcpyHostToDevice, st));
     int rc = cmoop_nds_crowding_dev(d_objs, cv ? d_cv : nullptr, n, m, batch, lam, eps, crowd_mode, d_rank, d_order,
                                     d_foff, d_nf, d_crowd, ws, ws_bytes, st);
     if (rc != CMOOP_OK) return rc;
-    if (rank) CMOOP_CUDA_OK(cudaMemcpyAsync(rank, d_rank, nb * 4, cudaMemcpyDeviceToHost, st));
-    if (order) CMOOP_CUDA_OK(cudaMemcpyAsync(order, d_order, nb * 4, cudaMemcpyDeviceToHost, st));
+    if (rank) CMOOP_CUDA_OK(cmoop::copy_async(rank, d_rank, nb * 4, cudaMemcpyDeviceToHost, st));
+    if (order) CMOOP_CUDA_OK(cmoop::copy_async(order, d_order, nb * 4, cudaMemcpyDeviceToHost, st));
     if (front_offsets)
-        CMOOP_CUDA_OK(cudaMemcpyAsync(front_offsets, d_foff, (size_t)(n + 1) * batch * 4, cudaMemcpyDeviceToHost, st));
-    if (n_fronts) CMOOP_CUDA_OK(cudaMemcpyAsync(n_fronts, d_nf, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
-    if (crowd) CMOOP_CUDA_OK(cudaMemcpyAsync(crowd, d_crowd, nb * 8, cudaMemcpyDeviceToHost, st));
+        CMOOP_CUDA_OK(cmoop::copy_async(front_offsets, d_foff, (size_t)(n + 1) * batch * 4, cudaMemcpyDeviceToHost, st));
+    if (n_fronts) CMOOP_CUDA_OK(cmoop::copy_async(n_fronts, d_nf, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+    if (crowd) CMOOP_CUDA_OK(cmoop::copy_async(crowd, d_crowd, nb * 8, cudaMemcpyDeviceToHost, st));
     CMOOP_CUDA_OK(cudaStreamSynchronize(st));
     return CMOOP_OK;
 }
@@ -453,8 +453,8 @@ int cmoop_crowding_distance_host(const double* objs, int n, int m, const int* fr
         ws = cmoop::device_scratch(1, ws_bytes);
         if (!ws) return CMOOP_ERR_CUDA;
     }
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d, objs, (size_t)n * m * 8, cudaMemcpyHostToDevice, st));
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d + b_objs, front, (size_t)front_len * 4, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d, objs, (size_t)n * m * 8, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d + b_objs, front, (size_t)front_len * 4, cudaMemcpyHostToDevice, st));
     Params p{};
     p.objs = (const double*)d;
     p.n = n;
@@ -467,7 +467,7 @@ int cmoop_crowding_distance_host(const double* objs, int n, int m, const int* fr
     p.given_len = front_len;
     int rc = launch(p, 1, st);
     if (rc != CMOOP_OK) return rc;
-    CMOOP_CUDA_OK(cudaMemcpyAsync(out, p.crowd, (size_t)front_len * 8, cudaMemcpyDeviceToHost, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(out, p.crowd, (size_t)front_len * 8, cudaMemcpyDeviceToHost, st));
     CMOOP_CUDA_OK(cudaStreamSynchronize(st));
     return CMOOP_OK;
 }

@@ -280,12 +280,12 @@ int cmoop_hypervolume_host(const double* points, int n, int m, const double* ref
     const size_t b_p = cmoop::align_up((size_t)n * m * 8, 256);
     char* d = (char*)cmoop::device_scratch(3, b_p + 512);
     if (!d) return CMOOP_ERR_CUDA;
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d, points, (size_t)n * m * 8, cudaMemcpyHostToDevice, st));
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d + b_p, ref, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d, points, (size_t)n * m * 8, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d + b_p, ref, (size_t)m * 8, cudaMemcpyHostToDevice, st));
     int rc = cmoop_hypervolume_dev((const double*)d, n, m, (const double*)(d + b_p), (double*)(d + b_p + 256), nullptr,
                                    0, st);
     if (rc != CMOOP_OK) return rc;
-    CMOOP_CUDA_OK(cudaMemcpyAsync(out, d + b_p + 256, 8, cudaMemcpyDeviceToHost, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(out, d + b_p + 256, 8, cudaMemcpyDeviceToHost, st));
     CMOOP_CUDA_OK(cudaStreamSynchronize(st));
     return CMOOP_OK;
 }
@@ -300,14 +300,14 @@ int cmoop_front_metrics_host(const double* front, int nf, const double* true_fro
     const size_t b_df = cmoop::align_up((size_t)nf * 8, 256), b_dt = cmoop::align_up((size_t)nt * 8, 256);
     char* d = (char*)cmoop::device_scratch(3, b_f + b_t + b_df + b_dt + 256);
     if (!d) return CMOOP_ERR_CUDA;
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d, front, (size_t)nf * m * 8, cudaMemcpyHostToDevice, st));
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d + b_f, true_front, (size_t)nt * m * 8, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d, front, (size_t)nf * m * 8, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d + b_f, true_front, (size_t)nt * m * 8, cudaMemcpyHostToDevice, st));
     double* d_out = (double*)(d + b_f + b_t + b_df + b_dt);
     front_metrics_kernel<<<1, kThreads, 0, st>>>((const double*)d, nf, (const double*)(d + b_f), nt, m,
                                                  (double*)(d + b_f + b_t), (double*)(d + b_f + b_t + b_df), d_out);
     cmoop::count_launch();
     CMOOP_CUDA_OK(cudaGetLastError());
-    CMOOP_CUDA_OK(cudaMemcpyAsync(out3, d_out, 24, cudaMemcpyDeviceToHost, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(out3, d_out, 24, cudaMemcpyDeviceToHost, st));
     CMOOP_CUDA_OK(cudaStreamSynchronize(st));
     return CMOOP_OK;
 }
@@ -318,17 +318,17 @@ static int dominated_host(const double* a, int na, const double* b, int nb, int 
     const size_t b_a = cmoop::align_up((size_t)na * m * 8, 256), b_b = cmoop::align_up((size_t)nb * m * 8, 256);
     char* d = (char*)cmoop::device_scratch(3, b_a + b_b + cmoop::align_up(nb, 256));
     if (!d) return CMOOP_ERR_CUDA;
-    CMOOP_CUDA_OK(cudaMemcpyAsync(d, a, (size_t)na * m * 8, cudaMemcpyHostToDevice, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(d, a, (size_t)na * m * 8, cudaMemcpyHostToDevice, st));
     const double* d_b = (const double*)d;
     if (!skip_self) {
-        CMOOP_CUDA_OK(cudaMemcpyAsync(d + b_a, b, (size_t)nb * m * 8, cudaMemcpyHostToDevice, st));
+        CMOOP_CUDA_OK(cmoop::copy_async(d + b_a, b, (size_t)nb * m * 8, cudaMemcpyHostToDevice, st));
         d_b = (const double*)(d + b_a);
     }
     uint8_t* d_c = (uint8_t*)(d + b_a + b_b);
     dominated_kernel<<<(nb + 255) / 256, 256, 0, st>>>((const double*)d, na, d_b, nb, m, skip_self, d_c);
     cmoop::count_launch();
     CMOOP_CUDA_OK(cudaGetLastError());
-    CMOOP_CUDA_OK(cudaMemcpyAsync(covered, d_c, nb, cudaMemcpyDeviceToHost, st));
+    CMOOP_CUDA_OK(cmoop::copy_async(covered, d_c, nb, cudaMemcpyDeviceToHost, st));
     CMOOP_CUDA_OK(cudaStreamSynchronize(st));
     return CMOOP_OK;
 }

@@ -84,7 +84,9 @@ def _final_front(ops, pop_data):
 
 
 def nsga2(pop_size, max_gen, ops, *, on_generation=None):
-    """nsga_penalty.py:610-776.  Returns (pareto_set, per-generation populations, timings)."""
+    """nsga_penalty.py:610-776.  Returns (pareto_set, per-generation populations, timings).  ``on_generation(gen,
+    pop_data)`` runs INSIDE the generation's timed region (the reference times the loop body, sa_nsga_penalty.py:540,602)
+    and its return value is kept under timings[gen]["indicators"]."""
     get_lambda = lambda g: _nsga.get_lambda(g, max_gen, LAMBDA_INITIAL, LAMBDA_FINAL)   # noqa: E731
     population = ops.initialize_population(pop_size)
     pop_data = ops.compute_objectives_and_constraints(population)
@@ -110,10 +112,10 @@ def nsga2(pop_size, max_gen, ops, *, on_generation=None):
         offspring = offspring[:pop_size]
         off_data = ops.compute_objectives_and_constraints(offspring)
         pop_data = _truncate(ops, pop_data + off_data, lam, pop_size)
-        timings.append({"generation": gen, "seconds": time.perf_counter() - t0, "true_evals": len(offspring)})
+        extra = on_generation(gen, pop_data) if on_generation else None     # e.g. HV / IGD / Spread of the generation
+        timings.append({"generation": gen, "seconds": time.perf_counter() - t0, "true_evals": len(offspring),
+                        "indicators": extra})
         history.append(list(pop_data))
-        if on_generation:
-            on_generation(gen, pop_data)
     return _final_front(ops, pop_data), history, timings
 
 
@@ -154,16 +156,17 @@ def sa_nsga2(pop_size, max_gen, infill_percent, ops, *, local_search=True, on_ge
         t_eval = time.perf_counter()
         infill_true = ops.compute_objectives_and_constraints(infill_hp)
         eval_s = time.perf_counter() - t_eval
+        t_upd = time.perf_counter()
         sm.update(infill_hp, infill_true)
+        upd_s = time.perf_counter() - t_upd
         off_data = list(final_pred)
         for i, true_res in enumerate(infill_true):
             off_data[infill_idx[i]] = true_res
         pop_data = _truncate(ops, pop_data + off_data, lam, pop_size)
+        extra = on_generation(gen, pop_data) if on_generation else None     # e.g. HV / IGD / Spread of the generation
         timings.append({"generation": gen, "seconds": time.perf_counter() - t0, "true_evals": len(infill_hp),
-                        "eval_seconds": eval_s})
+                        "eval_seconds": eval_s, "update_seconds": upd_s, "indicators": extra})
         history.append(list(pop_data))
-        if on_generation:
-            on_generation(gen, pop_data)
     return _final_front(ops, pop_data), history, timings
 
 

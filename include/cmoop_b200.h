@@ -45,6 +45,15 @@ int cmoop_device_count(void);
 int cmoop_set_device(int device);
 /* kernel launches issued by this library since load (bench.py "gpu_launches") */
 uint64_t cmoop_launch_count(void);
+/* host->device / device->host bytes copied by this library since load (bench.py "e2e.h2d_bytes_per_step" / "d2h_...") */
+void cmoop_copy_bytes(uint64_t* h2d, uint64_t* d2h);
+/* per-kernel-family device timing of the candidate-CNN engine (CUDA-event pairs around every grouped launch of its
+ * stream; off by default).  enable(1) clears the table.  read() writes one line per family, "name launches ms flops"
+ * (flops = algorithmic 2*M*K*N of the contraction kernels, 0 for the others), and returns the bytes needed. */
+int cmoop_profile_enable(int on);
+size_t cmoop_profile_read(char* buf, size_t cap);
+/* device time (CUDA events on the engine's stream) of the most recent cmoop_cnn_pop_train_eval call, milliseconds */
+double cmoop_cnn_last_device_ms(void);
 
 /* ------------------------------------------------------------------ (4) NDS + crowding
  * Replaces dominates / fast_non_dominated_sort / crowding_distance
