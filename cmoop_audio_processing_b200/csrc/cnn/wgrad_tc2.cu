@@ -30,11 +30,13 @@
 namespace cmoop_cnn {
 namespace {
 
-constexpr int W2_QC = 256;                   // positions per chunk (16 UMMA K steps)
+constexpr int W2_QC = 128;                   // positions per chunk (8 UMMA K steps)
 constexpr int W2_PRODUCERS = 256;            // 8 producer / epilogue warps
 constexpr int W2_THREADS = W2_PRODUCERS + 32;
 constexpr uint32_t W2_TMEM_COLS = 512;
 constexpr int W2_MAX_PAIRS = 13;             // (25 + 1) / 2
+constexpr int W2_ST = 3;                     // chunk buffers (X patch + dY tile) in the ring
+constexpr int W2_LOOK = 2;                   // chunks whose cp.async groups are in flight per producer thread
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -64,16 +66,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uin
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
                  : "memory");
 }
-// MN-major, SWIZZLE_128B: 64-element (128-byte) groups along M/N `lbo` bytes apart, 8-row groups along K 1024 B apart
-__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -86,10 +78,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void named_bar(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
 // Work item of a CTA: (task, split, input-channel slab, output-channel tile, tap-pair group).
 __global__ void __launch_bounds__(W2_THREADS, 1) wgrad_tc2_kernel(const TcWgradTask* __restrict__ tasks, int n_tasks, int n_b,
                                                                   int q_max) {
@@ -106,8 +94,10 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wgrad_tc2_kernel(const TcWgradT
     }
     __syncthreads();
     // ---- decode: local = ((split * n_slab + slab) * tiles_n + tn) * n_grp + grp
-    const int bn = T.bn, taps = T.k * T.k, n_pairs = (taps + 1) >> 1, gp = 512 / bn < W2_MAX_PAIRS ? 512 / bn : W2_MAX_PAIRS;
-    const int n_grp = (n_pairs + gp - 1) / gp, n_slab = (T.Cin + 63) >> 6;
+    const int bn = T.bn, taps = T.k * T.k, n_pairs = (taps + 1) >> 1;
+    const int gp_max = 512 / bn < W2_MAX_PAIRS ? 512 / bn : W2_MAX_PAIRS;      // accumulators that fit TMEM
+    const int n_grp = (n_pairs + gp_max - 1) / gp_max, gp = (n_pairs + n_grp - 1) / n_grp;     // balanced groups
+    const int n_slab = (T.Cin + 63) >> 6;
     int local = blockIdx.x - T.tile_begin;
     const int grp = local % n_grp; local /= n_grp;
     const int tn = local % T.tiles_n; local /= T.tiles_n;
@@ -126,16 +116,17 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wgrad_tc2_kernel(const TcWgradT
 
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const size_t xstride = ((size_t)q_max * 128 + 1023) & ~size_t(1023);
-    uint8_t* xbuf = base;                                        // [2][QX rows][128 B]
-    uint8_t* ybuf = xbuf + 2 * xstride;                          // [2][256 rows][128 B]
-    uint8_t* ones = ybuf + 2 * (size_t)W2_QC * 128;              // [256 rows][128 B]: element 0 of every row = 1
-    int* xoff = reinterpret_cast<int*>(ones + (size_t)W2_QC * 128);      // [q_max] element offset into xh, -1 = zero row
-    int* yoff = xoff + ((q_max + 3) & ~3);                               // [256]   element offset into dyh, -1 = zero row
-    uint64_t* bars = reinterpret_cast<uint64_t*>(yoff + W2_QC);
-    uint64_t* full = bars;           // [2]
-    uint64_t* empty = bars + 2;      // [2]
-    uint64_t* accum_bar = bars + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    uint8_t* xbuf = base;                                        // [W2_ST][QX rows][128 B]
+    const int yslabs = (bn + 63) >> 6;                           // 64-channel groups of the dY tile (MN-major atoms)
+    const size_t ystride = (size_t)yslabs * W2_QC * 128;
+    uint8_t* ybuf = xbuf + W2_ST * xstride;                      // [W2_ST][yslabs][QC rows][128 B]
+    uint8_t* ones = ybuf + W2_ST * ystride;                      // [QC rows][128 B]: element 0 of every row = 1
+    uint32_t* pair_lo = reinterpret_cast<uint32_t*>(ones + (size_t)W2_QC * 128);   // [W2_ST][16] A-descriptor low words
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pair_lo + W2_ST * 16);
+    uint64_t* full = bars;               // [W2_ST]
+    uint64_t* empty = bars + W2_ST;      // [W2_ST]
+    uint64_t* accum_bar = bars + 2 * W2_ST;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * W2_ST + 1);
 
     if (n_chunks == 0) {             // nothing of the (short) batch falls into this split: its partial is zero
         for (int pr = 0; pr < my_pairs; ++pr)
@@ -147,7 +138,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wgrad_tc2_kernel(const TcWgradT
         return;
     }
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < W2_ST; ++s) {
             mbar_init(&full[s], W2_PRODUCERS);
             mbar_init(&empty[s], 1);
         }
@@ -165,6 +156,20 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wgrad_tc2_kernel(const TcWgradT
         const int r = i >> 3, ch = i & 7;
         *reinterpret_cast<uint4*>(ones + (size_t)r * 128 + (ch << 4)) = make_uint4(ch == (r & 7) ? 0x00003F80u : 0u, 0u, 0u, 0u);
     }
+    // A-operand descriptors of every tap pair, built ONCE (the issue loop below only adds the K step to the address
+    // field): low word = start address >> 4 | (LBO >> 4) << 16 at K step 0 of buffer `b`.  Group 0 of M is tap 2*pair at
+    // its row shift, group 1 the next tap of the same patch (LBO = shift difference) or, after the last tap, the ones
+    // buffer (bias gradient).  A single issuing thread that rebuilt them per UMMA (integer divisions by k included) was
+    // the whole cost of the first version of this kernel: ~250 clk per UMMA against 62 clk for the lean loop
+    // (tools/microbench/umma_layouts.cu: operand layout, start-row alignment and LBO do NOT change the UMMA rate).
+    if (tid < W2_ST * my_pairs) {
+        const int b = tid / my_pairs, pr = tid - b * my_pairs;
+        const int ta = 2 * (pair0 + pr), tb = ta + 1;
+        const uint32_t xa = smem_u32(xbuf + (size_t)b * xstride);
+        const uint32_t a0 = xa + (uint32_t)((ta / T.k) * Wp + (ta % T.k)) * 128u;
+        const uint32_t a1 = tb < taps ? xa + (uint32_t)((tb / T.k) * Wp + (tb % T.k)) * 128u : smem_u32(ones);
+        pair_lo[b * 16 + pr] = ((a0 >> 4) & 0x3FFFu) | ((((a1 - a0) >> 4) & 0x3FFFu) << 16);
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -173,50 +178,62 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wgrad_tc2_kernel(const TcWgradT
 
     if (warp < W2_PRODUCERS / 32) {
         // ================= producers =================
+        // Thread -> (16-byte chunk column, first row) of the X patch and of the dY tile; every further row of the thread
+        // is `rstep` rows on, so its padded coordinates (n, hp, wp) advance incrementally (two integer divisions per
+        // thread and chunk instead of two per row).  W2_LOOK chunks of cp.async groups stay in flight per thread.
         const int xcs = cw >> 3;                                   // 16-byte chunks per X row
-        for (int c = 0; c < n_chunks; ++c) {
-            const int buf = c & 1;
-            const int q0 = (chunk_begin + c) * W2_QC;
-            mbar_wait(&empty[buf], (((uint32_t)(c >> 1)) & 1u) ^ 1u);
-            named_bar(1, W2_PRODUCERS);                            // everyone is done with the previous offsets
-            for (int i = tid; i < QX + W2_QC; i += W2_PRODUCERS) {
-                const bool is_x = i < QX;
-                const int q = is_x ? q0 - S + i : q0 + (i - QX);
-                int off = -1;
-                if (q >= 0 && q < Mq) {
-                    const int n = q / HpWp, rem = q - n * HpWp;
-                    const int hp = rem / Wp, wp = rem - hp * Wp;
-                    if (hp >= p && hp < T.H + p && wp >= p && wp < T.W + p)
-                        off = ((n * T.H + hp - p) * T.W + wp - p) * (is_x ? T.Cin : T.Cout);
+        const int ycs = bn >> 3;                                   // 16-byte chunks per dY row
+        const int x_chunk = tid % xcs, x_r0 = tid / xcs, x_step = W2_PRODUCERS / xcs;
+        const int y_chunk = tid % ycs, y_r0 = tid / ycs, y_step = W2_PRODUCERS / ycs;
+        const int x_dh = x_step / Wp, x_dw = x_step - x_dh * Wp, y_dh = y_step / Wp, y_dw = y_step - y_dh * Wp;
+        const int Hp = T.H + 2 * p;
+        const __nv_bfloat16* xsrc = T.xh + c0 + x_chunk * 8;
+        const __nv_bfloat16* ysrc = T.dyh + n0 + y_chunk * 8;
+        const uint32_t y_col = (uint32_t)(y_chunk >> 3) * (uint32_t)(W2_QC * 128), y_c7 = (uint32_t)(y_chunk & 7);
+        for (int c = 0; c < n_chunks + W2_LOOK; ++c) {
+            if (c < n_chunks) {
+                const int buf = c % W2_ST;
+                const int q0 = (chunk_begin + c) * W2_QC;
+                mbar_wait(&empty[buf], (((uint32_t)(c / W2_ST)) & 1u) ^ 1u);
+                uint8_t* xb = xbuf + (size_t)buf * xstride;
+                uint8_t* yb = ybuf + (size_t)buf * ystride;
+                if (x_r0 < x_step) {   // X patch rows q0 - S + i
+                    int q = q0 - S + x_r0;
+                    int n = 0, hp = 0, wp = 0;
+                    if (q >= 0) { n = q / HpWp; const int rem = q - n * HpWp; hp = rem / Wp; wp = rem - hp * Wp; }
+                    else { // rows before the first sample: walk up from a negative position (zero rows until q >= 0)
+                        const int qq = q + HpWp; n = -1; hp = qq / Wp; wp = qq - hp * Wp;
+                    }
+                    for (int i = x_r0; i < QX; i += x_step, q += x_step) {
+                        const bool ok = n >= 0 && q < Mq && hp >= p && hp < T.H + p && wp >= p && wp < T.W + p;
+                        const long long off = ok ? ((long long)(n * T.H + hp - p) * T.W + wp - p) * T.Cin : 0;
+                        cp_async16(xb + (size_t)i * 128 + ((x_chunk ^ (i & 7)) << 4), xsrc + off, ok ? 16u : 0u);
+                        wp += x_dw; hp += x_dh;
+                        if (wp >= Wp) { wp -= Wp; ++hp; }
+                        while (hp >= Hp) { hp -= Hp; ++n; }
+                    }
                 }
-                if (is_x) xoff[i] = off; else yoff[i - QX] = off;
-            }
-            named_bar(1, W2_PRODUCERS);
-            uint8_t* xb = xbuf + (size_t)buf * xstride;
-            uint8_t* yb = ybuf + (size_t)buf * W2_QC * 128;
-            {   // X patch: cw / 8 chunks per row
-                const int chunk = tid % xcs, r0 = tid / xcs, rstep = W2_PRODUCERS / xcs;
-                if (r0 < rstep)
-                    for (int i = r0; i < QX; i += rstep) {
-                        const int off = xoff[i];
-                        cp_async16(xb + (size_t)i * 128 + ((chunk ^ (i & 7)) << 4), off >= 0 ? T.xh + off + c0 + chunk * 8 : T.xh,
-                                   off >= 0 ? 16u : 0u);
+                if (y_r0 < y_step) {   // dY rows q0 + i
+                    int q = q0 + y_r0;
+                    int n = q / HpWp;
+                    const int rem = q - n * HpWp;
+                    int hp = rem / Wp, wp = rem - hp * Wp;
+                    for (int i = y_r0; i < W2_QC; i += y_step, q += y_step) {
+                        const bool ok = q < Mq && hp >= p && hp < T.H + p && wp >= p && wp < T.W + p;
+                        const long long off = ok ? ((long long)(n * T.H + hp - p) * T.W + wp - p) * T.Cout : 0;
+                        cp_async16(yb + y_col + (size_t)i * 128 + ((y_c7 ^ (uint32_t)(i & 7)) << 4), ysrc + off, ok ? 16u : 0u);
+                        wp += y_dw; hp += y_dh;
+                        if (wp >= Wp) { wp -= Wp; ++hp; }
+                        while (hp >= Hp) { hp -= Hp; ++n; }
                     }
-            }
-            {   // dY tile: bn / 8 chunks per row
-                const int ycs = bn >> 3;
-                const int chunk = tid % ycs, r0 = tid / ycs, rstep = W2_PRODUCERS / ycs;
-                if (r0 < rstep)
-                    for (int i = r0; i < W2_QC; i += rstep) {
-                        const int off = yoff[i];
-                        cp_async16(yb + (size_t)i * 128 + ((chunk ^ (i & 7)) << 4), off >= 0 ? T.dyh + off + n0 + chunk * 8 : T.dyh,
-                                   off >= 0 ? 16u : 0u);
-                    }
+                }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&full[buf]);
+            if (c >= W2_LOOK) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(W2_LOOK) : "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&full[(c - W2_LOOK) % W2_ST]);
+            }
         }
         // ================= epilogue: accumulator lanes = (tap of the pair, ci), columns = co =================
         mbar_wait(accum_bar, 0);
@@ -263,23 +280,24 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wgrad_tc2_kernel(const TcWgradT
             idesc |= (1u << 15) | (1u << 16);       // A and B are MN-major
             idesc |= (uint32_t)(bn >> 3) << 17;     // N
             idesc |= (uint32_t)(128 >> 4) << 24;    // M
-            const uint32_t ones_addr = smem_u32(ones);
+            // descriptor high word: SBO = 1024 B (8-row groups along K), version 1, SWIZZLE_128B
+            const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t y_lbo = (uint32_t)(((W2_QC * 128) >> 4) & 0x3FFF) << 16;        // second 64-channel group of dY
             for (int c = 0; c < n_chunks; ++c) {
-                const int buf = c & 1;
-                mbar_wait(&full[buf], ((uint32_t)(c >> 1)) & 1u);
+                const int buf = c % W2_ST;
+                mbar_wait(&full[buf], ((uint32_t)(c / W2_ST)) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t xa = smem_u32(xbuf + (size_t)buf * xstride), ya = smem_u32(ybuf + (size_t)buf * W2_QC * 128);
-                for (int ks = 0; ks < W2_QC / 16; ++ks) {
-                    const uint64_t bd = make_desc_mn_sw128(ya + (uint32_t)ks * 2048u, 8192);
-                    for (int pr = 0; pr < my_pairs; ++pr) {
-                        const int ta = 2 * (pair0 + pr), tb = ta + 1;
-                        const uint32_t sa = (uint32_t)((ta / T.k) * Wp + (ta % T.k));
-                        const uint32_t a0 = xa + (sa + (uint32_t)ks * 16u) * 128u;
-                        // second 64-row group of M: the next tap of the same patch, or the ones buffer after the last tap
-                        const uint32_t a1 = tb < taps ? xa + ((uint32_t)((tb / T.k) * Wp + (tb % T.k)) + (uint32_t)ks * 16u) * 128u
-                                                      : ones_addr + (uint32_t)ks * 2048u;
-                        const uint64_t ad = make_desc_mn_sw128(a0, a1 - a0);
-                        umma_bf16(tmem_base + (uint32_t)(pr * bn), ad, bd, idesc, (c | ks) != 0 ? 1u : 0u);
+                const uint32_t y_lo = ((smem_u32(ybuf + (size_t)buf * ystride) >> 4) & 0x3FFFu) | y_lbo;
+                const uint32_t* plo = pair_lo + buf * 16;
+#pragma unroll 1
+                for (int pr = 0; pr < my_pairs; ++pr) {
+                    const uint32_t a_lo = plo[pr];
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(pr * bn);
+#pragma unroll
+                    for (int ks = 0; ks < W2_QC / 16; ++ks) {      // 16 positions = 16 rows of 128 B further down
+                        const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (uint32_t)ks * 128u);
+                        const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(y_lo + (uint32_t)ks * 128u);
+                        umma_bf16(d_tmem, ad, bd, idesc, (c | ks) != 0 ? 1u : 0u);
                     }
                 }
                 umma_commit(&empty[buf]);
@@ -297,12 +315,13 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wgrad_tc2_kernel(const TcWgradT
 
 size_t w2_smem_bytes(int q_max) {
     const size_t xstride = ((size_t)q_max * 128 + 1023) & ~size_t(1023);
-    return 1024 + 2 * xstride + 3 * (size_t)W2_QC * 128 + (size_t)(((q_max + 3) & ~3) + W2_QC) * 4 + 256;
+    // X patches + dY tiles (two 64-channel slabs at bn = 128) + ones buffer + offsets + pair descriptors / barriers
+    return 1024 + W2_ST * xstride + (W2_ST * 2 + 1) * (size_t)W2_QC * 128 + 1024;
 }
 
 }  // namespace
 
-int Launch::wg2_bn(int Cout) { return Cout < 64 ? Cout : 64; }
+int Launch::wg2_bn(int Cout) { return Cout < 128 ? Cout : 128; }
 int Launch::wg2_q(int W, int k) {
     const int p = (k - 1) / 2;
     return W2_QC + 2 * (p * (W + 2 * p) + p);
@@ -310,7 +329,7 @@ int Launch::wg2_q(int W, int k) {
 // CTAs per split: slabs x output tiles x tap-pair groups
 int Launch::wg2_items(int Cin, int Cout, int k) {
     const int bn = wg2_bn(Cout), pairs = (k * k + 1) / 2, gp = 512 / bn < W2_MAX_PAIRS ? 512 / bn : W2_MAX_PAIRS;
-    return ((Cin + 63) / 64) * (Cout / bn) * ((pairs + gp - 1) / gp);
+    return ((Cin + 63) / 64) * (Cout / bn) * ((pairs + gp - 1) / gp);       // the kernel balances the pairs over these groups
 }
 // split geometry over the padded-linear positions of a full batch: chunk rows per split (multiple of 256)
 void Launch::wg2_splits(long long Mq, int* splits, int* m_chunk) {
@@ -324,7 +343,7 @@ void Launch::wg2_splits(long long Mq, int* splits, int* m_chunk) {
 bool Launch::wg2_ok(int H, int W, int Cin, int Cout, int k, int stride) {
     (void)H;
     if (stride != 1 || (k != 3 && k != 5) || Cin % 16 != 0 || Cout % 16 != 0) return false;
-    if (Cout > 64 && Cout % 64 != 0) return false;
+    if (Cout > 128 && Cout % 128 != 0) return false;
     return w2_smem_bytes(wg2_q(W, k)) <= 220 * 1024;
 }
 

@@ -40,13 +40,14 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
 }
 
 // a_mn / b_mn: operand is MN-major; row_shift: extra start offset in 128-byte rows applied to MN-major A (tap shift)
-__global__ void __launch_bounds__(64) bench(int N, int a_mn, int b_mn, int row_shift, int stages, int iters, float* out) {
+__global__ void __launch_bounds__(64) bench(int N, int a_mn, int b_mn, int row_shift, int stages, int iters, float* out,
+                                            int lbo_rows, int n_acc) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int a_bytes = 16384 + 2048, b_bytes = (N <= 128 ? 16384 : 32768);
-    for (int i = threadIdx.x; i < stages * (a_bytes + b_bytes) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base)[i] = 0;
+    for (int i = threadIdx.x; i < stages * (a_bytes + b_bytes) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base)[i] = 0x3F803F80u ^ (uint32_t)(i * 2654435761u & 0x007F007Fu);   // finite bf16 pairs
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -64,16 +65,26 @@ __global__ void __launch_bounds__(64) bench(int N, int a_mn, int b_mn, int row_s
         uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         if (a_mn) idesc |= 1u << 15;
         if (b_mn) idesc |= 1u << 16;
+        // lean issue loop: descriptors of stage 0 are built once; a stage / k step only adds to the 14-bit address field
+        const uint32_t a0 = smem_u32(base), b0 = a0 + a_bytes;
+        const uint64_t ad0 = a_mn ? desc_sw128(a0 + row_shift * 128, lbo_rows * 128) : desc_sw128(a0 + row_shift * 128, 16);
+        const uint64_t bd0 = b_mn ? desc_sw128(b0, 8192) : desc_sw128(b0, 16);
+        const uint64_t a_k = (uint64_t)((a_mn ? 2048 : 32) >> 4), b_k = (uint64_t)((b_mn ? 2048 : 32) >> 4);
+        const uint64_t st_step = (uint64_t)((a_bytes + b_bytes) >> 4);
+        const uint32_t acc_step = (uint32_t)N, acc_end = (uint32_t)(N * n_acc);
         const long long t0 = clock64();
+        uint64_t ad = ad0, bd = bd0;
+        int s = 0;
+        uint32_t acc = 0;
         for (int it = 0; it < iters; ++it) {
-            const int s = it % stages;
-            const uint32_t a = smem_u32(base + s * (a_bytes + b_bytes)), b = a + a_bytes;
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
-                const uint64_t ad = a_mn ? desc_sw128(a + k4 * 2048 + row_shift * 128, 8192) : desc_sw128(a + k4 * 32 + row_shift * 128, 16);
-                const uint64_t bd = b_mn ? desc_sw128(b + k4 * 2048, 8192) : desc_sw128(b + k4 * 32, 16);
-                umma(tmem, ad, bd, idesc, (it | k4) != 0);
+                umma(tmem + acc, ad + a_k * k4, bd + b_k * k4, idesc, it != 0);
+                acc += acc_step;
+                if (acc >= acc_end) acc = 0;
             }
+            ad += st_step; bd += st_step;
+            if (++s == stages) { s = 0; ad = ad0; bd = bd0; }
         }
         commit(&bar);
         mbar_wait(&bar, 0);
@@ -92,24 +103,36 @@ int main() {
     cudaMalloc(&d, 1024 * sizeof(float));
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(bench, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    printf("%-6s %-4s %-4s %-6s %-5s %-12s %-10s\n", "N", "Amn", "Bmn", "shift", "ctas", "clk/UMMA", "ideal");
+    printf("%-5s %-4s %-4s %-6s %-8s %-5s %-5s %-10s %-8s\n", "N", "Amn", "Bmn", "shift", "lboRows", "nacc", "ctas", "clk/UMMA", "mathclk");
+    struct Cfg { int N, a_mn, b_mn, shift, lbo_rows, n_acc, ctas; };
+    std::vector<Cfg> cfgs;
     for (int ctas : {1, 2})
-        for (int N : {64, 128, 256})
-            for (int a_mn : {0, 1})
-                for (int b_mn : {0, 1})
-                    for (int shift : {0, 3, 8}) {
-                        if (shift && !(a_mn || (!a_mn && !b_mn))) continue;
-                        const int stages = ctas == 1 ? 3 : 2;
-                        const size_t smem = 1024 + (size_t)stages * (16384 + 2048 + (N <= 128 ? 16384 : 32768));
-                        bench<<<148 * ctas, 64, smem>>>(N, a_mn, b_mn, shift, stages, 64, d);          // warm-up
-                        bench<<<148 * ctas, 64, smem>>>(N, a_mn, b_mn, shift, stages, 512, d);
-                        cudaError_t e = cudaDeviceSynchronize();
-                        if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
-                        std::vector<float> h(148 * ctas);
-                        cudaMemcpy(h.data(), d, h.size() * sizeof(float), cudaMemcpyDeviceToHost);
-                        double s = 0;
-                        for (float v : h) s += v;
-                        printf("%-6d %-4d %-4d %-6d %-5d %-12.1f %-10d\n", N, a_mn, b_mn, shift, ctas, s / h.size(), N / 2 * ctas);
-                    }
+        for (int N : {32, 64, 128, 256})
+            for (int n_acc : {1, 4}) {
+                if (n_acc * N > 256) continue;
+                cfgs.push_back({N, 0, 0, 0, 64, n_acc, ctas});          // K-major both
+                cfgs.push_back({N, 0, 0, 3, 64, n_acc, ctas});          // K-major, A start shifted by 3 rows (conv_tc2 taps)
+                cfgs.push_back({N, 1, 1, 0, 64, n_acc, ctas});          // MN-major both, aligned, LBO 8192 (wgrad_tc)
+                cfgs.push_back({N, 1, 1, 3, 64, n_acc, ctas});          // MN-major, unaligned start row
+                cfgs.push_back({N, 1, 1, 0, 1, n_acc, ctas});           // MN-major, LBO = one row (adjacent taps, wgrad_tc2)
+                cfgs.push_back({N, 1, 1, 3, 1, n_acc, ctas});
+                cfgs.push_back({N, 1, 1, 0, 22, n_acc, ctas});          // LBO = Wp rows, not a multiple of 8
+                cfgs.push_back({N, 1, 1, 3, 24, n_acc, ctas});          // LBO = 24 rows (multiple of 8), unaligned start
+                cfgs.push_back({N, 1, 0, 3, 24, n_acc, ctas});          // only A MN-major
+            }
+    for (const Cfg& c : cfgs) {
+        const int stages = c.ctas == 1 ? 3 : 2;
+        const size_t smem = 1024 + (size_t)stages * (16384 + 2048 + (c.N <= 128 ? 16384 : 32768));
+        bench<<<148 * c.ctas, 64, smem>>>(c.N, c.a_mn, c.b_mn, c.shift, stages, 64, d, c.lbo_rows, c.n_acc);          // warm-up
+        bench<<<148 * c.ctas, 64, smem>>>(c.N, c.a_mn, c.b_mn, c.shift, stages, 512, d, c.lbo_rows, c.n_acc);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+        std::vector<float> h(148 * c.ctas);
+        cudaMemcpy(h.data(), d, h.size() * sizeof(float), cudaMemcpyDeviceToHost);
+        double s = 0;
+        for (float v : h) s += v;
+        printf("%-5d %-4d %-4d %-6d %-8d %-5d %-5d %-10.1f %-8d\n", c.N, c.a_mn, c.b_mn, c.shift, c.lbo_rows, c.n_acc, c.ctas,
+               s / h.size(), c.N / 2);
+    }
     return 0;
 }
