@@ -34,8 +34,13 @@ struct ConvTask {
 };
 
 // tcgen05 implicit GEMM (conv_tc.cu): bf16 operands, fp32 accumulation in TMEM
+// A CUtensorMap (cuda.h) is an opaque 128-byte, 64-byte-aligned object; the kernels only pass its address to
+// cp.async.bulk.tensor, so the task structs carry it as const void* and this header stays free of the driver API.
+constexpr int kTmapBytes = 128;
+
 struct TcConvTask {
     const __nv_bfloat16* xh;     // bf16 NHWC input (shadow copy written by the producing kernel)
+    const void* tmap;            // conv_tc2: 4-D tiled tensor map {C, W, H, N} of xh, box {64, W + 2 pad, 1, 1} (device memory)
     const __nv_bfloat16* wt;     // bf16 weights, K-major [Cout][K_pad]
     const float* bias;           // fp32 [Cout] or null
     float* y;
@@ -50,6 +55,7 @@ struct TcConvTask {
 };
 
 struct TcWgradTask {
+    const void* tmaps;           // wgrad_tc2: 4 consecutive tensor maps {x, dy, x (tail batch), dy (tail batch)} as above
     const __nv_bfloat16* xh;     // forward input of the conv (bf16 NHWC shadow)
     const __nv_bfloat16* dyh;    // [M][Cout] bf16 shadow of the output gradient
     float* out;                  // grad [K+1][Cout] (splits == 1) or workspace [splits][K+1][Cout]
@@ -67,7 +73,9 @@ struct WtBf16Task {
 };
 
 struct StatTask {               // BN batch statistics of a conv output produced by the tensor-core path
-    const float* y;
+    const float* y;              // fp32 conv output, or
+    const __nv_bfloat16* yh;     // ... the bf16-only one (precision bf16: activations are STORED in bf16, statistics are taken
+                                 // from the stored values)
     float* part;
     int C, rows_per_sample, block_begin;
 };
@@ -75,7 +83,8 @@ struct StatTask {               // BN batch statistics of a conv output produced
 struct WgradTask {
     const float* x;        // forward input of the conv (same addressing as ConvTask)
     const int* gather;
-    const float* dy;       // [M][Cout] gradient of the conv output
+    const float* dy;       // [M][Cout] gradient of the conv output (fp32), or
+    const __nv_bfloat16* dyh;   // ... its bf16-only form (stem kernel, precision bf16)
     float* out;            // grad buffer [K+1][Cout] (splits == 1) or workspace [splits][K+1][Cout]
     long long x_step, gather_step;
     int H, W, Cin, Ho, Wo, Cout, k, stride, pad;
@@ -95,10 +104,14 @@ struct WtTask {           // dgrad weights: wt[(k-1-kh, k-1-kw, co)][ci] = w[(kh
     int k, Cin, Cout, block_begin;
 };
 
+// precision bf16 stores activations in bf16 ONLY: u / v / skip / du / dskip are then null and uh / vh / skiph / duh /
+// dskiph are the tensors; precision fp32 uses the fp32 pointers (vh / duh / dskiph optional shadows for tensor-core units)
 struct PostTask {
     const float* u;        // conv output [n,H,W,C]
+    const __nv_bfloat16* uh;
+    const __nv_bfloat16* skiph;
     float* v;              // unit output [n,Ho,Wo,C]
-    __nv_bfloat16* vh;     // optional bf16 shadow of v
+    __nv_bfloat16* vh;     // bf16 form / shadow of v
     __nv_bfloat16* duh;    // optional bf16 shadow of du
     __nv_bfloat16* dskiph; // optional bf16 shadow of dskip
     const float* skip;     // residual branch [n,Ho,Wo,C] or null
@@ -123,7 +136,8 @@ struct PostTask {
 };
 
 struct HeadTask {
-    const float* v;        // last feature map [n,Hf,Wf,C]
+    const float* v;        // last feature map [n,Hf,Wf,C] (fp32), or
+    const __nv_bfloat16* vh;   // ... bf16-only (precision bf16)
     float* gap;            // [n,C]
     const float* dgap;     // [n,C]
     float* dv;             // [n,Hf,Wf,C]
@@ -221,13 +235,16 @@ struct Launch {
     static int conv_tc2(const TcConvTask* tasks, int n_tasks, int total_tiles, int n_b, int step, int q_max, int max_cin,
                         void* stream);
     static int wt_bf16_v2(const WtBf16Task* tasks, int n_tasks, int total_blocks, void* stream);
+    // host side of the tiled-TMA operand loads (engine.cu): encodes the 4-D map {C, W, H, N} of a dense NHWC bf16 tensor
+    // whose box {64 channels, W + 2 pad, 1, 1} at (c0, -pad, h - pad, n) is one zero-padded image row; returns 0 on success
+    static int make_row_tmap(void* out128, const void* dptr, int C, int W, int H, int N, int pad);
     // wgrad_tc2.cu: tcgen05 weight gradient on the patch layout; tiles = splits * wg2_items(), TcWgradTask.m_chunk /
     // splits from wg2_splits(n_b * Hp * Wp), bn = wg2_bn(Cout), tiles_n = Cout / bn
     static bool wg2_ok(int H, int W, int Cin, int Cout, int k, int stride);
     static int wg2_bn(int Cout);
     static int wg2_q(int W, int k);
     static int wg2_items(int Cin, int Cout, int k);
-    static void wg2_splits(long long Mq, int* splits, int* m_chunk);
+    static void wg2_splits(long long Mq, int items, int* splits, int* m_chunk);
     static int wgrad_tc2(const TcWgradTask* tasks, int n_tasks, int total_tiles, int n_b, int q_max, void* stream);
     // stem.cu: dedicated Cin = 1 kernels; every task of a launch has the same M (= n_b*H*W) and W
     static bool stem_ok(int H, int W, int Cin, int Cout, int k, int stride, int n_b);

@@ -269,12 +269,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcConvTask
                     if (T.relu) {
                         o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                     }
-                    float4* d4 = reinterpret_cast<float4*>(dst + q);
-                    if (T.accumulate) {
-                        const float4 old = *d4;
-                        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                    if (T.y) {
+                        float4* d4 = reinterpret_cast<float4*>(dst + q);
+                        if (T.accumulate) {
+                            const float4 old = *d4;
+                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                        }
+                        *d4 = o;
                     }
-                    *d4 = o;
                     if (T.yh)
                         *reinterpret_cast<uint2*>(T.yh + obase + n0 + c0 + q) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
                 }
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(128) bn_stats_kernel(const StatTask* __restric
         float s1 = 0.f, s2 = 0.f;
         if (p_lane < lanes && c < T.C)
             for (long long r = r0 + p_lane; r < r1; r += lanes) {
-                const float v = T.y[r * T.C + c];
+                const float v = T.yh ? __bfloat162float(T.yh[r * T.C + c]) : T.y[r * T.C + c];
                 s1 += v;
                 s2 = fmaf(v, v, s2);
             }

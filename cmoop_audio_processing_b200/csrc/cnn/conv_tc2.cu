@@ -11,7 +11,12 @@
 //     a function of the absolute address, so any row offset is valid), so every tap reads the one resident patch.
 //     (A first version used the no-swizzle layout, whose start address is unconstrained; measured with the in-kernel
 //     phase clocks below it fetched the A operand at ~16 B/clk: 270 clk per UMMA whatever N.)  Loaded once per slab by
-//     256 producer threads with zero-filling 16-byte cp.async (padding, batch tail).
+//     TILED TMA: the input is a dense NHWC bf16 tensor described by a 4-D tensor map {C, W, H, N}; one
+//     cp.async.bulk.tensor.4d with box {64, Wp, 1, 1} at (slab * 64, -p, hp - p, n) delivers one whole zero-padded image
+//     row (out-of-bounds w / h / n / c read as zeros = the padding, the batch tail and the channel tail) already in the
+//     SWIZZLE_128B layout -- the TMA unit swizzles by absolute shared-memory address exactly as the UMMA descriptor reads
+//     it (tools/microbench/tma_probe.cu), so a row box may land at any 128-byte row of the buffer.  One thread issues the
+//     ~15 row boxes of a patch; the former 256 cp.async producer threads only run the epilogue now.
 //   * weights: pre-arranged and pre-swizzled per (slab, tap) as [cout][64 ch] rows of 128 B by wt_bf16_v2_kernel,
 //     16 KB stages of 128 / bn entries -> one 1-D bulk TMA each (cp.async.bulk + mbarrier), P2_WS-deep ring, own warp.
 //   * one elected thread issues, per (slab, tap, 16-channel step), two UMMAs 128 x bn x 16 (the CTA's two 128-row
@@ -65,34 +70,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > (1u << 26)) __trap();
     }
 }
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart (SBO).  The start address may be ANY 128-byte row
-// of a buffer that was written with the absolute-address swizzle (chunk ^ (row & 7)): measured here, the hardware XORs
+// one zero-padded image row of 64 channels: box {64, Wp, 1, 1} of the 4-D map at (c, w, h, n)
+__device__ __forceinline__ void tma_load_row(void* dst, const void* tmap, int c, int w, int h, int n, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(c), "r"(w), "r"(h), "r"(n), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+// Operand descriptors (K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart = SBO, LBO field 1, version 1) are
+// assembled in the issue loop from a constant high word and the start-address field.  The start address may be ANY
+// 128-byte row of a buffer that holds the absolute-address swizzle (chunk ^ (row & 7)): measured here, the hardware XORs
 // address bits [4:6] with bits [7:9] of the absolute shared-memory address, so a tap shift needs no base-offset field
 // (setting base_offset = (start >> 7) & 7 gave wrong results; 0 is exact for every shift).
-__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;                              // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
-    return d;
-}
 __device__ __forceinline__ uint32_t make_idesc_bf16(int bn) {
     uint32_t d = 0;
     d |= 1u << 4;                       // D = F32
@@ -143,7 +143,11 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
     const int q0 = tm * P2_ROWS;
     if (q0 >= Mq) return;
     const int S = p * Wp + p;
-    const int Q = P2_ROWS + 2 * S;                     // patch positions of this task (<= q_max)
+    // the patch holds whole padded image rows: global padded rows [R0, R1] cover positions [q0 - S, q0 + P2_ROWS + S)
+    const int Hp_rows = Hp;
+    const int R0 = floor_div(q0 - S, Wp), R1 = (q0 + P2_ROWS - 1 + S) / Wp;
+    const int n_rows = R1 - R0 + 1;                    // n_rows * Wp <= q_max positions
+    const int row0_off = (q0 - S) - R0 * Wp;           // patch row of position q0 - S (tap (0, 0) of GEMM row 0)
     const int bn = T.bn, n0 = tn * bn;
     const int taps = T.k * T.k, n_slab = (T.Cin + P2_SLAB - 1) / P2_SLAB;
     const uint32_t entry_bytes = 128u * (uint32_t)bn;  // one (slab, tap) weight block
@@ -152,10 +156,9 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
     const size_t patch_stride = ((size_t)q_max * 128 + 1023) & ~size_t(1023);
     uint8_t* patch = base;                                              // [pb][Q rows][128 B], swizzled
     uint8_t* wsm = patch + (size_t)pb * patch_stride;                   // [P2_WS][P2_W_STAGE]
-    int* src_off = reinterpret_cast<int*>(wsm + P2_WS * P2_W_STAGE);    // [q_max] element offset of a position's pixel, -1 = zero
-    float* bias_s = reinterpret_cast<float*>(src_off + ((q_max + 3) & ~3));   // [128] this N tile's bias (0 without bias)
+    float* bias_s = reinterpret_cast<float*>(wsm + P2_WS * P2_W_STAGE);       // [128] this N tile's bias (0 without bias)
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 128);
-    uint64_t* pfull = bars;                     // [2]  256 producer arrivals
+    uint64_t* pfull = bars;                     // [2]  one arrive.expect_tx + the row boxes' bytes
     uint64_t* pempty = bars + 2;                // [2]  tcgen05.commit
     uint64_t* wfull = bars + 4;                 // [P2_WS]  TMA transaction
     uint64_t* wempty = wfull + P2_WS;           // [P2_WS]  tcgen05.commit
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&pfull[s], P2_PRODUCERS);
+            mbar_init(&pfull[s], 1);
             mbar_init(&pempty[s], 1);
         }
         for (int s = 0; s < P2_WS; ++s) {
@@ -181,18 +184,6 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid < bn) bias_s[tid] = T.bias ? __ldg(T.bias + n0 + tid) : 0.f;
-    // element offsets of the patch positions (shared by every sub-slab)
-    for (int i = tid; i < Q; i += P2_THREADS) {
-        const int q = q0 - S + i;
-        int off = -1;
-        if (q >= 0 && q < Mq) {
-            const int n = q / HpWp, rem = q - n * HpWp;
-            const int hp = rem / Wp, wp = rem - hp * Wp;
-            if (hp >= p && hp < T.H + p && wp >= p && wp < T.W + p)
-                off = ((n * T.H + hp - p) * T.W + wp - p) * T.Cin;
-        }
-        src_off[i] = off;
-    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -204,27 +195,22 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
     }
 
     if (warp < P2_PRODUCERS / 32) {
-        // ================= producers: one 64-channel slab of the patch per buffer =================
-        const __nv_bfloat16* xbase = T.xh + T.x_step * step;
-        for (int sl = 0; sl < n_slab; ++sl) {
-            const int b = sl % pb;
-            mbar_wait(&pempty[b], (((uint32_t)(sl / pb)) & 1u) ^ 1u);
-            uint8_t* dst = patch + (size_t)b * patch_stride;
-            const int cs = min(T.Cin - sl * P2_SLAB, P2_SLAB) >> 3;      // 16-byte chunks per position in this slab
-            const int chunk = tid % cs, pix0 = tid / cs, pstep = P2_PRODUCERS / cs;
-            const int coff = sl * P2_SLAB + chunk * 8;
-            if (pix0 < pstep) {
-                for (int i = pix0; i < Q; i += pstep) {
-                    const int off = src_off[i];
-                    cp_async16(dst + (size_t)i * 128 + ((chunk ^ (i & 7)) << 4), off >= 0 ? xbase + off + coff : xbase,
-                               off >= 0 ? 16u : 0u);
+        // ================= patch loads: one 64-channel slab per buffer, one row box per padded image row =================
+        if (tid == 0) {
+            const uint32_t row_bytes = (uint32_t)Wp * 128u;
+            for (int sl = 0; sl < n_slab; ++sl) {
+                const int b = sl % pb;
+                mbar_wait(&pempty[b], (((uint32_t)(sl / pb)) & 1u) ^ 1u);
+                uint8_t* dst = patch + (size_t)b * patch_stride;
+                mbar_expect_tx(&pfull[b], (uint32_t)n_rows * row_bytes);
+                int n = floor_div(R0, Hp_rows), hp = R0 - n * Hp_rows;
+                for (int r = 0; r < n_rows; ++r) {
+                    tma_load_row(dst + (size_t)r * row_bytes, T.tmap, sl * P2_SLAB, -p, hp - p, n, &pfull[b]);
+                    if (++hp == Hp_rows) { hp = 0; ++n; }
                 }
             }
-            cp_async_commit();
-            cp_async_wait<0>();
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&pfull[b]);
         }
+        __syncwarp();
         // ================= epilogue =================
         mbar_wait(accum_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -265,12 +251,14 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
                         if (T.relu) {
                             o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                         }
-                        float4* d4 = reinterpret_cast<float4*>(dst + qd);
-                        if (T.accumulate) {
-                            const float4 old = *d4;
-                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                        if (T.y) {
+                            float4* d4 = reinterpret_cast<float4*>(dst + qd);
+                            if (T.accumulate) {
+                                const float4 old = *d4;
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            }
+                            *d4 = o;
                         }
-                        *d4 = o;
                         if (T.yh)
                             *reinterpret_cast<uint2*>(T.yh + obase + n0 + c0 + qd) =
                                 make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
@@ -287,6 +275,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(bn);
+            const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
             const int tps = 128 / bn;                  // (slab, tap) entries per 16 KB weight stage
             const int total = n_slab * taps;
             int st = 0, e = 0;                         // stage counter; entry = slab * taps + tap in weight-stream order
@@ -299,7 +288,10 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
                     t_first = clock64();
                 }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_base = smem_u32(patch + (size_t)b * patch_stride);
+                // descriptors: the high word is constant (SBO 1024 B, version 1, SWIZZLE_128B); the issue loop only adds to
+                // the 14-bit start-address field of the low word (a single issuing thread that rebuilds 64-bit descriptors
+                // per UMMA is slower than the tensor pipe: tools/microbench/umma_layouts.cu)
+                const uint32_t a_base = smem_u32(patch + (size_t)b * patch_stride) + (uint32_t)row0_off * 128u;
                 const int ksteps = min(T.Cin - sl * P2_SLAB, P2_SLAB) >> 4;
                 int kh = 0, kw = 0;
                 for (int t = 0; t < taps; ++t, ++e) {
@@ -308,13 +300,13 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
                         mbar_wait(&wfull[ws], ((uint32_t)(st / P2_WS)) & 1u);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
-                    const uint32_t a_tap = a_base + (uint32_t)(kh * Wp + kw) * 128u;
-                    const uint32_t b_ent = smem_u32(wsm + ws * P2_W_STAGE) + (uint32_t)sub * entry_bytes;
+                    const uint32_t a_lo = (((a_base + (uint32_t)(kh * Wp + kw) * 128u) >> 4) & 0x3FFFu) | (1u << 16);
+                    const uint32_t b_lo = (((smem_u32(wsm + ws * P2_W_STAGE) + (uint32_t)sub * entry_bytes) >> 4) & 0x3FFFu) | (1u << 16);
                     for (int k4 = 0; k4 < ksteps; ++k4) {
-                        const uint64_t bd = make_desc_k_sw128(b_ent + (uint32_t)k4 * 32u);
+                        const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (uint32_t)k4 * 2u);
 #pragma unroll
                         for (int mt = 0; mt < P2_MT; ++mt) {
-                            const uint64_t ad = make_desc_k_sw128(a_tap + (uint32_t)mt * 128u * 128u + (uint32_t)k4 * 32u);
+                            const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (uint32_t)mt * 1024u + (uint32_t)k4 * 2u);
                             umma_bf16(tmem_base + (uint32_t)(mt * 128), ad, bd, idesc, (sl | t | k4) != 0 ? 1u : 0u);
                         }
                     }
@@ -402,16 +394,17 @@ __global__ void __launch_bounds__(256) wt_bf16_v2_kernel(const WtBf16Task* __res
 
 size_t p2_smem_bytes(int q_max, int pb) {
     const size_t patch_stride = ((size_t)q_max * 128 + 1023) & ~size_t(1023);
-    return 1024 /*align*/ + (size_t)pb * patch_stride + (size_t)P2_WS * P2_W_STAGE + (size_t)((q_max + 3) & ~3) * 4 + 512 + 512;
+    return 1024 /*align*/ + (size_t)pb * patch_stride + (size_t)P2_WS * P2_W_STAGE + 512 + 512;
 }
 // two patch buffers (the next slab loads while the current one is multiplied) only when two CTAs still fit one SM
 int p2_buffers(int cin, int q_max) { return cin > P2_SLAB && p2_smem_bytes(q_max, 2) <= 113 * 1024 ? 2 : 1; }
 
 }  // namespace
 
+// positions a patch buffer must hold: whole padded rows covering [q0 - S, q0 + P2_ROWS + S) for any q0
 int Launch::tc2_q(int W, int k) {
-    const int p = (k - 1) / 2;
-    return P2_ROWS + 2 * (p * (W + 2 * p) + p);
+    const int p = (k - 1) / 2, Wp = W + 2 * p, S = p * Wp + p;
+    return ((P2_ROWS + 2 * S + Wp - 2) / Wp + 1) * Wp;
 }
 int Launch::tc2_rows() { return P2_ROWS; }
 long long Launch::tc2_weight_elems(int Cin, int Cout, int k) {

@@ -19,10 +19,45 @@
 #include <algorithm>
 #include <vector>
 
+#include <cuda.h>
+
 #include "../common.cuh"
 #include "cnn.cuh"
 
 using namespace cmoop_cnn;
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: the library is linked against the static runtime
+// only, so it still loads on a host without libcuda (tests/test_abi.py) and fails loudly at the first compute call.
+int cmoop_cnn::Launch::make_row_tmap(void* out128, const void* dptr, int C, int W, int H, int N, int pad) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+            cmoop::set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return -1;
+        }
+        encode = (encode_fn)fn;
+    }
+    static_assert(sizeof(CUtensorMap) == kTmapBytes, "CUtensorMap size");
+    alignas(64) CUtensorMap tm;
+    const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)(W + 2 * pad), 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dptr), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        cmoop::set_error("cuTensorMapEncodeTiled(C=%d, W=%d, H=%d, N=%d, pad=%d) -> %d", C, W, H, N, pad, (int)r);
+        return -1;
+    }
+    memcpy(out128, &tm, kTmapBytes);
+    return 0;
+}
 
 // ---- optional per-kernel-family device timing (cmoop_profile_enable): one cudaEvent pair around every grouped launch of
 // the engine's stream, resolved after the call.  Launches are serialised on one stream, so the pairs partition the device
@@ -121,6 +156,7 @@ struct Unit {
     __nv_bfloat16* Vh = nullptr;     // bf16 shadow of V
     __nv_bfloat16* wtb = nullptr;    // bf16 [cout][kpad_f]
     __nv_bfloat16* wtd = nullptr;    // bf16 [cin][kpad_d]
+    const char* tmaps = nullptr;     // device: 4 tensor maps {input Vh, dU (gBh), the same two for the tail batch} (tc2 units)
 };
 
 struct Cand {
@@ -287,11 +323,13 @@ void build_units(Cand& c, const cmoop_cnn_config& cfg, int H, int W, int batch) 
             chunk = kStemRows;
             splits = (int)((M + chunk - 1) / chunk);
         }
-        // wgrad_tc2 (patch layout, two taps per UMMA) is opt-in: MN-major operands whose start row is not a multiple of 8
-        // are fetched ~3x slower than aligned ones (tools/diag_wg2.py), which makes it 2.4x slower than wgrad_tc
-        static const bool use_wg2 = getenv("CMOOP_CNN_WG2") != nullptr;
-        u.wg2 = u.tc2 && use_wg2 && Launch::wg2_ok(u.H, u.W, u.cin, u.cout, u.k, u.stride);
-        if (u.wg2) Launch::wg2_splits((long long)batch * (u.H + 2 * u.pad) * (u.W + 2 * u.pad), &splits, &chunk);
+        // weight gradient of the patch-resident units on wgrad_tc2.cu (tiled-TMA operands, two taps per UMMA);
+        // CMOOP_CNN_NO_WG2=1 is the A/B switch back to the im2col-staging kernel wgrad_tc_kernel
+        static const bool no_wg2 = getenv("CMOOP_CNN_NO_WG2") != nullptr;
+        u.wg2 = u.tc2 && !no_wg2 && Launch::wg2_ok(u.H, u.W, u.cin, u.cout, u.k, u.stride);
+        if (u.wg2)
+            Launch::wg2_splits((long long)batch * (u.H + 2 * u.pad) * (u.W + 2 * u.pad), Launch::wg2_items(u.cin, u.cout, u.k),
+                               &splits, &chunk);
         u.wg_splits = splits;
         u.wg_chunk = chunk;
     }
@@ -402,6 +440,7 @@ struct Wave {
     double* d_acc = nullptr;         // [cands][12]: train / validation / predict accumulators (Cand::acc points into it)
     int* d_cm = nullptr;             // [cands][C][C] confusion matrices (Cand::confusion points into it)
     bool weights_dirty = true;
+    char* d_tmaps = nullptr;         // [tc2 units of the wave][4][128 B], written once per wave (build_tensor_maps)
     char* d_blob = nullptr;
     size_t blob_cap = 0;
 };
@@ -421,6 +460,37 @@ struct Engine {
     int batch;
     cudaStream_t stream;
     int global_step = 0;   // dropout hash stream
+
+    // ---- tiled-TMA descriptors of the wave's tensor-core units, encoded once per wave (buffers are fixed after place()):
+    // per unit {input activation Vh, output gradient dU} as 4-D maps over the dense NHWC bf16 tensors, plus the same two
+    // with N = the training split's tail batch, so that the samples past a short last batch read as zeros
+    int build_tensor_maps(Wave& wv) {
+        std::vector<char> host;
+        std::vector<Unit*> owners;
+        const int tail = data->n_train % batch ? data->n_train % batch : batch;
+        for (Cand* cp : wv.cands)
+            for (Unit& u : cp->units) {
+                u.tmaps = nullptr;
+                if (!u.tc2) continue;
+                const size_t at = host.size();
+                host.resize(at + 4 * kTmapBytes);
+                const void* xin = cp->units[u.input].Vh;
+                for (int t = 0; t < 2; ++t) {
+                    const int n = t == 0 ? batch : tail;
+                    if (Launch::make_row_tmap(host.data() + at + (2 * t + 0) * kTmapBytes, xin, u.cin, u.W, u.H, n, u.pad) != 0 ||
+                        Launch::make_row_tmap(host.data() + at + (2 * t + 1) * kTmapBytes, cp->gBh, u.cout, u.Wo, u.Ho, n, u.pad) != 0)
+                        return CMOOP_ERR_CUDA;
+                }
+                owners.push_back(&u);
+            }
+        if (host.empty()) return CMOOP_OK;
+        wv.d_tmaps = (char*)cmoop::device_scratch(11, host.size());
+        if (!wv.d_tmaps) return CMOOP_ERR_CUDA;
+        CMOOP_CUDA_OK(cmoop::copy_async(wv.d_tmaps, host.data(), host.size(), cudaMemcpyHostToDevice, stream));
+        CMOOP_CUDA_OK(cudaStreamSynchronize(stream));          // `host` goes out of scope
+        for (size_t i = 0; i < owners.size(); ++i) owners[i]->tmaps = wv.d_tmaps + i * 4 * kTmapBytes;
+        return CMOOP_OK;
+    }
 
     // ---- task-list construction for the currently active candidates of a wave
     int build_lists(Wave& wv) {
@@ -446,6 +516,7 @@ struct Engine {
                 if (u.tc) {
                     TcConvTask t{};
                     t.xh = c.units[u.input].Vh; t.wt = u.wtb; t.bias = c.p + u.w_off + (long long)u.k * u.k * u.cin * u.cout;
+                    t.tmap = u.tmaps;                                   // {C = cin, W, H, N} of the producer's bf16 output
                     t.y = u.U;
                     t.yh = (!u.post_fwd && u.need_vh) ? u.Vh : nullptr;
                     t.H = u.H; t.W = u.W; t.Cin = u.cin; t.Ho = u.Ho; t.Wo = u.Wo; t.Cout = u.cout;
@@ -586,6 +657,7 @@ struct Engine {
                     if (u.tc) {
                         TcWgradTask g{};
                         g.xh = c.units[u.input].Vh; g.dyh = u.is_skip ? c.gSh : c.gBh; g.out = dst;
+                        g.tmaps = u.tmaps;
                         g.H = u.H; g.W = u.W; g.Cin = u.cin; g.Ho = u.Ho; g.Wo = u.Wo; g.Cout = u.cout;
                         g.k = u.k; g.stride = u.stride; g.pad = u.pad;
                         g.splits = u.wg_splits; g.m_chunk = u.wg_chunk;
@@ -598,7 +670,8 @@ struct Engine {
                             S.wgrad_tc2.h.push_back(g);
                             S.wgrad_tc2.total += g.splits * Launch::wg2_items(u.cin, u.cout, u.k);
                             S.f_wg += 2.0 * u.Ho * u.Wo * kext * u.cout;
-                            S.wg2_q = std::max(S.wg2_q, Launch::wg2_q(u.W, u.k));
+                            const int wq = Launch::wg2_q(u.W, u.k);          // X patch | dY tile positions, 16 bits each
+                            S.wg2_q = std::max(S.wg2_q & 0xffff, wq & 0xffff) | (std::max(S.wg2_q >> 16, wq >> 16) << 16);
                         } else {
                             g.tile_begin = S.wgrad_tc.total;
                             S.wgrad_tc.h.push_back(g);
@@ -644,6 +717,7 @@ struct Engine {
                     }
                     TcConvTask d{};
                     d.xh = u.is_skip ? c.gSh : c.gBh;
+                    d.tmap = u.tmaps ? u.tmaps + kTmapBytes : nullptr;  // {C = cout, W, H, N} of this unit's dU
                     d.wt = u.wtd;
                     d.y = c.gA;
                     d.Cin = u.cout; d.Cout = u.cin; d.k = u.k; d.K_pad = u.kpad_d;
@@ -1153,6 +1227,7 @@ int run_wave(Engine& eng, Wave& wv, double* out, double* history, int debug_step
                                // so a candidate's masks must not depend on which wave it lands in
     int rc = eng.init_params(wv.cands);
     if (rc != CMOOP_OK) return rc;
+    if ((rc = eng.build_tensor_maps(wv)) != CMOOP_OK) return rc;
     rc = eng.build_lists(wv);
     if (rc != CMOOP_OK) return rc;
     const int steps_per_epoch = (data->n_train + batch - 1) / batch;
@@ -1530,6 +1605,14 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
         t.tiles_n = (t.Cout + t.bn - 1) / t.bn;
         CMOOP_CUDA_OK(cmoop::copy_async(d_task, &t, sizeof(t), cudaMemcpyHostToDevice, st));
         if (rc == 0 && use_tc == 3) {
+            // tiled-TMA descriptor of the GEMM input (the activation for mode 0, the output gradient for mode 1)
+            alignas(64) char tm[kTmapBytes];
+            if (Launch::make_row_tmap(tm, d_inh, t.Cin, t.W, t.H, n, t.pad) != 0) return CMOOP_ERR_CUDA;
+            char* d_tm = (char*)d_task + 512;
+            CMOOP_CUDA_OK(cmoop::copy_async(d_tm, tm, kTmapBytes, cudaMemcpyHostToDevice, st));
+            t.tmap = d_tm;
+            CMOOP_CUDA_OK(cmoop::copy_async(d_task, &t, sizeof(t), cudaMemcpyHostToDevice, st));
+            CMOOP_CUDA_OK(cudaStreamSynchronize(st));
             const long long mq = (long long)n * (H + 2 * pad) * (W + 2 * pad);
             rc = Launch::conv_tc2((const TcConvTask*)d_task, 1, (int)((mq + Launch::tc2_rows() - 1) / Launch::tc2_rows()) * t.tiles_n,
                                   n, 0, Launch::tc2_q(W, k), gi, st);
@@ -1574,7 +1657,8 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
         chunk = kStemRows;
         splits = (int)((M + chunk - 1) / chunk);
     }
-    if (use_tc == 3) Launch::wg2_splits((long long)n * (H + 2 * pad) * (W + 2 * pad), &splits, &chunk);
+    if (use_tc == 3)
+        Launch::wg2_splits((long long)n * (H + 2 * pad) * (W + 2 * pad), Launch::wg2_items(Cin, Cout, k), &splits, &chunk);
     float *d_x, *d_y, *d_ws, *d_o;
     __nv_bfloat16 *d_xh, *d_yh;
     void* d_task;
@@ -1599,7 +1683,18 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
         g.xh = d_xh; g.dyh = d_yh; g.out = d_ws; g.H = H; g.W = W; g.Cin = Cin; g.Ho = Ho; g.Wo = Wo; g.Cout = Cout;
         g.k = k; g.stride = stride; g.pad = pad; g.splits = splits; g.m_chunk = chunk;
         g.bn = Launch::wg2_bn(Cout); g.tiles_n = Cout / g.bn;
+        // tiled-TMA descriptors {x, dy, x (tail batch), dy (tail batch)}; the hook always runs the full-batch pair unless
+        // n < kBatch, where both pairs describe the n samples given
+        alignas(64) char tm[4 * kTmapBytes];
+        for (int t = 0; t < 2; ++t)
+            if (Launch::make_row_tmap(tm + (2 * t) * kTmapBytes, d_xh, Cin, W, H, n, pad) != 0 ||
+                Launch::make_row_tmap(tm + (2 * t + 1) * kTmapBytes, d_yh, Cout, Wo, Ho, n, pad) != 0)
+                return CMOOP_ERR_CUDA;
+        char* d_tm = (char*)d_task + 512;
+        CMOOP_CUDA_OK(cmoop::copy_async(d_tm, tm, sizeof(tm), cudaMemcpyHostToDevice, st));
+        g.tmaps = d_tm;
         CMOOP_CUDA_OK(cmoop::copy_async(d_task, &g, sizeof(g), cudaMemcpyHostToDevice, st));
+        CMOOP_CUDA_OK(cudaStreamSynchronize(st));
         rc = Launch::wgrad_tc2((const TcWgradTask*)d_task, 1, splits * Launch::wg2_items(Cin, Cout, k), n, Launch::wg2_q(W, k), st);
     } else if (use_tc == 1) {
         TcWgradTask g{};

@@ -171,10 +171,13 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvTask* __restri
             if (col >= T.Cout) continue;
             float v = acc[i][j];
             if (T.relu) v = fmaxf(v, 0.f);
-            if (T.accumulate)
-                T.y[base + col] += v;
-            else
-                T.y[base + col] = v;
+            if (!T.y) v = __bfloat162float(__float2bfloat16_rn(v));     // bf16-only output: the stored value is THE value
+            if (T.y) {
+                if (T.accumulate)
+                    T.y[base + col] += v;
+                else
+                    T.y[base + col] = v;
+            }
             if (T.yh) T.yh[base + col] = __float2bfloat16_rn(v);
             s1[j] += v;
             s2[j] = fmaf(v, v, s2[j]);
@@ -402,6 +405,33 @@ __device__ __forceinline__ uint2 bf16x4(float4 v) {
     return make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
 }
 
+// eight consecutive channels from the fp32 tensor or from its bf16-only form (exact widening)
+__device__ __forceinline__ void load8(const float* f, const __nv_bfloat16* h, long long e, float (&v)[8]) {
+    if (h) {
+        const uint4 r = *reinterpret_cast<const uint4*>(h + e);
+        v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+        v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+        v[4] = __uint_as_float(r.z << 16); v[5] = __uint_as_float(r.z & 0xffff0000u);
+        v[6] = __uint_as_float(r.w << 16); v[7] = __uint_as_float(r.w & 0xffff0000u);
+    } else {
+        const float4 a = ld4(f + e), b = ld4(f + e + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+}
+__device__ __forceinline__ void load4(const float* f, const __nv_bfloat16* h, long long e, float (&v)[4]) {
+    if (h) {
+        const uint2 r = *reinterpret_cast<const uint2*>(h + e);
+        v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+        v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+    } else {
+        const float4 a = ld4(f + e);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+}
+__device__ __forceinline__ float load1(const float* f, const __nv_bfloat16* h, long long e) {
+    return h ? __bfloat162float(h[e]) : f[e];
+}
+
 // [BN] -> [ReLU] -> [2x2/s2 'same' max-pool] -> [+skip, ReLU]; one thread = 4 consecutive channels of one output pixel
 __global__ void __launch_bounds__(256) post_fwd_kernel(const PostTask* __restrict__ tasks, int n_tasks, int n_b) {
     const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin; });
@@ -438,12 +468,7 @@ __global__ void __launch_bounds__(256) post_fwd_kernel(const PostTask* __restric
         for (int d = 0; d < 4; ++d) {
             const int hi = 2 * ho + (d >> 1), wi = 2 * wo + (d & 1);
             ok[d] = hi < T.H && wi < T.W;
-            if (ok[d]) {
-                const float* src = T.u + (((long long)n * T.H + hi) * T.W + wi) * T.C + c;
-                const float4 u0 = ld4(src), u1 = ld4(src + 4);
-                v[d][0] = u0.x; v[d][1] = u0.y; v[d][2] = u0.z; v[d][3] = u0.w;
-                v[d][4] = u1.x; v[d][5] = u1.y; v[d][6] = u1.z; v[d][7] = u1.w;
-            }
+            if (ok[d]) load8(T.u, T.uh, (((long long)n * T.H + hi) * T.W + wi) * T.C + c, v[d]);
         }
         int code[8];
 #pragma unroll
@@ -470,8 +495,8 @@ __global__ void __launch_bounds__(256) post_fwd_kernel(const PostTask* __restric
         pk.y = (unsigned)code[4] | ((unsigned)code[5] << 8) | ((unsigned)code[6] << 16) | ((unsigned)code[7] << 24);
         *reinterpret_cast<uint2*>(T.idx + e) = pk;
     } else {
-        const float4 u0 = ld4(T.u + e), u1 = ld4(T.u + e + 4);
-        const float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+        float v[8];
+        load8(T.u, T.uh, e, v);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             float x = v[q];
@@ -481,14 +506,16 @@ __global__ void __launch_bounds__(256) post_fwd_kernel(const PostTask* __restric
         }
     }
     if (T.add_skip) {
-        const float4 s0 = ld4(T.skip + e), s1 = ld4(T.skip + e + 4);
-        const float sk[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        float sk[8];
+        load8(T.skip, T.skiph, e, sk);
 #pragma unroll
         for (int q = 0; q < 8; ++q) z[q] = fmaxf(z[q] + sk[q], 0.f);
     }
     const float4 o0 = make_float4(z[0], z[1], z[2], z[3]), o1 = make_float4(z[4], z[5], z[6], z[7]);
-    *reinterpret_cast<float4*>(T.v + e) = o0;
-    *reinterpret_cast<float4*>(T.v + e + 4) = o1;
+    if (T.v) {
+        *reinterpret_cast<float4*>(T.v + e) = o0;
+        *reinterpret_cast<float4*>(T.v + e + 4) = o1;
+    }
     if (T.vh) {
         const uint2 h0 = bf16x4(o0), h1 = bf16x4(o1);
         *reinterpret_cast<uint4*>(T.vh + e) = make_uint4(h0.x, h0.y, h1.x, h1.y);
@@ -521,11 +548,11 @@ __global__ void __launch_bounds__(128) post_bwd_reduce_kernel(const PostTask* __
             const float4 gv = ld4(T.dv + e);
             float g[4] = {gv.x, gv.y, gv.z, gv.w};
             if (T.add_skip) {
-                const float4 vv = ld4(T.v + e);
-                if (!(vv.x > 0.f)) g[0] = 0.f;
-                if (!(vv.y > 0.f)) g[1] = 0.f;
-                if (!(vv.z > 0.f)) g[2] = 0.f;
-                if (!(vv.w > 0.f)) g[3] = 0.f;
+                float vv[4];
+                load4(T.v, T.vh, e, vv);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (!(vv[q] > 0.f)) g[q] = 0.f;
             }
             float u[4];
             if (T.pool) {
@@ -536,10 +563,9 @@ __global__ void __launch_bounds__(128) post_bwd_reduce_kernel(const PostTask* __
                 const long long base = (((long long)n * T.H + 2 * ho) * T.W + 2 * wo) * T.C + c;
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    u[q] = T.u[base + ((long long)(code[q] >> 1) * T.W + (code[q] & 1)) * T.C + q];
+                    u[q] = load1(T.u, T.uh, base + ((long long)(code[q] >> 1) * T.W + (code[q] & 1)) * T.C + q);
             } else {
-                const float4 uv = ld4(T.u + e);
-                u[0] = uv.x; u[1] = uv.y; u[2] = uv.z; u[3] = uv.w;
+                load4(T.u, T.uh, e, u);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -636,8 +662,8 @@ __global__ void __launch_bounds__(256) post_bwd_apply_kernel(const PostTask* __r
     const float4 g0 = ld4(T.dv + oe), g1 = ld4(T.dv + oe + 4);
     float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
     if (T.add_skip) {
-        const float4 v0 = ld4(T.v + oe), v1 = ld4(T.v + oe + 4);
-        const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        float vv[8];
+        load8(T.v, T.vh, oe, vv);
 #pragma unroll
         for (int q = 0; q < 8; ++q)
             if (!(vv[q] > 0.f)) g[q] = 0.f;
@@ -653,8 +679,8 @@ __global__ void __launch_bounds__(256) post_bwd_apply_kernel(const PostTask* __r
             }
         }
     }
-    const float4 u0 = ld4(T.u + e), u1 = ld4(T.u + e + 4);
-    const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    float u[8];
+    load8(T.u, T.uh, e, u);
     float du[8];
     if (T.has_bn) {
 #pragma unroll
@@ -708,7 +734,7 @@ __global__ void __launch_bounds__(256) gap_fwd_kernel(const HeadTask* __restrict
     const int c = e % T.C, n = e / T.C;
     const int hw = T.Hf * T.Wf;
     float s = 0.f;
-    for (int p = 0; p < hw; ++p) s += T.v[((long long)n * hw + p) * T.C + c];
+    for (int p = 0; p < hw; ++p) s += load1(T.v, T.vh, ((long long)n * hw + p) * T.C + c);
     T.gap[e] = s / (float)hw;
 }
 

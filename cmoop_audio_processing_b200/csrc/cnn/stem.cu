@@ -9,6 +9,7 @@
 // offsets into the staged tile, stores / gradient loads are 16-byte and coalesced.  Contracts are those of
 // conv_gemm_kernel / conv_wgrad_kernel (ConvTask / WgradTask): same BN partial-sum layout (64-row tiles), same
 // [split][K+1][Cout] partial gradients reduced by reduce_kernel, deterministic (no atomics).
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "cnn.cuh"
@@ -109,15 +110,26 @@ __device__ __forceinline__ void stem_conv_body(const ConvTask& T, float* sm, int
                     for (int j = 0; j < CPT / 2; ++j) acc[j] = make_float2(fmaxf(acc[j].x, 0.f), fmaxf(acc[j].y, 0.f));
                 }
                 const long long o = (long long)m * Cout + cg * CPT;
-                if constexpr (CPT == 4) {
-                    *reinterpret_cast<float4*>(T.y + o) = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
-                } else {
-                    *reinterpret_cast<float2*>(T.y + o) = acc[0];
+                if (T.y) {
+                    if constexpr (CPT == 4) {
+                        *reinterpret_cast<float4*>(T.y + o) = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+                    } else {
+                        *reinterpret_cast<float2*>(T.y + o) = acc[0];
+                    }
                 }
                 if (T.yh) {
+                    __nv_bfloat162 hb[CPT / 2];
 #pragma unroll
-                    for (int j = 0; j < CPT / 2; ++j)
-                        *reinterpret_cast<__nv_bfloat162*>(T.yh + o + 2 * j) = __floats2bfloat162_rn(acc[j].x, acc[j].y);
+                    for (int j = 0; j < CPT / 2; ++j) hb[j] = __floats2bfloat162_rn(acc[j].x, acc[j].y);
+                    if constexpr (CPT == 4) {
+                        *reinterpret_cast<uint2*>(T.yh + o) = make_uint2(*reinterpret_cast<uint32_t*>(&hb[0]), *reinterpret_cast<uint32_t*>(&hb[1]));
+                    } else {
+                        *reinterpret_cast<__nv_bfloat162*>(T.yh + o) = hb[0];
+                    }
+                    if (!T.y) {                       // bf16-only output: the BN statistics are those of the stored values
+#pragma unroll
+                        for (int j = 0; j < CPT / 2; ++j) acc[j] = __bfloat1622float2(hb[j]);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < CPT / 2; ++j) {
@@ -200,7 +212,16 @@ __device__ __forceinline__ void stem_wgrad_body(const WgradTask& T, float* sm, i
 #pragma unroll
             for (int j = 0; j < CPT; ++j) g[u][j] = 0.f;
             if (m < m1) {
-                if constexpr (CPT == 4) {
+                if (T.dyh) {                          // bf16-only gradient (precision bf16)
+                    if constexpr (CPT == 4) {
+                        const uint2 r = *reinterpret_cast<const uint2*>(T.dyh + (long long)m * Cout + cg * 4);
+                        g[u][0] = __uint_as_float(r.x << 16); g[u][1] = __uint_as_float(r.x & 0xffff0000u);
+                        g[u][2] = __uint_as_float(r.y << 16); g[u][3] = __uint_as_float(r.y & 0xffff0000u);
+                    } else {
+                        const uint32_t r = *reinterpret_cast<const uint32_t*>(T.dyh + (long long)m * Cout + cg * 2);
+                        g[u][0] = __uint_as_float(r << 16); g[u][1] = __uint_as_float(r & 0xffff0000u);
+                    }
+                } else if constexpr (CPT == 4) {
                     const float4 v = ld4(T.dy + (long long)m * Cout + cg * 4);
                     g[u][0] = v.x; g[u][1] = v.y; g[u][2] = v.z; g[u][3] = v.w;
                 } else {
