@@ -131,7 +131,8 @@ struct PostTask {
     int H, W, C, Ho, Wo;
     int pool, relu_mid, add_skip, relu_in, has_bn;
     int stat_tiles, bwd_rows;
-    int block_begin;       // grouped offset for the elementwise kernels (forward / backward-apply)
+    int block_begin;       // grouped offset for post_fwd_kernel
+    int block_begin_apply; // grouped offset for post_bwd_apply_kernel
     int block_begin_bwd;   // grouped offset for the backward reduce kernel
 };
 
@@ -209,10 +210,15 @@ struct Launch {
     static int reduce(const ReduceTask* tasks, int n_tasks, int total_blocks, void* stream);
     static int wt(const WtTask* tasks, int n_tasks, int total_blocks, void* stream);
     static int bn_finalize(const PostTask* tasks, int n_tasks, int max_c, int n_b, int training, float momentum, float eps, void* stream);
-    static int post_fwd(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
-    static int post_bwd_reduce(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
+    static int post_blocks(long long out_pixels, int C);     // blocks of post_fwd / post_bwd_apply for one task
+    // block_task (optional, device): task index of every block of the grouped grid -- one load instead of a binary search
+    // of ~log2(n_tasks) dependent global loads at the start of every CTA
+    static int post_fwd(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream, const int* block_task = nullptr,
+                        bool half = false);     // half: the launch's activations are stored in bf16 only
+    static int post_bwd_reduce(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream, const int* block_task = nullptr);
     static int bn_bwd_finalize(const PostTask* tasks, int n_tasks, int max_c, int n_b, void* stream);
-    static int post_bwd_apply(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
+    static int post_bwd_apply(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream, const int* block_task = nullptr,
+                              bool half = false);
     static int gap_fwd(const HeadTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
     static int gap_bwd(const HeadTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
     static int drop_fwd(const DropTask* tasks, int n_tasks, int total_blocks, int n_b, int step, int training, float rate, void* stream);
@@ -233,7 +239,7 @@ struct Launch {
     static int tc2_rows();
     static long long tc2_weight_elems(int Cin, int Cout, int k);     // bf16 elements of the (slab-padded) weight blocks
     static int conv_tc2(const TcConvTask* tasks, int n_tasks, int total_tiles, int n_b, int step, int q_max, int max_cin,
-                        void* stream);
+                        void* stream, const int* block_task = nullptr);
     static int wt_bf16_v2(const WtBf16Task* tasks, int n_tasks, int total_blocks, void* stream);
     // host side of the tiled-TMA operand loads (engine.cu): encodes the 4-D map {C, W, H, N} of a dense NHWC bf16 tensor
     // whose box {64 channels, W + 2 pad, 1, 1} at (c0, -pad, h - pad, n) is one zero-padded image row; returns 0 on success
@@ -245,7 +251,7 @@ struct Launch {
     static int wg2_q(int W, int k);
     static int wg2_items(int Cin, int Cout, int k);
     static void wg2_splits(long long Mq, int items, int* splits, int* m_chunk);
-    static int wgrad_tc2(const TcWgradTask* tasks, int n_tasks, int total_tiles, int n_b, int q_max, void* stream);
+    static int wgrad_tc2(const TcWgradTask* tasks, int n_tasks, int total_tiles, int n_b, int q_max, void* stream, const int* block_task = nullptr);
     // stem.cu: dedicated Cin = 1 kernels; every task of a launch has the same M (= n_b*H*W) and W
     static bool stem_ok(int H, int W, int Cin, int Cout, int k, int stride, int n_b);
     static int stem_conv(const ConvTask* tasks, int n_tasks, int max_k, int W, int max_cout, long long M, int n_b, int step,

@@ -122,18 +122,26 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // prof (CMOOP_TC2_PROF=1): per-launch sums of clock64 spans -- [0] CTAs, [1] prologue, [2] MMA thread: start -> first
 // operands ready, [3] MMA issue loop, [4] producers: start -> accumulator complete, [5] epilogue, [6] whole CTA
 __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTask* __restrict__ tasks, int n_tasks, int n_b,
-                                                                 int step, int q_max, int pb, unsigned long long* prof) {
+                                                                 int step, int q_max, int pb, unsigned long long* prof,
+                                                                 const int* __restrict__ block_task) {
     const long long t_start = clock64();
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ TcConvTask T;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        int lo = 0, hi = n_tasks - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (tasks[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    if (tid < (int)(sizeof(TcConvTask) / 4)) {
+        // block -> task: one load from the direct table (a binary search over the task list is ~log2(n) dependent global
+        // loads, several thousand cycles of a CTA that lives ~30 k); the record is then copied by 4-byte lanes
+        int lo = 0;
+        if (block_task) {
+            lo = __ldg(block_task + blockIdx.x);
+        } else {
+            int hi = n_tasks - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (tasks[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+            }
         }
-        T = tasks[lo];
+        reinterpret_cast<uint32_t*>(&T)[tid] = reinterpret_cast<const uint32_t*>(tasks + lo)[tid];
     }
     __syncthreads();
     const int local = blockIdx.x - T.tile_begin;
@@ -417,7 +425,8 @@ bool Launch::tc2_ok(int H, int W, int Cin, int Cout, int k, int stride) {
     return p2_smem_bytes(tc2_q(W, k), 1) <= 227 * 1024;
 }
 
-int Launch::conv_tc2(const TcConvTask* tasks, int n, int tiles, int n_b, int step, int q_max, int max_cin, void* st) {
+int Launch::conv_tc2(const TcConvTask* tasks, int n, int tiles, int n_b, int step, int q_max, int max_cin, void* st,
+                     const int* block_task) {
     if (n == 0 || tiles == 0) return 0;
     const int pb = p2_buffers(max_cin, q_max);
     const size_t smem = p2_smem_bytes(q_max, pb);
@@ -453,7 +462,7 @@ int Launch::conv_tc2(const TcConvTask* tasks, int n, int tiles, int n_b, int ste
     }
     static int launch_no = 0;
     unsigned long long* slot = prof ? prof + (size_t)(launch_no++ % 64) * 8 : nullptr;
-    conv_tc2_kernel<<<tiles, P2_THREADS, smem, (cudaStream_t)st>>>(tasks, n, n_b, step, q_max, pb, slot);
+    conv_tc2_kernel<<<tiles, P2_THREADS, smem, (cudaStream_t)st>>>(tasks, n, n_b, step, q_max, pb, slot, block_task);
     return (int)cudaGetLastError();
 }
 

@@ -153,6 +153,9 @@ struct Unit {
     bool wg2 = false;                // ... and its weight gradient on wgrad_tc2.cu
     int kpad_f = 0, kpad_d = 0;      // padded K of the forward / data-gradient GEMM
     bool need_vh = false;            // a tensor-core unit consumes this unit's output
+    // precision bf16 stores a convolution unit's activations in bf16 ONLY: U / V stay null, Uh / Vh are the tensors
+    // (Vh == Uh when the unit has no post stage); precision fp32 keeps U / V and Vh is an optional shadow of V
+    __nv_bfloat16* Uh = nullptr;
     __nv_bfloat16* Vh = nullptr;     // bf16 shadow of V
     __nv_bfloat16* wtb = nullptr;    // bf16 [cout][kpad_f]
     __nv_bfloat16* wtd = nullptr;    // bf16 [cin][kpad_d]
@@ -357,13 +360,21 @@ void place(Cand& c, Arena& a, const cmoop_cnn_config& cfg, int n_train, int n_va
     c.m = (float*)a.take(c.n_params * f4);
     c.v = (float*)a.take(c.n_params * f4);
     c.best = cfg.restore_best_weights ? (float*)a.take(c.n_params * f4) : nullptr;
-    long long maxV = (long long)batch * 1, maxU = 1, maxS = 1, maxWs = 1;
+    long long maxV = (long long)batch * 1, maxU = 1, maxUh = 1, maxS = 1, maxWs = 1;
     for (Unit& u : c.units) {
-        u.U = (float*)a.take(u.u_elems * f4);
+        const bool half_only = cfg.precision == 1 && !u.dense;      // activations of convolution units live in bf16 only
         const bool separate_v = u.post_fwd || (u.dense && u.use_dropout);
-        u.V = separate_v ? (float*)a.take(u.v_elems * f4) : u.U;
+        if (half_only) {
+            u.U = u.V = nullptr;
+            u.Uh = (__nv_bfloat16*)a.take(u.u_elems * 2);
+            u.Vh = separate_v ? (__nv_bfloat16*)a.take(u.v_elems * 2) : u.Uh;
+        } else {
+            u.Uh = nullptr;
+            u.U = (float*)a.take(u.u_elems * f4);
+            u.V = separate_v ? (float*)a.take(u.v_elems * f4) : u.U;
+            u.Vh = u.need_vh ? (__nv_bfloat16*)a.take(u.v_elems * 2) : nullptr;
+        }
         u.idx = u.pool ? (uint8_t*)a.take(u.v_elems) : nullptr;
-        u.Vh = u.need_vh ? (__nv_bfloat16*)a.take(u.v_elems * 2) : nullptr;
         if (u.has_bn) {
             u.stat = (float*)a.take((size_t)u.stat_tiles * 2 * u.cout * f4);
             u.bn = (float*)a.take((size_t)6 * u.cout * f4);
@@ -378,16 +389,17 @@ void place(Cand& c, Arena& a, const cmoop_cnn_config& cfg, int n_train, int n_va
         }
         maxV = std::max(maxV, u.v_elems);
         maxV = std::max(maxV, (long long)batch * u.H * u.W * u.cin);
-        maxU = std::max(maxU, u.u_elems);
+        if (!half_only) maxU = std::max(maxU, u.u_elems);
+        else maxUh = std::max(maxUh, u.u_elems);
         if (u.is_skip) maxS = std::max(maxS, u.u_elems);
         if (u.wg_splits > 1)
             maxWs = std::max(maxWs, (long long)u.wg_splits * ((long long)u.k * u.k * u.cin + 1) * u.cout);
     }
     const Unit& lc = c.units[c.last_conv];
     c.gA = (float*)a.take(maxV * f4);
-    c.gB = (float*)a.take(maxU * f4);
-    c.gS = (float*)a.take(maxS * f4);
-    c.gBh = cfg.precision == 1 ? (__nv_bfloat16*)a.take(maxU * 2) : nullptr;
+    c.gB = (float*)a.take(maxU * f4);                 // precision bf16: only the dense layers' pre-activation gradients
+    c.gS = cfg.precision == 1 ? nullptr : (float*)a.take(maxS * f4);
+    c.gBh = cfg.precision == 1 ? (__nv_bfloat16*)a.take(maxUh * 2) : nullptr;
     c.gSh = cfg.precision == 1 ? (__nv_bfloat16*)a.take(maxS * 2) : nullptr;
     c.gG = (float*)a.take((size_t)batch * lc.cout * f4);
     c.gap = (float*)a.take((size_t)batch * lc.cout * f4);
@@ -405,7 +417,21 @@ struct DevList {
     T* d = nullptr;
     int total = 0;   // tiles / blocks of the grouped grid
     size_t blob_off = 0;
+    // optional direct block -> task table of the grouped grid (hot kernels: one load instead of a binary search)
+    std::vector<int> bt;
+    int* d_bt = nullptr;
+    size_t bt_off = 0;
 };
+
+// fills l.bt from the tasks' begin offsets (begin_of(task) ascending; the last task ends at l.total)
+template <class T, class F>
+void fill_block_table(DevList<T>& l, F begin_of) {
+    l.bt.assign((size_t)l.total, 0);
+    for (size_t i = 0; i < l.h.size(); ++i) {
+        const int b0 = begin_of(l.h[i]), b1 = i + 1 < l.h.size() ? begin_of(l.h[i + 1]) : l.total;
+        for (int b = b0; b < b1; ++b) l.bt[(size_t)b] = (int)i;
+    }
+}
 
 struct StageLists {
     DevList<ConvTask> conv, conv_eval, dgrad;
@@ -450,6 +476,9 @@ void blob_add(std::vector<char>& blob, DevList<T>& l) {
     l.blob_off = (blob.size() + 255) / 256 * 256;
     blob.resize(l.blob_off + l.h.size() * sizeof(T));
     if (!l.h.empty()) memcpy(blob.data() + l.blob_off, l.h.data(), l.h.size() * sizeof(T));
+    l.bt_off = (blob.size() + 255) / 256 * 256;
+    blob.resize(l.bt_off + l.bt.size() * sizeof(int));
+    if (!l.bt.empty()) memcpy(blob.data() + l.bt_off, l.bt.data(), l.bt.size() * sizeof(int));
 }
 
 inline int blocks_for(long long elems) { return (int)((elems + 255) / 256); }
@@ -517,8 +546,8 @@ struct Engine {
                     TcConvTask t{};
                     t.xh = c.units[u.input].Vh; t.wt = u.wtb; t.bias = c.p + u.w_off + (long long)u.k * u.k * u.cin * u.cout;
                     t.tmap = u.tmaps;                                   // {C = cin, W, H, N} of the producer's bf16 output
-                    t.y = u.U;
-                    t.yh = (!u.post_fwd && u.need_vh) ? u.Vh : nullptr;
+                    t.y = nullptr;                                      // bf16-only activation storage
+                    t.yh = u.Uh;
                     t.H = u.H; t.W = u.W; t.Cin = u.cin; t.Ho = u.Ho; t.Wo = u.Wo; t.Cout = u.cout;
                     t.k = u.k; t.stride = u.stride; t.pad = u.pad; t.K_pad = u.kpad_f;
                     t.bn = u.cout < 128 ? u.cout : 128;
@@ -540,7 +569,7 @@ struct Engine {
                     }
                     if (u.has_bn) {
                         StatTask sk{};
-                        sk.y = u.U; sk.part = u.stat; sk.C = u.cout; sk.rows_per_sample = u.Ho * u.Wo;
+                        sk.y = u.U; sk.yh = u.Uh; sk.part = u.stat; sk.C = u.cout; sk.rows_per_sample = u.Ho * u.Wo;
                         sk.block_begin = S.stat.total;
                         S.stat.h.push_back(sk);
                         S.stat.total += u.stat_tiles;
@@ -561,8 +590,8 @@ struct Engine {
                     ConvTask t{};
                     t.x = xin;
                     t.w = c.p + u.w_off;
-                    t.y = u.U;
-                    t.yh = (!u.post_fwd && u.need_vh) ? u.Vh : nullptr;
+                    t.y = u.U;                                          // null for a convolution unit in precision bf16
+                    t.yh = u.Uh;
                     t.stat_part = u.has_bn ? u.stat : nullptr;
                     t.H = u.H; t.W = u.W; t.Cin = u.cin; t.Ho = u.Ho; t.Wo = u.Wo; t.Cout = u.cout;
                     t.k = u.k; t.stride = u.stride; t.pad = u.pad;
@@ -595,8 +624,9 @@ struct Engine {
                 // ---- post stage (forward / BN / backward lists)
                 if (!u.dense && !u.is_skip) {
                     PostTask p{};
-                    p.u = u.U; p.v = u.V;
+                    p.u = u.U; p.uh = u.Uh; p.v = u.V;
                     p.skip = u.add_skip ? c.units[u.skip_unit].U : nullptr;
+                    p.skiph = u.add_skip ? c.units[u.skip_unit].Uh : nullptr;
                     p.idx = u.idx;
                     if (u.has_bn) {
                         float* bnp = c.p + u.bn_off;
@@ -604,13 +634,13 @@ struct Engine {
                         p.dgamma = c.grad + u.bn_off; p.dbeta = c.grad + u.bn_off + u.cout;
                         p.stat_part = u.stat; p.bn = u.bn; p.bwd_part = u.bwd_part;
                     }
-                    // a tensor-core unit's weight and data gradients read the bf16 gradient only
-                    const bool skip_tc = u.add_skip && c.units[u.skip_unit].tc;
-                    p.dv = c.gA; p.du = u.tc ? nullptr : c.gB;
-                    p.dskip = (u.add_skip && !skip_tc) ? c.gS : nullptr;
+                    // precision bf16: every convolution's weight / data gradient reads the bf16 gradient only
+                    const bool half = cfg.precision == 1;
+                    p.dv = c.gA; p.du = half ? nullptr : c.gB;
+                    p.dskip = (u.add_skip && !half) ? c.gS : nullptr;
                     p.vh = u.post_fwd ? u.Vh : nullptr;
-                    p.duh = u.tc ? c.gBh : nullptr;
-                    p.dskiph = skip_tc ? c.gSh : nullptr;
+                    p.duh = half ? c.gBh : nullptr;
+                    p.dskiph = (u.add_skip && half) ? c.gSh : nullptr;
                     p.H = u.Ho; p.W = u.Wo; p.C = u.cout; p.Ho = u.Po; p.Wo = u.Qo;
                     p.pool = u.pool; p.relu_mid = u.relu_mid; p.add_skip = u.add_skip; p.relu_in = u.relu_epi;
                     p.has_bn = u.has_bn;
@@ -619,7 +649,7 @@ struct Engine {
                         PostTask q = p;
                         q.block_begin = S.post_fwd.total;
                         S.post_fwd.h.push_back(q);
-                        S.post_fwd.total += blocks_for(u.v_elems / 8);
+                        S.post_fwd.total += Launch::post_blocks((long long)batch * u.Po * u.Qo, u.cout);
                     }
                     if (u.has_bn) {
                         S.max_bn_c = std::max(S.max_bn_c, u.cout);
@@ -629,9 +659,9 @@ struct Engine {
                         S.post_bn.total += (int)(((long long)batch * u.Po * u.Qo + 127) / 128);
                     }
                     PostTask q = p;
-                    q.block_begin = S.post_bwd.total;
+                    q.block_begin_apply = S.post_bwd.total;
                     S.post_bwd.h.push_back(q);
-                    S.post_bwd.total += blocks_for(u.u_elems / 8);
+                    S.post_bwd.total += Launch::post_blocks((long long)batch * u.Po * u.Qo, u.cout);
                 }
                 // ---- dense ReLU / dropout
                 if (u.dense && u.fc_index >= 0) {
@@ -683,6 +713,7 @@ struct Engine {
                         g.x = xin;
                         if (u.input == -1) { g.gather = c.perm; g.gather_step = batch; }
                         g.dy = dy;
+                        g.dyh = (cfg.precision == 1 && !u.dense) ? (u.is_skip ? c.gSh : c.gBh) : nullptr;
                         g.out = dst;
                         g.H = u.H; g.W = u.W; g.Cin = u.cin; g.Ho = u.Ho; g.Wo = u.Wo; g.Cout = u.cout;
                         g.k = u.k; g.stride = u.stride; g.pad = u.pad;
@@ -771,7 +802,7 @@ struct Engine {
             }
             const Unit& lc = c.units[c.last_conv];
             HeadTask hd{};
-            hd.v = lc.V; hd.gap = c.gap; hd.dgap = c.gG; hd.dv = c.gA;
+            hd.v = lc.V; hd.vh = lc.V ? nullptr : lc.Vh; hd.gap = c.gap; hd.dgap = c.gG; hd.dv = c.gA;
             hd.Hf = lc.Po; hd.Wf = lc.Qo; hd.C = lc.cout;
             hd.block_begin = wv.head.total;
             wv.head.h.push_back(hd);
@@ -793,6 +824,13 @@ struct Engine {
             ad.block_begin = wv.adam.total;
             wv.adam.h.push_back(ad);
             wv.adam.total += blocks_for(c.n_params);
+        }
+        for (int s = 0; s < N_STAGES; ++s) {
+            StageLists& S = wv.st[s];
+            fill_block_table(S.conv_tc2, [](const TcConvTask& t) { return t.tile_begin; });
+            fill_block_table(S.dgrad_tc2, [](const TcConvTask& t) { return t.tile_begin; });
+            fill_block_table(S.wgrad_tc2, [](const TcWgradTask& t) { return t.tile_begin; });
+            // (the elementwise post kernels keep the shared binary search: a direct table measured slower there)
         }
         // ---- one blob upload, then fix the device pointers
         std::vector<char> blob;
@@ -817,7 +855,10 @@ struct Engine {
         }
         CMOOP_CUDA_OK(cudaStreamSynchronize(stream));   // previous launches may still read the old lists
         CMOOP_CUDA_OK(cmoop::copy_sync(wv.d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
-        auto fix = [&](auto& l) { l.d = reinterpret_cast<decltype(l.d)>(wv.d_blob + l.blob_off); };
+        auto fix = [&](auto& l) {
+            l.d = reinterpret_cast<decltype(l.d)>(wv.d_blob + l.blob_off);
+            l.d_bt = l.bt.empty() ? nullptr : reinterpret_cast<int*>(wv.d_blob + l.bt_off);
+        };
         for (int s = 0; s < N_STAGES; ++s) {
             StageLists& S = wv.st[s];
             fix(S.conv); fix(S.conv_eval); fix(S.dgrad); fix(S.post_fwd); fix(S.post_bn); fix(S.post_bwd);
@@ -872,14 +913,15 @@ struct Engine {
             if (!S.conv_tc2.h.empty())
                 CNN_LAUNCH_N("conv_tc2.fwd", S.f_fwd2 * n_b,
                              Launch::conv_tc2(S.conv_tc2.d, (int)S.conv_tc2.h.size(), S.conv_tc2.total, n_b, step, S.q_max,
-                                              S.tc2_cin, stream));
+                                              S.tc2_cin, stream, S.conv_tc2.d_bt));
             if (!S.stat.h.empty() && training)
                 CNN_LAUNCH(Launch::bn_stats(S.stat.d, (int)S.stat.h.size(), S.stat.total, n_b, stream));
             if (!S.post_bn.h.empty())
                 CNN_LAUNCH(Launch::bn_finalize(S.post_bn.d, (int)S.post_bn.h.size(), S.max_bn_c, n_b, training, cfg.bn_momentum,
                                                cfg.bn_eps, stream));
             if (!S.post_fwd.h.empty())
-                CNN_LAUNCH(Launch::post_fwd(S.post_fwd.d, (int)S.post_fwd.h.size(), S.post_fwd.total, n_b, stream));
+                CNN_LAUNCH(Launch::post_fwd(S.post_fwd.d, (int)S.post_fwd.h.size(), S.post_fwd.total, n_b, stream, nullptr,
+                                            cfg.precision == 1));
             if (!S.drop_fwd.h.empty())
                 CNN_LAUNCH(Launch::drop_fwd(S.drop_fwd.d, (int)S.drop_fwd.h.size(), S.drop_fwd.total, n_b, global_step,
                                             training, cfg.dropout_rate, stream));
@@ -903,7 +945,8 @@ struct Engine {
                 CNN_LAUNCH(Launch::bn_bwd_finalize(S.post_bn.d, (int)S.post_bn.h.size(), S.max_bn_c, n_b, stream));
             }
             if (!S.post_bwd.h.empty())
-                CNN_LAUNCH(Launch::post_bwd_apply(S.post_bwd.d, (int)S.post_bwd.h.size(), S.post_bwd.total, n_b, stream));
+                CNN_LAUNCH(Launch::post_bwd_apply(S.post_bwd.d, (int)S.post_bwd.h.size(), S.post_bwd.total, n_b, stream, nullptr,
+                                                  cfg.precision == 1));
             if (!S.wgrad.h.empty()) {
                 if (S.stem && S.stem_w > 0)
                     CNN_LAUNCH_N("stem_wgrad", S.f_simt_wg * n_b,
@@ -918,7 +961,8 @@ struct Engine {
                              Launch::wgrad_tc(S.wgrad_tc.d, (int)S.wgrad_tc.h.size(), S.wgrad_tc.total, n_b, stream));
             if (!S.wgrad_tc2.h.empty())
                 CNN_LAUNCH_N("wgrad_tc2", S.f_wg * n_b,
-                             Launch::wgrad_tc2(S.wgrad_tc2.d, (int)S.wgrad_tc2.h.size(), S.wgrad_tc2.total, n_b, S.wg2_q, stream));
+                             Launch::wgrad_tc2(S.wgrad_tc2.d, (int)S.wgrad_tc2.h.size(), S.wgrad_tc2.total, n_b, S.wg2_q, stream,
+                                               S.wgrad_tc2.d_bt));
             if (!S.wreduce.h.empty())
                 CNN_LAUNCH(Launch::reduce(S.wreduce.d, (int)S.wreduce.h.size(), S.wreduce.total, stream));
             if (!S.dgrad.h.empty())
@@ -930,7 +974,7 @@ struct Engine {
             if (!S.dgrad_tc2.h.empty())
                 CNN_LAUNCH_N("conv_tc2.dgrad", S.f_dg2 * n_b,
                              Launch::conv_tc2(S.dgrad_tc2.d, (int)S.dgrad_tc2.h.size(), S.dgrad_tc2.total, n_b, 0, S.q_max,
-                                              S.tc2_cin_d, stream));
+                                              S.tc2_cin_d, stream, S.dgrad_tc2.d_bt));
         }
         return CMOOP_OK;
     }
@@ -1016,6 +1060,12 @@ int check_config(const cmoop_genotype* g, int n, const cmoop_cnn_config* cfg) {
     for (int i = 0; i < n; ++i) {
         CMOOP_REQUIRE(g[i].filters >= 4 && g[i].filters <= 256 && g[i].filters % 4 == 0,
                       "cnn: genotype %d filters=%d must be a multiple of 4 in [4,256]", i, g[i].filters);
+        if (cfg->precision == 1 && g[i].filters % 16 != 0) {
+            // precision bf16 stores every convolution's activations in bf16 only and runs every Cin >= 16 convolution
+            // on the tensor cores: channel counts must be multiples of 16 (the reference's space is {16, 32, 64})
+            cmoop::set_error("cnn: genotype %d filters=%d: precision bf16 needs a multiple of 16", i, g[i].filters);
+            return CMOOP_ERR_UNSUPPORTED;
+        }
         CMOOP_REQUIRE(g[i].kernel_size == 1 || g[i].kernel_size == 3 || g[i].kernel_size == 5 || g[i].kernel_size == 7,
                       "cnn: genotype %d kernel_size=%d must be odd and <= 7", i, g[i].kernel_size);
         CMOOP_REQUIRE(g[i].residual_blocks >= 0 && g[i].residual_blocks <= 3, "cnn: genotype %d residual_blocks=%d", i,

@@ -32,7 +32,8 @@ __device__ __forceinline__ int find_task(const T* tasks, int n, int block, F beg
 // One binary search per block instead of one per thread (the elementwise kernels move 16 bytes per thread, so the
 // ~8 dependent loads of a per-thread search were most of their instruction stream).
 template <class T, class F>
-__device__ __forceinline__ int block_find_task(const T* tasks, int n, int block, F begin_of) {
+__device__ __forceinline__ int block_find_task(const T* tasks, int n, int block, F begin_of, const int* block_task = nullptr) {
+    if (block_task) return __ldg(block_task + block);      // direct table: one load
     __shared__ int s_task;
     if (threadIdx.x == 0) s_task = find_task(tasks, n, block, begin_of);
     __syncthreads();
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradTask* __rest
             ci[j] = (kj == K) ? -1 : -2;     // -1: ones column, -2: outside
         }
     }
-    const bool vec_b = (T.Cout & 3) == 0 && aligned16(T.dy);
+    const bool vec_b = !T.dyh && (T.Cout & 3) == 0 && aligned16(T.dy);
     const int tx = tid & 15, ty = tid >> 4;
     float acc[4][4];
 #pragma unroll
@@ -282,7 +283,11 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradTask* __rest
                 }
             }
             const float* dr = T.dy + (long long)m * T.Cout + n0 + q4;
-            if (vec_b && n0 + q4 + 3 < T.Cout) {
+            if (T.dyh) {                               // bf16-only gradient (precision bf16, Cin = 1 convolution)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n0 + q4 + j < T.Cout) b[j] = __bfloat162float(T.dyh[(long long)m * T.Cout + n0 + q4 + j]);
+            } else if (vec_b && n0 + q4 + 3 < T.Cout) {
                 const float4 v = *reinterpret_cast<const float4*>(dr);
                 b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
             } else {
@@ -431,102 +436,154 @@ __device__ __forceinline__ void load4(const float* f, const __nv_bfloat16* h, lo
 __device__ __forceinline__ float load1(const float* f, const __nv_bfloat16* h, long long e) {
     return h ? __bfloat162float(h[e]) : f[e];
 }
+// compile-time storage choice (the post kernels are instantiated per precision: no per-load branch, so the compiler can
+// issue all loads of an iteration back to back)
+template <bool HALF>
+__device__ __forceinline__ void load8t(const float* __restrict__ f, const __nv_bfloat16* __restrict__ h, long long e, float (&v)[8]) {
+    if constexpr (HALF) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(h + e));
+        v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+        v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+        v[4] = __uint_as_float(r.z << 16); v[5] = __uint_as_float(r.z & 0xffff0000u);
+        v[6] = __uint_as_float(r.w << 16); v[7] = __uint_as_float(r.w & 0xffff0000u);
+    } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(f + e)), b = __ldg(reinterpret_cast<const float4*>(f + e + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+}
+template <bool HALF>
+__device__ __forceinline__ void store8t(float* __restrict__ f, __nv_bfloat16* __restrict__ h, long long e, const float (&z)[8]) {
+    if constexpr (HALF) {
+        const uint2 h0 = bf16x4(make_float4(z[0], z[1], z[2], z[3])), h1 = bf16x4(make_float4(z[4], z[5], z[6], z[7]));
+        *reinterpret_cast<uint4*>(h + e) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    } else {
+        *reinterpret_cast<float4*>(f + e) = make_float4(z[0], z[1], z[2], z[3]);
+        *reinterpret_cast<float4*>(f + e + 4) = make_float4(z[4], z[5], z[6], z[7]);
+    }
+}
 
-// [BN] -> [ReLU] -> [2x2/s2 'same' max-pool] -> [+skip, ReLU]; one thread = 4 consecutive channels of one output pixel
-__global__ void __launch_bounds__(256) post_fwd_kernel(const PostTask* __restrict__ tasks, int n_tasks, int n_b) {
-    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin; });
-    const PostTask T = tasks[t];
-    // one thread = 8 channels of one output pixel (two float4 per source position: index math amortised over 32 B and
-    // twice the loads in flight); 32-bit index math: a unit's activation has < 2^31 elements
-    const int C8 = T.C >> 3;
-    const unsigned e8 = (unsigned)(blockIdx.x - T.block_begin) * 256u + threadIdx.x;
-    if (e8 >= (unsigned)n_b * T.Ho * T.Wo * C8) return;
-    const unsigned pix = e8 / (unsigned)C8;
-    const int c = (int)(e8 - pix * C8) * 8;
-    const long long e = (long long)pix * T.C + c;
-    const unsigned r1 = pix / (unsigned)T.Wo;
-    const int wo = (int)(pix - r1 * T.Wo);
-    const int n = (int)(r1 / (unsigned)T.Ho);
-    const int ho = (int)(r1 - (unsigned)n * T.Ho);
+// Thread mapping of the two elementwise post kernels: a thread OWNS 8 consecutive channels (its BN constants and the task
+// fields stay in registers) and walks over output pixels -- kPostIter per thread, 256 / (C / 8) pixel lanes per block.  The
+// first version gave every thread one (pixel, 8 channels) element: each thread then re-loaded the task record and twelve
+// 16-byte BN vectors for 16 bytes of output and the kernels ran at a third of the HBM rate whatever the activation width.
+constexpr int kPostIter = 8;
+__host__ __device__ inline int post_pixels_per_block(int C) {
+    const int cg = C >> 3;                               // 8-channel groups: 2 .. 64
+    return (256 / cg) * kPostIter;
+}
+__device__ __forceinline__ void store8(float* f, __nv_bfloat16* h, long long e, const float (&z)[8]) {
+    if (f) {
+        *reinterpret_cast<float4*>(f + e) = make_float4(z[0], z[1], z[2], z[3]);
+        *reinterpret_cast<float4*>(f + e + 4) = make_float4(z[4], z[5], z[6], z[7]);
+    }
+    if (h) {
+        const uint2 h0 = bf16x4(make_float4(z[0], z[1], z[2], z[3])), h1 = bf16x4(make_float4(z[4], z[5], z[6], z[7]));
+        *reinterpret_cast<uint4*>(h + e) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    }
+}
+
+// [BN] -> [ReLU] -> [2x2/s2 'same' max-pool] -> [+skip, ReLU].  HALF: activations are stored in bf16 only (precision bf16).
+// The (up to) four window loads of a pooled pixel are UNCONDITIONAL (coordinates clamped into the image, validity applied
+// in the compare chain): with per-load branches the compiler kept them in four separate reconvergence regions and every
+// iteration paid four dependent memory round trips.
+template <bool HALF>
+__global__ void __launch_bounds__(256, 2) post_fwd_kernel(const PostTask* __restrict__ tasks, int n_tasks, int n_b,
+                                                          const int* __restrict__ block_task) {
+    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin; }, block_task);
+    const PostTask* __restrict__ Tp = tasks + t;
+    const int C = Tp->C, cgs = C >> 3, lanes = 256 / cgs;
+    const int cg = threadIdx.x % cgs, pl = threadIdx.x / cgs;
+    if (pl >= lanes) return;
+    const int c = cg * 8;
+    const int H = Tp->H, W = Tp->W, Ho = Tp->Ho, Wo = Tp->Wo;
+    const int pool = Tp->pool, relu_mid = Tp->relu_mid, add_skip = Tp->add_skip, has_bn = Tp->has_bn;
+    const float* __restrict__ u = Tp->u;
+    const __nv_bfloat16* __restrict__ uh = Tp->uh;
+    const float* __restrict__ skip = Tp->skip;
+    const __nv_bfloat16* __restrict__ skiph = Tp->skiph;
+    float* __restrict__ v = Tp->v;
+    __nv_bfloat16* __restrict__ vh = Tp->vh;
+    uint8_t* __restrict__ idx = Tp->idx;
+    const int n_pix = n_b * Ho * Wo;
+    const int pixb = lanes * kPostIter;
+    const int p0 = (blockIdx.x - Tp->block_begin) * pixb;
+    const int p1 = min(n_pix, p0 + pixb);
     float sc[8], sh[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) { sc[q] = 1.f; sh[q] = 0.f; }
-    if (T.has_bn) {
+    if (has_bn) {
+        const float* bn = Tp->bn;
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
-            const float4 a = ld4(T.bn + 2 * T.C + c + 4 * h2), b = ld4(T.bn + 3 * T.C + c + 4 * h2);
+            const float4 a = ld4(bn + 2 * C + c + 4 * h2), b = ld4(bn + 3 * C + c + 4 * h2);
             sc[4 * h2 + 0] = a.x; sc[4 * h2 + 1] = a.y; sc[4 * h2 + 2] = a.z; sc[4 * h2 + 3] = a.w;
             sh[4 * h2 + 0] = b.x; sh[4 * h2 + 1] = b.y; sh[4 * h2 + 2] = b.z; sh[4 * h2 + 3] = b.w;
         }
     }
-    float z[8];
-    if (T.pool) {
-        // all (up to) eight loads first, then the max in the reference's scan order (first maximum wins)
-        float v[4][8];
-        bool ok[4];
+    for (int pix = p0 + pl; pix < p1; pix += lanes) {
+        const long long e = (long long)pix * C + c;
+        float z[8];
+        float sk[8];
+        if (add_skip) load8t<HALF>(skip, skiph, e, sk);
+        if (pool) {
+            const int r1 = pix / Wo, wo = pix - r1 * Wo;
+            const int n = r1 / Ho, ho = r1 - n * Ho;
+            const int h0 = 2 * ho, w0 = 2 * wo;
+            const bool okh = h0 + 1 < H, okw = w0 + 1 < W;             // (h0, w0) itself is always inside
+            const long long row0 = ((long long)n * H + h0) * W, row1 = ((long long)n * H + (okh ? h0 + 1 : h0)) * W;
+            const int wb = okw ? w0 + 1 : w0;
+            float x4[4][8];
+            load8t<HALF>(u, uh, (row0 + w0) * C + c, x4[0]);
+            load8t<HALF>(u, uh, (row0 + wb) * C + c, x4[1]);
+            load8t<HALF>(u, uh, (row1 + w0) * C + c, x4[2]);
+            load8t<HALF>(u, uh, (row1 + wb) * C + c, x4[3]);
+            const bool ok[4] = {true, okw, okh, okh && okw};
+            int code[8];
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            const int hi = 2 * ho + (d >> 1), wi = 2 * wo + (d & 1);
-            ok[d] = hi < T.H && wi < T.W;
-            if (ok[d]) load8(T.u, T.uh, (((long long)n * T.H + hi) * T.W + wi) * T.C + c, v[d]);
-        }
-        int code[8];
+            for (int q = 0; q < 8; ++q) code[q] = 0;
+            // the max in the reference's scan order (first maximum wins); position 0 is always valid
 #pragma unroll
-        for (int q = 0; q < 8; ++q) code[q] = 0;
-        bool first = true;
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            if (ok[d]) {
+            for (int d = 0; d < 4; ++d) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    float x = v[d][q];
-                    if (T.has_bn) x = fmaf(x, sc[q], sh[q]);
-                    if (T.relu_mid) x = fmaxf(x, 0.f);
-                    if (first || x > z[q]) {
+                    float x = x4[d][q];
+                    if (has_bn) x = fmaf(x, sc[q], sh[q]);
+                    if (relu_mid) x = fmaxf(x, 0.f);
+                    if (d == 0 || (ok[d] && x > z[q])) {
                         z[q] = x;
                         code[q] = d;
                     }
                 }
-                first = false;
+            }
+            uint2 pk;
+            pk.x = (unsigned)code[0] | ((unsigned)code[1] << 8) | ((unsigned)code[2] << 16) | ((unsigned)code[3] << 24);
+            pk.y = (unsigned)code[4] | ((unsigned)code[5] << 8) | ((unsigned)code[6] << 16) | ((unsigned)code[7] << 24);
+            *reinterpret_cast<uint2*>(idx + e) = pk;
+        } else {
+            float x8[8];
+            load8t<HALF>(u, uh, e, x8);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float x = x8[q];
+                if (has_bn) x = fmaf(x, sc[q], sh[q]);
+                if (relu_mid) x = fmaxf(x, 0.f);
+                z[q] = x;
             }
         }
-        uint2 pk;
-        pk.x = (unsigned)code[0] | ((unsigned)code[1] << 8) | ((unsigned)code[2] << 16) | ((unsigned)code[3] << 24);
-        pk.y = (unsigned)code[4] | ((unsigned)code[5] << 8) | ((unsigned)code[6] << 16) | ((unsigned)code[7] << 24);
-        *reinterpret_cast<uint2*>(T.idx + e) = pk;
-    } else {
-        float v[8];
-        load8(T.u, T.uh, e, v);
+        if (add_skip) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float x = v[q];
-            if (T.has_bn) x = fmaf(x, sc[q], sh[q]);
-            if (T.relu_mid) x = fmaxf(x, 0.f);
-            z[q] = x;
+            for (int q = 0; q < 8; ++q) z[q] = fmaxf(z[q] + sk[q], 0.f);
         }
-    }
-    if (T.add_skip) {
-        float sk[8];
-        load8(T.skip, T.skiph, e, sk);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) z[q] = fmaxf(z[q] + sk[q], 0.f);
-    }
-    const float4 o0 = make_float4(z[0], z[1], z[2], z[3]), o1 = make_float4(z[4], z[5], z[6], z[7]);
-    if (T.v) {
-        *reinterpret_cast<float4*>(T.v + e) = o0;
-        *reinterpret_cast<float4*>(T.v + e + 4) = o1;
-    }
-    if (T.vh) {
-        const uint2 h0 = bf16x4(o0), h1 = bf16x4(o1);
-        *reinterpret_cast<uint4*>(T.vh + e) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+        store8t<HALF>(v, vh, e, z);
+        if (!HALF && vh) store8t<true>(nullptr, vh, e, z);
     }
 }
 
 // BN backward, pass 1: per-channel partial sums of g and g*xhat over the unit's output elements.
 // A CTA covers 128 output pixels; thread = (pixel lane, 4 channels); one partial row per (CTA, pixel lane).
 __global__ void __launch_bounds__(128) post_bwd_reduce_kernel(const PostTask* __restrict__ tasks, int n_tasks,
-                                                              int n_b) {
-    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin_bwd; });
+                                                              int n_b, const int* __restrict__ block_task) {
+    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin_bwd; }, block_task);
     const PostTask T = tasks[t];
     const int blk = blockIdx.x - T.block_begin_bwd;
     const int C4 = T.C >> 2;
@@ -627,101 +684,120 @@ __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const PostTask* __
     }
 }
 
-// backward of the whole post stage, dense over the conv-output grid; one thread = 8 channels of one input pixel
-// (as post_fwd: index math amortised over 32 B, twice the loads in flight)
-__global__ void __launch_bounds__(256) post_bwd_apply_kernel(const PostTask* __restrict__ tasks, int n_tasks, int n_b) {
-    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin; });
-    const PostTask T = tasks[t];
-    const int C8 = T.C >> 3;
-    const unsigned e8 = (unsigned)(blockIdx.x - T.block_begin) * 256u + threadIdx.x;      // 32-bit index math (see post_fwd)
-    if (e8 >= (unsigned)n_b * T.H * T.W * C8) return;
-    const unsigned pix = e8 / (unsigned)C8;
-    const int c = (int)(e8 - pix * C8) * 8;
-    const long long e = (long long)pix * T.C + c;
-    const unsigned r1 = pix / (unsigned)T.W;
-    const int wi = (int)(pix - r1 * T.W);
-    const int n = (int)(r1 / (unsigned)T.H);
-    const int hi = (int)(r1 - (unsigned)n * T.H);
-    long long oe = e;
-    bool origin = true;
-    bool routed[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) routed[q] = true;
-    if (T.pool) {
-        const int ho = hi >> 1, wo = wi >> 1;
-        oe = (((long long)n * T.Ho + ho) * T.Wo + wo) * T.C + c;
-        origin = ((hi & 1) == 0) && ((wi & 1) == 0);
-        const uint2 cd = *reinterpret_cast<const uint2*>(T.idx + oe);
-        const unsigned me = (unsigned)((hi & 1) * 2 + (wi & 1));
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            routed[q] = ((cd.x >> (8 * q)) & 0xffu) == me;
-            routed[4 + q] = ((cd.y >> (8 * q)) & 0xffu) == me;
-        }
-    }
-    const float4 g0 = ld4(T.dv + oe), g1 = ld4(T.dv + oe + 4);
-    float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    if (T.add_skip) {
-        float vv[8];
-        load8(T.v, T.vh, oe, vv);
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-            if (!(vv[q] > 0.f)) g[q] = 0.f;
-        if (origin) {       // the tensor-core consumers read only the bf16 copy: the fp32 one is then not written at all
-            const float4 s0 = make_float4(g[0], g[1], g[2], g[3]), s1 = make_float4(g[4], g[5], g[6], g[7]);
-            if (T.dskip) {
-                *reinterpret_cast<float4*>(T.dskip + oe) = s0;
-                *reinterpret_cast<float4*>(T.dskip + oe + 4) = s1;
-            }
-            if (T.dskiph) {
-                const uint2 h0 = bf16x4(s0), h1 = bf16x4(s1);
-                *reinterpret_cast<uint4*>(T.dskiph + oe) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-            }
-        }
-    }
-    float u[8];
-    load8(T.u, T.uh, e, u);
-    float du[8];
-    if (T.has_bn) {
+// backward of the whole post stage.  Same thread mapping as post_fwd_kernel: a thread owns 8 channels (six BN vectors in
+// registers) and walks over OUTPUT pixels; for a pooled unit it reads the pooled gradient / mask / argmax code once and
+// writes the gradient of all (up to four) input pixels of the 2x2 window (unconditional, clamped loads as above).
+template <bool HALF>
+__global__ void __launch_bounds__(256, 2) post_bwd_apply_kernel(const PostTask* __restrict__ tasks, int n_tasks, int n_b,
+                                                                const int* __restrict__ block_task) {
+    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin_apply; }, block_task);
+    const PostTask* __restrict__ Tp = tasks + t;
+    const int C = Tp->C, cgs = C >> 3, lanes = 256 / cgs;
+    const int cg = threadIdx.x % cgs, pl = threadIdx.x / cgs;
+    if (pl >= lanes) return;
+    const int c = cg * 8;
+    const int H = Tp->H, W = Tp->W, Ho = Tp->Ho, Wo = Tp->Wo;
+    const int pool = Tp->pool, relu_mid = Tp->relu_mid, add_skip = Tp->add_skip, has_bn = Tp->has_bn, relu_in = Tp->relu_in;
+    const float* __restrict__ u = Tp->u;
+    const __nv_bfloat16* __restrict__ uh = Tp->uh;
+    const float* __restrict__ v = Tp->v;
+    const __nv_bfloat16* __restrict__ vh = Tp->vh;
+    const float* __restrict__ dv = Tp->dv;
+    const uint8_t* __restrict__ idx = Tp->idx;
+    float* __restrict__ du = Tp->du;
+    __nv_bfloat16* __restrict__ duh = Tp->duh;
+    float* __restrict__ dskip = Tp->dskip;
+    __nv_bfloat16* __restrict__ dskiph = Tp->dskiph;
+    const int n_pix = n_b * Ho * Wo;
+    const int pixb = lanes * kPostIter;
+    const int p0 = (blockIdx.x - Tp->block_begin_apply) * pixb;
+    const int p1 = min(n_pix, p0 + pixb);
+    float mu[8], is[8], sc[8], sh[8], mg[8], mgx[8];
+    if (has_bn) {
+        const float* bn = Tp->bn;
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
             const int ch = c + 4 * h2;
-            const float4 mean = ld4(T.bn + 0 * T.C + ch), invstd = ld4(T.bn + 1 * T.C + ch);
-            const float4 scale = ld4(T.bn + 2 * T.C + ch), shift = ld4(T.bn + 3 * T.C + ch);
-            const float4 mg = ld4(T.bn + 4 * T.C + ch), mgx = ld4(T.bn + 5 * T.C + ch);
-            const float mu[4] = {mean.x, mean.y, mean.z, mean.w}, is[4] = {invstd.x, invstd.y, invstd.z, invstd.w};
-            const float sc[4] = {scale.x, scale.y, scale.z, scale.w}, sh[4] = {shift.x, shift.y, shift.z, shift.w};
-            const float a4[4] = {mg.x, mg.y, mg.z, mg.w}, b4[4] = {mgx.x, mgx.y, mgx.z, mgx.w};
+            const float4 a0 = ld4(bn + 0 * C + ch), a1 = ld4(bn + 1 * C + ch), a2 = ld4(bn + 2 * C + ch);
+            const float4 a3 = ld4(bn + 3 * C + ch), a4 = ld4(bn + 4 * C + ch), a5 = ld4(bn + 5 * C + ch);
+            mu[4 * h2] = a0.x; mu[4 * h2 + 1] = a0.y; mu[4 * h2 + 2] = a0.z; mu[4 * h2 + 3] = a0.w;
+            is[4 * h2] = a1.x; is[4 * h2 + 1] = a1.y; is[4 * h2 + 2] = a1.z; is[4 * h2 + 3] = a1.w;
+            sc[4 * h2] = a2.x; sc[4 * h2 + 1] = a2.y; sc[4 * h2 + 2] = a2.z; sc[4 * h2 + 3] = a2.w;
+            sh[4 * h2] = a3.x; sh[4 * h2 + 1] = a3.y; sh[4 * h2 + 2] = a3.z; sh[4 * h2 + 3] = a3.w;
+            mg[4 * h2] = a4.x; mg[4 * h2 + 1] = a4.y; mg[4 * h2 + 2] = a4.z; mg[4 * h2 + 3] = a4.w;
+            mgx[4 * h2] = a5.x; mgx[4 * h2 + 1] = a5.y; mgx[4 * h2 + 2] = a5.z; mgx[4 * h2 + 3] = a5.w;
+        }
+    }
+    for (int pix = p0 + pl; pix < p1; pix += lanes) {
+        const long long oe = (long long)pix * C + c;
+        float g[8];
+        {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(dv + oe)), g1 = __ldg(reinterpret_cast<const float4*>(dv + oe + 4));
+            g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+        }
+        float vv[8];
+        if (add_skip) load8t<HALF>(v, vh, oe, vv);
+        long long ew[4] = {oe, oe, oe, oe};
+        bool ok[4] = {true, false, false, false};
+        unsigned code_lo = 0, code_hi = 0;
+        if (pool) {
+            const int r1 = pix / Wo, wo = pix - r1 * Wo;
+            const int n = r1 / Ho, ho = r1 - n * Ho;
+            const int h0 = 2 * ho, w0 = 2 * wo;
+            const bool okh = h0 + 1 < H, okw = w0 + 1 < W;
+            const long long row0 = ((long long)n * H + h0) * W, row1 = ((long long)n * H + (okh ? h0 + 1 : h0)) * W;
+            const int wb = okw ? w0 + 1 : w0;
+            ew[0] = (row0 + w0) * C + c; ew[1] = (row0 + wb) * C + c; ew[2] = (row1 + w0) * C + c; ew[3] = (row1 + wb) * C + c;
+            ok[1] = okw; ok[2] = okh; ok[3] = okh && okw;
+            const uint2 cd = __ldg(reinterpret_cast<const uint2*>(idx + oe));
+            code_lo = cd.x;
+            code_hi = cd.y;
+        }
+        float uw[4][8];
+        load8t<HALF>(u, uh, ew[0], uw[0]);
+        if (pool) {
+            load8t<HALF>(u, uh, ew[1], uw[1]);
+            load8t<HALF>(u, uh, ew[2], uw[2]);
+            load8t<HALF>(u, uh, ew[3], uw[3]);
+        }
+        if (add_skip) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int j = 4 * h2 + q;
-                float gq = routed[j] ? g[j] : 0.f;
-                if (T.relu_mid && !(fmaf(u[j], sc[q], sh[q]) > 0.f)) gq = 0.f;
-                const float xhat = (u[j] - mu[q]) * is[q];
-                du[j] = sc[q] * (gq - a4[q] - xhat * b4[q]);
+            for (int q = 0; q < 8; ++q)
+                if (!(vv[q] > 0.f)) g[q] = 0.f;
+            if (HALF) store8t<true>(nullptr, dskiph, oe, g);      // the tensor-core consumers read only the bf16 form
+            else {
+                if (dskip) store8t<false>(dskip, nullptr, oe, g);
+                if (dskiph) store8t<true>(nullptr, dskiph, oe, g);
             }
         }
-    } else {
+        const int n_win = pool ? 4 : 1;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float gq = routed[q] ? g[q] : 0.f;
-            if (T.relu_mid && !(u[q] > 0.f)) gq = 0.f;
-            du[q] = gq;
+        for (int d = 0; d < 4; ++d) {
+            if (d >= n_win || !ok[d]) continue;
+            float o[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const unsigned cq = ((q < 4 ? code_lo : code_hi) >> (8 * (q & 3))) & 0xffu;
+                float gq = (!pool || cq == (unsigned)d) ? g[q] : 0.f;
+                const float uq = uw[d][q];
+                float r;
+                if (has_bn) {
+                    if (relu_mid && !(fmaf(uq, sc[q], sh[q]) > 0.f)) gq = 0.f;
+                    const float xhat = (uq - mu[q]) * is[q];
+                    r = sc[q] * (gq - mg[q] - xhat * mgx[q]);
+                } else {
+                    if (relu_mid && !(uq > 0.f)) gq = 0.f;
+                    r = gq;
+                }
+                if (relu_in && !(uq > 0.f)) r = 0.f;
+                o[q] = r;
+            }
+            if (HALF) store8t<true>(nullptr, duh, ew[d], o);
+            else {
+                if (du) store8t<false>(du, nullptr, ew[d], o);
+                if (duh) store8t<true>(nullptr, duh, ew[d], o);
+            }
         }
-    }
-    if (T.relu_in) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-            if (!(u[q] > 0.f)) du[q] = 0.f;
-    }
-    const float4 o0 = make_float4(du[0], du[1], du[2], du[3]), o1 = make_float4(du[4], du[5], du[6], du[7]);
-    if (T.du) {
-        *reinterpret_cast<float4*>(T.du + e) = o0;
-        *reinterpret_cast<float4*>(T.du + e + 4) = o1;
-    }
-    if (T.duh) {
-        const uint2 h0 = bf16x4(o0), h1 = bf16x4(o1);
-        *reinterpret_cast<uint4*>(T.duh + e) = make_uint4(h0.x, h0.y, h1.x, h1.y);
     }
 }
 
@@ -945,14 +1021,21 @@ int Launch::bn_finalize(const PostTask* tasks, int n, int max_c, int n_b, int tr
     bn_finalize_kernel<<<dim3(n, (max_c + 7) / 8), 128, 0, (cudaStream_t)st>>>(tasks, n_b, training, momentum, eps);
     return check();
 }
-int Launch::post_fwd(const PostTask* tasks, int n, int blocks, int n_b, void* st) {
+int Launch::post_blocks(long long out_pixels, int C) {
+    const int pixb = post_pixels_per_block(C);
+    return (int)((out_pixels + pixb - 1) / pixb);
+}
+int Launch::post_fwd(const PostTask* tasks, int n, int blocks, int n_b, void* st, const int* bt, bool half) {
     if (n == 0 || blocks == 0) return 0;
-    post_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b);
+    if (half)
+        post_fwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b, bt);
+    else
+        post_fwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b, bt);
     return check();
 }
-int Launch::post_bwd_reduce(const PostTask* tasks, int n, int blocks, int n_b, void* st) {
+int Launch::post_bwd_reduce(const PostTask* tasks, int n, int blocks, int n_b, void* st, const int* bt) {
     if (n == 0 || blocks == 0) return 0;
-    post_bwd_reduce_kernel<<<blocks, 128, 0, (cudaStream_t)st>>>(tasks, n, n_b);
+    post_bwd_reduce_kernel<<<blocks, 128, 0, (cudaStream_t)st>>>(tasks, n, n_b, bt);
     return check();
 }
 int Launch::bn_bwd_finalize(const PostTask* tasks, int n, int max_c, int n_b, void* st) {
@@ -960,9 +1043,12 @@ int Launch::bn_bwd_finalize(const PostTask* tasks, int n, int max_c, int n_b, vo
     bn_bwd_finalize_kernel<<<dim3(n, (max_c + 7) / 8), 128, 0, (cudaStream_t)st>>>(tasks, n_b);
     return check();
 }
-int Launch::post_bwd_apply(const PostTask* tasks, int n, int blocks, int n_b, void* st) {
+int Launch::post_bwd_apply(const PostTask* tasks, int n, int blocks, int n_b, void* st, const int* bt, bool half) {
     if (n == 0 || blocks == 0) return 0;
-    post_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b);
+    if (half)
+        post_bwd_apply_kernel<true><<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b, bt);
+    else
+        post_bwd_apply_kernel<false><<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b, bt);
     return check();
 }
 int Launch::gap_fwd(const HeadTask* tasks, int n, int blocks, int n_b, void* st) {

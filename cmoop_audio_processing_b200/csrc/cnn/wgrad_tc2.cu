@@ -88,17 +88,22 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // Work item of a CTA: (task, split, input-channel slab, output-channel tile, tap-pair group).
 // qx_max / qy_max: positions (whole padded rows) a patch / dY buffer must hold for the widest task of the launch.
 __global__ void __launch_bounds__(W2_THREADS, 1) wgrad_tc2_kernel(const TcWgradTask* __restrict__ tasks, int n_tasks, int n_b,
-                                                                  int qx_max, int qy_max) {
+                                                                  int qx_max, int qy_max, const int* __restrict__ block_task) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ TcWgradTask T;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        int lo = 0, hi = n_tasks - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (tasks[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    if (tid < (int)(sizeof(TcWgradTask) / 4)) {
+        int lo = 0;
+        if (block_task) {                        // direct block -> task table (one load instead of a binary search)
+            lo = __ldg(block_task + blockIdx.x);
+        } else {
+            int hi = n_tasks - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (tasks[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+            }
         }
-        T = tasks[lo];
+        reinterpret_cast<uint32_t*>(&T)[tid] = reinterpret_cast<const uint32_t*>(tasks + lo)[tid];
     }
     __syncthreads();
     // ---- decode: local = ((split * n_slab + slab) * tiles_n + tn) * n_grp + grp
@@ -344,7 +349,7 @@ bool Launch::wg2_ok(int H, int W, int Cin, int Cout, int k, int stride) {
 }
 
 // q_max: the launch's largest wg2_q() components (engine: max of the low and of the high halves)
-int Launch::wgrad_tc2(const TcWgradTask* tasks, int n, int tiles, int n_b, int q_max, void* st) {
+int Launch::wgrad_tc2(const TcWgradTask* tasks, int n, int tiles, int n_b, int q_max, void* st, const int* block_task) {
     if (n == 0 || tiles == 0) return 0;
     const int qx = q_max & 0xffff, qy = q_max >> 16;
     const size_t smem = w2_smem_bytes(qx, qy);
@@ -354,7 +359,7 @@ int Launch::wgrad_tc2(const TcWgradTask* tasks, int n, int tiles, int n_b, int q
         if (e != cudaSuccess) return (int)e;
         configured = smem;
     }
-    wgrad_tc2_kernel<<<tiles, W2_THREADS, smem, (cudaStream_t)st>>>(tasks, n, n_b, qx, qy);
+    wgrad_tc2_kernel<<<tiles, W2_THREADS, smem, (cudaStream_t)st>>>(tasks, n, n_b, qx, qy, block_task);
     return (int)cudaGetLastError();
 }
 
