@@ -62,6 +62,7 @@ struct TcWgradTask {
     int H, W, Cin, Ho, Wo, Cout, k, stride, pad;
     int splits, m_chunk;         // m_chunk multiple of 64
     int bn, tiles_k, tiles_n, tile_begin;
+    int n_full;                  // wgrad_tc2: samples of a full batch (n_b == n_full uses the first pair of tensor maps)
 };
 
 struct WtBf16Task {
@@ -215,7 +216,8 @@ struct Launch {
     // of ~log2(n_tasks) dependent global loads at the start of every CTA
     static int post_fwd(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream, const int* block_task = nullptr,
                         bool half = false);     // half: the launch's activations are stored in bf16 only
-    static int post_bwd_reduce(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream, const int* block_task = nullptr);
+    static int post_bwd_reduce(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream, const int* block_task = nullptr,
+                               bool half = false);
     static int bn_bwd_finalize(const PostTask* tasks, int n_tasks, int max_c, int n_b, void* stream);
     static int post_bwd_apply(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream, const int* block_task = nullptr,
                               bool half = false);
@@ -229,8 +231,9 @@ struct Launch {
     static int init(const InitTask* tasks, int n_tasks, int total_blocks, void* stream);
     static bool perm_ok(int n);      // the permutation fits the kernel's shared memory
     static int perm(const PermTask* tasks, int n_tasks, int epoch, int n, void* stream);
-    static int conv_tc(const TcConvTask* tasks, int n_tasks, int total_tiles, int n_b, int step, void* stream);
-    static int wgrad_tc(const TcWgradTask* tasks, int n_tasks, int total_tiles, int n_b, void* stream);
+    static int conv_tc(const TcConvTask* tasks, int n_tasks, int total_tiles, int n_b, int step, void* stream,
+                       const int* block_task = nullptr);
+    static int wgrad_tc(const TcWgradTask* tasks, int n_tasks, int total_tiles, int n_b, void* stream, const int* block_task = nullptr);
     static int wt_bf16(const WtBf16Task* tasks, int n_tasks, int total_blocks, void* stream);
     static int bn_stats(const StatTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
     // conv_tc2.cu: patch-resident tcgen05 convolution (stride 1); tiles = ceil(n_b*Hp*Wp / tc2_rows()) * tiles_n

@@ -110,17 +110,22 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcConvTask* __restrict__ tasks, int n_tasks,
-                                                                int n_b, int step) {
+                                                                int n_b, int step, const int* __restrict__ block_task) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ TcConvTask T;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        int lo = 0, hi = n_tasks - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (tasks[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    if (tid < (int)(sizeof(TcConvTask) / 4)) {
+        int lo = 0;
+        if (block_task) {                        // direct block -> task table (one load instead of a binary search)
+            lo = __ldg(block_task + blockIdx.x);
+        } else {
+            int hi = n_tasks - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (tasks[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+            }
         }
-        T = tasks[lo];
+        reinterpret_cast<uint32_t*>(&T)[tid] = reinterpret_cast<const uint32_t*>(tasks + lo)[tid];
     }
     __syncthreads();
     const int local = blockIdx.x - T.tile_begin;
@@ -330,17 +335,22 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
 // 128 bytes -- A: two 64-wide kk groups (UMMA M = 128), B: bn/64 co groups -- which is exactly the natural
 // [pixel][channel] order of the im2col row and of dy.  Split-M partials are written per split (deterministic).
 __global__ void __launch_bounds__(TC_THREADS, 2) wgrad_tc_kernel(const TcWgradTask* __restrict__ tasks, int n_tasks,
-                                                                 int n_b) {
+                                                                 int n_b, const int* __restrict__ block_task) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ TcWgradTask T;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        int lo = 0, hi = n_tasks - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (tasks[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    if (tid < (int)(sizeof(TcWgradTask) / 4)) {
+        int lo = 0;
+        if (block_task) {                        // direct block -> task table (one load instead of a binary search)
+            lo = __ldg(block_task + blockIdx.x);
+        } else {
+            int hi = n_tasks - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (tasks[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+            }
         }
-        T = tasks[lo];
+        reinterpret_cast<uint32_t*>(&T)[tid] = reinterpret_cast<const uint32_t*>(tasks + lo)[tid];
     }
     __syncthreads();
     int local = blockIdx.x - T.tile_begin;
@@ -531,9 +541,11 @@ __global__ void __launch_bounds__(256) wt_bf16_kernel(const WtBf16Task* __restri
     T.out[e] = __float2bfloat16_rn(v);
 }
 
-// per-64-row-tile column sums of y and y^2 (same [tile][2][C] layout the SIMT conv epilogue writes)
+// per-64-row-tile column sums of y and y^2 (same [tile][2][C] layout the SIMT conv epilogue writes).
+// bf16-only activations (the only caller today): a thread owns 8 consecutive channels of some rows of the tile (one 16-byte
+// load per row instead of one 2-byte load per element), row lanes are combined through shared memory in lane order.
 __global__ void __launch_bounds__(128) bn_stats_kernel(const StatTask* __restrict__ tasks, int n_tasks, int n_b) {
-    __shared__ float red[2][128];
+    __shared__ float red[2][128 * 8];
     int lo = 0, hi = n_tasks - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -545,6 +557,49 @@ __global__ void __launch_bounds__(128) bn_stats_kernel(const StatTask* __restric
     const long long r0 = (long long)tile * 64;
     if (r0 >= M) return;
     const long long r1 = r0 + 64 < M ? r0 + 64 : M;
+    if (T.yh && (T.C & 7) == 0) {
+        const int cgs = T.C >> 3;                         // 8-channel groups
+        const int per = cgs < 128 ? cgs : 128;            // groups handled per pass
+        const int lanes = 128 / per;
+        const int g_lane = threadIdx.x % per, p_lane = threadIdx.x / per;
+        for (int g0 = 0; g0 < cgs; g0 += per) {
+            const int c = (g0 + g_lane) * 8;
+            float s1[8], s2[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s1[q] = s2[q] = 0.f;
+            if (p_lane < lanes)
+                for (long long r = r0 + p_lane; r < r1; r += lanes) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(T.yh + r * T.C + c));
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float a = __uint_as_float(w[q] << 16), b = __uint_as_float(w[q] & 0xffff0000u);
+                        s1[2 * q] += a; s2[2 * q] = fmaf(a, a, s2[2 * q]);
+                        s1[2 * q + 1] += b; s2[2 * q + 1] = fmaf(b, b, s2[2 * q + 1]);
+                    }
+                }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                red[0][threadIdx.x * 8 + q] = s1[q];
+                red[1][threadIdx.x * 8 + q] = s2[q];
+            }
+            __syncthreads();
+            if (p_lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float a1 = 0.f, a2 = 0.f;
+                    for (int l = 0; l < lanes; ++l) {
+                        a1 += red[0][(l * per + g_lane) * 8 + q];
+                        a2 += red[1][(l * per + g_lane) * 8 + q];
+                    }
+                    T.part[((long long)tile * 2 + 0) * T.C + c + q] = a1;
+                    T.part[((long long)tile * 2 + 1) * T.C + c + q] = a2;
+                }
+            }
+            __syncthreads();
+        }
+        return;
+    }
     const int cb = T.C < 128 ? T.C : 128;
     const int lanes = 128 / cb;
     const int p_lane = threadIdx.x / cb, c_lane = threadIdx.x - p_lane * cb;
@@ -575,7 +630,7 @@ __global__ void __launch_bounds__(128) bn_stats_kernel(const StatTask* __restric
 
 }  // namespace
 
-int Launch::conv_tc(const TcConvTask* tasks, int n, int tiles, int n_b, int step, void* st) {
+int Launch::conv_tc(const TcConvTask* tasks, int n, int tiles, int n_b, int step, void* st, const int* block_task) {
     if (n == 0 || tiles == 0) return 0;
     static bool configured = false;
     if (!configured) {
@@ -583,10 +638,10 @@ int Launch::conv_tc(const TcConvTask* tasks, int n, int tiles, int n_b, int step
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    conv_tc_kernel<<<tiles, TC_THREADS, TC_SMEM, (cudaStream_t)st>>>(tasks, n, n_b, step);
+    conv_tc_kernel<<<tiles, TC_THREADS, TC_SMEM, (cudaStream_t)st>>>(tasks, n, n_b, step, block_task);
     return (int)cudaGetLastError();
 }
-int Launch::wgrad_tc(const TcWgradTask* tasks, int n, int tiles, int n_b, void* st) {
+int Launch::wgrad_tc(const TcWgradTask* tasks, int n, int tiles, int n_b, void* st, const int* block_task) {
     if (n == 0 || tiles == 0) return 0;
     static bool configured = false;
     if (!configured) {
@@ -594,7 +649,7 @@ int Launch::wgrad_tc(const TcWgradTask* tasks, int n, int tiles, int n_b, void* 
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    wgrad_tc_kernel<<<tiles, TC_THREADS, TC_SMEM, (cudaStream_t)st>>>(tasks, n, n_b);
+    wgrad_tc_kernel<<<tiles, TC_THREADS, TC_SMEM, (cudaStream_t)st>>>(tasks, n, n_b, block_task);
     return (int)cudaGetLastError();
 }
 int Launch::wt_bf16(const WtBf16Task* tasks, int n, int blocks, void* st) {

@@ -83,6 +83,12 @@ __device__ __forceinline__ void tma_load_row(void* dst, const void* tmap, int c,
         ::"r"(smem_u32(dst)), "l"(tmap), "r"(c), "r"(w), "r"(h), "r"(n), "r"(smem_u32(bar))
         : "memory");
 }
+// The tensor maps live in GLOBAL memory and are rewritten by the host between launches (new buffers per wave): the TMA unit
+// caches descriptors by address, so the issuing thread acquires the current contents before its first use -- without this
+// a launch could run with the previous wave's (freed) addresses.
+__device__ __forceinline__ void tmap_acquire(const void* tmap) {
+    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -206,6 +212,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
         // ================= patch loads: one 64-channel slab per buffer, one row box per padded image row =================
         if (tid == 0) {
             const uint32_t row_bytes = (uint32_t)Wp * 128u;
+            tmap_acquire(T.tmap);
             for (int sl = 0; sl < n_slab; ++sl) {
                 const int b = sl % pb;
                 mbar_wait(&pempty[b], (((uint32_t)(sl / pb)) & 1u) ^ 1u);

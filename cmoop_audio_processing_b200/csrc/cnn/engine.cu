@@ -94,6 +94,12 @@ inline void prof_end(cudaStream_t st) {
     if (!g_prof_on) return;
     cudaEventRecord(g_prof_recs.back().b, st);
 }
+// CMOOP_CNN_SYNC=1: synchronise after every grouped launch so that an asynchronous fault is reported with the launch that
+// caused it (development aid; compute-sanitizer is not available on the GPU pool)
+inline bool debug_sync() {
+    static const bool on = getenv("CMOOP_CNN_SYNC") != nullptr;
+    return on;
+}
 // call after the stream has been synchronised
 void prof_resolve() {
     for (ProfRec& r : g_prof_recs) {
@@ -688,6 +694,7 @@ struct Engine {
                         TcWgradTask g{};
                         g.xh = c.units[u.input].Vh; g.dyh = u.is_skip ? c.gSh : c.gBh; g.out = dst;
                         g.tmaps = u.tmaps;
+                        g.n_full = batch;
                         g.H = u.H; g.W = u.W; g.Cin = u.cin; g.Ho = u.Ho; g.Wo = u.Wo; g.Cout = u.cout;
                         g.k = u.k; g.stride = u.stride; g.pad = u.pad;
                         g.splits = u.wg_splits; g.m_chunk = u.wg_chunk;
@@ -830,6 +837,9 @@ struct Engine {
             fill_block_table(S.conv_tc2, [](const TcConvTask& t) { return t.tile_begin; });
             fill_block_table(S.dgrad_tc2, [](const TcConvTask& t) { return t.tile_begin; });
             fill_block_table(S.wgrad_tc2, [](const TcWgradTask& t) { return t.tile_begin; });
+            fill_block_table(S.conv_tc, [](const TcConvTask& t) { return t.tile_begin; });
+            fill_block_table(S.dgrad_tc, [](const TcConvTask& t) { return t.tile_begin; });
+            fill_block_table(S.wgrad_tc, [](const TcWgradTask& t) { return t.tile_begin; });
             // (the elementwise post kernels keep the shared binary search: a direct table measured slower there)
         }
         // ---- one blob upload, then fix the device pointers
@@ -876,6 +886,7 @@ struct Engine {
         int _e = (expr);                                                                           \
         prof_end(stream);                                                                          \
         cmoop::count_launch();                                                                     \
+        if (_e == 0 && debug_sync()) _e = (int)cudaStreamSynchronize(stream);  /* CMOOP_CNN_SYNC=1 */ \
         if (_e != 0) {                                                                             \
             cmoop::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString((cudaError_t)_e)); \
             return CMOOP_ERR_CUDA;                                                                 \
@@ -909,7 +920,7 @@ struct Engine {
             }
             if (!S.conv_tc.h.empty())
                 CNN_LAUNCH_N("conv_tc.fwd", S.f_fwd1 * n_b,
-                             Launch::conv_tc(S.conv_tc.d, (int)S.conv_tc.h.size(), S.conv_tc.total, n_b, step, stream));
+                             Launch::conv_tc(S.conv_tc.d, (int)S.conv_tc.h.size(), S.conv_tc.total, n_b, step, stream, S.conv_tc.d_bt));
             if (!S.conv_tc2.h.empty())
                 CNN_LAUNCH_N("conv_tc2.fwd", S.f_fwd2 * n_b,
                              Launch::conv_tc2(S.conv_tc2.d, (int)S.conv_tc2.h.size(), S.conv_tc2.total, n_b, step, S.q_max,
@@ -941,7 +952,8 @@ struct Engine {
                 CNN_LAUNCH(Launch::drop_bwd(S.drop_bwd.d, (int)S.drop_bwd.h.size(), S.drop_bwd.total, n_b, global_step,
                                             cfg.dropout_rate, stream));
             if (!S.post_bn.h.empty()) {
-                CNN_LAUNCH(Launch::post_bwd_reduce(S.post_bn.d, (int)S.post_bn.h.size(), S.post_bn.total, n_b, stream));
+                CNN_LAUNCH(Launch::post_bwd_reduce(S.post_bn.d, (int)S.post_bn.h.size(), S.post_bn.total, n_b, stream, nullptr,
+                                                   cfg.precision == 1));
                 CNN_LAUNCH(Launch::bn_bwd_finalize(S.post_bn.d, (int)S.post_bn.h.size(), S.max_bn_c, n_b, stream));
             }
             if (!S.post_bwd.h.empty())
@@ -958,7 +970,7 @@ struct Engine {
             }
             if (!S.wgrad_tc.h.empty())
                 CNN_LAUNCH_N("wgrad_tc", S.f_wg * n_b,
-                             Launch::wgrad_tc(S.wgrad_tc.d, (int)S.wgrad_tc.h.size(), S.wgrad_tc.total, n_b, stream));
+                             Launch::wgrad_tc(S.wgrad_tc.d, (int)S.wgrad_tc.h.size(), S.wgrad_tc.total, n_b, stream, S.wgrad_tc.d_bt));
             if (!S.wgrad_tc2.h.empty())
                 CNN_LAUNCH_N("wgrad_tc2", S.f_wg * n_b,
                              Launch::wgrad_tc2(S.wgrad_tc2.d, (int)S.wgrad_tc2.h.size(), S.wgrad_tc2.total, n_b, S.wg2_q, stream,
@@ -970,7 +982,7 @@ struct Engine {
                              Launch::conv(S.dgrad.d, (int)S.dgrad.h.size(), S.dgrad.total, n_b, 0, stream));
             if (!S.dgrad_tc.h.empty())
                 CNN_LAUNCH_N("conv_tc.dgrad", S.f_dg1 * n_b,
-                             Launch::conv_tc(S.dgrad_tc.d, (int)S.dgrad_tc.h.size(), S.dgrad_tc.total, n_b, 0, stream));
+                             Launch::conv_tc(S.dgrad_tc.d, (int)S.dgrad_tc.h.size(), S.dgrad_tc.total, n_b, 0, stream, S.dgrad_tc.d_bt));
             if (!S.dgrad_tc2.h.empty())
                 CNN_LAUNCH_N("conv_tc2.dgrad", S.f_dg2 * n_b,
                              Launch::conv_tc2(S.dgrad_tc2.d, (int)S.dgrad_tc2.h.size(), S.dgrad_tc2.total, n_b, 0, S.q_max,
@@ -1292,7 +1304,8 @@ int run_wave(Engine& eng, Wave& wv, double* out, double* history, int debug_step
             // make_permutation / cmoop_cnn_debug_permutation); a training split too large for the kernel's shared memory
             // falls back to host-generated index arrays
             cudaStream_t stream = st;
-            if (Launch::perm_ok(data->n_train)) {
+            static const bool host_perm = getenv("CMOOP_CNN_HOST_PERM") != nullptr;     // A/B switch: host-generated shuffles
+            if (!host_perm && Launch::perm_ok(data->n_train)) {
                 CNN_LAUNCH(Launch::perm(wv.perm.d, (int)wv.perm.h.size(), epoch, data->n_train, st));
             } else {
                 int n_active = 0;
@@ -1499,6 +1512,11 @@ int run_population(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotype
             cands[i].acc = wv.d_acc + (size_t)(i - next) * 12;
             cands[i].confusion = wv.d_cm + (size_t)(i - next) * cm_elems;
             wv.cands.push_back(&cands[i]);
+        }
+        if (a.off > a.cap) {
+            cmoop::set_error("cnn: arena overflow placing candidates [%d,%d): laid out %zu bytes, sized %zu, capacity %zu", next, end,
+                             a.off, need, a.cap);
+            return CMOOP_ERR_CUDA;
         }
         rc = run_wave(eng, wv, out, history, debug_steps, dbg_losses, dbg_grads, dbg_params);
         if (rc != CMOOP_OK) break;
@@ -1743,6 +1761,7 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
         char* d_tm = (char*)d_task + 512;
         CMOOP_CUDA_OK(cmoop::copy_async(d_tm, tm, sizeof(tm), cudaMemcpyHostToDevice, st));
         g.tmaps = d_tm;
+        g.n_full = n;
         CMOOP_CUDA_OK(cmoop::copy_async(d_task, &g, sizeof(g), cudaMemcpyHostToDevice, st));
         CMOOP_CUDA_OK(cudaStreamSynchronize(st));
         rc = Launch::wgrad_tc2((const TcWgradTask*)d_task, 1, splits * Launch::wg2_items(Cin, Cout, k), n, Launch::wg2_q(W, k), st);

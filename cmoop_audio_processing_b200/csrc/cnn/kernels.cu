@@ -581,6 +581,7 @@ __global__ void __launch_bounds__(256, 2) post_fwd_kernel(const PostTask* __rest
 
 // BN backward, pass 1: per-channel partial sums of g and g*xhat over the unit's output elements.
 // A CTA covers 128 output pixels; thread = (pixel lane, 4 channels); one partial row per (CTA, pixel lane).
+template <bool HALF>
 __global__ void __launch_bounds__(128) post_bwd_reduce_kernel(const PostTask* __restrict__ tasks, int n_tasks,
                                                               int n_b, const int* __restrict__ block_task) {
     const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin_bwd; }, block_task);
@@ -606,7 +607,7 @@ __global__ void __launch_bounds__(128) post_bwd_reduce_kernel(const PostTask* __
             float g[4] = {gv.x, gv.y, gv.z, gv.w};
             if (T.add_skip) {
                 float vv[4];
-                load4(T.v, T.vh, e, vv);
+                if constexpr (HALF) load4(nullptr, T.vh, e, vv); else load4(T.v, nullptr, e, vv);
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     if (!(vv[q] > 0.f)) g[q] = 0.f;
@@ -620,9 +621,10 @@ __global__ void __launch_bounds__(128) post_bwd_reduce_kernel(const PostTask* __
                 const long long base = (((long long)n * T.H + 2 * ho) * T.W + 2 * wo) * T.C + c;
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    u[q] = load1(T.u, T.uh, base + ((long long)(code[q] >> 1) * T.W + (code[q] & 1)) * T.C + q);
+                    u[q] = HALF ? __bfloat162float(T.uh[base + ((long long)(code[q] >> 1) * T.W + (code[q] & 1)) * T.C + q])
+                                : T.u[base + ((long long)(code[q] >> 1) * T.W + (code[q] & 1)) * T.C + q];
             } else {
-                load4(T.u, T.uh, e, u);
+                if constexpr (HALF) load4(nullptr, T.uh, e, u); else load4(T.u, nullptr, e, u);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -1033,9 +1035,12 @@ int Launch::post_fwd(const PostTask* tasks, int n, int blocks, int n_b, void* st
         post_fwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b, bt);
     return check();
 }
-int Launch::post_bwd_reduce(const PostTask* tasks, int n, int blocks, int n_b, void* st, const int* bt) {
+int Launch::post_bwd_reduce(const PostTask* tasks, int n, int blocks, int n_b, void* st, const int* bt, bool half) {
     if (n == 0 || blocks == 0) return 0;
-    post_bwd_reduce_kernel<<<blocks, 128, 0, (cudaStream_t)st>>>(tasks, n, n_b, bt);
+    if (half)
+        post_bwd_reduce_kernel<true><<<blocks, 128, 0, (cudaStream_t)st>>>(tasks, n, n_b, bt);
+    else
+        post_bwd_reduce_kernel<false><<<blocks, 128, 0, (cudaStream_t)st>>>(tasks, n, n_b, bt);
     return check();
 }
 int Launch::bn_bwd_finalize(const PostTask* tasks, int n, int max_c, int n_b, void* st) {

@@ -71,6 +71,12 @@ __device__ __forceinline__ void tma_load_row(void* dst, const void* tmap, int c,
         ::"r"(smem_u32(dst)), "l"(tmap), "r"(c), "r"(w), "r"(h), "r"(n), "r"(smem_u32(bar))
         : "memory");
 }
+// The tensor maps live in GLOBAL memory and are rewritten by the host between launches (new buffers per wave): the TMA unit
+// caches descriptors by address, so the issuing thread acquires the current contents before its first use -- without this
+// a launch could run with the previous wave's (freed) addresses.
+__device__ __forceinline__ void tmap_acquire(const void* tmap) {
+    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
+}
 __device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -268,9 +274,11 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wgrad_tc2_kernel(const TcWgradT
     } else {
         // ================= TMA issuer: the padded image rows of the X patch and of the dY tile =================
         if (lane == 0) {
-            const char* maps = reinterpret_cast<const char*>(T.tmaps) + (n_b == kBatch ? 0 : 2 * kTmapBytes);
+            const char* maps = reinterpret_cast<const char*>(T.tmaps) + (n_b == T.n_full ? 0 : 2 * kTmapBytes);
             const void* tm_x = maps;
             const void* tm_y = maps + kTmapBytes;
+            tmap_acquire(tm_x);
+            tmap_acquire(tm_y);
             for (int c = 0; c < n_chunks; ++c) {
                 const int buf = c % W2_ST;
                 const int q0 = (chunk_begin + c) * W2_QC;

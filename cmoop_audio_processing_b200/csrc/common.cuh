@@ -19,9 +19,16 @@ inline cudaError_t copy_async(void* dst, const void* src, size_t bytes, cudaMemc
     count_copy(bytes, kind);
     return cudaMemcpyAsync(dst, src, bytes, kind, st);
 }
+// cudaMemcpy from PAGEABLE host memory returns once the source has been staged -- "the DMA to final destination may not
+// have completed" (CUDA runtime API, memcpy semantics).  Work on the legacy stream is ordered behind it, but this library
+// launches on a NON-BLOCKING stream that does not synchronise with the legacy stream: a kernel launched right after such a
+// copy read half-written task records (flaky illegal addresses, found with tools/calibrate_cost.py).  Host-to-device
+// copies therefore wait for the legacy stream before returning.
 inline cudaError_t copy_sync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
     count_copy(bytes, kind);
-    return cudaMemcpy(dst, src, bytes, kind);
+    cudaError_t e = cudaMemcpy(dst, src, bytes, kind);
+    if (e == cudaSuccess && kind == cudaMemcpyHostToDevice) e = cudaStreamSynchronize(cudaStreamLegacy);
+    return e;
 }
 
 // Grow-only device/pinned scratch owned by the library (one per slot).

@@ -285,9 +285,10 @@ class FitnessProblem:
         if dist is None or not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
             out, _ = self.train_eval(hparams_list, seeds)
             return out
-        from .dist import assign_lpt
+        from .dist import assign_lpt, candidate_cost
         world, rank = dist.get_world_size(), dist.get_rank()
-        cost = [forward_macs(hp, self.data.height, self.data.width, self.classes, self.config.variant)
+        # measured per-genotype device time (dist.py), not forward MACs: MACs over-weight wide candidates ~10x
+        cost = [candidate_cost(hp, self.data.height, self.data.width, self.classes, self.config.variant)
                 for hp in hparams_list]
         owner = assign_lpt(cost, world)
         mine = [i for i in range(p) if owner[i] == rank]

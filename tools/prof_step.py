@@ -23,6 +23,11 @@ xv = rng.standard_normal((768, 49, 40, 1)).astype(np.float32)
 yv = rng.integers(0, 12, 768)
 random.seed(0)
 hps = [{k: random.choice(v) for k, v in HPARAM_SPACE.items()} for _ in range(pop)]
+for spec in os.environ.get("PROF_FIX", "").split(","):          # e.g. PROF_FIX=filters=64,kernel_size=3: pin genes of every candidate
+    if "=" in spec:
+        key, val = spec.split("=")
+        for hp in hps:
+            hp[key] = type(HPARAM_SPACE[key][0])(int(val))
 prob = FitnessProblem(xt, yt, xv, yv, classes=12, config=TrainConfig(variant=variant, epochs=epochs, patience=epochs, precision=prec))
 prob.train_eval(hps, list(range(pop)))
 lib.cmoop_profile_enable(1)
