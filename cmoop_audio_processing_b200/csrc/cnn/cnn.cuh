@@ -261,6 +261,11 @@ struct Launch {
                          void* stream);
     static int stem_wgrad(const WgradTask* tasks, int n_tasks, int max_k, int W, int max_cout, int splits, int n_b, int step,
                           void* stream);
+    // stem_tc.cu: the same two operations on mma.sync (bf16 hi + lo operands) for precision bf16 -- tasks carry yh / dyh only
+    static bool stem_tc_ok(int H, int W, int Cout, int k);
+    static int stem_conv_tc(const ConvTask* tasks, int n_tasks, int max_k, int W, long long M, int n_b, int step, void* stream);
+    static int stem_wgrad_tc(const WgradTask* tasks, int n_tasks, int max_k, int W, int max_cout, int splits, int n_b, int step,
+                             void* stream);
 };
 
 }  // namespace cmoop_cnn

@@ -451,6 +451,7 @@ struct StageLists {
     // stem.cu path: every task of conv / conv_eval / wgrad is an eligible Cin = 1 convolution
     bool stem = true;
     int stem_k = 0, stem_w = 0, stem_cout = 0, stem_splits = 0;
+    bool stem_tc = true;             // ... and all of them go through the mma.sync kernels of stem_tc.cu (precision bf16)
     bool any = false;
     int max_bn_c = 0;                // widest BN unit of the stage (grid.y of the finalize kernels)
     DevList<PostTask> post_fwd, post_bn, post_bwd;
@@ -608,6 +609,10 @@ struct Engine {
                     if (u.stem && (S.stem_w == 0 || (S.stem_w == u.W && S.stem_splits == u.wg_splits))) {
                         S.stem_k = std::max(S.stem_k, u.k); S.stem_w = u.W; S.stem_cout = std::max(S.stem_cout, u.cout);
                         S.stem_splits = u.wg_splits;
+                        // CMOOP_CNN_NO_STEM_TC=1: A/B switch back to the fp32 SIMT stem kernels
+                        static const bool no_stem_tc = getenv("CMOOP_CNN_NO_STEM_TC") != nullptr;
+                        if (no_stem_tc || cfg.precision != 1 || t.y || !t.yh || !Launch::stem_tc_ok(u.H, u.W, u.cout, u.k))
+                            S.stem_tc = false;
                     } else {
                         S.stem = false;
                     }
@@ -830,7 +835,7 @@ struct Engine {
             ad.p = c.p; ad.g = c.grad; ad.m = c.m; ad.v = c.v; ad.n = (int)c.n_params;
             ad.block_begin = wv.adam.total;
             wv.adam.h.push_back(ad);
-            wv.adam.total += blocks_for(c.n_params);
+            wv.adam.total += (int)((c.n_params + 1023) / 1024);      // adam_kernel: 1 024 parameters per block
         }
         for (int s = 0; s < N_STAGES; ++s) {
             StageLists& S = wv.st[s];
@@ -910,7 +915,11 @@ struct Engine {
             if (!S.any) continue;
             DevList<ConvTask>& cl = (s == 0 && !training) ? S.conv_eval : S.conv;
             if (!cl.h.empty()) {
-                if (S.stem && S.stem_w > 0)
+                if (S.stem && S.stem_w > 0 && S.stem_tc)
+                    CNN_LAUNCH_N("stem_conv", S.f_simt * n_b,
+                                 Launch::stem_conv_tc(cl.d, (int)cl.h.size(), S.stem_k, S.stem_w,
+                                                      (long long)n_b * cl.h[0].H * cl.h[0].W, n_b, step, stream));
+                else if (S.stem && S.stem_w > 0)
                     CNN_LAUNCH_N("stem_conv", S.f_simt * n_b,
                                  Launch::stem_conv(cl.d, (int)cl.h.size(), S.stem_k, S.stem_w, S.stem_cout,
                                                    (long long)n_b * cl.h[0].H * cl.h[0].W, n_b, step, stream));
@@ -960,7 +969,11 @@ struct Engine {
                 CNN_LAUNCH(Launch::post_bwd_apply(S.post_bwd.d, (int)S.post_bwd.h.size(), S.post_bwd.total, n_b, stream, nullptr,
                                                   cfg.precision == 1));
             if (!S.wgrad.h.empty()) {
-                if (S.stem && S.stem_w > 0)
+                if (S.stem && S.stem_w > 0 && S.stem_tc)
+                    CNN_LAUNCH_N("stem_wgrad", S.f_simt_wg * n_b,
+                                 Launch::stem_wgrad_tc(S.wgrad.d, (int)S.wgrad.h.size(), S.stem_k, S.stem_w, S.stem_cout,
+                                                       S.stem_splits, n_b, step, stream));
+                else if (S.stem && S.stem_w > 0)
                     CNN_LAUNCH_N("stem_wgrad", S.f_simt_wg * n_b,
                                  Launch::stem_wgrad(S.wgrad.d, (int)S.wgrad.h.size(), S.stem_k, S.stem_w, S.stem_cout,
                                                     S.stem_splits, n_b, step, stream));
@@ -1598,6 +1611,8 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
                   "debug_conv: shape not eligible for the patch-resident tcgen05 kernel");
     CMOOP_REQUIRE(use_tc != 2 || (mode == 0 && Launch::stem_ok(H, W, Cin, Cout, k, stride, n)),
                   "debug_conv: shape not eligible for the stem (Cin = 1) kernel");
+    CMOOP_REQUIRE(use_tc != 4 || (mode == 0 && Launch::stem_ok(H, W, Cin, Cout, k, stride, n) && Launch::stem_tc_ok(H, W, Cout, k)),
+                  "debug_conv: shape not eligible for the mma.sync stem kernel");
     if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
     cudaStream_t st = cmoop::internal_stream();
     const int pad = stride == 1 ? (k - 1) / 2 : 0;
@@ -1648,7 +1663,45 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
         }
         t.tiles_n = (t.Cout + 63) / 64;
         CMOOP_CUDA_OK(cmoop::copy_async(d_task, &t, sizeof(t), cudaMemcpyHostToDevice, st));
-        if (rc == 0 && use_tc == 2)
+        if (rc == 0 && use_tc == 4) {
+            // bf16-only output, widened for the caller; the hook also checks the kernel's BN partial sums (64-row tiles of
+            // the STORED values) against fp64 sums of what it read back
+            __nv_bfloat16* d_yh = nullptr;
+            float* d_stat = nullptr;
+            const long long M = (long long)n * H * W;
+            const int tiles = (int)((M + 63) / 64);
+            CMOOP_CUDA_OK(cudaMalloc((void**)&d_yh, n_y * 2));
+            CMOOP_CUDA_OK(cudaMalloc((void**)&d_stat, (size_t)tiles * 2 * Cout * 4));
+            CMOOP_CUDA_OK(cudaMemsetAsync(d_stat, 0xff, (size_t)tiles * 2 * Cout * 4, st));
+            t.y = nullptr; t.yh = d_yh; t.stat_part = d_stat;
+            CMOOP_CUDA_OK(cmoop::copy_async(d_task, &t, sizeof(t), cudaMemcpyHostToDevice, st));
+            rc = Launch::stem_conv_tc((const ConvTask*)d_task, 1, k, W, M, n, 0, st);
+            std::vector<__nv_bfloat16> yh((size_t)n_y);
+            std::vector<float> stat((size_t)tiles * 2 * Cout), yf((size_t)n_y);
+            cudaError_t e2 = cudaStreamSynchronize(st);
+            if (rc == 0 && e2 == cudaSuccess) e2 = cmoop::copy_sync(yh.data(), d_yh, n_y * 2, cudaMemcpyDeviceToHost);
+            if (rc == 0 && e2 == cudaSuccess) e2 = cmoop::copy_sync(stat.data(), d_stat, stat.size() * 4, cudaMemcpyDeviceToHost);
+            cudaFree(d_yh); cudaFree(d_stat);
+            if (rc == 0 && e2 != cudaSuccess) rc = (int)e2;
+            for (long long i = 0; i < n_y; ++i) yf[i] = __bfloat162float(yh[i]);
+            for (int tl = 0; rc == 0 && tl < tiles; ++tl)
+                for (int c = 0; c < Cout; ++c) {
+                    double a1 = 0, a2 = 0;
+                    for (long long m = 64LL * tl; m < std::min<long long>(M, 64LL * tl + 64); ++m) {
+                        const double v = yf[m * Cout + c];
+                        a1 += v; a2 += v * v;
+                    }
+                    const double g1 = stat[(size_t)tl * 2 * Cout + c], g2 = stat[(size_t)tl * 2 * Cout + Cout + c];
+                    if (!(fabs(g1 - a1) <= 1e-4 * (fabs(a1) + 64.0) && fabs(g2 - a2) <= 1e-4 * (a2 + 64.0))) {
+                        cmoop::set_error("debug_conv: stem BN partial sums differ (tile %d channel %d: %g vs %g, %g vs %g)", tl, c,
+                                         g1, a1, g2, a2);
+                        cudaFree(d_in); cudaFree(d_w); cudaFree(d_out); cudaFree(d_wt); cudaFree(d_wb); cudaFree(d_task); cudaFree(d_inh);
+                        return CMOOP_ERR_CUDA;
+                    }
+                }
+            if (rc == 0) CMOOP_CUDA_OK(cmoop::copy_async(d_out, yf.data(), n_y * 4, cudaMemcpyHostToDevice, st));
+            CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+        } else if (rc == 0 && use_tc == 2)
             rc = Launch::stem_conv((const ConvTask*)d_task, 1, k, W, Cout, (long long)n * H * W, n, 0, st);
         else if (rc == 0)
             rc = Launch::conv((const ConvTask*)d_task, 1, tiles_m64 * t.tiles_n, n, 0, st);
@@ -1708,8 +1761,9 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
                   "debug_wgrad: unsupported shape");
     CMOOP_REQUIRE(use_tc != 1 || (Cin % 16 == 0 && Cout % 16 == 0), "debug_wgrad: tensor-core path needs Cin, Cout multiples of 16");
     CMOOP_REQUIRE(use_tc != 3 || Launch::wg2_ok(H, W, Cin, Cout, k, stride), "debug_wgrad: shape not eligible for wgrad_tc2");
-    CMOOP_REQUIRE(use_tc != 2 || Launch::stem_ok(H, W, Cin, Cout, k, stride, n),
+    CMOOP_REQUIRE((use_tc != 2 && use_tc != 4) || Launch::stem_ok(H, W, Cin, Cout, k, stride, n),
                   "debug_wgrad: shape not eligible for the stem (Cin = 1) kernel");
+    CMOOP_REQUIRE(use_tc != 4 || Launch::stem_tc_ok(H, W, Cout, k), "debug_wgrad: shape not eligible for the mma.sync stem kernel");
     if (!cmoop::ensure_device()) return CMOOP_ERR_CUDA;
     cudaStream_t st = cmoop::internal_stream();
     const int pad = stride == 1 ? (k - 1) / 2 : 0;
@@ -1721,7 +1775,7 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
     const int gran = use_tc ? 64 : 16;
     int chunk = (int)((M + splits - 1) / splits);
     chunk = (chunk + gran - 1) / gran * gran;
-    if (use_tc == 2) {                                   // the stem kernel fixes the split size
+    if (use_tc == 2 || use_tc == 4) {                                   // the stem kernel fixes the split size
         chunk = kStemRows;
         splits = (int)((M + chunk - 1) / chunk);
     }
@@ -1777,8 +1831,10 @@ int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, in
         g.x = d_x; g.dy = d_y; g.out = d_ws; g.H = H; g.W = W; g.Cin = Cin; g.Ho = Ho; g.Wo = Wo; g.Cout = Cout;
         g.k = k; g.stride = stride; g.pad = pad; g.splits = splits; g.m_chunk = chunk;
         g.tiles_k = (kext + 63) / 64; g.tiles_n = (Cout + 63) / 64;
+        if (use_tc == 4) { g.dy = nullptr; g.dyh = d_yh; }   // bf16-only output gradient (precision bf16)
         CMOOP_CUDA_OK(cmoop::copy_async(d_task, &g, sizeof(g), cudaMemcpyHostToDevice, st));
-        rc = use_tc == 2 ? Launch::stem_wgrad((const WgradTask*)d_task, 1, k, W, Cout, splits, n, 0, st)
+        rc = use_tc == 4 ? Launch::stem_wgrad_tc((const WgradTask*)d_task, 1, k, W, Cout, splits, n, 0, st)
+           : use_tc == 2 ? Launch::stem_wgrad((const WgradTask*)d_task, 1, k, W, Cout, splits, n, 0, st)
                          : Launch::wgrad((const WgradTask*)d_task, 1, g.tiles_k * g.tiles_n * splits, n, 0, st);
     }
     cmoop::count_launch();

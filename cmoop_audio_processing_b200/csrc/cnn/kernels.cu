@@ -947,18 +947,40 @@ __global__ void __launch_bounds__(256) confusion_kernel(const int* __restrict__ 
     }
 }
 
+// 1 024 parameters per block: four consecutive elements per thread as 16-byte accesses when the candidate's four flat
+// buffers are 16-byte aligned (they are: engine.cu takes them from a 256-byte-aligned arena), scalar otherwise / on the tail
 __global__ void __launch_bounds__(256) adam_kernel(const AdamTask* __restrict__ tasks, int n_tasks, float alpha, float b1,
                                                    float b2, float eps) {
     const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const AdamTask& r) { return r.block_begin; });
     const AdamTask T = tasks[t];
-    const int i = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
+    const int i = ((blockIdx.x - T.block_begin) * 256 + threadIdx.x) * 4;
     if (i >= T.n) return;
-    const float g = T.g[i];
-    const float m = b1 * T.m[i] + (1.f - b1) * g;
-    const float v = b2 * T.v[i] + (1.f - b2) * g * g;
-    T.m[i] = m;
-    T.v[i] = v;
-    T.p[i] -= alpha * m / (sqrtf(v) + eps);
+    auto upd = [&](float g, float& m, float& v, float& p) {
+        m = b1 * m + (1.f - b1) * g;
+        v = b2 * v + (1.f - b2) * g * g;
+        p -= alpha * m / (sqrtf(v) + eps);
+    };
+    const bool aligned = ((reinterpret_cast<uintptr_t>(T.p) | reinterpret_cast<uintptr_t>(T.g) | reinterpret_cast<uintptr_t>(T.m) |
+                           reinterpret_cast<uintptr_t>(T.v)) & 15) == 0;
+    if (aligned && i + 3 < T.n) {
+        const float4 g = *reinterpret_cast<const float4*>(T.g + i);
+        float4 m = *reinterpret_cast<float4*>(T.m + i), v = *reinterpret_cast<float4*>(T.v + i), p = *reinterpret_cast<float4*>(T.p + i);
+        upd(g.x, m.x, v.x, p.x);
+        upd(g.y, m.y, v.y, p.y);
+        upd(g.z, m.z, v.z, p.z);
+        upd(g.w, m.w, v.w, p.w);
+        *reinterpret_cast<float4*>(T.m + i) = m;
+        *reinterpret_cast<float4*>(T.v + i) = v;
+        *reinterpret_cast<float4*>(T.p + i) = p;
+    } else {
+        for (int j = i; j < min(i + 4, T.n); ++j) {
+            float m = T.m[j], v = T.v[j], p = T.p[j];
+            upd(T.g[j], m, v, p);
+            T.m[j] = m;
+            T.v[j] = v;
+            T.p[j] = p;
+        }
+    }
 }
 
 // Per-epoch shuffle on the device: the harness-imposed "Keras shuffle" is a Fisher-Yates walk driven by the fmix32 counter

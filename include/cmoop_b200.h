@@ -271,14 +271,17 @@ int cmoop_cnn_debug_train_steps(cmoop_cnn_dataset_handle data, const cmoop_genot
                                 float* params_out);
 
 /* one convolution through a chosen kernel; host pointers.  use_tc: 0 = generic fp32 SIMT, 1 = tcgen05 with im2col staging
- * (conv_tc.cu), 2 = dedicated Cin = 1 stem kernel (stem.cu, mode 0 only), 3 = patch-resident tcgen05 (conv_tc2.cu, stride 1).
+ * (conv_tc.cu), 2 = dedicated Cin = 1 stem kernel (stem.cu, mode 0 only), 3 = patch-resident tcgen05 (conv_tc2.cu, stride 1),
+ * 4 = mma.sync Cin = 1 stem kernel of precision bf16 (stem_tc.cu; the output is the bf16-stored one, widened; the hook also
+ * verifies the kernel's BN partial sums).
  * mode 0: out[n][Ho][Wo][Cout] = conv(in[n][H][W][Cin], w[k][k][Cin][Cout]) + bias (optional ReLU)
  * mode 1: out[n][H][W][Cin] = data gradient of that convolution for in = dy[n][Ho][Wo][Cout] */
 int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, const float* bias, int n, int H,
                          int W, int Cin, int Cout, int k, int stride, int relu, float* out);
 
 /* weight (+ bias, last row) gradient out[k*k*Cin + 1][Cout] of one convolution; `splits` deterministic split-M partials
- * (use_tc as above; 2 and 3 choose their own split geometry: stem_wgrad_kernel / wgrad_tc2_kernel) */
+ * (use_tc as above; 2, 3 and 4 choose their own split geometry: stem_wgrad_kernel / wgrad_tc2_kernel / stem_wgrad_tc_kernel;
+ * 4 reads dy rounded to bf16) */
 int cmoop_cnn_debug_wgrad(int use_tc, const float* x, const float* dy, int n, int H, int W, int Cin, int Cout, int k,
                           int stride, int splits, float* out);
 

@@ -142,6 +142,44 @@ def test_stem_kernels(n, H, W, Cout, k):
     np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-5 * np.abs(want).max())
 
 
+STEM_TC_CASES = [c for c in STEM_CASES if c[3] <= 64] + [
+    (64, 49, 40, 32, 3),
+    (64, 49, 40, 16, 5),
+    (13, 49, 40, 64, 5),       # 13 * 1960 pixels: last block and last BN tile partial
+    (2, 128, 313, 64, 5),      # odd width: zero pad column in the weight gradient's pixel pairs
+]
+
+
+@pytest.mark.parametrize("n,H,W,Cout,k", STEM_TC_CASES)
+def test_stem_tensor_core_kernels(n, H, W, Cout, k):
+    """stem_tc.cu (use_tc = 4, precision bf16): mma.sync on bf16 hi + lo operands.  The arithmetic is fp32-grade, the only
+    bf16 rounding is the STORED output (forward) / the stored output gradient (weight gradient), so the forward must be the
+    fp64 result rounded to bf16 (one-ulp slack where the fp32-grade sum sits on a rounding boundary) and the weight gradient
+    the fp64 one of the bf16-rounded dy and the UNROUNDED x.  The hook also verifies the fused BN partial sums."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(n + H + W + Cout + k)
+    x = rng.standard_normal((n, H, W, 1)).astype(np.float32)
+    w = (rng.standard_normal((k, k, 1, Cout)) / k).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    pad = (k - 1) // 2
+    full = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2).double(), torch.from_numpy(w).permute(3, 2, 0, 1).double(),
+                    torch.from_numpy(b).double(), padding=pad).permute(0, 2, 3, 1).numpy()
+    for relu in (0, 1):
+        want = np.maximum(full, 0) if relu else full
+        got = run_conv(0, 4, x, w, b, n, H, W, 1, Cout, k, 1, relu)
+        assert np.array_equal(got, bf16_round(got))                                  # stored values are bf16
+        np.testing.assert_allclose(got, want, rtol=2.0 ** -8, atol=2e-4)             # half a bf16 ulp + the hi/lo split error (2^-16 of the term magnitudes)
+        assert (got == bf16_round(want.astype(np.float32))).mean() > 0.98
+    dy = rng.standard_normal((n, H, W, Cout)).astype(np.float32)
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2).double()
+    yt = torch.from_numpy(bf16_round(dy)).permute(0, 3, 1, 2).double()
+    gw = torch.nn.grad.conv2d_weight(xt, (Cout, 1, k, k), yt, padding=pad)
+    want = np.concatenate([gw.permute(2, 3, 1, 0).reshape(k * k, Cout).numpy(), yt.sum(dim=(0, 2, 3)).numpy()[None]])
+    got = run_wgrad(4, x, dy, n, H, W, 1, Cout, k, 1, 1)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=5e-5 * np.abs(want).max())
+
+
 PATCH_CASES = [c for c in CASES if c[6] == 1] + [
     (64, 25, 20, 16, 32, 3, 1),      # first residual conv of the smallest genotype: one sub-slab, nine taps
     (64, 13, 10, 128, 256, 5, 1),    # deep block: 8 sub-slabs x 25 taps, two N tiles
