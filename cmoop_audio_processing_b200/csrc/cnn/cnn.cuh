@@ -143,7 +143,9 @@ struct HeadTask {
     float* gap;            // [n,C]
     const float* dgap;     // [n,C]
     float* dv;             // [n,Hf,Wf,C]
-    int Hf, Wf, C, block_begin;
+    int Hf, Wf, C;
+    int block_begin;       // gap_bwd grid: one thread per 4 consecutive elements of dv
+    int block_begin_fwd;   // gap_fwd grid: one thread per 4 consecutive channels of a sample
 };
 
 struct DropTask {          // dense ReLU output u -> v = u*keep/(1-rate); backward dz = dv*keep/(1-rate)*(u>0)
@@ -221,6 +223,7 @@ struct Launch {
     static int bn_bwd_finalize(const PostTask* tasks, int n_tasks, int max_c, int n_b, void* stream);
     static int post_bwd_apply(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream, const int* block_task = nullptr,
                               bool half = false);
+    static int gap_blocks(long long elems);                 // blocks of gap_fwd (elems = n*C) / gap_bwd (elems = n*Hf*Wf*C) for one task
     static int gap_fwd(const HeadTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
     static int gap_bwd(const HeadTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream);
     static int drop_fwd(const DropTask* tasks, int n_tasks, int total_blocks, int n_b, int step, int training, float rate, void* stream);
@@ -261,6 +264,12 @@ struct Launch {
                          void* stream);
     static int stem_wgrad(const WgradTask* tasks, int n_tasks, int max_k, int W, int max_cout, int splits, int n_b, int step,
                           void* stream);
+    // skip_tc.cu: the 1x1 / stride-2 skip projection (forward and data gradient) as a row-gathered mma.sync GEMM;
+    // tiles of a task = skip_tc_tiles_m(n_b * Ho * Wo) * skip_tc_tiles_n(Cout), TcConvTask.tiles_n = skip_tc_tiles_n(Cout)
+    static bool skip_tc_ok(const TcConvTask& t);
+    static int skip_tc_tiles_n(int Cout);
+    static int skip_tc_tiles_m(long long M);
+    static int skip_tc(const TcConvTask* tasks, int n_tasks, int total_tiles, int n_b, int step, int max_k, void* stream);
     // stem_tc.cu: the same two operations on mma.sync (bf16 hi + lo operands) for precision bf16 -- tasks carry yh / dyh only
     static bool stem_tc_ok(int H, int W, int Cout, int k);
     static int stem_conv_tc(const ConvTask* tasks, int n_tasks, int max_k, int W, long long M, int n_b, int step, void* stream);

@@ -67,7 +67,8 @@ int cmoop_cnn::Launch::make_row_tmap(void* out128, const void* dptr, int C, int 
 #include <string>
 namespace {
 struct ProfAgg { long long launches = 0; double ms = 0.0, flops = 0.0; };
-struct ProfRec { const char* name; cudaEvent_t a, b; double flops; };
+struct ProfRec { const char* name; cudaEvent_t a, b; double flops; int stage; };
+int g_prof_stage = -1;        // stage of the launches being recorded (CMOOP_PROF_STAGES=1 splits the table per stage)
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof_recs;
 std::vector<cudaEvent_t> g_prof_pool;
@@ -86,7 +87,7 @@ inline cudaEvent_t prof_event() {
 }
 inline void prof_begin(const char* name, double flops, cudaStream_t st) {
     if (!g_prof_on) return;
-    ProfRec r{name, prof_event(), prof_event(), flops};
+    ProfRec r{name, prof_event(), prof_event(), flops, g_prof_stage};
     cudaEventRecord(r.a, st);
     g_prof_recs.push_back(r);
 }
@@ -109,6 +110,8 @@ void prof_resolve() {
             const size_t cut = key.find('(');
             if (cut != std::string::npos) key.resize(cut);
             if (key.rfind("Launch::", 0) == 0) key = key.substr(8);
+            static const bool per_stage = getenv("CMOOP_PROF_STAGES") != nullptr;
+            if (per_stage && r.stage >= 0) key += "@" + std::to_string(r.stage);
             ProfAgg& a = g_prof_table[key];
             a.launches += 1;
             a.ms += ms;
@@ -439,9 +442,18 @@ void fill_block_table(DevList<T>& l, F begin_of) {
     }
 }
 
+// CMOOP_CNN_NO_SKIP_TC=1: A/B switch back to the tcgen05 kernel (conv_tc.cu) for the 1x1 / stride-2 projections
+inline bool use_skip_tc() {
+    static const bool off = getenv("CMOOP_CNN_NO_SKIP_TC") != nullptr;
+    return !off;
+}
+
 struct StageLists {
     DevList<ConvTask> conv, conv_eval, dgrad;
     DevList<TcConvTask> conv_tc, dgrad_tc, conv_tc2, dgrad_tc2;
+    DevList<TcConvTask> skip_fwd, skip_dg;       // 1x1 / stride-2 projections on skip_tc.cu (mma.sync)
+    int skip_k = 0, skip_k_d = 0;               // largest GEMM K of those lists (shared-memory size)
+    double f_skip = 0, f_skip_d = 0;
     int q_max = 0, tc2_cin = 0, tc2_cin_d = 0;   // largest patch; most GEMM input channels of the conv_tc2 / dgrad_tc2 tasks
     // algorithmic flop per SAMPLE of the stage's tensor-core launches (2*Ho*Wo*K*Cout summed over tasks; profiler only)
     double f_fwd2 = 0, f_fwd1 = 0, f_dg2 = 0, f_dg1 = 0, f_wg = 0, f_simt = 0, f_simt_dg = 0, f_simt_wg = 0;
@@ -464,6 +476,7 @@ struct Wave {
     std::vector<Cand*> cands;
     StageLists st[N_STAGES];
     DevList<HeadTask> head;
+    int head_fwd_total = 0;          // grid of gap_fwd (head.total is gap_bwd's)
     DevList<CeTask> ce_train, ce_val, ce_pred;
     DevList<AdamTask> adam;
     DevList<WtTask> wt;
@@ -532,6 +545,7 @@ struct Engine {
     int build_lists(Wave& wv) {
         for (int s = 0; s < N_STAGES; ++s) wv.st[s] = StageLists();
         wv.head = DevList<HeadTask>();
+        wv.head_fwd_total = 0;
         wv.ce_train = wv.ce_val = wv.ce_pred = DevList<CeTask>();
         wv.adam = DevList<AdamTask>();
         wv.wt = DevList<WtTask>();
@@ -568,6 +582,13 @@ struct Engine {
                         S.f_fwd2 += 2.0 * u.Ho * u.Wo * u.k * u.k * u.cin * u.cout;
                         S.q_max = std::max(S.q_max, Launch::tc2_q(u.W, u.k));
                         S.tc2_cin = std::max(S.tc2_cin, u.cin);
+                    } else if (use_skip_tc() && u.is_skip && Launch::skip_tc_ok(t)) {
+                        t.tiles_n = Launch::skip_tc_tiles_n(u.cout);
+                        t.tile_begin = S.skip_fwd.total;
+                        S.skip_fwd.h.push_back(t);
+                        S.skip_fwd.total += Launch::skip_tc_tiles_m((long long)batch * u.Ho * u.Wo) * t.tiles_n;
+                        S.skip_k = std::max(S.skip_k, u.cin);
+                        S.f_skip += 2.0 * u.Ho * u.Wo * u.cin * u.cout;
                     } else {
                         t.tile_begin = S.conv_tc.total;
                         S.conv_tc.h.push_back(t);
@@ -781,6 +802,13 @@ struct Engine {
                         S.f_dg2 += 2.0 * u.Ho * u.Wo * u.k * u.k * u.cin * u.cout;
                         S.q_max = std::max(S.q_max, Launch::tc2_q(u.W, u.k));
                         S.tc2_cin_d = std::max(S.tc2_cin_d, u.cout);
+                    } else if (use_skip_tc() && u.is_skip && Launch::skip_tc_ok(d)) {
+                        d.tiles_n = Launch::skip_tc_tiles_n(u.cin);
+                        d.tile_begin = S.skip_dg.total;
+                        S.skip_dg.h.push_back(d);
+                        S.skip_dg.total += Launch::skip_tc_tiles_m((long long)batch * u.Ho * u.Wo) * d.tiles_n;
+                        S.skip_k_d = std::max(S.skip_k_d, u.cout);
+                        S.f_skip_d += 2.0 * u.Ho * u.Wo * u.cin * u.cout;
                     } else {
                         d.tile_begin = S.dgrad_tc.total;
                         S.dgrad_tc.h.push_back(d);
@@ -817,8 +845,10 @@ struct Engine {
             hd.v = lc.V; hd.vh = lc.V ? nullptr : lc.Vh; hd.gap = c.gap; hd.dgap = c.gG; hd.dv = c.gA;
             hd.Hf = lc.Po; hd.Wf = lc.Qo; hd.C = lc.cout;
             hd.block_begin = wv.head.total;
+            hd.block_begin_fwd = wv.head_fwd_total;
             wv.head.h.push_back(hd);
-            wv.head.total += blocks_for((long long)batch * lc.Po * lc.Qo * lc.cout);
+            wv.head.total += Launch::gap_blocks((long long)batch * lc.Po * lc.Qo * lc.cout);
+            wv.head_fwd_total += Launch::gap_blocks((long long)batch * lc.cout);
             const Unit& ou = c.units.back();
             CeTask ce{};
             ce.logits = ou.U; ce.dlogits = c.dlogits; ce.n_classes = cfg.n_classes;
@@ -854,6 +884,7 @@ struct Engine {
             blob_add(blob, S.conv); blob_add(blob, S.conv_eval); blob_add(blob, S.dgrad);
             blob_add(blob, S.conv_tc); blob_add(blob, S.dgrad_tc); blob_add(blob, S.stat); blob_add(blob, S.wgrad_tc);
             blob_add(blob, S.conv_tc2); blob_add(blob, S.dgrad_tc2); blob_add(blob, S.wgrad_tc2);
+            blob_add(blob, S.skip_fwd); blob_add(blob, S.skip_dg);
             blob_add(blob, S.post_fwd); blob_add(blob, S.post_bn); blob_add(blob, S.post_bwd);
             blob_add(blob, S.wgrad); blob_add(blob, S.wreduce); blob_add(blob, S.drop_fwd); blob_add(blob, S.drop_bwd);
         }
@@ -878,7 +909,7 @@ struct Engine {
             StageLists& S = wv.st[s];
             fix(S.conv); fix(S.conv_eval); fix(S.dgrad); fix(S.post_fwd); fix(S.post_bn); fix(S.post_bwd);
             fix(S.conv_tc); fix(S.dgrad_tc); fix(S.stat); fix(S.wgrad_tc); fix(S.conv_tc2); fix(S.dgrad_tc2); fix(S.wgrad_tc2);
-            fix(S.wgrad); fix(S.wreduce); fix(S.drop_fwd); fix(S.drop_bwd);
+            fix(S.wgrad); fix(S.wreduce); fix(S.drop_fwd); fix(S.drop_bwd); fix(S.skip_fwd); fix(S.skip_dg);
         }
         fix(wv.head); fix(wv.ce_train); fix(wv.ce_val); fix(wv.ce_pred); fix(wv.adam); fix(wv.wt); fix(wv.wt_bf16); fix(wv.wt_bf16_v2);
         fix(wv.perm);
@@ -911,7 +942,8 @@ struct Engine {
         wv.weights_dirty = false;
         for (int s = 0; s < N_STAGES; ++s) {
             StageLists& S = wv.st[s];
-            if (s == ST_FC0) CNN_LAUNCH(Launch::gap_fwd(wv.head.d, (int)wv.head.h.size(), wv.head.total, n_b, stream));
+            g_prof_stage = s;
+            if (s == ST_FC0) CNN_LAUNCH(Launch::gap_fwd(wv.head.d, (int)wv.head.h.size(), wv.head_fwd_total, n_b, stream));
             if (!S.any) continue;
             DevList<ConvTask>& cl = (s == 0 && !training) ? S.conv_eval : S.conv;
             if (!cl.h.empty()) {
@@ -930,6 +962,9 @@ struct Engine {
             if (!S.conv_tc.h.empty())
                 CNN_LAUNCH_N("conv_tc.fwd", S.f_fwd1 * n_b,
                              Launch::conv_tc(S.conv_tc.d, (int)S.conv_tc.h.size(), S.conv_tc.total, n_b, step, stream, S.conv_tc.d_bt));
+            if (!S.skip_fwd.h.empty())
+                CNN_LAUNCH_N("skip_tc.fwd", S.f_skip * n_b,
+                             Launch::skip_tc(S.skip_fwd.d, (int)S.skip_fwd.h.size(), S.skip_fwd.total, n_b, step, S.skip_k, stream));
             if (!S.conv_tc2.h.empty())
                 CNN_LAUNCH_N("conv_tc2.fwd", S.f_fwd2 * n_b,
                              Launch::conv_tc2(S.conv_tc2.d, (int)S.conv_tc2.h.size(), S.conv_tc2.total, n_b, step, S.q_max,
@@ -946,6 +981,7 @@ struct Engine {
                 CNN_LAUNCH(Launch::drop_fwd(S.drop_fwd.d, (int)S.drop_fwd.h.size(), S.drop_fwd.total, n_b, global_step,
                                             training, cfg.dropout_rate, stream));
         }
+        g_prof_stage = -1;
         DevList<CeTask>& ce = mode == 0 ? wv.ce_train : (mode == 1 ? wv.ce_val : wv.ce_pred);
         CNN_LAUNCH(Launch::ce(ce.d, (int)ce.h.size(), n_b, step, training, stream));
         return CMOOP_OK;
@@ -955,6 +991,7 @@ struct Engine {
         if (!wv.wt.h.empty()) CNN_LAUNCH(Launch::wt(wv.wt.d, (int)wv.wt.h.size(), wv.wt.total, stream));
         for (int s = N_STAGES - 1; s >= 0; --s) {
             StageLists& S = wv.st[s];
+            g_prof_stage = s;
             if (s == ST_FC0 - 1) CNN_LAUNCH(Launch::gap_bwd(wv.head.d, (int)wv.head.h.size(), wv.head.total, n_b, stream));
             if (!S.any) continue;
             if (!S.drop_bwd.h.empty())      // dense: A (grad of the layer output) -> B (grad of the pre-activation)
@@ -996,11 +1033,15 @@ struct Engine {
             if (!S.dgrad_tc.h.empty())
                 CNN_LAUNCH_N("conv_tc.dgrad", S.f_dg1 * n_b,
                              Launch::conv_tc(S.dgrad_tc.d, (int)S.dgrad_tc.h.size(), S.dgrad_tc.total, n_b, 0, stream, S.dgrad_tc.d_bt));
+            if (!S.skip_dg.h.empty())
+                CNN_LAUNCH_N("skip_tc.dgrad", S.f_skip_d * n_b,
+                             Launch::skip_tc(S.skip_dg.d, (int)S.skip_dg.h.size(), S.skip_dg.total, n_b, 0, S.skip_k_d, stream));
             if (!S.dgrad_tc2.h.empty())
                 CNN_LAUNCH_N("conv_tc2.dgrad", S.f_dg2 * n_b,
                              Launch::conv_tc2(S.dgrad_tc2.d, (int)S.dgrad_tc2.h.size(), S.dgrad_tc2.total, n_b, 0, S.q_max,
                                               S.tc2_cin_d, stream, S.dgrad_tc2.d_bt));
         }
+        g_prof_stage = -1;
         return CMOOP_OK;
     }
 
@@ -1606,7 +1647,7 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
                          int Cin, int Cout, int k, int stride, int relu, float* out) {
     CMOOP_REQUIRE(in && w && out, "debug_conv: null pointer");
     CMOOP_REQUIRE(n >= 1 && n <= kBatch && (stride == 1 || (stride == 2 && k == 1)), "debug_conv: unsupported shape");
-    CMOOP_REQUIRE((use_tc != 1 && use_tc != 3) || (Cin % 16 == 0 && Cout % 16 == 0), "debug_conv: tensor-core path needs Cin, Cout multiples of 16");
+    CMOOP_REQUIRE((use_tc != 1 && use_tc != 3 && use_tc != 5) || (Cin % 16 == 0 && Cout % 16 == 0), "debug_conv: tensor-core path needs Cin, Cout multiples of 16");
     CMOOP_REQUIRE(use_tc != 3 || (Launch::tc2_ok(H, W, Cin, Cout, k, stride) && Launch::tc2_ok(H, W, Cout, Cin, k, stride)),
                   "debug_conv: shape not eligible for the patch-resident tcgen05 kernel");
     CMOOP_REQUIRE(use_tc != 2 || (mode == 0 && Launch::stem_ok(H, W, Cin, Cout, k, stride, n)),
@@ -1644,7 +1685,7 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
     CMOOP_CUDA_OK(cudaMemsetAsync(d_out, 0, n_out * 4, st));
     const int tiles_m64 = (int)(((long long)n * Ho * Wo + 63) / 64), tiles_m128 = (int)(((long long)n * Ho * Wo + 127) / 128);
     int rc = 0;
-    if (use_tc != 1 && use_tc != 3) {
+    if (use_tc != 1 && use_tc != 3 && use_tc != 5) {
         ConvTask t{};
         t.x = d_in; t.y = d_out;
         t.Ho = Ho; t.Wo = Wo; t.k = k;
@@ -1737,6 +1778,16 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
             const long long mq = (long long)n * (H + 2 * pad) * (W + 2 * pad);
             rc = Launch::conv_tc2((const TcConvTask*)d_task, 1, (int)((mq + Launch::tc2_rows() - 1) / Launch::tc2_rows()) * t.tiles_n,
                                   n, 0, Launch::tc2_q(W, k), gi, st);
+        } else if (rc == 0 && use_tc == 5) {             // skip_tc.cu: the 1x1 projection on mma.sync (fp32 output form)
+            if (!Launch::skip_tc_ok(t)) {
+                cmoop::set_error("debug_conv: shape not eligible for the mma.sync 1x1 kernel");
+                return CMOOP_ERR_UNSUPPORTED;
+            }
+            t.tiles_n = Launch::skip_tc_tiles_n(t.Cout);
+            CMOOP_CUDA_OK(cmoop::copy_async(d_task, &t, sizeof(t), cudaMemcpyHostToDevice, st));
+            CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+            rc = Launch::skip_tc((const TcConvTask*)d_task, 1, Launch::skip_tc_tiles_m((long long)n * Ho * Wo) * t.tiles_n, n, 0,
+                                 t.Cin, st);
         } else if (rc == 0) {
             rc = Launch::conv_tc((const TcConvTask*)d_task, 1, tiles_m128 * t.tiles_n, n, 0, st);
         }

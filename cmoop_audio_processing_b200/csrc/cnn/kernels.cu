@@ -804,27 +804,46 @@ __global__ void __launch_bounds__(256, 2) post_bwd_apply_kernel(const PostTask* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// global average pooling: a thread owns 4 consecutive channels (C is a multiple of 16 for every conv stack of the space)
 __global__ void __launch_bounds__(256) gap_fwd_kernel(const HeadTask* __restrict__ tasks, int n_tasks, int n_b) {
-    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const HeadTask& r) { return r.block_begin; });
+    const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const HeadTask& r) { return r.block_begin_fwd; });
     const HeadTask T = tasks[t];
-    const int e = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
-    if (e >= n_b * T.C) return;
-    const int c = e % T.C, n = e / T.C;
+    const int e4 = (blockIdx.x - T.block_begin_fwd) * 256 + threadIdx.x;
+    const int C4 = T.C >> 2;
+    if (e4 >= n_b * C4) return;
+    const int n = e4 / C4, c = (e4 - n * C4) * 4;
     const int hw = T.Hf * T.Wf;
-    float s = 0.f;
-    for (int p = 0; p < hw; ++p) s += load1(T.v, T.vh, ((long long)n * hw + p) * T.C + c);
-    T.gap[e] = s / (float)hw;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    const long long base = (long long)n * hw * T.C + c;
+    if (T.vh) {
+#pragma unroll 5
+        for (int p = 0; p < hw; ++p) {
+            const uint2 r = __ldg(reinterpret_cast<const uint2*>(T.vh + base + (long long)p * T.C));
+            s[0] += __uint_as_float(r.x << 16); s[1] += __uint_as_float(r.x & 0xffff0000u);
+            s[2] += __uint_as_float(r.y << 16); s[3] += __uint_as_float(r.y & 0xffff0000u);
+        }
+    } else {
+#pragma unroll 5
+        for (int p = 0; p < hw; ++p) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(T.v + base + (long long)p * T.C));
+            s[0] += r.x; s[1] += r.y; s[2] += r.z; s[3] += r.w;
+        }
+    }
+    const float inv = (float)hw;
+    *reinterpret_cast<float4*>(T.gap + (long long)n * T.C + c) = make_float4(s[0] / inv, s[1] / inv, s[2] / inv, s[3] / inv);
 }
 
 __global__ void __launch_bounds__(256) gap_bwd_kernel(const HeadTask* __restrict__ tasks, int n_tasks, int n_b) {
     const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const HeadTask& r) { return r.block_begin; });
     const HeadTask T = tasks[t];
-    const long long e = (long long)(blockIdx.x - T.block_begin) * 256 + threadIdx.x;
-    const int hw = T.Hf * T.Wf;
-    if (e >= (long long)n_b * hw * T.C) return;
-    const int c = (int)(e % T.C);
-    const int n = (int)(e / ((long long)hw * T.C));
-    T.dv[e] = T.dgap[n * T.C + c] / (float)hw;
+    const int e4 = (blockIdx.x - T.block_begin) * 256 + threadIdx.x;
+    const int C4 = T.C >> 2, hw = T.Hf * T.Wf;
+    if (e4 >= n_b * hw * C4) return;
+    const int pix = e4 / C4, c = (e4 - pix * C4) * 4;
+    const int n = pix / hw;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(T.dgap + n * T.C + c));
+    const float inv = (float)hw;
+    *reinterpret_cast<float4*>(T.dv + (long long)e4 * 4) = make_float4(g.x / inv, g.y / inv, g.z / inv, g.w / inv);
 }
 
 __global__ void __launch_bounds__(256) drop_fwd_kernel(const DropTask* __restrict__ tasks, int n_tasks, int n_b, int step,
@@ -1078,6 +1097,7 @@ int Launch::post_bwd_apply(const PostTask* tasks, int n, int blocks, int n_b, vo
         post_bwd_apply_kernel<false><<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b, bt);
     return check();
 }
+int Launch::gap_blocks(long long elems) { return (int)((elems / 4 + 255) / 256); }
 int Launch::gap_fwd(const HeadTask* tasks, int n, int blocks, int n_b, void* st) {
     if (n == 0 || blocks == 0) return 0;
     gap_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b);

@@ -233,8 +233,15 @@ def test_bf16_and_fp32_paths_agree_after_training():
         prob = FitnessProblem(xt, yt, xv, yv, classes=N_CLASSES, config=cfg)
         outs[prec], _ = prob.train_eval(hps, [5, 6, 7, 8, 9])
     np.testing.assert_array_equal(outs["fp32"][:, 1], outs["bf16"][:, 1])          # size is exact in both
-    assert np.abs(outs["fp32"][:, 0] - outs["bf16"][:, 0]).max() <= 0.08          # accuracy after 4 epochs
-    assert np.abs(outs["fp32"][:, 5] - outs["bf16"][:, 5]).max() <= 0.15          # best validation loss
+    # Toy-sized smoke statement (384 / 192 clips: one validation clip is 0.0052 of accuracy); the sized, statistical
+    # statement is tests/test_gpu_bf16_parity.py.  The continuous quantity is tight: best validation loss within 0.03
+    # (measured 0.007).  Accuracy after 4 epochs: four of the five candidates agree to one clip; the fifth is in the steep
+    # part of its learning curve (0.88 -> 0.96 between adjacent epochs of the SAME precision), where a last-bit change of
+    # the accumulation order moves the epoch-4 reading by up to 0.083 (measured with two different summation orders of the
+    # 1x1 projection: 0.073 and 0.083), hence median <= 0.01, max <= 0.10.
+    d_acc = np.abs(outs["fp32"][:, 0] - outs["bf16"][:, 0])
+    assert np.median(d_acc) <= 0.01 and d_acc.max() <= 0.10
+    assert np.abs(outs["fp32"][:, 5] - outs["bf16"][:, 5]).max() <= 0.03          # best validation loss
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

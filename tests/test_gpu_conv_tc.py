@@ -180,6 +180,42 @@ def test_stem_tensor_core_kernels(n, H, W, Cout, k):
     np.testing.assert_allclose(got, want, rtol=1e-4, atol=5e-5 * np.abs(want).max())
 
 
+SKIP_CASES = [  # n, H, W, Cin, Cout   (1x1 / stride 2, skip_tc.cu, use_tc = 5)
+    (64, 25, 20, 16, 32),      # smallest genotype: 16-channel K tail only, 32-channel slice
+    (64, 25, 20, 64, 128),
+    (7, 13, 10, 32, 64),       # odd height, ragged last batch
+    (5, 13, 10, 128, 256),
+    (3, 7, 5, 256, 512),       # deepest block: K = 256 forward, K = 512 data gradient
+    (9, 25, 20, 32, 64),
+]
+
+
+@pytest.mark.parametrize("n,H,W,Cin,Cout", SKIP_CASES)
+def test_skip_projection_kernel(n, H, W, Cin, Cout):
+    """skip_tc.cu: forward (+bias, ReLU) and strided-scatter data gradient vs torch fp64 on bf16-rounded operands, and
+    bit-for-bit agreement in kind with the tcgen05 kernel it replaces (same operands, fp32 accumulation)."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(n * 1000 + Cin + Cout)
+    x = rng.standard_normal((n, H, W, Cin)).astype(np.float32)
+    w = (rng.standard_normal((1, 1, Cin, Cout)) / np.sqrt(Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    xt = torch.from_numpy(bf16_round(x)).permute(0, 3, 1, 2).double()
+    wt = torch.from_numpy(bf16_round(w)).permute(3, 2, 0, 1).double()
+    ref = F.conv2d(xt, wt, torch.from_numpy(b).double(), stride=2).permute(0, 2, 3, 1).numpy()
+    for relu in (0, 1):
+        got = run_conv(0, 5, x, w, b, n, H, W, Cin, Cout, 1, 2, relu)
+        np.testing.assert_allclose(got, np.maximum(ref, 0) if relu else ref, rtol=2e-4, atol=2e-4)
+    Ho, Wo = ref.shape[1:3]
+    dy = rng.standard_normal((n, Ho, Wo, Cout)).astype(np.float32)
+    dyt = torch.from_numpy(bf16_round(dy)).permute(0, 3, 1, 2).double()
+    xin = torch.zeros((n, Cin, H, W), dtype=torch.float64, requires_grad=True)
+    F.conv2d(xin, wt, None, stride=2).backward(dyt)
+    got_dx = run_conv(1, 5, dy, w, None, n, H, W, Cin, Cout, 1, 2, 0)
+    np.testing.assert_allclose(got_dx, xin.grad.permute(0, 2, 3, 1).numpy(), rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(got_dx, run_conv(1, 1, dy, w, None, n, H, W, Cin, Cout, 1, 2, 0), rtol=1e-5, atol=1e-5)
+
+
 PATCH_CASES = [c for c in CASES if c[6] == 1] + [
     (64, 25, 20, 16, 32, 3, 1),      # first residual conv of the smallest genotype: one sub-slab, nine taps
     (64, 13, 10, 128, 256, 5, 1),    # deep block: 8 sub-slabs x 25 taps, two N tiles
