@@ -244,8 +244,9 @@ struct Launch {
     static int tc2_q(int W, int k);
     static int tc2_rows();
     static long long tc2_weight_elems(int Cin, int Cout, int k);     // bf16 elements of the (slab-padded) weight blocks
+    // out_bf16: every task stores the bf16-only form (yh, optionally y next to it); false: fp32 y (data gradient)
     static int conv_tc2(const TcConvTask* tasks, int n_tasks, int total_tiles, int n_b, int step, int q_max, int max_cin,
-                        void* stream, const int* block_task = nullptr);
+                        void* stream, const int* block_task = nullptr, bool out_bf16 = false);
     static int wt_bf16_v2(const WtBf16Task* tasks, int n_tasks, int total_blocks, void* stream);
     // host side of the tiled-TMA operand loads (engine.cu): encodes the 4-D map {C, W, H, N} of a dense NHWC bf16 tensor
     // whose box {64 channels, W + 2 pad, 1, 1} at (c0, -pad, h - pad, n) is one zero-padded image row; returns 0 on success

@@ -46,6 +46,14 @@ constexpr uint32_t P2_TMEM_COLS = 256;
 constexpr int P2_W_STAGE = 128 * 128;       // bytes of a weight stage: 128 rows x 128 B
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tmem_ld16(uint32_t* v, uint32_t taddr) {      // 16 consecutive accumulator columns of this lane's row
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -127,6 +135,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // prof (CMOOP_TC2_PROF=1): per-launch sums of clock64 spans -- [0] CTAs, [1] prologue, [2] MMA thread: start -> first
 // operands ready, [3] MMA issue loop, [4] producers: start -> accumulator complete, [5] epilogue, [6] whole CTA
+// OUT_BF16: every task of the launch stores bf16 (the forward of precision bf16) / fp32 (data gradient) -- one epilogue per
+// instantiation keeps the kernel small
+template <bool OUT_BF16>
 __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTask* __restrict__ tasks, int n_tasks, int n_b,
                                                                  int step, int q_max, int pb, unsigned long long* prof,
                                                                  const int* __restrict__ block_task) {
@@ -243,30 +254,62 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
                 if (hp >= p && hp < T.H + p && wp >= p && wp < T.W + p)
                     obase = ((long long)(n * T.H + hp - p) * T.W + wp - p) * T.Cout;
             }
-            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-                uint32_t v[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(mt * 128 + c0);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                    : "r"(taddr)
-                    : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (obase >= 0) {
-                    float* dst = T.y + obase + n0 + c0;
+            if constexpr (OUT_BF16) {
+                // bf16-only output (forward): 32 accumulator columns per pass (two tcgen05.ld in flight, one wait); a lane owns
+                // one GEMM row, so 8 consecutive channels leave as ONE 16-byte store (round 2: 2 539 -> 2 255 us on the 25x20 block)
+                for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                    uint32_t v[32];
+                    const int ncol = min(32, c_end - c0);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(mt * 128 + c0);
+                    tmem_ld16(v, taddr);
+                    if (ncol > 16) tmem_ld16(v + 16, taddr + 16);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (obase >= 0) {
 #pragma unroll
-                    for (int qd = 0; qd < 16; qd += 4) {
-                        const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + qd);
-                        float4 o;
-                        o.x = __uint_as_float(v[qd + 0]) + bb.x;
-                        o.y = __uint_as_float(v[qd + 1]) + bb.y;
-                        o.z = __uint_as_float(v[qd + 2]) + bb.z;
-                        o.w = __uint_as_float(v[qd + 3]) + bb.w;
-                        if (T.relu) {
-                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                        for (int qd = 0; qd < 32; qd += 8) {
+                            if (qd >= ncol) break;
+                            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c0 + qd);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c0 + qd + 4);
+                            float o[8];
+                            o[0] = __uint_as_float(v[qd + 0]) + b0.x; o[1] = __uint_as_float(v[qd + 1]) + b0.y;
+                            o[2] = __uint_as_float(v[qd + 2]) + b0.z; o[3] = __uint_as_float(v[qd + 3]) + b0.w;
+                            o[4] = __uint_as_float(v[qd + 4]) + b1.x; o[5] = __uint_as_float(v[qd + 5]) + b1.y;
+                            o[6] = __uint_as_float(v[qd + 6]) + b1.z; o[7] = __uint_as_float(v[qd + 7]) + b1.w;
+                            if (T.relu) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+                            }
+                            if (T.y) {                       // fp32 copy next to the bf16 one (not used by the engine today)
+                                float4* d4 = reinterpret_cast<float4*>(T.y + obase + n0 + c0 + qd);
+                                d4[0] = make_float4(o[0], o[1], o[2], o[3]);
+                                d4[1] = make_float4(o[4], o[5], o[6], o[7]);
+                            }
+                            *reinterpret_cast<uint4*>(T.yh + obase + n0 + c0 + qd) =
+                                make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
                         }
-                        if (T.y) {
+                    }
+                }
+            } else {
+                // fp32 output (data gradient, precision-fp32 callers): 16-column passes, the stores of one pass overlap the load
+                // of the next (32-column passes measured 4 % slower here: the store count does not shrink)
+                for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                    uint32_t v[16];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(mt * 128 + c0);
+                    tmem_ld16(v, taddr);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (obase >= 0) {
+                        float* dst = T.y + obase + n0 + c0;
+#pragma unroll
+                        for (int qd = 0; qd < 16; qd += 4) {
+                            const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + qd);
+                            float4 o;
+                            o.x = __uint_as_float(v[qd + 0]) + bb.x;
+                            o.y = __uint_as_float(v[qd + 1]) + bb.y;
+                            o.z = __uint_as_float(v[qd + 2]) + bb.z;
+                            o.w = __uint_as_float(v[qd + 3]) + bb.w;
+                            if (T.relu) {
+                                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                            }
                             float4* d4 = reinterpret_cast<float4*>(dst + qd);
                             if (T.accumulate) {
                                 const float4 old = *d4;
@@ -274,9 +317,6 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
                             }
                             *d4 = o;
                         }
-                        if (T.yh)
-                            *reinterpret_cast<uint2*>(T.yh + obase + n0 + c0 + qd) =
-                                make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
                     }
                 }
             }
@@ -433,17 +473,20 @@ bool Launch::tc2_ok(int H, int W, int Cin, int Cout, int k, int stride) {
 }
 
 int Launch::conv_tc2(const TcConvTask* tasks, int n, int tiles, int n_b, int step, int q_max, int max_cin, void* st,
-                     const int* block_task) {
+                     const int* block_task, bool out_bf16) {
     if (n == 0 || tiles == 0) return 0;
     const int pb = p2_buffers(max_cin, q_max);
     const size_t smem = p2_smem_bytes(q_max, pb);
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        // all of the SM's unified L1/shared storage as shared memory: two ~100 KB CTAs must be co-resident
-        e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return (int)e;
+        for (int v = 0; v < 2; ++v) {
+            const void* fn = v ? (const void*)conv_tc2_kernel<true> : (const void*)conv_tc2_kernel<false>;
+            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            // all of the SM's unified L1/shared storage as shared memory: two ~100 KB CTAs must be co-resident
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return (int)e;
+        }
         configured = smem;
     }
     // optional phase profile (development aid): CMOOP_TC2_PROF=1 prints per-launch clock sums at process exit
@@ -469,7 +512,10 @@ int Launch::conv_tc2(const TcConvTask* tasks, int n, int tiles, int n_b, int ste
     }
     static int launch_no = 0;
     unsigned long long* slot = prof ? prof + (size_t)(launch_no++ % 64) * 8 : nullptr;
-    conv_tc2_kernel<<<tiles, P2_THREADS, smem, (cudaStream_t)st>>>(tasks, n, n_b, step, q_max, pb, slot, block_task);
+    if (out_bf16)
+        conv_tc2_kernel<true><<<tiles, P2_THREADS, smem, (cudaStream_t)st>>>(tasks, n, n_b, step, q_max, pb, slot, block_task);
+    else
+        conv_tc2_kernel<false><<<tiles, P2_THREADS, smem, (cudaStream_t)st>>>(tasks, n, n_b, step, q_max, pb, slot, block_task);
     return (int)cudaGetLastError();
 }
 

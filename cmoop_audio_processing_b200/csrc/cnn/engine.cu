@@ -968,7 +968,7 @@ struct Engine {
             if (!S.conv_tc2.h.empty())
                 CNN_LAUNCH_N("conv_tc2.fwd", S.f_fwd2 * n_b,
                              Launch::conv_tc2(S.conv_tc2.d, (int)S.conv_tc2.h.size(), S.conv_tc2.total, n_b, step, S.q_max,
-                                              S.tc2_cin, stream, S.conv_tc2.d_bt));
+                                              S.tc2_cin, stream, S.conv_tc2.d_bt, /*out_bf16=*/true));
             if (!S.stat.h.empty() && training)
                 CNN_LAUNCH(Launch::bn_stats(S.stat.d, (int)S.stat.h.size(), S.stat.total, n_b, stream));
             if (!S.post_bn.h.empty())
@@ -1777,7 +1777,7 @@ int cmoop_cnn_debug_conv(int mode, int use_tc, const float* in, const float* w, 
             CMOOP_CUDA_OK(cudaStreamSynchronize(st));
             const long long mq = (long long)n * (H + 2 * pad) * (W + 2 * pad);
             rc = Launch::conv_tc2((const TcConvTask*)d_task, 1, (int)((mq + Launch::tc2_rows() - 1) / Launch::tc2_rows()) * t.tiles_n,
-                                  n, 0, Launch::tc2_q(W, k), gi, st);
+                                  n, 0, Launch::tc2_q(W, k), gi, st, nullptr, t.yh != nullptr);
         } else if (rc == 0 && use_tc == 5) {             // skip_tc.cu: the 1x1 projection on mma.sync (fp32 output form)
             if (!Launch::skip_tc_ok(t)) {
                 cmoop::set_error("debug_conv: shape not eligible for the mma.sync 1x1 kernel");
