@@ -474,6 +474,7 @@ struct StageLists {
 
 struct Wave {
     std::vector<Cand*> cands;
+    int lane = 0;                    // concurrent lane of the wave (own stream, own scratch slots)
     StageLists st[N_STAGES];
     DevList<HeadTask> head;
     int head_fwd_total = 0;          // grid of gap_fwd (head.total is gap_bwd's)
@@ -533,7 +534,7 @@ struct Engine {
                 owners.push_back(&u);
             }
         if (host.empty()) return CMOOP_OK;
-        wv.d_tmaps = (char*)cmoop::device_scratch(11, host.size());
+        wv.d_tmaps = (char*)cmoop::device_scratch(11 + wv.lane, host.size());
         if (!wv.d_tmaps) return CMOOP_ERR_CUDA;
         CMOOP_CUDA_OK(cmoop::copy_async(wv.d_tmaps, host.data(), host.size(), cudaMemcpyHostToDevice, stream));
         CMOOP_CUDA_OK(cudaStreamSynchronize(stream));          // `host` goes out of scope
@@ -1332,34 +1333,53 @@ int cmoop_cnn_debug_permutation(uint64_t seed, int epoch, int n, int* out) {
 
 namespace {
 
-// Trains and scores one wave of candidates to completion.
-int run_wave(Engine& eng, Wave& wv, double* out, double* history, int debug_steps, float* dbg_losses, float* dbg_grads,
-             float* dbg_params) {
+// host-generated shuffles: A/B switch, or a training split too large for perm_kernel's shared memory
+bool host_permutations(int n_train) {
+    static const bool host_perm = getenv("CMOOP_CNN_HOST_PERM") != nullptr;
+    return host_perm || !Launch::perm_ok(n_train);
+}
+
+// Trains and scores one wave of candidates to completion.  The wave's candidates are split over `n_lanes` LANES, each with
+// its own task lists and CUDA stream, stepped in lock-step by this one host thread: lane 0's forward / backward / Adam
+// launches of a step are enqueued on stream 0, lane 1's on stream 1, ...  The lanes share nothing but the read-only
+// dataset, so the device overlaps one lane's latency-bound small kernels and launch tails with the other lane's wide
+// kernels (a single stream serialises ~350 grouped launches per step; at 32 candidates per GPU a third of them are
+// bound by fixed latency, not by throughput).  Results are independent of the lane split (candidates never interact).
+int run_wave(Engine& eng, Wave* lanes, int n_lanes, cudaStream_t* streams, double* out, double* history, int debug_steps,
+             float* dbg_losses, float* dbg_grads, float* dbg_params) {
     const cmoop_cnn_dataset* data = eng.data;
     const cmoop_cnn_config& cfg = eng.cfg;
     const int batch = eng.batch;
-    cudaStream_t st = eng.stream;
-    eng.global_step = 0;       // the dropout stream counts a candidate's own optimiser steps (oracle: drop_ctx=(seed, step)),
-                               // so a candidate's masks must not depend on which wave it lands in
-    int rc = eng.init_params(wv.cands);
-    if (rc != CMOOP_OK) return rc;
-    if ((rc = eng.build_tensor_maps(wv)) != CMOOP_OK) return rc;
-    rc = eng.build_lists(wv);
-    if (rc != CMOOP_OK) return rc;
+    int rc = CMOOP_OK;
+    // the dropout stream counts a candidate's own optimiser steps (oracle: drop_ctx=(seed, step)), so a candidate's masks
+    // must not depend on which wave / lane it lands in
+    for (int l = 0; l < n_lanes; ++l) {
+        eng.stream = streams[l];
+        if ((rc = eng.init_params(lanes[l].cands)) != CMOOP_OK) return rc;
+        if ((rc = eng.build_tensor_maps(lanes[l])) != CMOOP_OK) return rc;
+        if ((rc = eng.build_lists(lanes[l])) != CMOOP_OK) return rc;
+    }
     const int steps_per_epoch = (data->n_train + batch - 1) / batch;
     const int val_steps = (data->n_val + batch - 1) / batch;
-    int t_adam = 0;
+    int t_adam = 0, global_step = 0;
     const int max_epochs = debug_steps > 0 ? 1 : cfg.max_epochs;
+    std::vector<char> lane_live(n_lanes, 1);
     for (int epoch = 0; epoch < max_epochs; ++epoch) {
-        bool any = false;
-        for (Cand* c : wv.cands) any = any || c->active;
-        if (any) {
+        bool any_lane = false;
+        for (int l = 0; l < n_lanes; ++l) {
+            Wave& wv = lanes[l];
+            cudaStream_t st = streams[l];
+            eng.stream = st;
+            bool any = false;
+            for (Cand* c : wv.cands) any = any || c->active;
+            lane_live[l] = any ? 1 : 0;
+            if (!any) continue;
+            any_lane = true;
             // per-epoch shuffles: generated on the device for every active candidate in one launch (same fmix32 stream as
             // make_permutation / cmoop_cnn_debug_permutation); a training split too large for the kernel's shared memory
-            // falls back to host-generated index arrays
+            // falls back to host-generated index arrays (single lane: the staging buffer is shared)
             cudaStream_t stream = st;
-            static const bool host_perm = getenv("CMOOP_CNN_HOST_PERM") != nullptr;     // A/B switch: host-generated shuffles
-            if (!host_perm && Launch::perm_ok(data->n_train)) {
+            if (!host_permutations(data->n_train)) {
                 CNN_LAUNCH(Launch::perm(wv.perm.d, (int)wv.perm.h.size(), epoch, data->n_train, st));
             } else {
                 int n_active = 0;
@@ -1376,115 +1396,152 @@ int run_wave(Engine& eng, Wave& wv, double* out, double* history, int debug_step
             }
             CMOOP_CUDA_OK(cudaMemsetAsync(wv.d_acc, 0, wv.cands.size() * 12 * sizeof(double), st));
         }
-        if (!any) break;
+        if (!any_lane) break;
         const int n_steps = debug_steps > 0 ? std::min(debug_steps, steps_per_epoch) : steps_per_epoch;
         for (int s = 0; s < n_steps; ++s) {
             const int n_b = std::min(batch, data->n_train - s * batch);
-            if ((rc = eng.run_forward(wv, 0, s, n_b)) != CMOOP_OK) return rc;
-            if ((rc = eng.run_backward(wv, s, n_b)) != CMOOP_OK) return rc;
-            if (debug_steps > 0) {
-                Cand* c = wv.cands[0];
-                if (s == 0 && dbg_grads)
-                    CMOOP_CUDA_OK(cmoop::copy_async(dbg_grads, c->grad, c->n_params * sizeof(float), cudaMemcpyDeviceToHost, st));
-                if (dbg_losses) {
-                    double a[4];
-                    CMOOP_CUDA_OK(cmoop::copy_async(a, c->acc, sizeof(a), cudaMemcpyDeviceToHost, st));
-                    CMOOP_CUDA_OK(cudaStreamSynchronize(st));
-                    dbg_losses[s] = (float)(a[0] / a[1]);
-                    CMOOP_CUDA_OK(cudaMemsetAsync(c->acc, 0, 4 * sizeof(double), st));
-                }
-            }
             ++t_adam;
-            if ((rc = eng.adam_step(wv, t_adam)) != CMOOP_OK) return rc;
-            ++eng.global_step;
+            for (int l = 0; l < n_lanes; ++l) {
+                if (!lane_live[l]) continue;
+                Wave& wv = lanes[l];
+                cudaStream_t st = streams[l];
+                eng.stream = st;
+                eng.global_step = global_step;
+                if ((rc = eng.run_forward(wv, 0, s, n_b)) != CMOOP_OK) return rc;
+                if ((rc = eng.run_backward(wv, s, n_b)) != CMOOP_OK) return rc;
+                if (debug_steps > 0) {
+                    Cand* c = wv.cands[0];
+                    if (s == 0 && dbg_grads)
+                        CMOOP_CUDA_OK(cmoop::copy_async(dbg_grads, c->grad, c->n_params * sizeof(float), cudaMemcpyDeviceToHost, st));
+                    if (dbg_losses) {
+                        double a[4];
+                        CMOOP_CUDA_OK(cmoop::copy_async(a, c->acc, sizeof(a), cudaMemcpyDeviceToHost, st));
+                        CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+                        dbg_losses[s] = (float)(a[0] / a[1]);
+                        CMOOP_CUDA_OK(cudaMemsetAsync(c->acc, 0, 4 * sizeof(double), st));
+                    }
+                }
+                if ((rc = eng.adam_step(wv, t_adam)) != CMOOP_OK) return rc;
+            }
+            ++global_step;
         }
         if (debug_steps > 0) {
-            Cand* c = wv.cands[0];
+            Cand* c = lanes[0].cands[0];
             if (dbg_params)
-                CMOOP_CUDA_OK(cmoop::copy_async(dbg_params, c->p, c->n_params * sizeof(float), cudaMemcpyDeviceToHost, st));
-            CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+                CMOOP_CUDA_OK(cmoop::copy_async(dbg_params, c->p, c->n_params * sizeof(float), cudaMemcpyDeviceToHost, streams[0]));
+            CMOOP_CUDA_OK(cudaStreamSynchronize(streams[0]));
             return CMOOP_OK;
         }
         for (int s = 0; s < val_steps; ++s) {
             const int n_b = std::min(batch, data->n_val - s * batch);
-            if ((rc = eng.run_forward(wv, 1, s, n_b)) != CMOOP_OK) return rc;
+            for (int l = 0; l < n_lanes; ++l) {
+                if (!lane_live[l]) continue;
+                eng.stream = streams[l];
+                eng.global_step = global_step;
+                if ((rc = eng.run_forward(lanes[l], 1, s, n_b)) != CMOOP_OK) return rc;
+            }
         }
-        bool changed = false;
-        // ONE device->host copy and ONE synchronisation per epoch for the whole wave (accumulators are contiguous)
-        double* h_acc = (double*)cmoop::pinned_scratch(6, wv.cands.size() * 12 * sizeof(double));
-        if (!h_acc) return CMOOP_ERR_CUDA;
-        CMOOP_CUDA_OK(cmoop::copy_async(h_acc, wv.d_acc, wv.cands.size() * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        CMOOP_CUDA_OK(cudaStreamSynchronize(st));
-        for (size_t ci = 0; ci < wv.cands.size(); ++ci) {
-            Cand* c = wv.cands[ci];
-            if (!c->active) continue;
-            const double* acc = h_acc + ci * 12;
-            const double train_loss = acc[0] / acc[1], val_loss = acc[4] / acc[5], val_acc = acc[6] / acc[5];
-            c->epochs_run = epoch + 1;
-            c->last_val_loss = val_loss;
-            c->last_val_acc = val_acc;
-            if (history) {
-                double* hrow = history + ((size_t)c->index * cfg.max_epochs + epoch) * 3;
-                hrow[0] = train_loss; hrow[1] = val_loss; hrow[2] = val_acc;
-            }
-            // keras.callbacks.EarlyStopping(monitor='val_loss', patience, restore_best_weights)
-            if (cfg.restore_best_weights && !c->has_best) {
-                CMOOP_CUDA_OK(cmoop::copy_async(c->best, c->p, c->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
-                c->has_best = true;
-            }
-            c->wait += 1;
-            if (val_loss < c->best_loss) {
-                c->best_loss = val_loss;
-                c->wait = 0;
-                if (cfg.restore_best_weights)
+        // ONE device->host copy and ONE synchronisation per epoch and lane (a lane's accumulators are contiguous); the copies of
+        // all lanes are enqueued before the first wait
+        std::vector<double*> h_accs(n_lanes, nullptr);
+        for (int l = 0; l < n_lanes; ++l) {
+            if (!lane_live[l]) continue;
+            Wave& wv = lanes[l];
+            h_accs[l] = (double*)cmoop::pinned_scratch(l == 0 ? 6 : 8, wv.cands.size() * 12 * sizeof(double));
+            if (!h_accs[l]) return CMOOP_ERR_CUDA;
+            CMOOP_CUDA_OK(cmoop::copy_async(h_accs[l], wv.d_acc, wv.cands.size() * 12 * sizeof(double), cudaMemcpyDeviceToHost, streams[l]));
+        }
+        for (int l = 0; l < n_lanes; ++l) {
+            if (!lane_live[l]) continue;
+            Wave& wv = lanes[l];
+            cudaStream_t st = streams[l];
+            eng.stream = st;
+            const double* h_acc = h_accs[l];
+            CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+            bool changed = false;
+            for (size_t ci = 0; ci < wv.cands.size(); ++ci) {
+                Cand* c = wv.cands[ci];
+                if (!c->active) continue;
+                const double* acc = h_acc + ci * 12;
+                const double train_loss = acc[0] / acc[1], val_loss = acc[4] / acc[5], val_acc = acc[6] / acc[5];
+                c->epochs_run = epoch + 1;
+                c->last_val_loss = val_loss;
+                c->last_val_acc = val_acc;
+                if (history) {
+                    double* hrow = history + ((size_t)c->index * cfg.max_epochs + epoch) * 3;
+                    hrow[0] = train_loss; hrow[1] = val_loss; hrow[2] = val_acc;
+                }
+                // keras.callbacks.EarlyStopping(monitor='val_loss', patience, restore_best_weights)
+                if (cfg.restore_best_weights && !c->has_best) {
                     CMOOP_CUDA_OK(cmoop::copy_async(c->best, c->p, c->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            } else if (c->wait >= cfg.patience && epoch > 0) {
-                c->active = false;
-                changed = true;
+                    c->has_best = true;
+                }
+                c->wait += 1;
+                if (val_loss < c->best_loss) {
+                    c->best_loss = val_loss;
+                    c->wait = 0;
+                    if (cfg.restore_best_weights)
+                        CMOOP_CUDA_OK(cmoop::copy_async(c->best, c->p, c->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                } else if (c->wait >= cfg.patience && epoch > 0) {
+                    c->active = false;
+                    changed = true;
+                }
             }
-        }
-        if (changed) {
-            bool left = false;
-            for (Cand* c : wv.cands) left = left || c->active;
-            if (!left) break;
-            if ((rc = eng.build_lists(wv)) != CMOOP_OK) return rc;
+            if (changed) {
+                bool left = false;
+                for (Cand* c : wv.cands) left = left || c->active;
+                if (left && (rc = eng.build_lists(wv)) != CMOOP_OK) return rc;
+            }
         }
     }
     // ---- final scoring: [restore best] -> predict on the validation split -> accuracy / confusion / FPR
-    for (Cand* c : wv.cands) {
-        c->active = true;
-        if (cfg.restore_best_weights && c->has_best)
-            CMOOP_CUDA_OK(cmoop::copy_async(c->p, c->best, c->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    }
     const size_t cm_elems = (size_t)cfg.n_classes * cfg.n_classes;
-    CMOOP_CUDA_OK(cudaMemsetAsync(wv.d_acc, 0, wv.cands.size() * 12 * sizeof(double), st));
-    CMOOP_CUDA_OK(cudaMemsetAsync(wv.d_cm, 0, wv.cands.size() * cm_elems * sizeof(int), st));
-    if ((rc = eng.build_lists(wv)) != CMOOP_OK) return rc;
+    for (int l = 0; l < n_lanes; ++l) {
+        Wave& wv = lanes[l];
+        cudaStream_t st = streams[l];
+        eng.stream = st;
+        for (Cand* c : wv.cands) {
+            c->active = true;
+            if (cfg.restore_best_weights && c->has_best)
+                CMOOP_CUDA_OK(cmoop::copy_async(c->p, c->best, c->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+        CMOOP_CUDA_OK(cudaMemsetAsync(wv.d_acc, 0, wv.cands.size() * 12 * sizeof(double), st));
+        CMOOP_CUDA_OK(cudaMemsetAsync(wv.d_cm, 0, wv.cands.size() * cm_elems * sizeof(int), st));
+        if ((rc = eng.build_lists(wv)) != CMOOP_OK) return rc;
+    }
     for (int s = 0; s < val_steps; ++s) {
         const int n_b = std::min(batch, data->n_val - s * batch);
-        if ((rc = eng.run_forward(wv, 2, s, n_b)) != CMOOP_OK) return rc;
+        for (int l = 0; l < n_lanes; ++l) {
+            eng.stream = streams[l];
+            eng.global_step = global_step;
+            if ((rc = eng.run_forward(lanes[l], 2, s, n_b)) != CMOOP_OK) return rc;
+        }
     }
-    double* h_acc = (double*)cmoop::pinned_scratch(6, wv.cands.size() * 12 * sizeof(double));
-    int* h_cm = (int*)cmoop::pinned_scratch(7, wv.cands.size() * cm_elems * sizeof(int));
-    if (!h_acc || !h_cm) return CMOOP_ERR_CUDA;
-    CMOOP_CUDA_OK(cmoop::copy_async(h_acc, wv.d_acc, wv.cands.size() * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CMOOP_CUDA_OK(cmoop::copy_async(h_cm, wv.d_cm, wv.cands.size() * cm_elems * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CMOOP_CUDA_OK(cudaStreamSynchronize(st));
-    std::vector<int> cm(cm_elems);
-    for (size_t ci = 0; ci < wv.cands.size(); ++ci) {
-        Cand* c = wv.cands[ci];
-        const double* acc = h_acc + ci * 12 + 8;
-        memcpy(cm.data(), h_cm + ci * cm_elems, cm_elems * sizeof(int));
-        const double acc_eval = acc[2] / acc[1];
-        c->final_acc = cfg.acc_from_history ? c->last_val_acc : acc_eval;
-        c->fpr = fpr_from_confusion(cm, cfg.n_classes, cfg.fpr_filtered != 0);
-        double* o = out + (size_t)c->index * 6;
-        o[0] = c->final_acc;
-        o[1] = (double)c->n_params * 4.0 / (1024.0 * 1024.0);
-        o[2] = c->fpr;
-        o[3] = (double)c->epochs_run;
-        o[4] = c->last_val_loss;
-        o[5] = c->best_loss;
+    for (int l = 0; l < n_lanes; ++l) {
+        Wave& wv = lanes[l];
+        cudaStream_t st = streams[l];
+        double* h_acc = (double*)cmoop::pinned_scratch(l == 0 ? 6 : 8, wv.cands.size() * 12 * sizeof(double));
+        int* h_cm = (int*)cmoop::pinned_scratch(l == 0 ? 7 : 9, wv.cands.size() * cm_elems * sizeof(int));
+        if (!h_acc || !h_cm) return CMOOP_ERR_CUDA;
+        CMOOP_CUDA_OK(cmoop::copy_async(h_acc, wv.d_acc, wv.cands.size() * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CMOOP_CUDA_OK(cmoop::copy_async(h_cm, wv.d_cm, wv.cands.size() * cm_elems * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CMOOP_CUDA_OK(cudaStreamSynchronize(st));
+        std::vector<int> cm(cm_elems);
+        for (size_t ci = 0; ci < wv.cands.size(); ++ci) {
+            Cand* c = wv.cands[ci];
+            const double* acc = h_acc + ci * 12 + 8;
+            memcpy(cm.data(), h_cm + ci * cm_elems, cm_elems * sizeof(int));
+            const double acc_eval = acc[2] / acc[1];
+            c->final_acc = cfg.acc_from_history ? c->last_val_acc : acc_eval;
+            c->fpr = fpr_from_confusion(cm, cfg.n_classes, cfg.fpr_filtered != 0);
+            double* o = out + (size_t)c->index * 6;
+            o[0] = c->final_acc;
+            o[1] = (double)c->n_params * 4.0 / (1024.0 * 1024.0);
+            o[2] = c->fpr;
+            o[3] = (double)c->epochs_run;
+            o[4] = c->last_val_loss;
+            o[5] = c->best_loss;
+        }
     }
     return CMOOP_OK;
 }
@@ -1524,9 +1581,24 @@ int run_population(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotype
     size_t free_b = 0, total_b = 0;
     CMOOP_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
     size_t budget = cfg->memory_budget_bytes > 0 ? (size_t)cfg->memory_budget_bytes : (size_t)(0.6 * (double)free_b);
-    // ---- waves: consecutive candidates while they fit the arena
+    // ---- waves: consecutive candidates while they fit the arena; a wave runs as up to kMaxLanes concurrent lanes
     int next = 0;
-    Wave wv;
+    constexpr int kMaxLanes = 2;
+    static Wave lanes[kMaxLanes];             // task-list blobs are kept across calls (grow-only, like the arena)
+    static cudaStream_t lane_streams[kMaxLanes] = {nullptr, nullptr};
+    static cudaEvent_t lane_fork = nullptr, lane_join[kMaxLanes] = {nullptr, nullptr};
+    cudaStream_t main_stream = eng.stream;
+    lane_streams[0] = main_stream;
+    for (int l = 1; l < kMaxLanes; ++l)
+        if (!lane_streams[l]) CMOOP_CUDA_OK(cudaStreamCreateWithFlags(&lane_streams[l], cudaStreamNonBlocking));
+    if (!lane_fork) {
+        CMOOP_CUDA_OK(cudaEventCreateWithFlags(&lane_fork, cudaEventDisableTiming));
+        for (int l = 0; l < kMaxLanes; ++l) CMOOP_CUDA_OK(cudaEventCreateWithFlags(&lane_join[l], cudaEventDisableTiming));
+    }
+    // CMOOP_CNN_LANES=1 switches the concurrency off (A/B); per-kernel profiling and the debug hooks need one stream
+    static const int lanes_env = getenv("CMOOP_CNN_LANES") ? atoi(getenv("CMOOP_CNN_LANES")) : kMaxLanes;
+    const int lanes_wanted = (g_prof_on || debug_steps > 0 || host_permutations(data->n_train) || debug_sync())
+                                 ? 1 : std::max(1, std::min(kMaxLanes, lanes_env));
     static char* arena_base = nullptr;        // grow-only, kept across calls (one process drives one GPU)
     static size_t arena_cap = 0;
     if (arena_cap > 0 && !(cfg->memory_budget_bytes > 0)) budget += arena_cap;   // already ours, not in the free figure
@@ -1556,23 +1628,53 @@ int run_population(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotype
         Arena a;
         a.base = arena_base;
         a.cap = arena_cap;
-        wv.cands.clear();
         const size_t n_wave = (size_t)(end - next), cm_elems = (size_t)cfg->n_classes * cfg->n_classes;
-        wv.d_acc = (double*)cmoop::device_scratch(9, n_wave * 12 * sizeof(double));
-        wv.d_cm = (int*)cmoop::device_scratch(10, n_wave * cm_elems * sizeof(int));
-        if (!wv.d_acc || !wv.d_cm) return CMOOP_ERR_CUDA;
-        for (int i = next; i < end; ++i) {
-            place(cands[i], a, *cfg, data->n_train, data->n_val, eng.batch);
-            cands[i].acc = wv.d_acc + (size_t)(i - next) * 12;
-            cands[i].confusion = wv.d_cm + (size_t)(i - next) * cm_elems;
-            wv.cands.push_back(&cands[i]);
+        double* d_acc = (double*)cmoop::device_scratch(9, n_wave * 12 * sizeof(double));
+        int* d_cm = (int*)cmoop::device_scratch(10, n_wave * cm_elems * sizeof(int));
+        if (!d_acc || !d_cm) return CMOOP_ERR_CUDA;
+        // lanes: the wave's candidates dealt out by descending arena footprint (a proxy of their cost) so that the lanes
+        // carry similar work; at least 8 candidates per lane
+        // measured (tools/bench_cnn.py, one epoch of 3 072 clips, B200): 2 lanes vs 1 -- 32 candidates 0.31 -> 0.28 s, 64: 0.46 ->
+        // 0.42 s, 128: 0.84 -> 0.80 s, 256: 1.61 -> 1.66 s (wide launches already fill the GPU; two of them only contend)
+        static const bool lanes_forced = getenv("CMOOP_CNN_LANES") != nullptr;
+        const int n_lanes = (n_wave >= 16 && (lanes_forced || n_wave <= 160)) ? lanes_wanted : 1;
+        std::vector<int> order((size_t)n_wave);
+        for (size_t i = 0; i < n_wave; ++i) order[i] = next + (int)i;
+        if (n_lanes > 1)
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cands[x].arena_bytes > cands[y].arena_bytes; });
+        for (int l = 0; l < kMaxLanes; ++l) lanes[l].cands.clear();
+        std::vector<size_t> lane_load((size_t)n_lanes, 0);
+        for (size_t i = 0; i < n_wave; ++i) {
+            const int l = (int)(std::min_element(lane_load.begin(), lane_load.end()) - lane_load.begin());
+            lanes[l].cands.push_back(&cands[order[i]]);
+            lane_load[l] += cands[order[i]].arena_bytes;
+        }
+        size_t slot = 0;
+        for (int l = 0; l < n_lanes; ++l) {
+            lanes[l].lane = l;
+            lanes[l].d_acc = d_acc + slot * 12;
+            lanes[l].d_cm = d_cm + slot * cm_elems;
+            for (Cand* c : lanes[l].cands) {
+                place(*c, a, *cfg, data->n_train, data->n_val, eng.batch);
+                c->acc = d_acc + slot * 12;
+                c->confusion = d_cm + slot * cm_elems;
+                ++slot;
+            }
         }
         if (a.off > a.cap) {
             cmoop::set_error("cnn: arena overflow placing candidates [%d,%d): laid out %zu bytes, sized %zu, capacity %zu", next, end,
                              a.off, need, a.cap);
             return CMOOP_ERR_CUDA;
         }
-        rc = run_wave(eng, wv, out, history, debug_steps, dbg_losses, dbg_grads, dbg_params);
+        // fork: the lanes start after everything enqueued on the main stream so far; join: the main stream continues after them
+        CMOOP_CUDA_OK(cudaEventRecord(lane_fork, main_stream));
+        for (int l = 1; l < n_lanes; ++l) CMOOP_CUDA_OK(cudaStreamWaitEvent(lane_streams[l], lane_fork, 0));
+        rc = run_wave(eng, lanes, n_lanes, lane_streams, out, history, debug_steps, dbg_losses, dbg_grads, dbg_params);
+        eng.stream = main_stream;
+        for (int l = 1; l < n_lanes; ++l) {
+            cudaEventRecord(lane_join[l], lane_streams[l]);
+            cudaStreamWaitEvent(main_stream, lane_join[l], 0);
+        }
         if (rc != CMOOP_OK) break;
         next = end;
     }
@@ -1584,7 +1686,7 @@ int run_population(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotype
         (void)cudaGetLastError();
     }
     prof_resolve();
-    if (wv.d_blob) cudaFree(wv.d_blob);
+    if (rc != CMOOP_OK) cudaDeviceSynchronize();     // a failed wave may have left work on a lane stream
     return rc;
 }
 

@@ -288,6 +288,25 @@ def test_waves_and_bf16_batching_invariance():
     assert np.isfinite(outs[0][0]).all()
 
 
+def test_concurrent_lanes_do_not_change_results():
+    """A wave of 16...160 candidates runs as two concurrent lanes (own task lists and CUDA stream each, engine.cu run_wave);
+    candidates never interact, so every row must equal the one-at-a-time evaluation (single lane) bit for bit -- with early
+    stopping active, so that the lanes rebuild their task lists at different epochs."""
+    import random
+    from cmoop_audio_processing_b200.nsga import HPARAM_SPACE
+    from cmoop_audio_processing_b200.problem import FitnessProblem, TrainConfig
+    xt, yt, xv, yv = make_data(192, 128)
+    rng = random.Random(3)
+    hps = [{k: rng.choice(v) for k, v in HPARAM_SPACE.items()} for _ in range(20)]
+    seeds = list(range(40, 60))
+    cfg = TrainConfig(variant="B", epochs=4, patience=1, restore_best_weights=True, acc_from="evaluate", precision="bf16")
+    prob = FitnessProblem(xt, yt, xv, yv, classes=N_CLASSES, config=cfg)
+    together, _ = prob.train_eval(hps, seeds)
+    for i in (0, 7, 13, 19):
+        alone, _ = prob.train_eval([hps[i]], [seeds[i]])
+        np.testing.assert_array_equal(alone[0], together[i])
+
+
 def test_birdclef_shaped_problem():
     """BASELINE configs[3] shape: 128 x 313 feature maps, 397 classes (sa_nsga_penalty.py:61,102,141).  Exercises the stem
     kernels on wide rows, the patch-resident convolution with its widest patch (one CTA per SM) and the im2col fallback;
