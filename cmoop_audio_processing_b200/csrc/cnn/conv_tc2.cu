@@ -331,13 +331,24 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(bn);
             const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-            const int tps = 128 / bn;                  // (slab, tap) entries per 16 KB weight stage
-            const int total = n_slab * taps;
-            int st = 0, e = 0;                         // stage counter; entry = slab * taps + tap in weight-stream order
-            long long t_first = 0;
+            // Lean issue loop (round 2): the per-tap bookkeeping runs on ONE thread, so every dependent integer instruction is
+            // ~5 clk of the tile's critical path.  No runtime division / modulo (tps is a power of two, the ring has two
+            // stages), running byte addresses instead of kh * Wp + kw products, task fields read once from shared memory.
+            // Measured with CMOOP_TC2_PROF=1 before: ~300 clk per tap of a 16-filter tile for 2 UMMAs of 16 clk each.
+            const uint32_t tps = 128u / (uint32_t)bn;  // (slab, tap) entries per 16 KB weight stage: 8 / 4 / 2 / 1
+            const int kk = T.k, cin = T.Cin;
+            const uint32_t wsm_s = smem_u32(wsm);
+            const uint32_t row_skip = (uint32_t)(Wp - kk) * 128u;     // from the end of one kernel row to the start of the next
+            uint32_t st = 0, sub = 0;                  // stage counter; entry within the stage
+            uint32_t b_addr = wsm_s;                   // byte address of the current weight entry
+            uint32_t acc = 0;                          // 0 for the very first UMMA of the tile
+            long long t_first = 0, t_wwait = 0, t_pwait = 0;
             for (int sl = 0; sl < n_slab; ++sl) {
-                const int b = sl % pb;
-                mbar_wait(&pfull[b], ((uint32_t)(sl / pb)) & 1u);
+                const int b = pb == 2 ? (sl & 1) : 0;
+                const uint32_t pph = pb == 2 ? ((uint32_t)sl >> 1) & 1u : (uint32_t)sl & 1u;
+                const long long tp0 = prof ? clock64() : 0;
+                mbar_wait(&pfull[b], pph);
+                if (prof && sl > 0) t_pwait += clock64() - tp0;
                 if (sl == 0) {
                     mbar_wait(&wfull[0], 0);
                     t_first = clock64();
@@ -346,30 +357,39 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
                 // descriptors: the high word is constant (SBO 1024 B, version 1, SWIZZLE_128B); the issue loop only adds to
                 // the 14-bit start-address field of the low word (a single issuing thread that rebuilds 64-bit descriptors
                 // per UMMA is slower than the tensor pipe: tools/microbench/umma_layouts.cu)
-                const uint32_t a_base = smem_u32(patch + (size_t)b * patch_stride) + (uint32_t)row0_off * 128u;
-                const int ksteps = min(T.Cin - sl * P2_SLAB, P2_SLAB) >> 4;
-                int kh = 0, kw = 0;
-                for (int t = 0; t < taps; ++t, ++e) {
-                    const int sub = e % tps, ws = st % P2_WS;
+                uint32_t a_tap = smem_u32(patch + (size_t)b * patch_stride) + (uint32_t)row0_off * 128u;   // tap (0, 0)
+                const int ksteps = min(cin - sl * P2_SLAB, P2_SLAB) >> 4;
+                const bool last_slab = sl == n_slab - 1;
+                int kw = 0;
+                for (int t = 0; t < taps; ++t) {
+                    const uint32_t ws = st & 1u;
                     if (sub == 0) {
-                        mbar_wait(&wfull[ws], ((uint32_t)(st / P2_WS)) & 1u);
+                        const long long tw0 = prof ? clock64() : 0;
+                        mbar_wait(&wfull[ws], (st >> 1) & 1u);
+                        if (prof) t_wwait += clock64() - tw0;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
-                    const uint32_t a_lo = (((a_base + (uint32_t)(kh * Wp + kw) * 128u) >> 4) & 0x3FFFu) | (1u << 16);
-                    const uint32_t b_lo = (((smem_u32(wsm + ws * P2_W_STAGE) + (uint32_t)sub * entry_bytes) >> 4) & 0x3FFFu) | (1u << 16);
+                    const uint32_t a_lo = ((a_tap >> 4) & 0x3FFFu) | (1u << 16);
+                    const uint32_t b_lo = ((b_addr >> 4) & 0x3FFFu) | (1u << 16);
                     for (int k4 = 0; k4 < ksteps; ++k4) {
                         const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (uint32_t)k4 * 2u);
 #pragma unroll
                         for (int mt = 0; mt < P2_MT; ++mt) {
                             const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (uint32_t)mt * 1024u + (uint32_t)k4 * 2u);
-                            umma_bf16(tmem_base + (uint32_t)(mt * 128), ad, bd, idesc, (sl | t | k4) != 0 ? 1u : 0u);
+                            umma_bf16(tmem_base + (uint32_t)(mt * 128), ad, bd, idesc, acc);
                         }
+                        acc = 1u;
                     }
-                    if (sub == tps - 1 || e == total - 1) {        // last entry of the stage (or of the tile)
+                    ++sub;
+                    b_addr += entry_bytes;
+                    if (sub == tps || (last_slab && t == taps - 1)) {      // last entry of the stage (or of the tile)
                         umma_commit(&wempty[ws]);
                         ++st;
+                        sub = 0;
+                        b_addr = wsm_s + ((st & 1u) ? (uint32_t)P2_W_STAGE : 0u);
                     }
-                    if (++kw == T.k) { kw = 0; ++kh; }
+                    a_tap += 128u;
+                    if (++kw == kk) { kw = 0; a_tap += row_skip; }
                 }
                 umma_commit(&pempty[b]);
             }
@@ -377,6 +397,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
             if (prof) {
                 atomicAdd(prof + 2, (unsigned long long)(t_first - t_pro));
                 atomicAdd(prof + 3, (unsigned long long)(clock64() - t_first));
+                atomicAdd(prof + 7, (unsigned long long)(t_wwait + t_pwait));
             }
         }
         __syncwarp();
@@ -504,8 +525,8 @@ int Launch::conv_tc2(const TcConvTask* tasks, int n, int tiles, int n_b, int ste
                     const unsigned long long* r = h + i * 8;
                     if (!r[0]) continue;
                     fprintf(stderr, "tc2 prof slot %2d: ctas %6llu  per-CTA clk: prologue %6llu  first-operands %6llu  mma-loop %6llu  "
-                            "to-accum %6llu  epilogue %6llu  total %6llu\n", i, r[0], r[1] / r[0], r[2] / r[0], r[3] / r[0],
-                            r[4] / r[0], r[5] / r[0], r[6] / r[0]);
+                            "to-accum %6llu  epilogue %6llu  total %6llu  loop-waits %6llu\n", i, r[0], r[1] / r[0], r[2] / r[0], r[3] / r[0],
+                            r[4] / r[0], r[5] / r[0], r[6] / r[0], r[7] / r[0]);
                 }
             });
         }
