@@ -201,6 +201,19 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
         }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&pfull[0], (uint32_t)n_rows * (uint32_t)Wp * 128u);
+    }
+    if (warp == 0) {
+        // slab 0 of the patch is requested right here, by the warp whose lane 0 initialised the barriers: the ~2 k clk of TMA
+        // latency run under the TMEM allocation, the bias load and the block barrier below instead of after them; one row
+        // box per lane (a single thread spends ~120 clk per box: 1.8 k clk for the ~15 rows of a patch)
+        __syncwarp();
+        const uint32_t row_bytes = (uint32_t)Wp * 128u;
+        tmap_acquire(T.tmap);
+        for (int r = lane; r < n_rows; r += 32) {
+            const int R = R0 + r, n = floor_div(R, Hp_rows), hp = R - n * Hp_rows;
+            tma_load_row(patch + (size_t)r * row_bytes, T.tmap, 0, -p, hp - p, n, &pfull[0]);
+        }
     }
     if (warp == P2_PRODUCERS / 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -223,8 +236,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) conv_tc2_kernel(const TcConvTas
         // ================= patch loads: one 64-channel slab per buffer, one row box per padded image row =================
         if (tid == 0) {
             const uint32_t row_bytes = (uint32_t)Wp * 128u;
-            tmap_acquire(T.tmap);
-            for (int sl = 0; sl < n_slab; ++sl) {
+            for (int sl = 1; sl < n_slab; ++sl) {          // slab 0 was requested in the prologue
                 const int b = sl % pb;
                 mbar_wait(&pempty[b], (((uint32_t)(sl / pb)) & 1u) ^ 1u);
                 uint8_t* dst = patch + (size_t)b * patch_stride;
