@@ -1339,7 +1339,7 @@ bool host_permutations(int n_train) {
     return host_perm || !Launch::perm_ok(n_train);
 }
 
-// Trains and scores one wave of candidates to completion.  The wave's candidates (8...160 of them) are split over `n_lanes` LANES, each with
+// Trains and scores one wave of candidates to completion.  The wave's candidates (8 or more) are split over `n_lanes` LANES, each with
 // its own task lists and CUDA stream, stepped in lock-step by this one host thread: lane 0's forward / backward / Adam
 // launches of a step are enqueued on stream 0, lane 1's on stream 1, ...  The lanes share nothing but the read-only
 // dataset, so the device overlaps one lane's latency-bound small kernels and launch tails with the other lane's wide
@@ -1634,11 +1634,11 @@ int run_population(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotype
         if (!d_acc || !d_cm) return CMOOP_ERR_CUDA;
         // lanes: the wave's candidates dealt out by descending arena footprint (a proxy of their cost) so that the lanes
         // carry similar work; at least 4 candidates per lane (11 candidates: 0.33 -> 0.29 s for two epochs, 24: 0.46 -> 0.41 s)
-        // measured (tools/bench_cnn.py, one epoch of 3 072 clips, B200): 2 lanes vs 1 -- 32 candidates 0.31 -> 0.28 s, 64: 0.46 ->
-        // 0.42 s, 128: 0.84 -> 0.80 s, 256: 1.61 -> 1.66 s (wide launches already fill the GPU; two of them only contend)
-        static const bool lanes_forced = getenv("CMOOP_CNN_LANES") != nullptr;
+        // measured on B200, 2 lanes vs 1 (tools/bench_cnn.py, one epoch of 3 072 clips): 11 candidates 0.33 -> 0.29 s (two epochs),
+        // 32: 0.31 -> 0.28 s, 64: 0.46 -> 0.42 s, 128: 0.84 -> 0.80 s; bench.py headline (256 candidates x 4 epochs, two runs
+        // each): 43.3 -> 45.0 evals/s; true evaluations of a generation (85 candidates): 0.75-0.88 -> 0.65-0.82 s
         static const size_t lane_min = getenv("CMOOP_CNN_LANE_MIN") ? (size_t)atoi(getenv("CMOOP_CNN_LANE_MIN")) : 8;
-        const int n_lanes = (n_wave >= lane_min && (lanes_forced || n_wave <= 160)) ? lanes_wanted : 1;
+        const int n_lanes = n_wave >= lane_min ? lanes_wanted : 1;
         std::vector<int> order((size_t)n_wave);
         for (size_t i = 0; i < n_wave; ++i) order[i] = next + (int)i;
         if (n_lanes > 1)

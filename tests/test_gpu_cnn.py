@@ -289,7 +289,7 @@ def test_waves_and_bf16_batching_invariance():
 
 
 def test_concurrent_lanes_do_not_change_results():
-    """A wave of 8...160 candidates runs as two concurrent lanes (own task lists and CUDA stream each, engine.cu run_wave);
+    """A wave of 8 or more candidates runs as two concurrent lanes (own task lists and CUDA stream each, engine.cu run_wave);
     candidates never interact, so every row must equal the one-at-a-time evaluation (single lane) bit for bit -- with early
     stopping active, so that the lanes rebuild their task lists at different epochs."""
     import random
