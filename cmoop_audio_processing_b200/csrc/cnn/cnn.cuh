@@ -132,6 +132,7 @@ struct PostTask {
     int H, W, C, Ho, Wo;
     int pool, relu_mid, add_skip, relu_in, has_bn;
     int stat_tiles, bwd_rows;
+    int bwd_pix;           // output pixels per CTA of post_bwd_reduce (= per partial row of bwd_part)
     int block_begin;       // grouped offset for post_fwd_kernel
     int block_begin_apply; // grouped offset for post_bwd_apply_kernel
     int block_begin_bwd;   // grouped offset for the backward reduce kernel
@@ -218,6 +219,7 @@ struct Launch {
     // of ~log2(n_tasks) dependent global loads at the start of every CTA
     static int post_fwd(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream, const int* block_task = nullptr,
                         bool half = false);     // half: the launch's activations are stored in bf16 only
+    static int bwd_pix(long long out_pixels);               // pixels per CTA / partial row of post_bwd_reduce for one task
     static int post_bwd_reduce(const PostTask* tasks, int n_tasks, int total_blocks, int n_b, void* stream, const int* block_task = nullptr,
                                bool half = false);
     static int bn_bwd_finalize(const PostTask* tasks, int n_tasks, int max_c, int n_b, void* stream);

@@ -148,7 +148,7 @@ struct Unit {
     int fc_index = -1;
     long long w_off = 0, bn_off = -1;
     long long u_elems = 0, v_elems = 0;
-    int stat_tiles = 0, bwd_rows = 0, wg_splits = 1, wg_chunk = 0;
+    int stat_tiles = 0, bwd_rows = 0, bwd_pix = 128, wg_splits = 1, wg_chunk = 0;
     float* U = nullptr;
     float* V = nullptr;
     float* stat = nullptr;
@@ -322,8 +322,8 @@ void build_units(Cand& c, const cmoop_cnn_config& cfg, int H, int W, int batch) 
         const long long M = (long long)batch * u.Ho * u.Wo;
         u.stat_tiles = (int)((M + 63) / 64);
         const long long npix = (long long)batch * u.Po * u.Qo;
-        const int cb = (u.cout / 4) < 128 ? (u.cout / 4) : 128;     // post_bwd_reduce: 4 channels per thread
-        u.bwd_rows = (int)(((npix + 127) / 128) * (128 / cb));
+        u.bwd_pix = Launch::bwd_pix(npix);                         // post_bwd_reduce: one partial row per CTA
+        u.bwd_rows = (int)((npix + u.bwd_pix - 1) / u.bwd_pix);
         int splits = (int)std::min<long long>(32, std::max<long long>(1, M / 2048));
         int chunk = (int)((M + splits - 1) / splits);
         const int gran = u.tc ? 64 : 16;
@@ -677,7 +677,7 @@ struct Engine {
                     p.H = u.Ho; p.W = u.Wo; p.C = u.cout; p.Ho = u.Po; p.Wo = u.Qo;
                     p.pool = u.pool; p.relu_mid = u.relu_mid; p.add_skip = u.add_skip; p.relu_in = u.relu_epi;
                     p.has_bn = u.has_bn;
-                    p.stat_tiles = u.stat_tiles; p.bwd_rows = u.bwd_rows;
+                    p.stat_tiles = u.stat_tiles; p.bwd_rows = u.bwd_rows; p.bwd_pix = u.bwd_pix;
                     if (u.post_fwd) {
                         PostTask q = p;
                         q.block_begin = S.post_fwd.total;
@@ -689,7 +689,7 @@ struct Engine {
                         PostTask q = p;
                         q.block_begin_bwd = S.post_bn.total;
                         S.post_bn.h.push_back(q);
-                        S.post_bn.total += (int)(((long long)batch * u.Po * u.Qo + 127) / 128);
+                        S.post_bn.total += u.bwd_rows;
                     }
                     PostTask q = p;
                     q.block_begin_apply = S.post_bwd.total;

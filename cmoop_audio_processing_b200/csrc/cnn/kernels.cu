@@ -580,28 +580,34 @@ __global__ void __launch_bounds__(256, 2) post_fwd_kernel(const PostTask* __rest
 }
 
 // BN backward, pass 1: per-channel partial sums of g and g*xhat over the unit's output elements.
-// A CTA covers 128 output pixels; thread = (pixel lane, 4 channels); one partial row per (CTA, pixel lane).
+// A CTA covers T.bwd_pix output pixels (128 on the large maps, 32 on the small ones: the deep blocks have 768-2 240 pooled
+// pixels per batch, and a thread that walks 128 of them alone is a ~200 us chain of dependent gathers); thread = (pixel
+// lane, 4 channels); the pixel lanes are summed in lane order through shared memory: ONE partial row per CTA.
 template <bool HALF>
-__global__ void __launch_bounds__(128) post_bwd_reduce_kernel(const PostTask* __restrict__ tasks, int n_tasks,
+__global__ void __launch_bounds__(256) post_bwd_reduce_kernel(const PostTask* __restrict__ tasks, int n_tasks,
                                                               int n_b, const int* __restrict__ block_task) {
+    __shared__ float red[256 * 8];
     const int t = block_find_task(tasks, n_tasks, blockIdx.x, [](const PostTask& r) { return r.block_begin_bwd; }, block_task);
     const PostTask T = tasks[t];
     const int blk = blockIdx.x - T.block_begin_bwd;
     const int C4 = T.C >> 2;
     const int cb = C4 < 128 ? C4 : 128;
-    const int lanes = 128 / cb;
+    const int lanes = 256 / cb;
     const int p_lane = threadIdx.x / cb, c_lane = threadIdx.x - p_lane * cb;
-    if (p_lane >= lanes) return;
+    const bool active = p_lane < lanes;
     const int n_pix = n_b * T.Ho * T.Wo;
-    const int pix0 = blk * 128, pix1 = pix0 + 128 < n_pix ? pix0 + 128 : n_pix;
-    for (int c4 = c_lane; c4 < C4; c4 += cb) {
-        const int c = c4 * 4;
+    const int pix0 = blk * T.bwd_pix, pix1 = pix0 + T.bwd_pix < n_pix ? pix0 + T.bwd_pix : n_pix;
+    if (pix0 >= n_pix) return;                          // uniform for the block (short last batch)
+    for (int cbase = 0; cbase < C4; cbase += cb) {      // same trip count for every thread (block barriers inside)
+        const int c4 = cbase + c_lane;
+        const bool live = active && c4 < C4;
+        const int c = (live ? c4 : 0) * 4;
         const float4 mean = ld4(T.bn + 0 * T.C + c), invstd = ld4(T.bn + 1 * T.C + c);
         const float4 scale = ld4(T.bn + 2 * T.C + c), shift = ld4(T.bn + 3 * T.C + c);
         const float mu[4] = {mean.x, mean.y, mean.z, mean.w}, is[4] = {invstd.x, invstd.y, invstd.z, invstd.w};
         const float sc[4] = {scale.x, scale.y, scale.z, scale.w}, sh[4] = {shift.x, shift.y, shift.z, shift.w};
         float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int pix = pix0 + p_lane; pix < pix1; pix += lanes) {
+        for (int pix = pix0 + p_lane; live && pix < pix1; pix += lanes) {
             const long long e = (long long)pix * T.C + c;
             const float4 gv = ld4(T.dv + e);
             float g[4] = {gv.x, gv.y, gv.z, gv.w};
@@ -634,9 +640,32 @@ __global__ void __launch_bounds__(128) post_bwd_reduce_kernel(const PostTask* __
                 sgx[q] = fmaf(gq, (u[q] - mu[q]) * is[q], sgx[q]);
             }
         }
-        const long long rowi = (long long)blk * lanes + p_lane;
-        *reinterpret_cast<float4*>(T.bwd_part + (rowi * 2 + 0) * T.C + c) = make_float4(sg[0], sg[1], sg[2], sg[3]);
-        *reinterpret_cast<float4*>(T.bwd_part + (rowi * 2 + 1) * T.C + c) = make_float4(sgx[0], sgx[1], sgx[2], sgx[3]);
+        // pixel lanes -> one row: lanes that share a warp (cb < 32) are combined by shuffles first, then the per-warp (or
+        // per-lane) partials go through shared memory and the first cb threads add them in a fixed order
+        float a[8] = {sg[0], sg[1], sg[2], sg[3], sgx[0], sgx[1], sgx[2], sgx[3]};
+        for (int msk = cb; msk < 32; msk <<= 1) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a[q] += __shfl_xor_sync(0xffffffffu, a[q], msk);
+        }
+        const int groups = cb < 32 ? 8 : lanes;                 // partial rows in shared memory: per warp / per pixel lane
+        const int grp = cb < 32 ? (threadIdx.x >> 5) : p_lane;
+        if (cb >= 32 || (threadIdx.x & 31) < cb) {
+            float* mine = red + (grp * cb + c_lane) * 8;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) mine[q] = a[q];
+        }
+        __syncthreads();
+        if (live && p_lane == 0) {
+            float r8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int l = 0; l < groups; ++l) {
+                const float* r = red + (l * cb + c_lane) * 8;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) r8[q] += r[q];
+            }
+            *reinterpret_cast<float4*>(T.bwd_part + ((long long)blk * 2 + 0) * T.C + c) = make_float4(r8[0], r8[1], r8[2], r8[3]);
+            *reinterpret_cast<float4*>(T.bwd_part + ((long long)blk * 2 + 1) * T.C + c) = make_float4(r8[4], r8[5], r8[6], r8[7]);
+        }
+        __syncthreads();
     }
 }
 
@@ -646,10 +675,8 @@ __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const PostTask* __
     const int c = blockIdx.y * 8 + (threadIdx.x & 7);
     if (!T.has_bn || blockIdx.y * 8 >= T.C) return;
     const int r_lane = threadIdx.x >> 3;
-    const int C4 = T.C >> 2;
-    const int lanes_w = 128 / (C4 < 128 ? C4 : 128);          // partial rows per CTA written by post_bwd_reduce
     const long long n_pix = (long long)n_b * T.Ho * T.Wo;
-    const long long rows = ((n_pix + 127) / 128) * lanes_w;
+    const long long rows = (n_pix + T.bwd_pix - 1) / T.bwd_pix;      // one partial row per CTA of post_bwd_reduce
     const double count = (double)n_b * T.H * T.W;
     double sg = 0.0, sgx = 0.0;
     if (c < T.C) {
@@ -1076,12 +1103,13 @@ int Launch::post_fwd(const PostTask* tasks, int n, int blocks, int n_b, void* st
         post_fwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b, bt);
     return check();
 }
+int Launch::bwd_pix(long long npix) { return npix >= 8192 ? 128 : 32; }
 int Launch::post_bwd_reduce(const PostTask* tasks, int n, int blocks, int n_b, void* st, const int* bt, bool half) {
     if (n == 0 || blocks == 0) return 0;
     if (half)
-        post_bwd_reduce_kernel<true><<<blocks, 128, 0, (cudaStream_t)st>>>(tasks, n, n_b, bt);
+        post_bwd_reduce_kernel<true><<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b, bt);
     else
-        post_bwd_reduce_kernel<false><<<blocks, 128, 0, (cudaStream_t)st>>>(tasks, n, n_b, bt);
+        post_bwd_reduce_kernel<false><<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b, bt);
     return check();
 }
 int Launch::bn_bwd_finalize(const PostTask* tasks, int n, int max_c, int n_b, void* st) {
