@@ -1103,7 +1103,7 @@ int Launch::post_fwd(const PostTask* tasks, int n, int blocks, int n_b, void* st
         post_fwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)st>>>(tasks, n, n_b, bt);
     return check();
 }
-int Launch::bwd_pix(long long npix) { return npix >= 8192 ? 128 : 32; }
+int Launch::bwd_pix(long long npix) { return npix >= 16384 ? 256 : (npix >= 4096 ? 128 : 32); }
 int Launch::post_bwd_reduce(const PostTask* tasks, int n, int blocks, int n_b, void* st, const int* bt, bool half) {
     if (n == 0 || blocks == 0) return 0;
     if (half)
