@@ -624,7 +624,9 @@ def run_ours(args) -> None:
     h_xv = torch.empty(x_val.shape, dtype=torch.float32, pin_memory=True).copy_(x_val)
     torch.cuda.synchronize()
     np_xt, np_xv = h_xt.numpy(), h_xv.numpy()
-    gens_w, gens_k = min(args.warmup, 2), max(1, min(args.steps, args.e2e_generations))
+    # timed generations: a fixed count (not tied to --steps): one generation in ~8 hits an optimiser start of the surrogate
+    # fit that L-BFGS-B walks for seconds, so a short run is dominated by whether it caught one
+    gens_w, gens_k = min(args.warmup, 2), max(1, args.e2e_generations)
     e2e_prob = FitnessProblem.sa_nsga_local(prob.data, None, None, None, classes=N_CLASSES, config=cfg, seed=10_000)
     ops = drivers.default_ops(e2e_prob)
     ops.SurrogateManager = lambda: __import__("cmoop_audio_processing_b200.surrogate", fromlist=["x"]).SurrogateManager(
@@ -761,7 +763,7 @@ def main() -> None:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--pop", type=int, default=POP, help="population (BASELINE configs[4]: 256)")
     ap.add_argument("--epoch-cap", type=int, default=4, help="epoch ceiling of every candidate (reference: 300, ES patience 5)")
-    ap.add_argument("--e2e-generations", type=int, default=6, help="timed SA-NSGA-II generations of the e2e leg (<= steps)")
+    ap.add_argument("--e2e-generations", type=int, default=8, help="timed SA-NSGA-II generations of the e2e leg")
     ap.add_argument("--gp-fit-backend", choices=["device", "host"], default="device")
     ap.add_argument("--cpu-candidates", type=int, default=4, help="whole candidates of the N=1 cpu_baseline sample")
     ap.add_argument("--mfcc-clips", type=int, default=65536, help="clips per GPU of the MFCC extra (BASELINE configs[1])")
