@@ -31,6 +31,12 @@ static void* g_pin[kSlots];
 static size_t g_pin_bytes[kSlots];
 static cudaStream_t g_stream = nullptr;
 
+// The library keeps process-global device state (scratch slots, the internal stream, the CNN activation arena, the lanes'
+// task-list blobs): ONE device per process, as in the one-process-per-GPU launch (torchrun).  The first entry point that needs
+// the device binds the current one; running on another device afterwards is refused instead of silently reusing pointers
+// that belong to the first.
+static int g_bound_device = -1;
+
 bool ensure_device() {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -40,8 +46,20 @@ bool ensure_device() {
         (void)cudaGetLastError();
         return false;
     }
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return true;                                    // reported by the first real CUDA call
+    }
+    if (g_bound_device < 0) g_bound_device = cur;
+    if (cur != g_bound_device) {
+        set_error("libcmoop_b200 is bound to device %d in this process (scratch, arena and streams live there) but the current "
+                  "device is %d: run one process per GPU", g_bound_device, cur);
+        return false;
+    }
     return true;
 }
+int bound_device() { return g_bound_device; }
 
 cudaStream_t internal_stream() {
     if (!g_stream) {
@@ -106,6 +124,11 @@ int cmoop_device_count(void) {
 }
 
 int cmoop_set_device(int device) {
+    if (cmoop::bound_device() >= 0 && device != cmoop::bound_device()) {
+        cmoop::set_error("cmoop_set_device(%d): this process already runs on device %d (one process per GPU)", device,
+                         cmoop::bound_device());
+        return CMOOP_ERR_UNSUPPORTED;
+    }
     CMOOP_CUDA_OK(cudaSetDevice(device));
     return CMOOP_OK;
 }

@@ -32,6 +32,7 @@ inline cudaError_t copy_sync(void* dst, const void* src, size_t bytes, cudaMemcp
 }
 
 // Grow-only device/pinned scratch owned by the library (one per slot).
+int bound_device();                 // device this process is bound to (-1 before the first device entry point)
 void* device_scratch(int slot, size_t bytes);
 void* pinned_scratch(int slot, size_t bytes);
 cudaStream_t internal_stream();

@@ -41,7 +41,8 @@ int cmoop_abi_version(void);
 const char* cmoop_last_error(void);
 /* number of CUDA devices visible; 0 (not an error) on a CPU-only host */
 int cmoop_device_count(void);
-/* bind the calling thread (and the library's scratch/streams) to a device; one process per GPU */
+/* bind the calling thread (and the library's scratch / streams / arena) to a device; ONE device per process (one process
+ * per GPU): once an entry point has used a device, another device is refused with CMOOP_ERR_UNSUPPORTED */
 int cmoop_set_device(int device);
 /* kernel launches issued by this library since load (bench.py "gpu_launches") */
 uint64_t cmoop_launch_count(void);
