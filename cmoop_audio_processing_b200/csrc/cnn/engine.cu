@@ -1447,7 +1447,7 @@ int run_wave(Engine& eng, Wave* lanes, int n_lanes, cudaStream_t* streams, doubl
         for (int l = 0; l < n_lanes; ++l) {
             if (!lane_live[l]) continue;
             Wave& wv = lanes[l];
-            h_accs[l] = (double*)cmoop::pinned_scratch(l == 0 ? 6 : 8, wv.cands.size() * 12 * sizeof(double));
+            h_accs[l] = (double*)cmoop::pinned_scratch(6 + 2 * l, wv.cands.size() * 12 * sizeof(double));
             if (!h_accs[l]) return CMOOP_ERR_CUDA;
             CMOOP_CUDA_OK(cmoop::copy_async(h_accs[l], wv.d_acc, wv.cands.size() * 12 * sizeof(double), cudaMemcpyDeviceToHost, streams[l]));
         }
@@ -1520,8 +1520,8 @@ int run_wave(Engine& eng, Wave* lanes, int n_lanes, cudaStream_t* streams, doubl
     for (int l = 0; l < n_lanes; ++l) {
         Wave& wv = lanes[l];
         cudaStream_t st = streams[l];
-        double* h_acc = (double*)cmoop::pinned_scratch(l == 0 ? 6 : 8, wv.cands.size() * 12 * sizeof(double));
-        int* h_cm = (int*)cmoop::pinned_scratch(l == 0 ? 7 : 9, wv.cands.size() * cm_elems * sizeof(int));
+        double* h_acc = (double*)cmoop::pinned_scratch(6 + 2 * l, wv.cands.size() * 12 * sizeof(double));
+        int* h_cm = (int*)cmoop::pinned_scratch(7 + 2 * l, wv.cands.size() * cm_elems * sizeof(int));
         if (!h_acc || !h_cm) return CMOOP_ERR_CUDA;
         CMOOP_CUDA_OK(cmoop::copy_async(h_acc, wv.d_acc, wv.cands.size() * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
         CMOOP_CUDA_OK(cmoop::copy_async(h_cm, wv.d_cm, wv.cands.size() * cm_elems * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1583,10 +1583,10 @@ int run_population(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotype
     size_t budget = cfg->memory_budget_bytes > 0 ? (size_t)cfg->memory_budget_bytes : (size_t)(0.6 * (double)free_b);
     // ---- waves: consecutive candidates while they fit the arena; a wave runs as up to kMaxLanes concurrent lanes
     int next = 0;
-    constexpr int kMaxLanes = 2;
+    constexpr int kMaxLanes = 4;              // compiled-in ceiling (CMOOP_CNN_LANES overrides the size-based default)
     static Wave lanes[kMaxLanes];             // task-list blobs are kept across calls (grow-only, like the arena)
-    static cudaStream_t lane_streams[kMaxLanes] = {nullptr, nullptr};
-    static cudaEvent_t lane_fork = nullptr, lane_join[kMaxLanes] = {nullptr, nullptr};
+    static cudaStream_t lane_streams[kMaxLanes] = {};
+    static cudaEvent_t lane_fork = nullptr, lane_join[kMaxLanes] = {};
     cudaStream_t main_stream = eng.stream;
     lane_streams[0] = main_stream;
     for (int l = 1; l < kMaxLanes; ++l)
@@ -1596,9 +1596,8 @@ int run_population(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotype
         for (int l = 0; l < kMaxLanes; ++l) CMOOP_CUDA_OK(cudaEventCreateWithFlags(&lane_join[l], cudaEventDisableTiming));
     }
     // CMOOP_CNN_LANES=1 switches the concurrency off (A/B); per-kernel profiling and the debug hooks need one stream
-    static const int lanes_env = getenv("CMOOP_CNN_LANES") ? atoi(getenv("CMOOP_CNN_LANES")) : kMaxLanes;
-    const int lanes_wanted = (g_prof_on || debug_steps > 0 || host_permutations(data->n_train) || debug_sync())
-                                 ? 1 : std::max(1, std::min(kMaxLanes, lanes_env));
+    static const int lanes_env = getenv("CMOOP_CNN_LANES") ? atoi(getenv("CMOOP_CNN_LANES")) : 0;      // 0: by wave size
+    const bool one_lane = g_prof_on || debug_steps > 0 || host_permutations(data->n_train) || debug_sync();
     static char* arena_base = nullptr;        // grow-only, kept across calls (one process drives one GPU)
     static size_t arena_cap = 0;
     if (arena_cap > 0 && !(cfg->memory_budget_bytes > 0)) budget += arena_cap;   // already ours, not in the free figure
@@ -1638,7 +1637,10 @@ int run_population(cmoop_cnn_dataset_handle data, const cmoop_genotype* genotype
         // 32: 0.31 -> 0.28 s, 64: 0.46 -> 0.42 s, 128: 0.84 -> 0.80 s; bench.py headline (256 candidates x 4 epochs, two runs
         // each): 43.3 -> 45.0 evals/s; true evaluations of a generation (85 candidates): 0.75-0.88 -> 0.65-0.82 s
         static const size_t lane_min = getenv("CMOOP_CNN_LANE_MIN") ? (size_t)atoi(getenv("CMOOP_CNN_LANE_MIN")) : 8;
-        const int n_lanes = n_wave >= lane_min ? lanes_wanted : 1;
+        // 4 lanes for waves of up to 64 candidates (32: 124 -> 132 evals/s, 64: 159 -> 165 against 2 lanes), 2 above (85 / 256
+        // candidates: no difference between 2 and 4 lanes)
+        const int lanes_wanted = one_lane ? 1 : std::max(1, std::min(kMaxLanes, lanes_env > 0 ? lanes_env : (n_wave <= 64 ? 4 : 2)));
+        const int n_lanes = n_wave >= lane_min ? std::max(1, std::min(lanes_wanted, (int)(n_wave / 4))) : 1;
         std::vector<int> order((size_t)n_wave);
         for (size_t i = 0; i < n_wave; ++i) order[i] = next + (int)i;
         if (n_lanes > 1)
